@@ -1,0 +1,122 @@
+/* sgcdet_b200 -- C ABI of the B200-native SGCDet view-transform hot path.
+ *
+ * One shared library (sgcdet_b200/_C/libsgcdet_b200.so, sm_100a only).  Conventions for EVERY entry point:
+ *   - plain device pointers + sizes, no torch types; fp32 data, int32 indices unless stated (int64 for the
+ *     reference's spatial_shapes / level_start_index tensors);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it; nothing allocates, nothing syncs;
+ *   - the current device must already be the one that owns the pointers;
+ *   - return value is 0 on success, otherwise a cudaError_t (launch/argument error) -- the reference only
+ *     printf()s launch failures (wms_deform_attn_cuda.cu:45-48,207-210); here they are returned and the Python
+ *     shim raises RuntimeError.
+ * Reference file abbreviations:
+ *   CSRC = packages/3D-deformable-attention/DFA3D/dfa3D/ops/csrc
+ *   DSK  = CSRC/common/cuda/ms_depth_score_sample_cuda_kernel.cuh     DSL = CSRC/cuda/ms_depth_score_sample_cuda.cu
+ *   WMSK = CSRC/common/cuda/wms_deform_attn_cuda_kernel.cuh           WMSL = CSRC/cuda/wms_deform_attn_cuda.cu
+ *   F3D  = mmdet3d_plugin/models/im2voxel/transformer_utils/multi_scale_3ddeformable_attn_function.py
+ *   DCA  = mmdet3d_plugin/models/im2voxel/transformer_utils/deformable_cross_attention.py
+ *   ENC  = mmdet3d_plugin/models/im2voxel/transformer_utils/encoder.py
+ *   ASH  = mmdet3d_plugin/models/im2voxel/AdaptiveSparseHead.py       DH = mmdet3d_plugin/models/im2voxel/DenseHead.py
+ */
+#ifndef SGCDET_B200_H
+#define SGCDET_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------------
+ * B2: DFA3D operator boundary  (replaces the four functions of dfa3D._ext, CSRC/pybind.cpp:42-67)
+ *   value [B,S,M,Cm]  dist [B,S,M,D]  shapes3d [L,3] i64 (H,W,D)  shapes2d [L,2] i64  lsi [L] i64
+ *   loc [B,Q,M,L,P,3] (x=w,y=h,z=d in [0,1])  loc2d [...,2]  attn [B,Q,M,L,P]  depth_score [B,Q,M,L,P,4]
+ *   (corner order TL,TR,BR,BL: DSK:89-92).  im2col_step batching (WMSL:250-283) is a launch detail of the
+ *   reference and has no numerical effect; it is accepted and ignored by the Python shim.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* ms_depth_score_sample_forward (DSL:49-111, kernel DSK:94-148). out fully written. */
+int dfa3d_depth_score_fwd(const float* dist, const int64_t* shapes3d, const int64_t* lsi, const float* loc,
+                          int B, int S, int M, int D, int L, int Q, int P, float* out, void* stream);
+/* ms_depth_score_sample_backward (DSL:138-201, kernel DSK:242-327). grad_dist accumulated (atomics),
+ * grad_loc [B,Q,M,L,P,3] written: (0, 0, D * sum_corner g*(v_hi - v_lo)) (DSK:238-240). */
+int dfa3d_depth_score_bwd(const float* dist, const int64_t* shapes3d, const int64_t* lsi, const float* loc,
+                          const float* grad_out, int B, int S, int M, int D, int L, int Q, int P,
+                          float* grad_dist, float* grad_loc, void* stream);
+/* wms_deform_attn_forward (WMSL:213-288, kernel WMSK:240-303). out [B,Q,M*Cm] fully written. */
+int dfa3d_wms_fwd(const float* value, const int64_t* shapes2d, const int64_t* lsi, const float* loc2d,
+                  const float* attn, const float* depth_score, int B, int S, int M, int Cm, int L, int Q, int P,
+                  float* out, void* stream);
+/* wms_deform_attn_backward (WMSL:291-370, kernels WMSK:305-531). grad_value accumulated; grad_loc2d,
+ * grad_attn, grad_depth_score written. */
+int dfa3d_wms_bwd(const float* value, const int64_t* shapes2d, const int64_t* lsi, const float* loc2d,
+                  const float* attn, const float* depth_score, const float* grad_out, int B, int S, int M, int Cm,
+                  int L, int Q, int P, float* grad_value, float* grad_loc2d, float* grad_attn,
+                  float* grad_depth_score, void* stream);
+/* One-stage operator = MultiScale3DDeformableAttnFunction_fp32.forward/backward (F3D:277-351) without the
+ * depth-score round trip.  depth_score_out may be NULL. */
+int dfa3d_fused_fwd(const float* value, const float* dist, const int64_t* shapes3d, const int64_t* lsi,
+                    const float* loc, const float* attn, int B, int S, int M, int Cm, int D, int L, int Q, int P,
+                    float* out, float* depth_score_out, void* stream);
+int dfa3d_fused_bwd(const float* value, const float* dist, const int64_t* shapes3d, const int64_t* lsi,
+                    const float* loc, const float* attn, const float* grad_out, int B, int S, int M, int Cm, int D,
+                    int L, int Q, int P, float* grad_value, float* grad_dist, float* grad_loc, float* grad_attn,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * B1: path entry points (one DenseHead level of AdaptiveSparseHead; M = 8 heads, P = 4 points, L = 1)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Projection + visibility + view-major pair list.  Replaces VoxFormerEncoder_DFA3D.point_sampling
+ * (ENC:179-223) and the per-view nonzero()/rebatch loops (DCA:758-773).  proj [V,3,4] is built on the host
+ * exactly as ENC:168-177 does.  sel [Q] = selected voxel ids (NULL = identity), ref3d [N,3] (DH:44-45).
+ * Outputs: ref_cam [V,Q,3], mask [V,Q] u8, pair_index [V,Q] (-1 invisible), pair_vq [>= #pairs],
+ * view_offsets [V+1] (last = #pairs), count [Q].  scratch: sgc_project_scratch_ints(V,Q) int32. */
+int sgc_project_scratch_ints(int V, int Q);
+int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, int V, int Q, float ox, float oy,
+                        float oz, float eps, float one_minus_eps, float img_w, float img_h, float dbound0,
+                        float dscale, float* ref_cam, uint8_t* mask, int* pair_index, int* pair_vq,
+                        int* view_offsets, int* count, int* scratch, void* stream);
+
+/* Lift: reference-point sample (DCA:67-116) + offset/weight heads + softmax (DCA:423-436) + sampling
+ * locations (DCA:445-461) + 8-head 4-point DFA3D (F3D:277-302) for every visible pair.
+ * value [V,S,ldv] (no bias), G [V,S,ldg] (128 ch, [m][p][ox,oy,od,logit]), dist [V,S,D], vbias [C], gbias [128],
+ * n_pairs = device pointer to the pair count (view_offsets + V).  Writes samp [cap,32,4], slots [cap,C]. */
+int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
+                 const float* gbias, const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam,
+                 int S, int H, int W, int D, int Q, int C, float* samp, float* slots, void* stream);
+/* Backward of the above (F3D:303-351 + autograd of the Linear heads).  All grads ACCUMULATE (caller zeroes). */
+int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
+                 const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam, const float* samp,
+                 const float* grad_slots, int S, int H, int W, int D, int Q, int C, float* grad_value,
+                 float* grad_G, float* grad_dist, float* grad_vbias, float* grad_gbias, void* stream);
+
+/* Cross-view fusion (DCA:815-833).  mean [Q,C]: masked mean over views (zeros when no view sees q).
+ * attn: qt [8,Q,C] (scaled, key-projected query), t_out [8,Q,C] = sum_v softmax_v(qt.s_v) s_v, alpha [cap,8]. */
+int sgc_crossview_mean_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* mean, void* stream);
+int sgc_crossview_attn_fwd(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
+                           float* t_out, float* alpha, void* stream);
+/* Backward in two steps, because grad_mean depends on grad_qt through the host GEMMs:
+ *   _qt    : gscore [cap,8] (softmax backward of the view scores) and grad_qt [8,Q,C], both fully written;
+ *   _slots : grad_slots [#pairs,C] = grad_mean/n + sum_h (alpha grad_t[h] + gscore qt[h]), fully written. */
+int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q, int C,
+                              const float* grad_t, float* gscore, float* grad_qt, void* stream);
+int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index,
+                                 int V, int Q, int C, const float* grad_t, const float* grad_mean,
+                                 float* grad_slots, void* stream);
+
+/* Sparse volume construction on channel-last volumes [X,Y,Z,C].
+ * upsample: F.interpolate(x2, trilinear, align_corners=False) (ASH:64-69) fused with the occupancy head
+ * Linear(C,1)+Sigmoid (ASH:37-39,71).  bwd: grad_in written; grad_w [C], grad_b [1] accumulated. */
+int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ, const float* b_occ,
+                           float* vol_out, float* occ, void* stream);
+int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ, const float* occ,
+                           const float* grad_up, const float* grad_occ, float* gpre_scratch, float* grad_in,
+                           float* grad_w, float* grad_b, void* stream);
+/* topk_wo_grad (ASH:9-13) + nonzero compaction (DH:66): k largest, ties -> lower index; sel ascending. */
+int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream);
+/* vol[sel[i],:] += y[i,:] (DH:80-81 + ASH:77) and y[i,:] = vol[sel[i],:] (its backward). */
+int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
+int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGCDET_B200_H */

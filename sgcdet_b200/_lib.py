@@ -1,0 +1,80 @@
+"""ctypes binding of include/sgcdet_b200.h.  There is NO fallback: if the CUDA library is missing or a
+tensor is not a contiguous CUDA tensor the call raises."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / '_C' / 'libsgcdet_b200.so'
+_lib = None
+
+P = c_void_p
+I = c_int
+F = c_float
+
+# name -> argtypes (must mirror include/sgcdet_b200.h)
+SIGNATURES = {
+    'dfa3d_depth_score_fwd': [P, P, P, P, I, I, I, I, I, I, I, P, P],
+    'dfa3d_depth_score_bwd': [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
+    'dfa3d_wms_fwd': [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P],
+    'dfa3d_wms_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    'dfa3d_fused_fwd': [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P],
+    'dfa3d_fused_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P],
+    'sgc_project_scratch_ints': [I, I],
+    'sgc_project_compact': [P, P, P, I, I, F, F, F, F, F, F, F, F, F, P, P, P, P, P, P, P, P],
+    'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],
+    'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P],
+    'sgc_crossview_mean_fwd': [P, P, I, I, I, P, P],
+    'sgc_crossview_attn_fwd': [P, P, P, I, I, I, P, P, P],
+    'sgc_crossview_attn_bwd_qt': [P, P, P, I, I, I, P, P, P, P],
+    'sgc_crossview_attn_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P],
+    'sgc_upsample2x_occ_fwd': [P, I, I, I, I, P, P, P, P, P],
+    'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
+    'sgc_topk_select': [P, I, I, P, P, P],
+    'sgc_scatter_add_rows': [P, P, P, I, I, P],
+    'sgc_gather_rows': [P, P, P, I, I, P],
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f'{_LIB_PATH} is missing: build it with `python -m sgcdet_b200.build` '
+                '(sgcdet_b200 has no CPU or PyTorch fallback)')
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('sgcdet_b200: expected a CUDA tensor (there is no CPU implementation)')
+    if not t.is_contiguous():
+        raise RuntimeError('sgcdet_b200: tensor has to be contiguous')
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'sgcdet_b200.{name} failed with cudaError {rc}')

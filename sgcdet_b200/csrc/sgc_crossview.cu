@@ -1,0 +1,321 @@
+// sgc_crossview_*: cross-view fusion of the per-pair lifted features, one warp per voxel.
+//
+// Replaces DeformCrossAttention_DFA3D.forward lines 815-833 (deformable_cross_attention.py):
+//   slots scatter + count (815-820), masked mean over views (826), and the 8-head
+//   nn.MultiheadAttention over views with key_padding_mask = ~visible (829-833).
+//
+// The dense projections stay GEMMs of *voxel* count (static shapes), by commuting the linear maps:
+//   score[v,h]  = (W_k,h s_v + b_k,h) . q_h / sqrt(dh)  ==  qt[h] . s_v  + const(h)      (const cancels in softmax)
+//   out_h       = sum_v alpha[v,h] (W_v,h s_v + b_v,h)  ==  W_v,h t[h] + b_v,h,   t[h] = sum_v alpha[v,h] s_v
+// so the kernels here only need   qt [8,Q,C] = scale * W_k,h^T q_h   (host GEMM)   and emit   t [8,Q,C].
+//
+// Layout: slots [cap,C] pair-major; pair_index [V,Q] (-1 = invisible); count [Q]; alpha [cap,8] saved for bwd.
+// Lane l owns channels [l*CPL, l*CPL+CPL), CPL = C/32.
+#include "common.cuh"
+
+namespace sgc {
+
+constexpr int kMaxViews = 128;  // per-warp score scratch is [kMaxViews][8]
+constexpr int kCvWarps = 4;
+
+template <int CPL>
+__device__ __forceinline__ void load_row_cv(float (&dst)[CPL], const float* p) {
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const float4 t = ldg4(p + j);
+    dst[j] = t.x; dst[j + 1] = t.y; dst[j + 2] = t.z; dst[j + 3] = t.w;
+  }
+}
+template <int CPL>
+__device__ __forceinline__ void store_row_cv(float* p, const float (&src)[CPL]) {
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(src[j], src[j + 1], src[j + 2], src[j + 3]);
+}
+
+// Collect the pair ids of the views that see voxel q into ids[] (warp-shared), return how many.
+__device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, int V, int Q, int q, int lane,
+                                            int* ids) {
+  int n = 0;
+  for (int base = 0; base < V; base += 32) {
+    const int v = base + lane;
+    const int id = (v < V) ? __ldg(pair_index + (size_t)v * Q + q) : -1;
+    const unsigned b = __ballot_sync(SGC_FULL_MASK, id >= 0);
+    if (id >= 0) ids[n + __popc(b & ((1u << lane) - 1))] = id;
+    n += __popc(b);
+  }
+  __syncwarp();
+  return n;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __restrict__ slots,
+                                                                 const int* __restrict__ pair_index, int V, int Q,
+                                                                 float* __restrict__ mean) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float x[CPL];
+    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] += x[j];
+  }
+  if (n > 0) {
+    const float fn = (float)n;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] = acc[j] / fn;  // DCA:826
+  }
+  store_row_cv<CPL>(mean + (size_t)q * C + lane * CPL, acc);
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __restrict__ qt,
+                                                                 const float* __restrict__ slots,
+                                                                 const int* __restrict__ pair_index, int V, int Q,
+                                                                 float* __restrict__ t_out, float* __restrict__ alpha) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  __shared__ float s_sc[kCvWarps][kMaxViews][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  float(*sc)[8] = s_sc[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  if (n == 0) {
+    float z[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) z[j] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(t_out + h * hq + off, z);
+    return;
+  }
+  {  // phase 1: scores
+    float qv[8][CPL];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) load_row_cv<CPL>(qv[h], qt + h * hq + off);
+    for (int i = 0; i < n; ++i) {
+      float x[CPL];
+      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) p += qv[h][j] * x[j];
+        p = warp_sum(p);
+        if (lane == h) sc[i][h] = p;
+      }
+    }
+  }
+  __syncwarp();
+  // softmax over the visible views, per head: lane -> (head = lane & 7, views lane>>3, +4, ...)
+  {
+    const int h = lane & 7;
+    float mx = -INFINITY;
+    for (int i = lane >> 3; i < n; i += 4) mx = fmaxf(mx, sc[i][h]);
+    mx = fmaxf(mx, __shfl_xor_sync(SGC_FULL_MASK, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(SGC_FULL_MASK, mx, 16));
+    float sum = 0.f;
+    for (int i = lane >> 3; i < n; i += 4) {
+      const float e = expf(sc[i][h] - mx);
+      sc[i][h] = e;
+      sum += e;
+    }
+    sum += __shfl_xor_sync(SGC_FULL_MASK, sum, 8);
+    sum += __shfl_xor_sync(SGC_FULL_MASK, sum, 16);
+    for (int i = lane >> 3; i < n; i += 4) {
+      const float a = sc[i][h] / sum;
+      sc[i][h] = a;
+      alpha[(size_t)ids[i] * 8 + h] = a;
+    }
+  }
+  __syncwarp();
+  {  // phase 2: t[h] = sum_v alpha[v,h] s_v
+    float t[8][CPL];
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) t[h][j] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      float x[CPL];
+      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const float a = sc[i][h];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) t[h][j] += a * x[j];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(t_out + h * hq + off, t[h]);
+  }
+}
+
+// backward, step 1: g_alpha -> softmax backward -> gscore [cap,8] (stored) and grad_qt [8,Q,C]
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_qt_kernel(
+    const float* __restrict__ slots, const float* __restrict__ alpha, const int* __restrict__ pair_index, int V, int Q,
+    const float* __restrict__ grad_t, float* __restrict__ gscore, float* __restrict__ grad_qt) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  __shared__ float s_al[kCvWarps][kMaxViews][8];  // alpha
+  __shared__ float s_gs[kCvWarps][kMaxViews][8];  // grad of the scores
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  float(*al)[8] = s_al[wid];
+  float(*gs)[8] = s_gs[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  if (n == 0) {
+    float z[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) z[j] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(grad_qt + h * hq + off, z);
+    return;
+  }
+  for (int i = lane >> 3; i < n; i += 4) al[i][lane & 7] = __ldg(alpha + (size_t)ids[i] * 8 + (lane & 7));
+  {
+    float gt[8][CPL];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) load_row_cv<CPL>(gt[h], grad_t + h * hq + off);
+    // pass A: g_alpha[v,h] = grad_t[h] . s_v
+    for (int i = 0; i < n; ++i) {
+      float x[CPL];
+      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) p += gt[h][j] * x[j];
+        p = warp_sum(p);
+        if (lane == h) gs[i][h] = p;
+      }
+    }
+  }
+  __syncwarp();
+  {  // softmax backward per head
+    const int h = lane & 7;
+    float d = 0.f;
+    for (int i = lane >> 3; i < n; i += 4) d += al[i][h] * gs[i][h];
+    d += __shfl_xor_sync(SGC_FULL_MASK, d, 8);
+    d += __shfl_xor_sync(SGC_FULL_MASK, d, 16);
+    for (int i = lane >> 3; i < n; i += 4) {
+      const float g = al[i][h] * (gs[i][h] - d);
+      gs[i][h] = g;
+      gscore[(size_t)ids[i] * 8 + h] = g;
+    }
+  }
+  __syncwarp();
+  // pass B: grad_qt[h] = sum_v gscore[v,h] s_v
+  {
+    float gq[8][CPL];
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) gq[h][j] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      float x[CPL];
+      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const float g = gs[i][h];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) gq[h][j] += g * x[j];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(grad_qt + h * hq + off, gq[h]);
+  }
+}
+
+// backward, step 2 (after the host GEMMs produced grad_mean):
+//   grad_slots[v] = grad_mean/n + sum_h (alpha[v,h] grad_t[h] + gscore[v,h] qt[h])
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_slots_kernel(
+    const float* __restrict__ qt, const float* __restrict__ alpha, const float* __restrict__ gscore,
+    const int* __restrict__ pair_index, int V, int Q, const float* __restrict__ grad_t,
+    const float* __restrict__ grad_mean, float* __restrict__ grad_slots) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  if (n == 0) return;
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  float gm[CPL];
+  load_row_cv<CPL>(gm, grad_mean + off);
+  const float fn = (float)n;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) gm[j] = gm[j] / fn;
+  float gt[8][CPL], qv[8][CPL];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    load_row_cv<CPL>(gt[h], grad_t + h * hq + off);
+    load_row_cv<CPL>(qv[h], qt + h * hq + off);
+  }
+  for (int i = 0; i < n; ++i) {
+    const float* ap = alpha + (size_t)ids[i] * 8;
+    const float* gp = gscore + (size_t)ids[i] * 8;
+    const float4 a0 = ldg4(ap), a1 = ldg4(ap + 4), g0 = ldg4(gp), g1 = ldg4(gp + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float o[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) o[j] = gm[j];
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) o[j] += a[h] * gt[h][j] + g[h] * qv[h][j];
+    store_row_cv<CPL>(grad_slots + (size_t)ids[i] * C + lane * CPL, o);
+  }
+}
+
+}  // namespace sgc
+
+#define SGC_CV_LAUNCH(KERNEL, ...)                                                              \
+  do {                                                                                          \
+    if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;                                \
+    if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;                                  \
+    const int grid = (Q + sgc::kCvWarps - 1) / sgc::kCvWarps;                                   \
+    if (C == 256) sgc::KERNEL<8><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
+    else sgc::KERNEL<4><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);    \
+    SGC_CUDA_CHECK_LAST();                                                                      \
+    return 0;                                                                                   \
+  } while (0)
+
+extern "C" int sgc_crossview_mean_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* mean,
+                                      void* stream) {
+  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean);
+}
+
+extern "C" int sgc_crossview_attn_fwd(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
+                                      float* t_out, float* alpha, void* stream) {
+  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha);
+}
+
+extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
+                                         int C, const float* grad_t, float* gscore, float* grad_qt, void* stream) {
+  SGC_CV_LAUNCH(attn_bwd_qt_kernel, slots, alpha, pair_index, V, Q, grad_t, gscore, grad_qt);
+}
+
+extern "C" int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const float* gscore,
+                                            const int* pair_index, int V, int Q, int C, const float* grad_t,
+                                            const float* grad_mean, float* grad_slots, void* stream) {
+  SGC_CV_LAUNCH(attn_bwd_slots_kernel, qt, alpha, gscore, pair_index, V, Q, grad_t, grad_mean, grad_slots);
+}

@@ -1,0 +1,381 @@
+// Sparse-volume construction kernels (AdaptiveSparseHead.py:43-98, DenseHead.py:64-83), channel-last volumes.
+//
+//   sgc_upsample2x_occ_fwd/bwd : F.interpolate(scale_factor=2, 'trilinear', align_corners=False)
+//                                (AdaptiveSparseHead.py:64-69) fused with the occupancy head
+//                                Linear(C,1)+Sigmoid (AdaptiveSparseHead.py:37-39,71)
+//   sgc_topk_select            : topk_wo_grad (AdaptiveSparseHead.py:9-13) + nonzero compaction
+//                                (DenseHead.py:66): deterministic, ties broken by lower index
+//   sgc_scatter_add_rows / sgc_gather_rows : volume[sel] (+)= y (DenseHead.py:80-81 and the residual add
+//                                AdaptiveSparseHead.py:77) and its backward
+//
+// Volumes are stored [X,Y,Z,C] (== torch.channels_last_3d of the reference's [1,C,X,Y,Z]); voxel flat index
+// n = x*(Y*Z) + y*Z + z as in DenseHead.get_voxel_indices (DenseHead.py:32-37).
+#include "common.cuh"
+
+namespace sgc {
+
+// source index/weights of one output coordinate, align_corners=False, scale 2 (ATen
+// area_pixel_compute_source_index): src = max(0.5*(o+0.5)-0.5, 0)
+__device__ __forceinline__ void up_src(int o, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  float s = 0.5f * ((float)o + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+constexpr int kUpWarps = 8;
+
+// one warp per output voxel; lane owns channels [lane*CPL, +CPL)
+template <int CPL>
+__global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_fwd_kernel(const float* __restrict__ in, int X, int Y,
+                                                                        int Z, const float* __restrict__ w_occ,
+                                                                        const float* __restrict__ b_occ,
+                                                                        float* __restrict__ out,
+                                                                        float* __restrict__ occ) {
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+  const int n_out = X2 * Y2 * Z2;
+  const int n = blockIdx.x * kUpWarps + (threadIdx.x >> 5);
+  if (n >= n_out) return;
+  const int z = n % Z2, y = (n / Z2) % Y2, x = n / (Z2 * Y2);
+  int xi[2], yi[2], zi[2];
+  float xl[2], yl[2], zl[2];
+  up_src(x, X, xi[0], xi[1], xl[0], xl[1]);
+  up_src(y, Y, yi[0], yi[1], yl[0], yl[1]);
+  up_src(z, Z, zi[0], zi[1], zl[0], zl[1]);
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float wgt = xl[a] * yl[b] * zl[c];
+        const float* p = in + ((size_t)(xi[a] * Y + yi[b]) * Z + zi[c]) * C + lane * CPL;
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+          const float4 t = ldg4(p + j);
+          acc[j] += wgt * t.x; acc[j + 1] += wgt * t.y; acc[j + 2] += wgt * t.z; acc[j + 3] += wgt * t.w;
+        }
+      }
+  float dot = 0.f;
+  float* o = out + (size_t)n * C + lane * CPL;
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const float4 wv = ldg4(w_occ + lane * CPL + j);
+    dot += acc[j] * wv.x + acc[j + 1] * wv.y + acc[j + 2] * wv.z + acc[j + 3] * wv.w;
+    *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) occ[n] = 1.f / (1.f + expf(-(dot + __ldg(b_occ))));
+}
+
+// per-voxel pre-activation gradient: gpre[n] = g_occ[n] * occ*(1-occ); also reduces grad_b
+__global__ void occ_gpre_kernel(const float* __restrict__ occ, const float* __restrict__ g_occ, int n_out,
+                                float* __restrict__ gpre, float* __restrict__ grad_b) {
+  float local = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+    const float s = occ[i];
+    const float g = g_occ[i] * s * (1.f - s);
+    gpre[i] = g;
+    local += g;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red_add1(grad_b, local);
+}
+
+// grad_w_occ[c] += sum_n gpre[n] * up[n,c], with up recomputed from the coarse volume.
+// one warp per output voxel chunk; block partials reduced through shared memory then one RED per channel.
+template <int CPL>
+__global__ void __launch_bounds__(kUpWarps * 32) occ_gradw_kernel(const float* __restrict__ in, int X, int Y, int Z,
+                                                                 const float* __restrict__ gpre,
+                                                                 float* __restrict__ grad_w) {
+  constexpr int C = CPL * 32;
+  __shared__ float part[kUpWarps][C];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+  const int n_out = X2 * Y2 * Z2;
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+  for (int n = blockIdx.x * kUpWarps + wid; n < n_out; n += gridDim.x * kUpWarps) {
+    const float g = __ldg(gpre + n);
+    if (g == 0.f) continue;
+    const int z = n % Z2, y = (n / Z2) % Y2, x = n / (Z2 * Y2);
+    int xi[2], yi[2], zi[2];
+    float xl[2], yl[2], zl[2];
+    up_src(x, X, xi[0], xi[1], xl[0], xl[1]);
+    up_src(y, Y, yi[0], yi[1], yl[0], yl[1]);
+    up_src(z, Z, zi[0], zi[1], zl[0], zl[1]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float wgt = g * xl[a] * yl[b] * zl[c];
+          const float* p = in + ((size_t)(xi[a] * Y + yi[b]) * Z + zi[c]) * C + lane * CPL;
+#pragma unroll
+          for (int j = 0; j < CPL; j += 4) {
+            const float4 t = ldg4(p + j);
+            acc[j] += wgt * t.x; acc[j + 1] += wgt * t.y; acc[j + 2] += wgt * t.z; acc[j + 3] += wgt * t.w;
+          }
+        }
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) part[wid][lane * CPL + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kUpWarps; ++w) s += part[w][c];
+    red_add1(grad_w + c, s);
+  }
+}
+
+// grad_in[i] = sum over the (<=4 per axis) outputs that read input i of  weight * (grad_up[o] + gpre[o]*w_occ)
+// (gather form of the transposed upsample: deterministic, no atomics).  One warp per input voxel.
+__device__ __forceinline__ int up_adj(int i, int n_in, int (&o)[4], float (&w)[4]) {
+  // outputs 2i-1, 2i, 2i+1, 2i+2 can touch input i; recompute their true weights to honour edge clamping
+  int cnt = 0;
+  for (int d = -1; d <= 2; ++d) {
+    const int oo = 2 * i + d;
+    if (oo < 0 || oo >= 2 * n_in) continue;
+    int i0, i1;
+    float l0, l1;
+    up_src(oo, n_in, i0, i1, l0, l1);
+    float ww = 0.f;
+    if (i0 == i) ww += l0;
+    if (i1 == i) ww += l1;
+    if (ww != 0.f) { o[cnt] = oo; w[cnt] = ww; ++cnt; }
+  }
+  return cnt;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_bwd_kernel(const float* __restrict__ grad_up,
+                                                                        const float* __restrict__ gpre,
+                                                                        const float* __restrict__ w_occ, int X, int Y,
+                                                                        int Z, float* __restrict__ grad_in) {
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int n_in = X * Y * Z;
+  const int n = blockIdx.x * kUpWarps + (threadIdx.x >> 5);
+  if (n >= n_in) return;
+  const int z = n % Z, y = (n / Z) % Y, x = n / (Z * Y);
+  const int Y2 = 2 * Y, Z2 = 2 * Z;
+  int xo[4], yo[4], zo[4];
+  float xw[4], yw[4], zw[4];
+  const int nx = up_adj(x, X, xo, xw), ny = up_adj(y, Y, yo, yw), nz = up_adj(z, Z, zo, zw);
+  float wv[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const float4 t = ldg4(w_occ + lane * CPL + j);
+    wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w;
+  }
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+  for (int a = 0; a < nx; ++a)
+    for (int b = 0; b < ny; ++b)
+      for (int c = 0; c < nz; ++c) {
+        const size_t o = ((size_t)xo[a] * Y2 + yo[b]) * Z2 + zo[c];
+        const float wgt = xw[a] * yw[b] * zw[c];
+        const float gp = gpre ? __ldg(gpre + o) : 0.f;
+        const float* p = grad_up + o * C + lane * CPL;
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+          const float4 t = ldg4(p + j);
+          acc[j] += wgt * (t.x + gp * wv[j]);
+          acc[j + 1] += wgt * (t.y + gp * wv[j + 1]);
+          acc[j + 2] += wgt * (t.z + gp * wv[j + 2]);
+          acc[j + 3] += wgt * (t.w + gp * wv[j + 3]);
+        }
+      }
+  float* g = grad_in + (size_t)n * C + lane * CPL;
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(g + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+// ---------------------------------------------------------------------------------- rows
+// out[sel[i], :] += y[i, :]   (sel entries are unique -> plain read-modify-write)
+__global__ void scatter_add_rows_kernel(float* __restrict__ vol, const int* __restrict__ sel, const float* __restrict__ y,
+                                        int k, int C4) {
+  const int total = k * C4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / C4, c = i - r * C4;
+    float4* dst = reinterpret_cast<float4*>(vol) + (size_t)__ldg(sel + r) * C4 + c;
+    const float4 a = *dst, b = __ldg(reinterpret_cast<const float4*>(y) + i);
+    *dst = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+__global__ void gather_rows_kernel(const float* __restrict__ vol, const int* __restrict__ sel, float* __restrict__ y,
+                                   int k, int C4) {
+  const int total = k * C4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / C4, c = i - r * C4;
+    reinterpret_cast<float4*>(y)[i] = __ldg(reinterpret_cast<const float4*>(vol) + (size_t)__ldg(sel + r) * C4 + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------- top-k
+// Single-CTA radix select (4 x 8 bits, MSB first) + ordered compaction.  Deterministic:
+// the k largest values, ties at the threshold taken in ascending index order; sel is ascending.
+__device__ __forceinline__ uint32_t topk_key(float f) {
+  f += 0.f;  // -0 -> +0
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) topk_select_kernel(const float* __restrict__ occ, int N, int k,
+                                                          int* __restrict__ sel, uint8_t* __restrict__ mask) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need;  // how many more are needed among keys matching the prefix so far
+  __shared__ int warp_a[32], warp_b[32];
+  __shared__ int s_carry_sel, s_carry_eq;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { s_prefix = 0u; s_need = k; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < 256; i += 1024) hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int base = 0; base < N; base += 1024) {
+      const int i = base + tid;
+      bool act = false;
+      uint32_t bin = 0;
+      if (i < N) {
+        const uint32_t key = topk_key(occ[i]);
+        act = (key & pmask) == prefix;
+        bin = (key >> shift) & 0xffu;
+      }
+      // warp-aggregated histogram update
+      const unsigned am = __ballot_sync(SGC_FULL_MASK, act);
+      if (act) {
+        const unsigned peers = __match_any_sync(am, bin);
+        if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[bin], __popc(peers));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= need) break;
+        need -= hist[b];
+      }
+      s_need = need;  // still needed inside bin b
+      s_prefix = prefix | ((uint32_t)b << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t T = s_prefix;  // threshold key
+  const int need_eq = s_need;   // number of keys == T to take (lowest indices first)
+  if (tid == 0) { s_carry_sel = 0; s_carry_eq = 0; }
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int i = base + tid;
+    uint32_t key = 0;
+    if (i < N) key = topk_key(occ[i]);
+    const bool gt = (i < N) && key > T;
+    const bool eq = (i < N) && key == T;
+    const unsigned bg = __ballot_sync(SGC_FULL_MASK, gt), be = __ballot_sync(SGC_FULL_MASK, eq);
+    if (lane == 0) { warp_a[wid] = __popc(bg); warp_b[wid] = __popc(be); }
+    __syncthreads();
+    if (wid == 0) {
+      int a = warp_a[lane], b = warp_b[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ya = __shfl_up_sync(SGC_FULL_MASK, a, o), yb = __shfl_up_sync(SGC_FULL_MASK, b, o);
+        if (lane >= o) { a += ya; b += yb; }
+      }
+      warp_a[lane] = a; warp_b[lane] = b;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+    const int gt_before = s_carry_sel + (wid ? warp_a[wid - 1] : 0) + __popc(bg & lt);  // counts only gt so far
+    const int eq_before = s_carry_eq + (wid ? warp_b[wid - 1] : 0) + __popc(be & lt);
+    const bool take = gt || (eq && eq_before < need_eq);
+    if (i < N) {
+      mask[i] = take ? 1 : 0;
+      if (take) sel[gt_before + (eq_before < need_eq ? eq_before : need_eq)] = i;
+    }
+    __syncthreads();
+    if (tid == 1023) { s_carry_sel = gt_before + (gt ? 1 : 0); s_carry_eq = eq_before + (eq ? 1 : 0); }
+    __syncthreads();
+  }
+}
+
+}  // namespace sgc
+
+extern "C" int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ,
+                                      const float* b_occ, float* vol_out, float* occ, void* stream) {
+  if (C != 256 && C != 128 && C != 64) return (int)cudaErrorInvalidValue;
+  const int n_out = 8 * X * Y * Z;
+  const int grid = (n_out + sgc::kUpWarps - 1) / sgc::kUpWarps;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 256) sgc::upsample_occ_fwd_kernel<8><<<grid, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
+  else if (C == 128) sgc::upsample_occ_fwd_kernel<4><<<grid, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
+  else return (int)cudaErrorInvalidValue;
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// grad_up [2X,2Y,2Z,C], grad_occ [8XYZ] (may be null), occ = forward output.
+// Outputs: grad_in [X,Y,Z,C] (written), grad_w [C] and grad_b [1] (accumulated; caller zeroes), gpre scratch [8XYZ].
+extern "C" int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ,
+                                      const float* occ, const float* grad_up, const float* grad_occ, float* gpre,
+                                      float* grad_in, float* grad_w, float* grad_b, void* stream) {
+  if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
+  const int n_out = 8 * X * Y * Z, n_in = X * Y * Z;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* gp = nullptr;
+  if (grad_occ) {
+    sgc::occ_gpre_kernel<<<(n_out + 1023) / 1024 < 148 ? (n_out + 1023) / 1024 : 148, 1024, 0, st>>>(occ, grad_occ, n_out, gpre, grad_b);
+    SGC_CUDA_CHECK_LAST();
+    const int g2 = 148 * 2;
+    if (C == 256) sgc::occ_gradw_kernel<8><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
+    else sgc::occ_gradw_kernel<4><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
+    SGC_CUDA_CHECK_LAST();
+    gp = gpre;
+  }
+  const int grid = (n_in + sgc::kUpWarps - 1) / sgc::kUpWarps;
+  if (C == 256) sgc::upsample_occ_bwd_kernel<8><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
+  else sgc::upsample_occ_bwd_kernel<4><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream) {
+  if (C & 3) return (int)cudaErrorInvalidValue;
+  const int total = k * (C / 4);
+  if (total == 0) return 0;
+  const int grid = (total + 255) / 256;
+  sgc::scatter_add_rows_kernel<<<grid < 148 * 8 ? grid : 148 * 8, 256, 0, (cudaStream_t)stream>>>(vol, sel, y, k, C / 4);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream) {
+  if (C & 3) return (int)cudaErrorInvalidValue;
+  const int total = k * (C / 4);
+  if (total == 0) return 0;
+  const int grid = (total + 255) / 256;
+  sgc::gather_rows_kernel<<<grid < 148 * 8 ? grid : 148 * 8, 256, 0, (cudaStream_t)stream>>>(vol, sel, y, k, C / 4);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream) {
+  if (k < 0 || k > N) return (int)cudaErrorInvalidValue;
+  sgc::topk_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

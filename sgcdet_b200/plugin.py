@@ -1,0 +1,475 @@
+"""Drop-in modules for the view-transform path of ``mmdet3d_plugin`` (boundary B1).
+
+Same registered ``type`` names, constructor kwargs, forward signatures, return contract and state-dict
+keys as the reference, so ``configs/SGCDet_*.py`` select them unchanged and the published checkpoints load:
+
+  AdaptiveSparseHead            models/im2voxel/AdaptiveSparseHead.py:16-103
+  DenseHead                     models/im2voxel/DenseHead.py:10-84
+  PerceptionTransformer_DFA3D   models/im2voxel/transformer_utils/transformer.py:26-37,115-185
+  VoxFormerEncoder_DFA3D        models/im2voxel/transformer_utils/encoder.py:158-223
+  VoxFormerLayer                models/im2voxel/transformer_utils/encoder.py:226-340
+  DeformCrossAttention_DFA3D    models/im2voxel/transformer_utils/deformable_cross_attention.py:691-837
+  MSDeformableAttention3D_DFA3D models/im2voxel/transformer_utils/deformable_cross_attention.py:343-501
+
+The sub-modules own the parameters under the reference's names; the arithmetic of a level runs in
+``DenseHead.forward_rows`` through the kernels of ``functional.py`` (no per-view Python loops, no host syncs).
+When mmcv/mmdet are importable the classes are registered into their registries (force=True); otherwise a
+minimal local ``Registry`` with the same ``build`` semantics is used.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as SF
+
+
+# ---------------------------------------------------------------------------------------------
+# registries
+# ---------------------------------------------------------------------------------------------
+
+class Registry:
+    """Minimal stand-in for ``mmcv.utils.Registry`` (register_module / build from a ``dict(type=...)``)."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self._modules: Dict[str, type] = {}
+
+    def register_module(self, name: Optional[str] = None, force: bool = False, module: Optional[type] = None):
+        def _reg(cls):
+            key = name or cls.__name__
+            if key in self._modules and not force:
+                raise KeyError(f'{key} is already registered in {self.name}')
+            self._modules[key] = cls
+            return cls
+        return _reg(module) if module is not None else _reg
+
+    def get(self, key: str):
+        return self._modules.get(key)
+
+    def build(self, cfg: dict, **default_args):
+        cfg = dict(copy.deepcopy(cfg))
+        for k, v in default_args.items():
+            cfg.setdefault(k, v)
+        typ = cfg.pop('type')
+        cls = self._modules[typ] if isinstance(typ, str) else typ
+        return cls(**cfg)
+
+
+HEADS = Registry('head')
+TRANSFORMER = Registry('transformer')
+TRANSFORMER_LAYER_SEQUENCE = Registry('transformer_layer_sequence')
+TRANSFORMER_LAYER = Registry('transformer_layer')
+ATTENTION = Registry('attention')
+_LOCAL = dict(HEADS=HEADS, TRANSFORMER=TRANSFORMER, TRANSFORMER_LAYER_SEQUENCE=TRANSFORMER_LAYER_SEQUENCE,
+              TRANSFORMER_LAYER=TRANSFORMER_LAYER, ATTENTION=ATTENTION)
+
+
+def _register(reg_name: str):
+    def deco(cls):
+        _LOCAL[reg_name].register_module(force=True, module=cls)
+        return cls
+    return deco
+
+
+def register_into_mmcv() -> bool:
+    """Register the classes into the mmcv / mmdet registries the reference uses, overriding the plugin's own
+    classes (call after ``import mmdet3d_plugin``).  Returns False when mmcv/mmdet are not installed."""
+    try:
+        from mmcv.cnn.bricks.registry import ATTENTION as A, TRANSFORMER_LAYER as TL, TRANSFORMER_LAYER_SEQUENCE as TLS
+        from mmdet.models import HEADS as H
+        from mmdet.models.utils.builder import TRANSFORMER as T
+    except Exception:
+        return False
+    for reg, local in ((H, HEADS), (T, TRANSFORMER), (TLS, TRANSFORMER_LAYER_SEQUENCE), (TL, TRANSFORMER_LAYER),
+                       (A, ATTENTION)):
+        for name, cls in local._modules.items():
+            reg.register_module(name=name, force=True, module=cls)
+    return True
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (state-dict compatible)
+# ---------------------------------------------------------------------------------------------
+
+@_register('ATTENTION')
+class MSDeformableAttention3D_DFA3D(nn.Module):
+    """DCA:343-362 / 145-212: owns value_proj, sampling_offsets, sampling_offsets_depth, attention_weights."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=8, im2col_step=64, dropout=0.1,
+                 batch_first=True, norm_cfg=None, init_cfg=None):
+        super().__init__()
+        if embed_dims % num_heads != 0:
+            raise ValueError(f'embed_dims must be divisible by num_heads, but got {embed_dims} and {num_heads}')
+        self.embed_dims, self.num_heads, self.num_levels, self.num_points = embed_dims, num_heads, num_levels, num_points
+        self.im2col_step = im2col_step
+        self.batch_first = batch_first
+        self.output_proj = None
+        self.fp16_enabled = False
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.sampling_offsets_depth = nn.Linear(embed_dims, num_heads * num_levels * num_points * 1)
+        self.init_weights()
+
+    def init_weights(self):
+        """DCA:194-212 and 351-362."""
+        M, L, P = self.num_heads, self.num_levels, self.num_points
+        nn.init.constant_(self.sampling_offsets.weight, 0.)
+        thetas = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        grid = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(M, 1, 1, 2).repeat(1, L, P, 1)
+        gd = ((thetas.cos() + thetas.sin()) / 2).view(M, 1, 1, 1).repeat(1, L, P, 1)
+        for i in range(P):
+            grid[:, :, i, :] *= i + 1
+            gd[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(grid.view(-1))
+            nn.init.constant_(self.attention_weights.weight, 0.)
+            nn.init.constant_(self.attention_weights.bias, 0.)
+            nn.init.xavier_uniform_(self.value_proj.weight)
+            nn.init.constant_(self.value_proj.bias, 0.)
+            nn.init.constant_(self.sampling_offsets_depth.weight, 0.)
+            self.sampling_offsets_depth.bias.copy_(gd.view(-1))
+
+    def folded_weights(self):
+        """(Wcat [C+128,C], vbias [C], gbias [128]): value_proj rows followed by the offset / depth-offset /
+        attention-weight rows permuted to the kernel's [m][p][ox,oy,od,logit] channel order."""
+        M, P = self.num_heads, self.num_points
+        C = self.embed_dims
+        wo = self.sampling_offsets.weight.view(M, P, 2, C)
+        wd = self.sampling_offsets_depth.weight.view(M, P, 1, C)
+        wa = self.attention_weights.weight.view(M, P, 1, C)
+        wg = torch.cat([wo, wd, wa], dim=2).reshape(4 * M * P, C)
+        bg = torch.cat([self.sampling_offsets.bias.view(M, P, 2), self.sampling_offsets_depth.bias.view(M, P, 1),
+                        self.attention_weights.bias.view(M, P, 1)], dim=2).reshape(4 * M * P)
+        return torch.cat([self.value_proj.weight, wg], dim=0), self.value_proj.bias, bg
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError('MSDeformableAttention3D_DFA3D is evaluated inside DenseHead (fused level); '
+                           'use sgcdet_b200.dfa3D ops for the stand-alone operator')
+
+
+@_register('ATTENTION')
+class DeformCrossAttention_DFA3D(nn.Module):
+    """DCA:518-548, 691-702: owns deformable_attention, output_proj, attention_pooling."""
+
+    def __init__(self, embed_dims=256, deformable_attn=True, inter_view_aggregation='attn', dropout=0.1,
+                 init_cfg=None, batch_first=False, deformable_attention=None, **kwargs):
+        super().__init__()
+        if deformable_attention is None:
+            deformable_attention = dict(type='MSDeformableAttention3D_DFA3D', embed_dims=embed_dims, num_levels=1)
+        if not deformable_attn or inter_view_aggregation != 'attn':
+            raise NotImplementedError('only deformable_attn=True, inter_view_aggregation="attn" '
+                                      '(what every shipped SGCDet config selects) is implemented')
+        self.dropout = nn.Dropout(dropout)
+        self.fp16_enabled = False
+        self.deformable_attention = ATTENTION.build(deformable_attention)
+        self.embed_dims = embed_dims
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.batch_first = batch_first
+        self.deformable_attn = deformable_attn
+        self.inter_view_aggregation = inter_view_aggregation
+        self.attention_pooling = nn.MultiheadAttention(embed_dim=embed_dims, num_heads=8, batch_first=False)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.constant_(self.output_proj.bias, 0.)
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError('DeformCrossAttention_DFA3D is evaluated inside DenseHead (fused level)')
+
+
+class FFN(nn.Module):
+    """State-dict-compatible stand-in for mmcv's FFN (``layers.0.0``, ``layers.1``): x + W2 relu(W1 x)."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2, ffn_drop=0., act_cfg=None,
+                 add_identity=True, **kwargs):
+        super().__init__()
+        assert num_fcs == 2
+        self.embed_dims = embed_dims
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
+            nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
+        self.add_identity = add_identity
+
+    def forward(self, x, identity=None):
+        out = self.layers(x)
+        if not self.add_identity:
+            return out
+        return (x if identity is None else identity) + out
+
+
+@_register('TRANSFORMER_LAYER')
+class VoxFormerLayer(nn.Module):
+    """encoder.py:226-340 + custom_base_transformer_layer.py:72-156 for operation_order
+    ('cross_attn', 'norm', 'ffn', 'norm')."""
+
+    def __init__(self, attn_cfgs, ffn_cfgs=None, operation_order=None, act_cfg=dict(type='ReLU', inplace=True),
+                 norm_cfg=dict(type='LN'), init_cfg=None, batch_first=True, **kwargs):
+        super().__init__()
+        assert tuple(operation_order) == ('cross_attn', 'norm', 'ffn', 'norm'), \
+            'only the operation order used by the SGCDet configs is implemented'
+        if isinstance(attn_cfgs, dict):
+            attn_cfgs = [attn_cfgs]
+        assert len(attn_cfgs) == 1
+        self.operation_order = tuple(operation_order)
+        self.batch_first = batch_first
+        self.pre_norm = False
+        self.attentions = nn.ModuleList()
+        cfg = dict(copy.deepcopy(attn_cfgs[0]))
+        cfg.setdefault('batch_first', batch_first)
+        self.attentions.append(ATTENTION.build(cfg))
+        self.embed_dims = self.attentions[0].embed_dims
+        ffn = dict(copy.deepcopy(ffn_cfgs)) if isinstance(ffn_cfgs, dict) else dict(copy.deepcopy(ffn_cfgs[0]))
+        ffn.pop('type', None)
+        ffn.setdefault('embed_dims', self.embed_dims)
+        assert ffn['embed_dims'] == self.embed_dims
+        self.ffns = nn.ModuleList([FFN(**ffn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims), nn.LayerNorm(self.embed_dims)])
+        self.fp16_enabled = False
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError('VoxFormerLayer is evaluated inside DenseHead (fused level)')
+
+
+@_register('TRANSFORMER_LAYER_SEQUENCE')
+class VoxFormerEncoder_DFA3D(nn.Module):
+    """encoder.py:158-166 (+ mmcv TransformerLayerSequence: ``layers`` ModuleList)."""
+
+    def __init__(self, *args, transformerlayers=None, num_layers=None, return_intermediate=False, dbound=None,
+                 init_cfg=None, **kwargs):
+        super().__init__()
+        assert num_layers == 1, 'the SGCDet configs use one encoder layer'
+        if isinstance(transformerlayers, dict):
+            transformerlayers = [copy.deepcopy(transformerlayers) for _ in range(num_layers)]
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([TRANSFORMER_LAYER.build(c) for c in transformerlayers])
+        self.embed_dims = self.layers[0].embed_dims
+        self.return_intermediate = return_intermediate
+        self.dbound = dbound
+        self.fp16_enabled = False
+
+    _compute_projection = staticmethod(SF.compute_projection)
+
+
+@_register('TRANSFORMER')
+class PerceptionTransformer_DFA3D(nn.Module):
+    """transformer.py:26-50,115-185."""
+
+    def __init__(self, encoder=None, embed_dims=256, **kwargs):
+        super().__init__()
+        self.encoder = TRANSFORMER_LAYER_SEQUENCE.build(encoder)
+        self.embed_dims = embed_dims
+        self.fp16_enabled = False
+
+    def init_weights(self):
+        """transformer.py:39-50: xavier on every >1-D parameter, then the deformable-attention re-init."""
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformableAttention3D_DFA3D):
+                m.init_weights()
+
+
+# ---------------------------------------------------------------------------------------------
+# the heads
+# ---------------------------------------------------------------------------------------------
+
+@_register('HEADS')
+class DenseHead(nn.Module):
+    """DenseHead.py:10-84.  ``forward`` keeps the reference signature/return ([1,C,X,Y,Z] dense volume);
+    ``forward_rows`` is the fused level returning the selected rows [Q,C] (used by AdaptiveSparseHead)."""
+
+    def __init__(self, *args, voxel_size=None, n_voxels=None, embed_dims, cross_transformer, **kwargs):
+        super().__init__()
+        self.voxel_size = torch.tensor(voxel_size)
+        self.n_voxels = torch.tensor(n_voxels)
+        self.embed_dims = embed_dims
+        self.cross_transformer = TRANSFORMER.build(cross_transformer)
+        vox_coords, ref_3d = self.get_voxel_indices()
+        self.register_buffer('vox_coords', vox_coords)
+        self.register_buffer('ref_3d', ref_3d)
+
+    def get_voxel_indices(self):
+        """DenseHead.py:32-48 (voxel 'centres' are lower corners: idx*size - n/2*size)."""
+        n = self.n_voxels
+        xv, yv, zv = torch.meshgrid(torch.arange(n[0]), torch.arange(n[1]), torch.arange(n[2]), indexing='ij')
+        idx = torch.arange(int(n[0] * n[1] * n[2]))
+        vox_coords = torch.cat([xv.reshape(-1, 1), yv.reshape(-1, 1), zv.reshape(-1, 1), idx.reshape(-1, 1)], dim=-1)
+        points = torch.stack([xv, yv, zv])
+        new_origin = -n / 2. * self.voxel_size
+        points = points * self.voxel_size.view(3, 1, 1, 1) + new_origin.view(3, 1, 1, 1)
+        return vox_coords, points.view(3, -1).permute(1, 0).contiguous()
+
+    @property
+    def num_voxels(self) -> int:
+        return int(self.n_voxels.prod())
+
+    def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
+                     proj: Optional[torch.Tensor] = None, return_intermediates: bool = False):
+        """feat [1,V,C,H0,W0] (uncropped), dpt_dist [1,V,D,H0,W0], hw = cropped (h,w), sel [Q] int32 or None.
+        Returns y [Q,C] (rows of the dense volume at ``sel``)."""
+        assert feat.shape[0] == 1  # bs == 1 (DenseHead.py:60)
+        if not feat.is_cuda:
+            raise RuntimeError('sgcdet_b200 has no CPU implementation: inputs must be CUDA tensors')
+        h, w = hw
+        layer = self.cross_transformer.encoder.layers[0]
+        attn = layer.attentions[0]
+        da = attn.deformable_attention
+        dbound = self.cross_transformer.encoder.dbound
+        if proj is None:
+            proj = SF.compute_projection(img_meta).to(feat.device, non_blocking=True)
+        pl = SF.project_compact(proj, self.ref_3d, sel, img_meta, dbound)
+        wcat, vbias, gbias = da.folded_weights()
+        vg = SF.ProjectFeatures.apply(feat[0], h, w, wcat)
+        dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
+        slots, samp = SF.Lift.apply(vg, dist, vbias.contiguous(), gbias, pl, h, w)
+        mha = attn.attention_pooling
+        x = SF.CrossView.apply(slots, pl, attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight,
+                               mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias)
+        x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
+        x = layer.norms[0](x)
+        x = layer.ffns[0](x)
+        x = layer.norms[1](x)
+        if return_intermediates:
+            return x, dict(pairs=pl, slots=slots, samp=samp)
+        return x
+
+    def forward(self, mlvl_feats, img_meta=None, proposal=None, mlvl_dpt_dists=None, **kwargs):
+        feat, dist = mlvl_feats[0], mlvl_dpt_dists[0]
+        if not feat.is_contiguous():
+            feat = feat.contiguous()  # the reference is handed an already-cropped view
+        N, C = self.num_voxels, self.embed_dims
+        sel = None
+        if proposal is not None:
+            sel = torch.nonzero(proposal > 0).view(-1).to(torch.int32)
+        y = self.forward_rows(feat, dist, img_meta, feat.shape[-2:], sel)
+        if sel is None:
+            vol = y
+        else:
+            vol = SF.ScatterAddRows.apply(torch.zeros(N, C, device=y.device), y, sel)
+        X, Y, Z = (int(v) for v in self.n_voxels)
+        return vol.view(X, Y, Z, C).permute(3, 0, 1, 2).unsqueeze(0)
+
+
+def topk_wo_grad(occ_preds_flatten: torch.Tensor, topk: int = 10) -> torch.Tensor:
+    """AdaptiveSparseHead.py:9-13, made deterministic (ties -> lower index)."""
+    assert occ_preds_flatten.shape[0] == 1
+    _, mask = SF.topk_select(occ_preds_flatten[0].contiguous(), topk)
+    return mask.to(occ_preds_flatten.dtype).unsqueeze(0)
+
+
+@_register('HEADS')
+class AdaptiveSparseHead(nn.Module):
+    """AdaptiveSparseHead.py:16-103."""
+
+    def __init__(self, embed_dims=256, topk_list=None, voxel_size_list=None, n_voxels_list=None,
+                 base_head_configs=None, **kwargs):
+        super().__init__()
+        self.embed_dims = embed_dims
+        self.topk_list = topk_list if topk_list is not None else []
+        self.voxel_size_list = voxel_size_list if voxel_size_list is not None else []
+        self.n_voxels_list = n_voxels_list if n_voxels_list is not None else []
+        self.base_heads = nn.ModuleList()
+        for config in (base_head_configs or []):
+            self.base_heads.append(HEADS.build(config))
+        self.occ_pred_heads = nn.ModuleList()
+        for _ in range(len(self.base_heads) - 1):
+            self.occ_pred_heads.append(nn.Sequential(nn.Linear(embed_dims, 1), nn.Sigmoid()))
+        self.loss = nn.BCELoss()
+
+    def forward(self, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection: Optional[List] = None,
+                return_intermediates: bool = False):
+        """-> (volume [1,C,X,Y,Z], valid [1,1,X,Y,Z] int64, occ_preds [1, sum N]).
+
+        ``forced_selection[i]`` (int32 ascending voxel ids) overrides the top-k of level i (parity tests).
+        The returned volume is a channels_last_3d view of the internal [X,Y,Z,C] buffer."""
+        bs = mlvl_feats[0].shape[0]
+        assert bs == 1
+        nl = len(self.base_heads)
+        proj = SF.compute_projection(img_meta).to(mlvl_feats[0].device, non_blocking=True)
+        vol = None
+        occ_list, masks, inters = [], [None] * nl, []
+        for i in range(nl):
+            ds = 4 * 2 ** (nl - 1 - i)
+            hw = (img_meta['img_shape'][0] // ds, img_meta['img_shape'][1] // ds)
+            fi = nl - 1 - i
+            head = self.base_heads[i]
+            if i == 0:
+                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, None, proj, return_intermediates)
+                y, it = r if return_intermediates else (r, None)
+                X, Y, Z = (int(v) for v in head.n_voxels)
+                vol = y.view(X, Y, Z, self.embed_dims)
+            else:
+                lin = self.occ_pred_heads[i - 1][0]
+                up, occ = SF.UpsampleOcc.apply(vol, lin.weight.view(-1), lin.bias)
+                occ_list.append(occ.view(1, -1))
+                if (i - 1) < len(self.topk_list):
+                    if forced_selection is not None and forced_selection[i] is not None:
+                        sel = forced_selection[i]
+                        mask = torch.zeros(occ.numel(), device=occ.device, dtype=torch.uint8)
+                        mask[sel.long()] = 1
+                    else:
+                        sel, mask = SF.topk_select(occ, min(self.topk_list[i - 1], occ.numel()))
+                    masks[i] = mask
+                else:
+                    sel = None
+                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates)
+                y, it = r if return_intermediates else (r, None)
+                if sel is None:
+                    vol = up + y.view_as(up)
+                else:
+                    vol = SF.ScatterAddRows.apply(up.view(-1, self.embed_dims), y, sel).view_as(up)
+            if it is not None:
+                it['sel'] = None if i == 0 else sel
+            inters.append(it)
+        volume_out = vol.permute(3, 0, 1, 2).unsqueeze(0)
+        if not occ_list:
+            occ_preds = None
+            valid = torch.ones([bs, 1, *vol.shape[:3]], device=vol.device)
+        else:
+            occ_preds = torch.cat(occ_list[::-1], dim=1)
+            valid = self.get_valid(masks[nl - 1]).unsqueeze(0).unsqueeze(0).detach()
+        if return_intermediates:
+            return volume_out, valid, occ_preds, inters
+        return volume_out, valid, occ_preds
+
+    def get_valid(self, indices_0):
+        n = self.n_voxels_list[-1]
+        return indices_0.view(n[0], n[1], n[2]).bool().long()
+
+    def occ_loss(self, occ_pred, sem_occ_gt, geo_occ_gt):
+        bs, N = occ_pred.shape
+        loss_occ = self.loss(occ_pred, geo_occ_gt[:, 0:N].float()).mean() * 0.5
+        return {'loss_occ': loss_occ}
+
+
+def build_voxel_head(cfg) -> AdaptiveSparseHead:
+    """Build from a PathConfig (synthetic.py) or from the ``voxel_head`` dict of an ``SGCDet_*.py`` config."""
+    if isinstance(cfg, dict):
+        return HEADS.build(cfg)
+    C = cfg.embed_dims
+    cross_transformer = dict(
+        type='PerceptionTransformer_DFA3D', embed_dims=C,
+        encoder=dict(
+            type='VoxFormerEncoder_DFA3D', num_layers=1, return_intermediate=False, dbound=list(cfg.dbound),
+            transformerlayers=dict(
+                type='VoxFormerLayer',
+                attn_cfgs=[dict(type='DeformCrossAttention_DFA3D',
+                                deformable_attention=dict(type='MSDeformableAttention3D_DFA3D', embed_dims=C,
+                                                          num_heads=cfg.num_heads, num_points=cfg.num_points,
+                                                          num_levels=1, im2col_step=128),
+                                embed_dims=C, inter_view_aggregation='attn', dropout=0)],
+                ffn_cfgs=dict(type='FFN', embed_dims=C, feedforward_channels=C * 2, num_fcs=2, ffn_drop=0.1,
+                              act_cfg=dict(type='ReLU', inplace=True)),
+                operation_order=('cross_attn', 'norm', 'ffn', 'norm'))))
+    heads = [dict(type='DenseHead', voxel_size=cfg.voxel_size_list[i], n_voxels=cfg.n_voxels_list[i], embed_dims=C,
+                  cross_transformer=cross_transformer) for i in range(cfg.num_levels)]
+    return AdaptiveSparseHead(embed_dims=C, topk_list=list(cfg.topk_list), voxel_size_list=list(cfg.voxel_size_list),
+                              n_voxels_list=list(cfg.n_voxels_list), base_head_configs=heads)

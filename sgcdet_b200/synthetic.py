@@ -71,7 +71,7 @@ CONFIGS: Dict[str, PathConfig] = {
         (240, 320), (192, 256), _ARKIT_K),
     # reduced shape for fast CPU/GPU parity tests (same structure, 3 levels)
     'tiny': PathConfig(
-        'tiny', 64, ((4, 4, 2), (8, 8, 4), (16, 16, 8)),
+        'tiny', 128, ((4, 4, 2), (8, 8, 4), (16, 16, 8)),
         ((1.6, 1.6, 1.6), (.8, .8, .8), (.4, .4, .4)), (64, 512),
         (95, 128), (968, 1296), _SCANNET_K, feat_hw=((24, 32), (12, 16), (6, 8))),
 }
