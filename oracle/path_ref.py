@@ -265,7 +265,7 @@ def adaptive_sparse_head_forward(sd, mlvl_feats, img_meta, mlvl_dpt_dists, cfg, 
 def occ_loss(occ_pred: torch.Tensor, geo_occ_gt: torch.Tensor) -> torch.Tensor:
     """AdaptiveSparseHead.py:100-103."""
     N = occ_pred.shape[1]
-    return F.binary_cross_entropy(occ_pred, geo_occ_gt[:, 0:N].float()).mean() * 0.5
+    return F.binary_cross_entropy(occ_pred, geo_occ_gt[:, 0:N].to(occ_pred.dtype)).mean() * 0.5
 
 
 def path_loss(sd, scene, *, forced_proposals=None):

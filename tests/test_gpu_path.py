@@ -54,18 +54,6 @@ def test_project_compact_bit_exact(cuda_lib, cfg_name, V, level):
         assert torch.equal(pl.view_offsets.cpu().long(), offs)
 
 
-def test_projection_matches_literal_matmul_form():
-    """The pinned-order projection agrees with the reference's tensor program (encoder.py:179-223) to fp32
-    round-off on visible points and gives the same mask (CPU only; no kernel involved)."""
-    cfg = syn.CONFIGS['SGCDet_ScanNet']
-    meta = syn.make_img_meta(cfg, 40, torch.Generator().manual_seed(3))
-    ref3d = syn.make_state_dict(cfg)['base_heads.2.ref_3d']
-    a, ma = path_ref.point_sampling(ref3d, meta, cfg.dbound)
-    b, mb = path_ref.point_sampling_matmul(ref3d, meta, cfg.dbound)
-    assert (ma != mb).sum() == 0
-    torch.testing.assert_close(a[ma], b[mb], rtol=1e-5, atol=1e-6)
-
-
 # ------------------------------------------------------------------------------ top-k
 
 @pytest.mark.parametrize('N,k', [(3200, 800), (25600, 6400), (204800, 51200), (1000, 1000), (1000, 1), (777, 0)])
