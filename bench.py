@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- view-transform throughput (voxel volumes/s, forward+backward) of sgcdet_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One *step* = one synthetic scene (one voxel volume) through all three levels of AdaptiveSparseHead, forward
+plus backward from a fixed upstream gradient and the occupancy loss.  Workload at N=1:
+``SGCDet_ScanNet`` at the train shape V=40 (BASELINE.json configs[1]).  For N>1 every rank owns its own
+scene (scene-batch data parallel, weak scaling) and the path's weight gradients are all-reduced with NCCL
+inside the step.  Rank 0 prints ONE JSON line.
+
+Arms:
+  ours          the CUDA path (CUDA-graph replay of fwd+bwd), device-timed with CUDA events, max over ranks
+  reference     the CPU restatement of the reference (oracle/, kind "port": the reference has no CPU
+                implementation and its plugin cannot be imported without mmcv) on all host cores, bounded sample
+  reference-gpu (extra, not part of the driver contract) the restated reference glue driving the reference's
+                own DFA3D kernels compiled unmodified for sm_100a (oracle/_ref) on the same B200
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'voxel volumes/sec (fwd+bwd view transform)'
+UNIT = 'volumes/s'
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks
+# -------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# -------------------------------------------------------------------------------------------------
+# kernel accounting
+# -------------------------------------------------------------------------------------------------
+
+# kernels launched per C-ABI entry point (csrc/*.cu)
+LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_crossview_mean_fwd=1,
+                sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
+                sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
+                sgc_gather_rows=1, sgc_split_bf16x3=1)
+
+
+class CallRecorder:
+    """Wraps sgcdet_b200._lib.call: counts launches; optionally brackets every call with CUDA events on the
+    launching stream (instrumented pass only)."""
+
+    def __init__(self):
+        from sgcdet_b200 import _lib, functional
+        self._lib, self._fn = _lib, functional
+        self.orig = _lib.call
+        self.count = 0
+        self.timed = False
+        self.events = []
+
+    def __enter__(self):
+        def call(name, *args):
+            self.count += LAUNCHES.get(name, 1)
+            if self.timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                self.orig(name, *args)
+                b.record()
+                self.events.append((name, args, a, b))
+            else:
+                self.orig(name, *args)
+        self._lib.call = call
+        self._fn.call = call
+        return self
+
+    def __exit__(self, *exc):
+        self._lib.call = self.orig
+        self._fn.call = self.orig
+
+
+def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
+    """Unique bytes a launch has to move (DESIGN.md "Kernels"): inputs read once + outputs written once."""
+    f = 4.0
+    if name in ('sgc_lift_fwd', 'sgc_lift_bwd'):
+        if name == 'sgc_lift_fwd':
+            ldv, S, H, W, D, Q, C = args[1], args[11], args[12], args[13], args[14], args[15], args[16]
+        else:
+            ldv, S, H, W, D, Q, C = args[1], args[12], args[13], args[14], args[15], args[16], args[17]
+        V = n_pairs_by_q[Q][1]
+        P = n_pairs_by_q[Q][0]
+        maps = f * V * S * (ldv + D)          # value + G + depth maps
+        pairs = f * P * (C + 128) + P * 16    # slots + samp rows, pair id + ref point
+        return maps + pairs if name == 'sgc_lift_fwd' else 2 * maps + pairs
+    if name.startswith('sgc_crossview'):
+        V, Q, C = (args[2], args[3], args[4]) if name == 'sgc_crossview_mean_fwd' else \
+                  (args[3], args[4], args[5]) if name == 'sgc_crossview_attn_fwd' else \
+                  (args[3], args[4], args[5]) if name == 'sgc_crossview_attn_bwd_qt' else (args[4], args[5], args[6])
+        P = n_pairs_by_q[Q][0]
+        if name == 'sgc_crossview_mean_fwd':
+            return f * (P * C + Q * C) + 4 * V * Q
+        if name == 'sgc_crossview_attn_fwd':
+            return f * (P * C + 16 * Q * C + 8 * P) + 4 * V * Q
+        if name == 'sgc_crossview_attn_bwd_qt':
+            return f * (P * C + 16 * Q * C + 16 * P) + 4 * V * Q
+        return f * (P * C + 17 * Q * C + 16 * P) + 4 * V * Q
+    if name == 'sgc_upsample2x_occ_fwd':
+        X, Y, Z, C = args[1:5]
+        return f * (X * Y * Z * C + 8 * X * Y * Z * (C + 1))
+    if name == 'sgc_upsample2x_occ_bwd':
+        X, Y, Z, C = args[1:5]
+        return f * (2 * X * Y * Z * C + 8 * X * Y * Z * (C + 3))
+    if name == 'sgc_project_compact':
+        V, Q = args[3], args[4]
+        return V * Q * (12 + 1 + 4 + 1) + 4 * n_pairs_by_q.get(Q, (0, V))[0]
+    if name == 'sgc_topk_select':
+        return 5.0 * args[1] * 4
+    if name in ('sgc_scatter_add_rows', 'sgc_gather_rows'):
+        return f * 3 * args[3] * args[4]
+    return 0.0
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sgcdet_b200 import plugin, synthetic as syn
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (ours): no CUDA device -- sgcdet_b200 has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = syn.CONFIGS[args.config]
+    V = args.views
+    sc_cpu = syn.make_scene(cfg, V, seed=1234 + rank, shift_origin=True)
+    head = plugin.build_voxel_head(cfg)
+    head.load_state_dict(syn.make_state_dict(cfg), strict=True)
+    head = head.to(dev)
+    head.train(not args.eval_mode)
+    params = [p for p in head.parameters()]
+    sc = sc_cpu.to(dev)
+    from sgcdet_b200 import functional as SF
+    sc.img_meta['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)  # static buffer for graph replay
+    feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats[:cfg.num_levels]]
+    dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists[:cfg.num_levels]]
+    gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)  # channels_last_3d, like the volume
+    loss_buf = torch.zeros(1, device=dev)
+    flat_grads = None
+
+    def step():
+        vol, valid, occ = head(feats, sc.img_meta, dists)
+        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        loss.backward()
+        loss_buf.copy_(loss.detach().view(1))
+        if world > 1 and not args.no_grad_allreduce:
+            # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            torch._foreach_copy_([p.grad.view(-1) for p in params], list(flat.split([p.numel() for p in params])))
+
+    def zero_grads():
+        for t in params + feats + dists:
+            t.grad = None
+
+    # warm-up (eager) on a side stream, then capture fwd+bwd into one CUDA graph
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(1, min(args.warmup, 3))):
+            zero_grads()
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    rec = CallRecorder()
+    graph = None
+    launches_per_step = 0
+    if not args.no_graph:
+        zero_grads()
+        graph = torch.cuda.CUDAGraph()
+        with rec:
+            with torch.cuda.graph(graph):
+                step()
+        launches_per_step = rec.count
+        run_step = graph.replay
+    else:
+        def run_step():
+            zero_grads()
+            step()
+        with rec:
+            run_step()
+        launches_per_step = rec.count
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        run_step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    total_ms = timed(run_step, args.steps)
+    loss_val = float(loss_buf.item())
+
+    # ---- end to end: host buffers -> H2D -> step -> D2H of the loss, every step -------------------------
+    host_in = [t.detach().cpu().pin_memory() for t in feats + dists]
+    dev_in = feats + dists
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
+        run_step()
+        loss_host.copy_(loss_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    if args.skip_e2e:
+        e2e_ms = float('nan')
+    else:
+        for _ in range(2):
+            e2e_step()
+        e2e_ms = timed(e2e_step, e2e_steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- instrumented eager pass: per-kernel device time with CUDA events (not part of `value`) --------
+    kernels, roof, path_roof = {}, None, None
+    ab = syn.algorithmic_bytes(cfg, V)
+    if rank == 0 and not args.skip_e2e:
+        rec2 = CallRecorder()
+        rec2.timed = True
+        n_inst = 3
+        with rec2:
+            for _ in range(n_inst):
+                zero_grads()
+                vol, valid, occ, its = head(feats, sc.img_meta, dists, return_intermediates=True)
+                ((vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']).backward()
+        torch.cuda.synchronize()
+        pairs_by_q = {it['pairs'].Q: (int(it['pairs'].view_offsets[-1]), V) for it in its}
+        agg = {}
+        for name, a, e0, e1 in rec2.events:
+            key = name
+            if name.startswith(('sgc_lift', 'sgc_crossview', 'sgc_project')):
+                q = {'sgc_lift_fwd': 15, 'sgc_lift_bwd': 16, 'sgc_crossview_mean_fwd': 3, 'sgc_crossview_attn_fwd': 4,
+                     'sgc_crossview_attn_bwd_qt': 4, 'sgc_crossview_attn_bwd_slots': 5, 'sgc_project_compact': 4}[name]
+                key = f'{name}[Q={a[q]}]'
+            elif name.startswith('sgc_upsample'):
+                key = f'{name}[{a[1]}x{a[2]}x{a[3]}]'
+            d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=kernel_algorithmic_bytes(name, a, pairs_by_q)))
+            d['ms'] += e0.elapsed_time(e1)
+            d['n'] += 1
+        mine_ms = sum(d['ms'] for d in agg.values()) / n_inst
+        top = sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
+        peaks = load_peaks()
+        for k, d in top[:8]:
+            avg = d['ms'] / d['n']
+            kernels[k] = dict(avg_ms=round(avg, 4), gbs=round(d['bytes'] / (avg * 1e-3) / 1e9, 1) if avg > 0 else None)
+        k0, d0 = top[0]
+        avg0 = d0['ms'] / d0['n']
+        ach = d0['bytes'] / (avg0 * 1e-3) / 1e9
+        roof = dict(bound='hbm', kernel=k0, achieved=round(ach, 1), peak=peaks['hbm_gbs'], unit='GB/s',
+                    frac=round(ach / peaks['hbm_gbs'], 4), traffic=None, peak_source=peaks['source'],
+                    algorithmic_bytes_per_launch=int(d0['bytes']), avg_launch_ms=round(avg0, 4),
+                    timing='CUDA events around each launch in an eager instrumented pass after the timed region')
+        step_ms = total_ms / args.steps
+        path_roof = dict(algorithmic_bytes_fwd_bwd=int(ab['fwd_bwd']), achieved_gbs=round(ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9, 1),
+                         frac_of_hbm=round(ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4),
+                         own_kernels_ms_per_step=round(mine_ms, 3), pairs_per_level=[pairs_by_q[q][0] for q in sorted(pairs_by_q)])
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample --------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.config, V, volumes=1)
+
+    if rank == 0:
+        step_ms = total_ms / args.steps
+        line = {
+            'metric': METRIC, 'value': round(world * args.steps / (total_ms * 1e-3), 2), 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(step_ms, 4),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, 1 scene per GPU per step',
+                       'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
+                       'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else ' + NCCL weight-grad all-reduce'),
+                       'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
+                       'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
+                       'cuda_graph': not args.no_graph, 'gemm': 'feature-map projections: bf16x3 operand split (own kernel) + library bf16 GEMM with fp32 accumulate; voxel-count GEMMs: library fp32'},
+            'e2e': {'value': None if args.skip_e2e else round(world * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': 4, 'steps': e2e_steps},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'gpu_launches_per_step': int(launches_per_step),
+            'clocks': clk, 'roofline': roof, 'path_roofline': path_roof, 'kernels': kernels, 'cpu_baseline': cpu,
+            'loss': round(loss_val, 4),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d['hbm_gbs']), source='MEASURED_PEAKS.json (of measured)')
+    return dict(hbm_gbs=6650.0, source='B200_PROFILING.md fallback (of fallback)')
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arms
+# -------------------------------------------------------------------------------------------------
+
+def cpu_baseline(config: str, V: int, volumes: int = 1, warm: bool = False):
+    """The oracle port (torch CPU fp32, every host thread) on a bounded sample of the same workload."""
+    from oracle import path_ref
+    from sgcdet_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = syn.CONFIGS[config]
+    sc = syn.make_scene(cfg, V, shift_origin=True)
+    sd = syn.make_state_dict(cfg)
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'ref_3d' not in k else v) for k, v in sd.items()}
+    feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
+    dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists]
+
+    def one():
+        vol, valid, occ = path_ref.adaptive_sparse_head_forward(sdg, feats, sc.img_meta, dists, cfg)
+        loss = (vol * sc.grad_volume).sum() + path_ref.occ_loss(occ, sc.geo_occ)
+        loss.backward()
+        return float(loss)
+
+    if warm:
+        one()
+    t0 = time.perf_counter()
+    for _ in range(volumes):
+        one()
+    dt = time.perf_counter() - t0
+    return dict(value=round(volumes / dt, 4), unit=UNIT, cores=cores, kind='port',
+                sample=f'{volumes} volume(s) fwd+bwd of {cfg.name} V={V} on the CPU oracle port '
+                       f'(torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads), {dt:.1f} s')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if rank != 0:
+        return
+    from sgcdet_b200 import synthetic as syn
+    cfg = syn.CONFIGS[args.config]
+    steps = max(1, min(args.steps, 3))
+    warm = max(0, min(args.warmup, 1))
+    t0 = time.perf_counter()
+    cpu = cpu_baseline(args.config, args.views, volumes=steps, warm=warm > 0)
+    v = cpu['value']
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
+        'ms_per_step': round(1e3 / v, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={args.views} views (CPU restatement of the reference path; '
+                               'the reference has no CPU implementation: DFA3D is CUDA only)'},
+        'cpu_baseline': cpu,
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': f'steps/warmup clamped to {steps}/{warm} so the run ends within minutes; rank 0 only',
+    }
+    print(json.dumps(line))
+
+
+def run_reference_gpu(args):
+    """Extra arm: the reference's own CUDA kernels (oracle/_ref, unmodified, sm_100a) under the restated
+    reference glue (per-view Python loops, padded rebatch, torch MHA) on the same GPU."""
+    try:
+        from oracle import gpu_ref
+    except ImportError as e:
+        print(json.dumps({'impl': 'reference-gpu', 'unavailable': str(e)}))
+        return
+    line = gpu_ref.bench(args.config, args.views, args.steps, args.warmup)
+    line.update({'impl': 'reference-gpu', 'metric': METRIC, 'unit': UNIT})
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
+    ap.add_argument('--config', default='SGCDet_ScanNet')
+    ap.add_argument('--views', type=int, default=40)
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--eval-mode', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-grad-allreduce', action='store_true')
+    ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the e2e and instrumented passes')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    elif args.impl == 'reference-gpu':
+        run_reference_gpu(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -75,6 +75,12 @@ int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, i
                         float dscale, float* ref_cam, uint8_t* mask, int* pair_index, int* pair_vq,
                         int* view_offsets, int* count, int* scratch, void* stream);
 
+/* fp32 -> [bf16 hi | bf16 lo | bf16 hi] operand split for the tensor-core projections (value_proj /
+ * sampling_offsets / sampling_offsets_depth / attention_weights, DCA:417-436): rows of length cols (source row
+ * stride src_stride), out[((r / rpg) * 3 + slot) * rpg + r % rpg][col] as bf16.  See csrc/sgc_gemm_prep.cu. */
+int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group, void* out,
+                     void* stream);
+
 /* Lift: reference-point sample (DCA:67-116) + offset/weight heads + softmax (DCA:423-436) + sampling
  * locations (DCA:445-461) + 8-head 4-point DFA3D (F3D:277-302) for every visible pair.
  * value [V,S,ldv] (no bias), G [V,S,ldg] (128 ch, [m][p][ox,oy,od,logit]), dist [V,S,D], vbias [C], gbias [128],
@@ -82,11 +88,14 @@ int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, i
 int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
                  const float* gbias, const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam,
                  int S, int H, int W, int D, int Q, int C, float* samp, float* slots, void* stream);
-/* Backward of the above (F3D:303-351 + autograd of the Linear heads).  All grads ACCUMULATE (caller zeroes). */
+/* Backward of the above (F3D:303-351 + autograd of the Linear heads).  All grads ACCUMULATE (caller zeroes).
+ * scratch: sgc_lift_bwd_scratch_floats(cap_pairs, C) floats (per-CTA bias partials, reduced deterministically). */
+int sgc_lift_bwd_scratch_floats(int cap_pairs, int C);
 int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
                  const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam, const float* samp,
                  const float* grad_slots, int S, int H, int W, int D, int Q, int C, float* grad_value,
-                 float* grad_G, float* grad_dist, float* grad_vbias, float* grad_gbias, void* stream);
+                 float* grad_G, float* grad_dist, float* grad_vbias, float* grad_gbias, float* scratch,
+                 void* stream);
 
 /* Cross-view fusion (DCA:815-833).  mean [Q,C]: masked mean over views (zeros when no view sees q).
  * attn: qt [8,Q,C] (scaled, key-projected query), t_out [8,Q,C] = sum_v softmax_v(qt.s_v) s_v, alpha [cap,8]. */

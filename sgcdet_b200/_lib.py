@@ -3,7 +3,7 @@ tensor is not a contiguous CUDA tensor the call raises."""
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_float, c_int, c_void_p
+from ctypes import c_float, c_int, c_longlong, c_void_p
 from pathlib import Path
 
 import torch
@@ -14,6 +14,7 @@ _lib = None
 P = c_void_p
 I = c_int
 F = c_float
+LL = c_longlong
 
 # name -> argtypes (must mirror include/sgcdet_b200.h)
 SIGNATURES = {
@@ -25,8 +26,10 @@ SIGNATURES = {
     'dfa3d_fused_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P],
     'sgc_project_scratch_ints': [I, I],
     'sgc_project_compact': [P, P, P, I, I, F, F, F, F, F, F, F, F, F, P, P, P, P, P, P, P, P],
+    'sgc_split_bf16x3': [P, LL, I, LL, I, P, P],
     'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],
-    'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P],
+    'sgc_lift_bwd_scratch_floats': [I, I],
+    'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P],
     'sgc_crossview_mean_fwd': [P, P, I, I, I, P, P],
     'sgc_crossview_attn_fwd': [P, P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_bwd_qt': [P, P, P, I, I, I, P, P, P, P],

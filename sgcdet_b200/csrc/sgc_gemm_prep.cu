@@ -1,0 +1,70 @@
+// fp32 -> (bf16 hi, bf16 lo) operand split for the dense projections.
+//
+// The value / offset / attention-weight projections (deformable_cross_attention.py:417-436) are fp32 GEMMs in
+// the reference; to run them on the tensor cores at fp32-level accuracy each operand is split as
+// x = hi + lo (+ O(2^-17 |x|)), hi = bf16(x), lo = bf16(x - hi), and the product is evaluated as
+// hi*hi' + lo*hi' + hi*lo' with fp32 accumulation (relative error ~1e-5, inside the rtol 1e-3 budget).
+// The three terms are folded into ONE GEMM by concatenating along K:  [hi | lo | hi] x [hi' ; hi' ; lo'].
+//
+// This kernel writes the [hi | lo | hi] operand in one pass over x:
+//   rows r of length `cols` (source row stride `src_stride`), grouped by `rpg` rows:
+//   out[((r / rpg) * 3 + slot) * rpg + (r % rpg)][col],  slot 0 = hi, 1 = lo, 2 = hi.
+//   rpg = C  -> feature maps  [V,C,S]   -> [V,3,C,S]     (K = channel concat, S stays contiguous)
+//   rpg = 1  -> row-major     [R,N]     -> [R,3N]        (K = column concat)
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace sgc {
+
+__device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ x, long long rows, int cols,
+                                                          long long src_stride, int rpg,
+                                                          __nv_bfloat16* __restrict__ out) {
+  const int cpr = VEC ? cols / 4 : cols;  // work items per row
+  const long long total = rows * cpr;
+  const long long slot_stride = (long long)rpg * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = (int)(i - r * cpr) * (VEC ? 4 : 1);
+    const long long base = ((r / rpg) * 3 * rpg + (r % rpg)) * (long long)cols + c;
+    if (VEC) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * src_stride + c));
+      __nv_bfloat16 h[4], l[4];
+      split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
+      const uint2 hv = *reinterpret_cast<uint2*>(h), lv = *reinterpret_cast<uint2*>(l);
+      *reinterpret_cast<uint2*>(out + base) = hv;
+      *reinterpret_cast<uint2*>(out + base + slot_stride) = lv;
+      *reinterpret_cast<uint2*>(out + base + 2 * slot_stride) = hv;
+    } else {
+      __nv_bfloat16 h, l;
+      split1(__ldg(x + r * src_stride + c), h, l);
+      out[base] = h; out[base + slot_stride] = l; out[base + 2 * slot_stride] = h;
+    }
+  }
+}
+
+}  // namespace sgc
+
+extern "C" int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group,
+                                void* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (rows_per_group <= 0 || rows % rows_per_group) return (int)cudaErrorInvalidValue;
+  const bool vec = (cols % 4 == 0) && (src_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  const long long items = rows * (vec ? cols / 4 : cols);
+  long long blocks = (items + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (vec)
+    sgc::split_bf16x3_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, src_stride, rows_per_group,
+                                                                                 (__nv_bfloat16*)out);
+  else
+    sgc::split_bf16x3_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, src_stride, rows_per_group,
+                                                                                  (__nv_bfloat16*)out);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(
     const float* __restrict__ samp, const float* __restrict__ grad_slots,
     int S, int H, int W, int D, int Q,
     float* __restrict__ grad_value, float* __restrict__ grad_G, float* __restrict__ grad_dist,
-    float* __restrict__ grad_vbias, float* __restrict__ grad_gbias) {
+    float* __restrict__ bias_partials) {
   constexpr int C = CPL * 32;
+  __shared__ float s_part[8][C + 128];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int n_pairs = __ldg(n_pairs_ptr);
@@ -270,10 +271,39 @@ __global__ void __launch_bounds__(256) lift_bwd_kernel(
       }
     }
   }
-  // flush the per-warp bias partials
+  // per-CTA reduction of the bias partials (same-address REDs from ~10^4 warps serialise in L2; instead each
+  // CTA stores one row of [C + 128] partials and bias_reduce_kernel sums the rows deterministically)
+  const int wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < CPL; j += 4) red_add4(grad_vbias + lane * CPL + j, gvb[j], gvb[j + 1], gvb[j + 2], gvb[j + 3]);
-  red_add4(grad_gbias + lane * 4, ggb.x, ggb.y, ggb.z, ggb.w);
+  for (int j = 0; j < CPL; ++j) s_part[wid][lane * CPL + j] = gvb[j];
+  s_part[wid][C + lane * 4 + 0] = ggb.x; s_part[wid][C + lane * 4 + 1] = ggb.y;
+  s_part[wid][C + lane * 4 + 2] = ggb.z; s_part[wid][C + lane * 4 + 3] = ggb.w;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C + 128; c += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) a += s_part[w][c];
+    bias_partials[(size_t)blockIdx.x * (C + 128) + c] = a;
+  }
+}
+
+// grad_vbias[c] += sum_rows partials[row][c] (c < C);  grad_gbias[c-C] += ... (c >= C).
+// block = 32 channels x 8 row-groups; fixed summation order -> deterministic.
+__global__ void __launch_bounds__(256) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
+                                                         float* __restrict__ grad_vbias,
+                                                         float* __restrict__ grad_gbias) {
+  __shared__ float s[8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a = 0.f;
+  for (int r = ry; r < rows; r += 8) a += __ldg(partials + (size_t)r * (C + 128) + c);
+  s[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][cx];
+    if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
+  }
 }
 
 }  // namespace sgc
@@ -310,19 +340,22 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
                             const float* ref_cam, const float* samp, const float* grad_slots,
                             int S, int H, int W, int D, int Q, int C,
                             float* grad_value, float* grad_G, float* grad_dist, float* grad_vbias,
-                            float* grad_gbias, void* stream) {
+                            float* grad_gbias, float* scratch, void* stream) {
   if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
   if (C == 256)
     sgc::lift_bwd_kernel<8><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp,
-                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist,
-                                                  grad_vbias, grad_gbias);
+                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist, scratch);
   else
     sgc::lift_bwd_kernel<4><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp,
-                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist,
-                                                  grad_vbias, grad_gbias);
+                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist, scratch);
+  SGC_CUDA_CHECK_LAST();
+  sgc::bias_reduce_kernel<<<(C + 128) / 32, 256, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
+
+// floats of scratch sgc_lift_bwd needs for a given pair capacity
+extern "C" int sgc_lift_bwd_scratch_floats(int cap_pairs, int C) { return lift_grid(cap_pairs) * (C + 128); }

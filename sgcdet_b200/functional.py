@@ -82,8 +82,14 @@ def project_compact(proj: torch.Tensor, ref3d: torch.Tensor, sel: Optional[torch
 
 
 # ----------------------------------------------------------------------------------------------
-# dense projection of the feature maps (library GEMM; tensor-core kernel is a later round)
+# dense projection of the feature maps (tensor cores via bf16 hi/lo operand split)
 # ----------------------------------------------------------------------------------------------
+
+def _split_weight(w: torch.Tensor):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
 
 class ProjectFeatures(torch.autograd.Function):
     """VG[v,s,:] = Wcat @ feat[v,:,s]   with feat the NCHW map cropped to (h,w).
@@ -91,40 +97,57 @@ class ProjectFeatures(torch.autograd.Function):
     Wcat [C+128, C] = [value_proj.weight ; folded offset/depth-offset/attention-weight rows] (no bias: the
     biases are applied inside the lift kernel).  Reads NCHW directly (transposed GEMM operand) and writes
     channel-last, so the NCHW->NHWC copy of ``transformer.py:151-170`` never happens.
+
+    Tensor cores at fp32-level accuracy: both operands are split into bf16 hi/lo (csrc/sgc_gemm_prep.cu) and
+    hi*hi + lo*hi + hi*lo is evaluated as ONE bf16 GEMM with K concatenated 3x and fp32 accumulation/output
+    (library GEMM for now; relative error ~1e-5).
     """
 
     @staticmethod
     def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor):
-        # feat [V,C,H0,W0]
         V, C, H0, W0 = feat.shape
-        fv = feat[:, :, :h, :w]
-        if w != W0:
-            fv = fv.contiguous()
-        ft = fv.flatten(2).transpose(1, 2)  # [V,S,C] view, S contiguous in memory
-        vg = torch.bmm(ft, wcat.t().unsqueeze(0).expand(V, -1, -1))  # [V,S,C+128]
-        ctx.save_for_backward(feat, wcat)
-        ctx.hw = (h, w)
+        S = h * w
+        src = feat
+        if w != W0 or not feat.is_contiguous():
+            src = feat[:, :, :h, :w].contiguous()
+            stride = S
+        else:
+            stride = H0 * W0  # row crop only: the first h*w elements of every channel plane
+        acat = torch.empty(V, 3, C, S, device=feat.device, dtype=torch.bfloat16)
+        call('sgc_split_bf16x3', ptr(src), V * C, S, stride, C, ptr(acat), stream())
+        w_hi, w_lo = _split_weight(wcat)
+        bcat = torch.cat([w_hi, w_hi, w_lo], dim=1)  # [N, 3C] pairs with [a_hi | a_lo | a_hi]
+        vg = torch.bmm(acat.view(V, 3 * C, S).transpose(1, 2), bcat.t().unsqueeze(0).expand(V, -1, -1),
+                       out_dtype=torch.float32)  # [V,S,N]
+        ctx.save_for_backward(acat, w_hi, w_lo)
+        ctx.dims = (V, C, H0, W0, h, w)
         return vg
 
     @staticmethod
     def backward(ctx, gvg: torch.Tensor):
-        feat, wcat = ctx.saved_tensors
-        h, w = ctx.hw
-        V, C, H0, W0 = feat.shape
+        acat, w_hi, w_lo = ctx.saved_tensors
+        V, C, H0, W0, h, w = ctx.dims
+        S = h * w
+        N = w_hi.shape[0]
+        gvg = gvg.contiguous()
+        gcat = torch.empty(V, S, 3, N, device=gvg.device, dtype=torch.bfloat16)
+        call('sgc_split_bf16x3', ptr(gvg), V * S, N, N, 1, ptr(gcat), stream())
         gfeat = gw = None
-        fv = feat[:, :, :h, :w]
-        if w != W0:
-            fv = fv.contiguous()
-        ft = fv.flatten(2).transpose(1, 2)  # [V,S,C]
         if ctx.needs_input_grad[0]:
-            g = torch.bmm(wcat.t().unsqueeze(0).expand(V, -1, -1), gvg.transpose(1, 2))  # [V,C,S]
+            wk = torch.cat([w_hi.t(), w_hi.t(), w_lo.t()], dim=1)  # [C, 3N] pairs with [g_hi | g_lo | g_hi]
+            g = torch.bmm(wk.unsqueeze(0).expand(V, -1, -1), gcat.view(V, S, 3 * N).transpose(1, 2),
+                          out_dtype=torch.float32)  # [V,C,S]
             if h == H0 and w == W0:
                 gfeat = g.view(V, C, H0, W0)
             else:
-                gfeat = feat.new_zeros(V, C, H0, W0)
+                gfeat = g.new_zeros(V, C, H0, W0)
                 gfeat[:, :, :h, :w] = g.view(V, C, h, w)
         if ctx.needs_input_grad[3]:
-            gw = torch.bmm(gvg.transpose(1, 2), ft).sum(0)  # [C+128, C]
+            g_hi_t = gcat[:, :, 0].transpose(1, 2)  # [V,N,S]
+            g_lo_t = gcat[:, :, 1].transpose(1, 2)
+            x = torch.bmm(g_hi_t, acat[:, :2].reshape(V, 2 * C, S).transpose(1, 2), out_dtype=torch.float32)  # [V,N,2C]
+            y = torch.bmm(g_lo_t, acat[:, 0].transpose(1, 2), out_dtype=torch.float32)  # [V,N,C]
+            gw = (x[..., :C] + x[..., C:] + y).sum(0)
         return gfeat, None, None, gw
 
 
@@ -161,9 +184,10 @@ class Lift(torch.autograd.Function):
         gvb = torch.zeros_like(vbias)
         ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
         base, gbase = ptr(vg), ptr(gvg)
+        scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device, dtype=torch.float32)
         call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
              pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots.contiguous()), S, H, W, D, pl.Q, C,
-             gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), stream())
+             gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
         return gvg, gdist, gvb, ggb, None, None, None
 
 

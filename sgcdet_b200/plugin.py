@@ -281,6 +281,16 @@ class PerceptionTransformer_DFA3D(nn.Module):
 # the heads
 # ---------------------------------------------------------------------------------------------
 
+def projection_on_device(img_meta: dict, device) -> torch.Tensor:
+    """[V,3,4] projection matrices on ``device``.  Built on the host exactly like encoder.py:168-177 and
+    uploaded; a caller that replays the step from a CUDA graph stores the device tensor under
+    ``img_meta['sgc_projection']`` beforehand (and updates it in place per scene) so no H2D copy is issued."""
+    cached = img_meta.get('sgc_projection')
+    if cached is not None and cached.device == torch.device(device):
+        return cached
+    return SF.compute_projection(img_meta).to(device)
+
+
 @_register('HEADS')
 class DenseHead(nn.Module):
     """DenseHead.py:10-84.  ``forward`` keeps the reference signature/return ([1,C,X,Y,Z] dense volume);
@@ -324,7 +334,7 @@ class DenseHead(nn.Module):
         da = attn.deformable_attention
         dbound = self.cross_transformer.encoder.dbound
         if proj is None:
-            proj = SF.compute_projection(img_meta).to(feat.device, non_blocking=True)
+            proj = projection_on_device(img_meta, feat.device)
         pl = SF.project_compact(proj, self.ref_3d, sel, img_meta, dbound)
         wcat, vbias, gbias = da.folded_weights()
         vg = SF.ProjectFeatures.apply(feat[0], h, w, wcat)
@@ -393,7 +403,7 @@ class AdaptiveSparseHead(nn.Module):
         bs = mlvl_feats[0].shape[0]
         assert bs == 1
         nl = len(self.base_heads)
-        proj = SF.compute_projection(img_meta).to(mlvl_feats[0].device, non_blocking=True)
+        proj = projection_on_device(img_meta, mlvl_feats[0].device)
         vol = None
         occ_list, masks, inters = [], [None] * nl, []
         for i in range(nl):
