@@ -77,9 +77,15 @@ int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, i
 
 /* fp32 -> [bf16 hi | bf16 lo | bf16 hi] operand split for the tensor-core projections (value_proj /
  * sampling_offsets / sampling_offsets_depth / attention_weights, DCA:417-436): rows of length cols (source row
- * stride src_stride), out[((r / rpg) * 3 + slot) * rpg + r % rpg][col] as bf16.  See csrc/sgc_gemm_prep.cu. */
-int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group, void* out,
-                     void* stream);
+ * stride src_stride), out[((r / rpg) * 3 + slot) * rpg + r % rpg][col] as bf16; slots (hi,lo,hi) for pattern 0,
+ * (hi,hi,lo) for pattern 1.  See csrc/sgc_gemm_prep.cu. */
+int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group, int pattern,
+                     void* out, void* stream);
+
+/* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
+ * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */
+int sgc_colsum_scratch_floats(int R, int C);
+int sgc_colsum(const float* x, int R, int C, float* out, float* scratch, unsigned int* counter, void* stream);
 
 /* Lift: reference-point sample (DCA:67-116) + offset/weight heads + softmax (DCA:423-436) + sampling
  * locations (DCA:445-461) + 8-head 4-point DFA3D (F3D:277-302) for every visible pair.

@@ -26,7 +26,9 @@ SIGNATURES = {
     'dfa3d_fused_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P],
     'sgc_project_scratch_ints': [I, I],
     'sgc_project_compact': [P, P, P, I, I, F, F, F, F, F, F, F, F, F, P, P, P, P, P, P, P, P],
-    'sgc_split_bf16x3': [P, LL, I, LL, I, P, P],
+    'sgc_split_bf16x3': [P, LL, I, LL, I, I, P, P],
+    'sgc_colsum_scratch_floats': [I, I],
+    'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],
     'sgc_lift_bwd_scratch_floats': [I, I],
     'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P],

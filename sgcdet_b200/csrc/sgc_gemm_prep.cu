@@ -8,7 +8,8 @@
 //
 // This kernel writes the [hi | lo | hi] operand in one pass over x:
 //   rows r of length `cols` (source row stride `src_stride`), grouped by `rpg` rows:
-//   out[((r / rpg) * 3 + slot) * rpg + (r % rpg)][col],  slot 0 = hi, 1 = lo, 2 = hi.
+//   out[((r / rpg) * 3 + slot) * rpg + (r % rpg)][col],  slots = (hi, lo, hi) for pattern 0 and (hi, hi, lo)
+//   for pattern 1 (the two operands of one product use opposite patterns).
 //   rpg = C  -> feature maps  [V,C,S]   -> [V,3,C,S]     (K = channel concat, S stays contiguous)
 //   rpg = 1  -> row-major     [R,N]     -> [R,3N]        (K = column concat)
 #include <cuda_bf16.h>
@@ -23,7 +24,7 @@ __device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ x, long long rows, int cols,
-                                                          long long src_stride, int rpg,
+                                                          long long src_stride, int rpg, int pattern,
                                                           __nv_bfloat16* __restrict__ out) {
   const int cpr = VEC ? cols / 4 : cols;  // work items per row
   const long long total = rows * cpr;
@@ -38,12 +39,12 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
       split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
       const uint2 hv = *reinterpret_cast<uint2*>(h), lv = *reinterpret_cast<uint2*>(l);
       *reinterpret_cast<uint2*>(out + base) = hv;
-      *reinterpret_cast<uint2*>(out + base + slot_stride) = lv;
-      *reinterpret_cast<uint2*>(out + base + 2 * slot_stride) = hv;
+      *reinterpret_cast<uint2*>(out + base + slot_stride) = pattern ? hv : lv;
+      *reinterpret_cast<uint2*>(out + base + 2 * slot_stride) = pattern ? lv : hv;
     } else {
       __nv_bfloat16 h, l;
       split1(__ldg(x + r * src_stride + c), h, l);
-      out[base] = h; out[base + slot_stride] = l; out[base + 2 * slot_stride] = h;
+      out[base] = h; out[base + slot_stride] = pattern ? h : l; out[base + 2 * slot_stride] = pattern ? l : h;
     }
   }
 }
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
 }  // namespace sgc
 
 extern "C" int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group,
-                                void* out, void* stream) {
+                                int pattern, void* out, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   if (rows_per_group <= 0 || rows % rows_per_group) return (int)cudaErrorInvalidValue;
   const bool vec = (cols % 4 == 0) && (src_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
@@ -61,10 +62,56 @@ extern "C" int sgc_split_bf16x3(const float* x, long long rows, int cols, long l
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (vec)
     sgc::split_bf16x3_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, src_stride, rows_per_group,
-                                                                                 (__nv_bfloat16*)out);
+                                                                                 pattern, (__nv_bfloat16*)out);
   else
     sgc::split_bf16x3_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, src_stride, rows_per_group,
-                                                                                  (__nv_bfloat16*)out);
+                                                                                  pattern, (__nv_bfloat16*)out);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Column sums of a row-major [R,C] matrix (bias gradients of the Linear layers), deterministic:
+// every CTA reduces a slab of rows into partial[b][:], the last CTA to finish (atomic ticket) adds the
+// partials in slab order.  `counter` must be zero on entry and is reset to zero on exit.
+namespace sgc {
+constexpr int kColsumRows = 32;
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int C,
+                                                    float* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                    float* __restrict__ out) {
+  __shared__ bool is_last;
+  const int r0 = blockIdx.x * kColsumRows;
+  const int r1 = min(R, r0 + kColsumRows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int r = r0; r < r1; ++r) a += __ldg(x + (size_t)r * C + c);
+    partial[(size_t)blockIdx.x * C + c] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += partial[(size_t)b * C + c];
+    out[c] = a;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+}  // namespace sgc
+
+extern "C" int sgc_colsum_scratch_floats(int R, int C) {
+  return ((R + sgc::kColsumRows - 1) / sgc::kColsumRows) * C;
+}
+
+extern "C" int sgc_colsum(const float* x, int R, int C, float* out, float* scratch, unsigned int* counter,
+                          void* stream) {
+  if (R <= 0 || C <= 0) return (int)cudaErrorInvalidValue;
+  const int blocks = (R + sgc::kColsumRows - 1) / sgc::kColsumRows;
+  sgc::colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, R, C, scratch, counter, out);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -85,10 +85,56 @@ def project_compact(proj: torch.Tensor, ref3d: torch.Tensor, sel: Optional[torch
 # dense projection of the feature maps (tensor cores via bf16 hi/lo operand split)
 # ----------------------------------------------------------------------------------------------
 
-def _split_weight(w: torch.Tensor):
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
-    return hi, lo
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
+    """[R,K] fp32 -> [R,3K] bf16 = (hi|lo|hi) for pattern 0, (hi|hi|lo) for pattern 1 (K-concatenation)."""
+    x = x.contiguous()
+    R, K = x.shape
+    out = torch.empty(R, 3 * K, device=x.device, dtype=BF16)
+    call('sgc_split_bf16x3', ptr(x), R, K, K, 1, pattern, ptr(out), stream())
+    return out
+
+
+def split_rows(x: torch.Tensor, group: int, pattern: int) -> torch.Tensor:
+    """[G*group, K] fp32 -> [G, 3*group, K] bf16: the three slots are stacked along the ROW (reduction) axis of
+    every group of ``group`` rows."""
+    x = x.contiguous()
+    R, K = x.shape
+    out = torch.empty(R // group, 3 * group, K, device=x.device, dtype=BF16)
+    call('sgc_split_bf16x3', ptr(x), R, K, K, group, pattern, ptr(out), stream())
+    return out
+
+
+def mm_nt(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """a [R,K] @ w[N,K]^T -> [R,N] fp32, tensor cores with bf16 hi/lo split (hi*hi + lo*hi + hi*lo)."""
+    return torch.mm(split_cols(a, 0), split_cols(w, 1).t(), out_dtype=F32)
+
+
+def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """g[Q,N]^T @ x[Q,K] -> [N,K] fp32 (reduction over the rows)."""
+    Q = g.shape[0]
+    return torch.mm(split_rows(g, Q, 0)[0].t(), split_rows(x, Q, 1)[0], out_dtype=F32)
+
+
+_COUNTERS = {}
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """x[R,C] -> [C] column sums (bias gradients), deterministic two-stage reduction in one launch."""
+    x = x.contiguous()
+    R, C = x.shape
+    dev = x.device
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ctr = _COUNTERS.get(key)
+    if ctr is None:
+        ctr = _COUNTERS[key] = torch.zeros(1, device=dev, dtype=torch.int32)
+    out = torch.empty(C, device=dev, dtype=F32)
+    scratch = torch.empty(_lib.load().sgc_colsum_scratch_floats(R, C), device=dev, dtype=F32)
+    call('sgc_colsum', ptr(x), R, C, ptr(out), ptr(scratch), ptr(ctr), stream())
+    return out
 
 
 class ProjectFeatures(torch.autograd.Function):
@@ -113,40 +159,43 @@ class ProjectFeatures(torch.autograd.Function):
             stride = S
         else:
             stride = H0 * W0  # row crop only: the first h*w elements of every channel plane
-        acat = torch.empty(V, 3, C, S, device=feat.device, dtype=torch.bfloat16)
-        call('sgc_split_bf16x3', ptr(src), V * C, S, stride, C, ptr(acat), stream())
-        w_hi, w_lo = _split_weight(wcat)
-        bcat = torch.cat([w_hi, w_hi, w_lo], dim=1)  # [N, 3C] pairs with [a_hi | a_lo | a_hi]
-        vg = torch.bmm(acat.view(V, 3 * C, S).transpose(1, 2), bcat.t().unsqueeze(0).expand(V, -1, -1),
-                       out_dtype=torch.float32)  # [V,S,N]
-        ctx.save_for_backward(acat, w_hi, w_lo)
+        acat = torch.empty(V, 3 * C, S, device=feat.device, dtype=BF16)  # (hi|lo|hi) along channels
+        call('sgc_split_bf16x3', ptr(src), V * C, S, stride, C, 0, ptr(acat), stream())
+        bcat = split_cols(wcat, 1)  # [N, 3C]
+        vg = torch.bmm(acat.transpose(1, 2), bcat.t().unsqueeze(0).expand(V, -1, -1), out_dtype=F32)  # [V,S,N]
+        ctx.save_for_backward(acat, wcat)
         ctx.dims = (V, C, H0, W0, h, w)
         return vg
 
     @staticmethod
     def backward(ctx, gvg: torch.Tensor):
-        acat, w_hi, w_lo = ctx.saved_tensors
+        acat, wcat = ctx.saved_tensors
         V, C, H0, W0, h, w = ctx.dims
         S = h * w
-        N = w_hi.shape[0]
+        N = wcat.shape[0]
         gvg = gvg.contiguous()
-        gcat = torch.empty(V, S, 3, N, device=gvg.device, dtype=torch.bfloat16)
-        call('sgc_split_bf16x3', ptr(gvg), V * S, N, N, 1, ptr(gcat), stream())
-        gfeat = gw = None
+        gfeat = gw = gcat = None
         if ctx.needs_input_grad[0]:
-            wk = torch.cat([w_hi.t(), w_hi.t(), w_lo.t()], dim=1)  # [C, 3N] pairs with [g_hi | g_lo | g_hi]
-            g = torch.bmm(wk.unsqueeze(0).expand(V, -1, -1), gcat.view(V, S, 3 * N).transpose(1, 2),
-                          out_dtype=torch.float32)  # [V,C,S]
-            if h == H0 and w == W0:
-                gfeat = g.view(V, C, H0, W0)
+            gcat = split_cols(gvg.view(V * S, N), 0).view(V, S, 3 * N)
+            wk = split_cols(wcat.t(), 1)  # [C, 3N]
+            if w == W0:
+                # write straight into the padded NCHW gradient; only the cropped rows need zeroing
+                gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
+                if h != H0:
+                    gfeat[:, :, h:].zero_()
+                torch.bmm(wk.unsqueeze(0).expand(V, -1, -1), gcat.transpose(1, 2), out_dtype=F32,
+                          out=gfeat.view(V, C, H0 * W0)[:, :, :S])
             else:
+                g = torch.bmm(wk.unsqueeze(0).expand(V, -1, -1), gcat.transpose(1, 2), out_dtype=F32)
                 gfeat = g.new_zeros(V, C, H0, W0)
                 gfeat[:, :, :h, :w] = g.view(V, C, h, w)
         if ctx.needs_input_grad[3]:
-            g_hi_t = gcat[:, :, 0].transpose(1, 2)  # [V,N,S]
-            g_lo_t = gcat[:, :, 1].transpose(1, 2)
-            x = torch.bmm(g_hi_t, acat[:, :2].reshape(V, 2 * C, S).transpose(1, 2), out_dtype=torch.float32)  # [V,N,2C]
-            y = torch.bmm(g_lo_t, acat[:, 0].transpose(1, 2), out_dtype=torch.float32)  # [V,N,C]
+            # gw[n,c] = sum_{v,s} g[v,s,n] f[v,c,s] = g_hi f_hi + g_hi f_lo + g_lo f_hi, straight from the
+            # already split operands (strided views, no copies): acat = (f_hi | f_lo | f_hi) along channels
+            if gcat is None:
+                gcat = split_cols(gvg.view(V * S, N), 0).view(V, S, 3 * N)
+            x = torch.bmm(gcat[:, :, :N].transpose(1, 2), acat[:, :2 * C].transpose(1, 2), out_dtype=F32)  # [V,N,2C]
+            y = torch.bmm(gcat[:, :, N:2 * N].transpose(1, 2), acat[:, :C].transpose(1, 2), out_dtype=F32)  # [V,N,C]
             gw = (x[..., :C] + x[..., C:] + y).sum(0)
         return gfeat, None, None, gw
 
@@ -195,36 +244,53 @@ class Lift(torch.autograd.Function):
 # cross-view fusion
 # ----------------------------------------------------------------------------------------------
 
+def _heads_cols(x: torch.Tensor, pattern: int, heads: int = NUM_HEADS) -> torch.Tensor:
+    """[Q, heads*dh] -> [heads, Q, 3dh] (strided view): per-head operand whose reduction axis is dh."""
+    Q, C = x.shape
+    dh = C // heads
+    return split_cols(x.reshape(Q * heads, dh), pattern).view(Q, heads, 3 * dh).transpose(0, 1)
+
+
+def _heads_rows_t(x: torch.Tensor, pattern: int, heads: int = NUM_HEADS) -> torch.Tensor:
+    """[Q, heads*dh] -> [heads, dh, 3Q] (strided view): per-head transposed operand, reduction over Q."""
+    Q, C = x.shape
+    dh = C // heads
+    return split_rows(x, Q, pattern)[0].view(3 * Q, heads, dh).permute(1, 2, 0)
+
+
 class CrossView(torch.autograd.Function):
     """DCA:815-837: masked mean over views -> output_proj -> 8-head attention pooling over views.
 
-    The dense projections are voxel-count GEMMs (torch.mm/bmm = library GEMMs) around the two
-    cross-view kernels; the backward is written out by hand so that no pair-capacity-sized tensor is ever
-    touched outside the kernels.
+    The dense projections are voxel-count GEMMs (static shapes; library bf16 GEMMs on bf16x3-split operands,
+    fp32 accumulate) around the two cross-view kernels; the backward is written out by hand so that no
+    pair-capacity-sized tensor is ever touched outside the kernels.
     """
 
     @staticmethod
     def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo):
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
-        dh = C // NUM_HEADS
+        H = NUM_HEADS
+        dh = C // H
         scale = 1.0 / math.sqrt(dh)
         dev = slots.device
-        mean = torch.empty(Q, C, device=dev, dtype=torch.float32)
+        mean = torch.empty(Q, C, device=dev, dtype=F32)
         call('sgc_crossview_mean_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), stream())
-        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
+        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
         bq, bv = in_b[:C], in_b[2 * C:]
-        g = torch.addmm(b_out, mean, w_out.t())
-        qv = torch.addmm(bq, g, wq.t())
-        qv_h = qv.view(Q, NUM_HEADS, dh).transpose(0, 1)  # [8,Q,dh]
-        qt = torch.bmm(qv_h, wk.view(NUM_HEADS, dh, C)) * scale  # [8,Q,C]
-        t = torch.empty(NUM_HEADS, Q, C, device=dev, dtype=torch.float32)
-        alpha = torch.empty(pl.cap, NUM_HEADS, device=dev, dtype=torch.float32)
+        g = mm_nt(mean, w_out) + b_out
+        qv = mm_nt(g, wq) + bq
+        # qt[h] = qv_h @ (scale * Wk_h)   [8,Q,dh] x [8,dh,C]
+        qt = torch.bmm(_heads_cols(qv, 0), split_rows(wk, dh, 1), out_dtype=F32)
+        t = torch.empty(H, Q, C, device=dev, dtype=F32)
+        alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         call('sgc_crossview_attn_fwd', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), stream())
-        o = torch.bmm(t, wv.view(NUM_HEADS, dh, C).transpose(1, 2))  # [8,Q,dh]
+        # o[h] = t[h] @ Wv_h^T   [8,Q,C] x [8,C,dh]
+        o = torch.bmm(split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
+                      split_cols(wv, 1).view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         o2 = o.transpose(0, 1).reshape(Q, C) + bv
-        has = (pl.count > 0).to(torch.float32).unsqueeze(1)
-        out = torch.addmm(bo, o2, wo.t()) * has
+        has = (pl.count > 0).to(F32).unsqueeze(1)
+        out = (mm_nt(o2, wo) + bo) * has
         ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, w_out, in_w, wo)
         ctx.pl = pl
         return out
@@ -235,38 +301,57 @@ class CrossView(torch.autograd.Function):
         pl = ctx.pl
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
-        dh = C // NUM_HEADS
+        H = NUM_HEADS
+        dh = C // H
         scale = 1.0 / math.sqrt(dh)
         dev = slots.device
-        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
+        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
         gout = gout * has
-        g_wo = gout.t() @ o2
-        g_bo = gout.sum(0)
-        go2 = gout @ wo
-        g_bv = go2.sum(0)
-        go_h = go2.view(Q, NUM_HEADS, dh).transpose(0, 1)  # [8,Q,dh]
-        gt = torch.bmm(go_h, wv.view(NUM_HEADS, dh, C)).contiguous()  # [8,Q,C]
-        g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
-        gscore = torch.empty(pl.cap, NUM_HEADS, device=dev, dtype=torch.float32)
-        gqt = torch.empty(NUM_HEADS, Q, C, device=dev, dtype=torch.float32)
+        g_wo = mm_tn(gout, o2)
+        g_bo = colsum(gout)
+        go2 = mm_nt(gout, wo.t())
+        g_bv = colsum(go2)
+        # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
+        gt = torch.bmm(_heads_cols(go2, 0), split_rows(wv, dh, 1), out_dtype=F32)
+        # g_wv[h] = go_h^T @ t[h]   [8,dh,Q] x [8,Q,C]
+        g_wv = torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
+        gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
+        gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         call('sgc_crossview_attn_bwd_qt', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
              ptr(gqt), stream())
-        gqv_h = torch.bmm(gqt, wk.view(NUM_HEADS, dh, C).transpose(1, 2)) * scale  # [8,Q,dh]
-        qv_h = qv.view(Q, NUM_HEADS, dh).transpose(0, 1)
-        g_wk = (torch.bmm(qv_h.transpose(1, 2), gqt) * scale).reshape(C, C)
+        # gqv[h] = gqt[h] @ (scale*Wk_h)^T   [8,Q,C] x [8,C,dh]
+        gqv_h = torch.bmm(split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
+                          split_cols(wk, 1).view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         gqv = gqv_h.transpose(0, 1).reshape(Q, C)
-        g_wq = gqv.t() @ g
-        g_bq = gqv.sum(0)
-        gg = gqv @ wq
-        g_wout = gg.t() @ mean
-        g_bout = gg.sum(0)
-        gmean = (gg @ w_out).contiguous()
+        # g_wk[h] = scale * qv_h^T @ gqt[h]   [8,dh,Q] x [8,Q,C]
+        g_wk = torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
+        g_wq = mm_tn(gqv, g)
+        g_bq = colsum(gqv)
+        gg = mm_nt(gqv, wq.t())
+        g_wout = mm_tn(gg, mean)
+        g_bout = colsum(gg)
+        gmean = mm_nt(gg, w_out.t())
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
         g_in_w = torch.cat([g_wq, g_wk, g_wv], dim=0)
         g_in_b = torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)
         return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo
+
+
+class Linear3(torch.autograd.Function):
+    """y = x W^T + b on the tensor cores with bf16x3-split operands (used for the FFN, encoder.py:335-338)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return mm_nt(x, w) + b
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        return mm_nt(gy, w.t()), mm_tn(gy, x), colsum(gy)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     build.build()
     lib = ctypes.CDLL(str(_lib.lib_path()))
     decls = _header_decls()
-    assert len(decls) == 21
+    assert len(decls) == 23
     for name in decls:
         assert hasattr(lib, name), f'{name} declared in include/sgcdet_b200.h but not exported'
 
@@ -40,6 +40,8 @@ def test_python_bindings_mirror_header():
         for p, t in zip(params, sig):
             if '*' in p:
                 assert t is ctypes.c_void_p, (name, p)
+            elif p.startswith('unsigned'):
+                assert False, (name, p)
             elif p.startswith('float'):
                 assert t is ctypes.c_float, (name, p)
             elif p.startswith('long long'):
