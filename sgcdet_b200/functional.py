@@ -108,9 +108,40 @@ def split_rows(x: torch.Tensor, group: int, pattern: int) -> torch.Tensor:
     return out
 
 
-def mm_nt(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """a [R,K] @ w[N,K]^T -> [R,N] fp32, tensor cores with bf16 hi/lo split (hi*hi + lo*hi + hi*lo)."""
-    return torch.mm(split_cols(a, 0), split_cols(w, 1).t(), out_dtype=F32)
+def mm_nt(a: torch.Tensor, w: torch.Tensor = None, ws: torch.Tensor = None) -> torch.Tensor:
+    """a [R,K] @ w[N,K]^T -> [R,N] fp32, tensor cores with bf16 hi/lo split (hi*hi + lo*hi + hi*lo).
+    ``ws`` = pre-split weight ``split_cols(w, 1)`` (computed once per step by ``LevelWeights``)."""
+    if ws is None:
+        ws = split_cols(w, 1)
+    return torch.mm(split_cols(a, 0), ws.t(), out_dtype=F32)
+
+
+class LevelWeights:
+    """Every bf16x3 split of one level's weights (both orientations), computed once per step -- normally on a
+    side stream, off the critical path of the level.  Constants for the autograd Functions below (weight
+    gradients are formed from the fp32 activations, not from these)."""
+
+    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS):
+        with torch.no_grad():
+            C = w_out.shape[0]
+            dh = C // num_heads
+            scale = 1.0 / math.sqrt(dh)
+            wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
+            self.wcat = split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
+            self.wcat_t = split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
+            self.w_out, self.w_out_t = split_cols(w_out, 1), split_cols(w_out.t(), 1)
+            self.wq, self.wq_t = split_cols(wq, 1), split_cols(wq.t(), 1)
+            self.wo, self.wo_t = split_cols(wo, 1), split_cols(wo.t(), 1)
+            self.wk_rows = split_rows(wk, dh, 1)     # [8,3dh,C]  qv_h @ (scale Wk_h)
+            self.wk_cols = split_cols(wk, 1)         # [C,3C]     gqt[h] @ (scale Wk_h)^T
+            self.wv_rows = split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
+            self.wv_cols = split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
+            self.w1, self.w1_t = split_cols(w1, 1), split_cols(w1.t(), 1)
+            self.w2, self.w2_t = split_cols(w2, 1), split_cols(w2.t(), 1)
+
+    def record_stream(self, s):
+        for t in self.__dict__.values():
+            t.record_stream(s)
 
 
 def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -150,7 +181,7 @@ class ProjectFeatures(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor):
+    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
         V, C, H0, W0 = feat.shape
         S = h * w
         src = feat
@@ -161,10 +192,11 @@ class ProjectFeatures(torch.autograd.Function):
             stride = H0 * W0  # row crop only: the first h*w elements of every channel plane
         acat = torch.empty(V, 3 * C, S, device=feat.device, dtype=BF16)  # (hi|lo|hi) along channels
         call('sgc_split_bf16x3', ptr(src), V * C, S, stride, C, 0, ptr(acat), stream())
-        bcat = split_cols(wcat, 1)  # [N, 3C]
+        bcat = lw.wcat if lw is not None else split_cols(wcat, 1)  # [N, 3C]
         vg = torch.bmm(acat.transpose(1, 2), bcat.t().unsqueeze(0).expand(V, -1, -1), out_dtype=F32)  # [V,S,N]
         ctx.save_for_backward(acat, wcat)
         ctx.dims = (V, C, H0, W0, h, w)
+        ctx.lw = lw
         return vg
 
     @staticmethod
@@ -177,7 +209,7 @@ class ProjectFeatures(torch.autograd.Function):
         gfeat = gw = gcat = None
         if ctx.needs_input_grad[0]:
             gcat = split_cols(gvg.view(V * S, N), 0).view(V, S, 3 * N)
-            wk = split_cols(wcat.t(), 1)  # [C, 3N]
+            wk = ctx.lw.wcat_t if ctx.lw is not None else split_cols(wcat.t(), 1)  # [C, 3N]
             if w == W0:
                 # write straight into the padded NCHW gradient; only the cropped rows need zeroing
                 gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
@@ -197,7 +229,7 @@ class ProjectFeatures(torch.autograd.Function):
             x = torch.bmm(gcat[:, :, :N].transpose(1, 2), acat[:, :2 * C].transpose(1, 2), out_dtype=F32)  # [V,N,2C]
             y = torch.bmm(gcat[:, :, N:2 * N].transpose(1, 2), acat[:, :C].transpose(1, 2), out_dtype=F32)  # [V,N,C]
             gw = (x[..., :C] + x[..., C:] + y).sum(0)
-        return gfeat, None, None, gw
+        return gfeat, None, None, gw, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -267,30 +299,32 @@ class CrossView(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo):
+    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, lw=None):
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
         H = NUM_HEADS
+        if lw is None:
+            lw = LevelWeights(w_out, w_out, in_w, wo, w_out, w_out)
+        ctx.lw = lw
         dh = C // H
         scale = 1.0 / math.sqrt(dh)
         dev = slots.device
         mean = torch.empty(Q, C, device=dev, dtype=F32)
         call('sgc_crossview_mean_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), stream())
-        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
         bq, bv = in_b[:C], in_b[2 * C:]
-        g = mm_nt(mean, w_out) + b_out
-        qv = mm_nt(g, wq) + bq
+        g = mm_nt(mean, ws=lw.w_out) + b_out
+        qv = mm_nt(g, ws=lw.wq) + bq
         # qt[h] = qv_h @ (scale * Wk_h)   [8,Q,dh] x [8,dh,C]
-        qt = torch.bmm(_heads_cols(qv, 0), split_rows(wk, dh, 1), out_dtype=F32)
+        qt = torch.bmm(_heads_cols(qv, 0), lw.wk_rows, out_dtype=F32)
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         call('sgc_crossview_attn_fwd', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), stream())
         # o[h] = t[h] @ Wv_h^T   [8,Q,C] x [8,C,dh]
         o = torch.bmm(split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
-                      split_cols(wv, 1).view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+                      lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         o2 = o.transpose(0, 1).reshape(Q, C) + bv
         has = (pl.count > 0).to(F32).unsqueeze(1)
-        out = (mm_nt(o2, wo) + bo) * has
+        out = (mm_nt(o2, ws=lw.wo) + bo) * has
         ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, w_out, in_w, wo)
         ctx.pl = pl
         return out
@@ -305,14 +339,14 @@ class CrossView(torch.autograd.Function):
         dh = C // H
         scale = 1.0 / math.sqrt(dh)
         dev = slots.device
-        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
+        lw = ctx.lw
         gout = gout * has
         g_wo = mm_tn(gout, o2)
         g_bo = colsum(gout)
-        go2 = mm_nt(gout, wo.t())
+        go2 = mm_nt(gout, ws=lw.wo_t)
         g_bv = colsum(go2)
         # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
-        gt = torch.bmm(_heads_cols(go2, 0), split_rows(wv, dh, 1), out_dtype=F32)
+        gt = torch.bmm(_heads_cols(go2, 0), lw.wv_rows, out_dtype=F32)
         # g_wv[h] = go_h^T @ t[h]   [8,dh,Q] x [8,Q,C]
         g_wv = torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
@@ -321,37 +355,39 @@ class CrossView(torch.autograd.Function):
              ptr(gqt), stream())
         # gqv[h] = gqt[h] @ (scale*Wk_h)^T   [8,Q,C] x [8,C,dh]
         gqv_h = torch.bmm(split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
-                          split_cols(wk, 1).view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+                          lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         gqv = gqv_h.transpose(0, 1).reshape(Q, C)
         # g_wk[h] = scale * qv_h^T @ gqt[h]   [8,dh,Q] x [8,Q,C]
         g_wk = torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
         g_wq = mm_tn(gqv, g)
         g_bq = colsum(gqv)
-        gg = mm_nt(gqv, wq.t())
+        gg = mm_nt(gqv, ws=lw.wq_t)
         g_wout = mm_tn(gg, mean)
         g_bout = colsum(gg)
-        gmean = mm_nt(gg, w_out.t())
+        gmean = mm_nt(gg, ws=lw.w_out_t)
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
         g_in_w = torch.cat([g_wq, g_wk, g_wv], dim=0)
         g_in_b = torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)
-        return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo
+        return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None
 
 
 class Linear3(torch.autograd.Function):
     """y = x W^T + b on the tensor cores with bf16x3-split operands (used for the FFN, encoder.py:335-338)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, ws=None, ws_t=None):
         ctx.save_for_backward(x, w)
-        return mm_nt(x, w) + b
+        ctx.ws_t = ws_t
+        return mm_nt(x, w, ws) + b
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
-        return mm_nt(gy, w.t()), mm_tn(gy, x), colsum(gy)
+        gx = mm_nt(gy, ws=ctx.ws_t) if ctx.ws_t is not None else mm_nt(gy, w.t())
+        return gx, mm_tn(gy, x), colsum(gy), None, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -197,12 +197,13 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
         self.add_identity = add_identity
 
-    def forward(self, x, identity=None):
+    def forward(self, x, identity=None, lw=None):
         if x.is_cuda and x.dim() == 2:
             # same arithmetic as ``self.layers`` with the two Linear layers on the tensor cores (bf16x3 split)
             l0, drop0 = self.layers[0][0], self.layers[0][2]
-            hdn = drop0(F.relu(SF.Linear3.apply(x, l0.weight, l0.bias)))
-            out = self.layers[2](SF.Linear3.apply(hdn, self.layers[1].weight, self.layers[1].bias))
+            w = (lw.w1, lw.w1_t, lw.w2, lw.w2_t) if lw is not None else (None,) * 4
+            hdn = drop0(F.relu(SF.Linear3.apply(x, l0.weight, l0.bias, w[0], w[1])))
+            out = self.layers[2](SF.Linear3.apply(hdn, self.layers[1].weight, self.layers[1].bias, w[2], w[3]))
         else:
             out = self.layers(x)
         if not self.add_identity:
@@ -287,6 +288,17 @@ class PerceptionTransformer_DFA3D(nn.Module):
 # the heads
 # ---------------------------------------------------------------------------------------------
 
+_STREAMS = {}
+
+
+def _side_streams(device, n: int):
+    key = torch.device(device)
+    pool = _STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=key))
+    return pool[:n]
+
+
 def projection_on_device(img_meta: dict, device) -> torch.Tensor:
     """[V,3,4] projection matrices on ``device``.  Built on the host exactly like encoder.py:168-177 and
     uploaded; a caller that replays the step from a CUDA graph stores the device tensor under
@@ -327,8 +339,26 @@ class DenseHead(nn.Module):
     def num_voxels(self) -> int:
         return int(self.n_voxels.prod())
 
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw):
+        """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
+        the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
+        map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
+        kernels overlap the latency-bound per-voxel chain of the coarser levels."""
+        h, w = hw
+        layer = self.cross_transformer.encoder.layers[0]
+        attn = layer.attentions[0]
+        da = attn.deformable_attention
+        mha = attn.attention_pooling
+        ffn = layer.ffns[0]
+        wcat, vbias, gbias = da.folded_weights()
+        lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
+                             ffn.layers[0][0].weight, ffn.layers[1].weight)
+        vg = SF.ProjectFeatures.apply(feat[0], h, w, wcat, lw)
+        dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
+        return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous(), gbias=gbias)
+
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
-                     proj: Optional[torch.Tensor] = None, return_intermediates: bool = False):
+                     proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None):
         """feat [1,V,C,H0,W0] (uncropped), dpt_dist [1,V,D,H0,W0], hw = cropped (h,w), sel [Q] int32 or None.
         Returns y [Q,C] (rows of the dense volume at ``sel``)."""
         assert feat.shape[0] == 1  # bs == 1 (DenseHead.py:60)
@@ -337,21 +367,20 @@ class DenseHead(nn.Module):
         h, w = hw
         layer = self.cross_transformer.encoder.layers[0]
         attn = layer.attentions[0]
-        da = attn.deformable_attention
         dbound = self.cross_transformer.encoder.dbound
         if proj is None:
             proj = projection_on_device(img_meta, feat.device)
         pl = SF.project_compact(proj, self.ref_3d, sel, img_meta, dbound)
-        wcat, vbias, gbias = da.folded_weights()
-        vg = SF.ProjectFeatures.apply(feat[0], h, w, wcat)
-        dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
-        slots, samp = SF.Lift.apply(vg, dist, vbias.contiguous(), gbias, pl, h, w)
+        if prepared is None:
+            prepared = self.prepare(feat, dpt_dist, hw)
+        lw = prepared['lw']
+        slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w)
         mha = attn.attention_pooling
         x = SF.CrossView.apply(slots, pl, attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight,
-                               mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias)
+                               mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lw)
         x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
         x = layer.norms[0](x)
-        x = layer.ffns[0](x)
+        x = layer.ffns[0](x, lw=lw)
         x = layer.norms[1](x)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
@@ -409,16 +438,32 @@ class AdaptiveSparseHead(nn.Module):
         bs = mlvl_feats[0].shape[0]
         assert bs == 1
         nl = len(self.base_heads)
-        proj = projection_on_device(img_meta, mlvl_feats[0].device)
+        dev = mlvl_feats[0].device
+        proj = projection_on_device(img_meta, dev)
         vol = None
         occ_list, masks, inters = [], [None] * nl, []
+        hws = [(img_meta['img_shape'][0] // (4 * 2 ** (nl - 1 - i)), img_meta['img_shape'][1] // (4 * 2 ** (nl - 1 - i)))
+               for i in range(nl)]
+        # selection-independent work of every level (weight splits, dense feature projection) goes to side
+        # streams up front; level i joins its stream right before it needs the projected maps
+        main = torch.cuda.current_stream(dev)
+        streams = _side_streams(dev, nl)
+        prepared = []
         for i in range(nl):
-            ds = 4 * 2 ** (nl - 1 - i)
-            hw = (img_meta['img_shape'][0] // ds, img_meta['img_shape'][1] // ds)
+            streams[i].wait_stream(main)
+            with torch.cuda.stream(streams[i]):
+                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i]))
+        for i in range(nl):
+            hw = hws[i]
             fi = nl - 1 - i
             head = self.base_heads[i]
+            main.wait_stream(streams[i])
+            pre = prepared[i]
+            for t in (pre['vg'], pre['dist'], pre['vbias'], pre['gbias']):
+                t.record_stream(main)
+            pre['lw'].record_stream(main)
             if i == 0:
-                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, None, proj, return_intermediates)
+                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, None, proj, return_intermediates, pre)
                 y, it = r if return_intermediates else (r, None)
                 X, Y, Z = (int(v) for v in head.n_voxels)
                 vol = y.view(X, Y, Z, self.embed_dims)
@@ -436,7 +481,7 @@ class AdaptiveSparseHead(nn.Module):
                     masks[i] = mask
                 else:
                     sel = None
-                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates)
+                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre)
                 y, it = r if return_intermediates else (r, None)
                 if sel is None:
                     vol = up + y.view_as(up)
