@@ -75,18 +75,36 @@ extern "C" int sgc_split_bf16x3(const float* x, long long rows, int cols, long l
 // every CTA reduces a slab of rows into partial[b][:], the last CTA to finish (atomic ticket) adds the
 // partials in slab order.  `counter` must be zero on entry and is reset to zero on exit.
 namespace sgc {
-constexpr int kColsumRows = 32;
+constexpr int kColsumRows = 64;
 
+// block = 64 float4-column lanes x 4 row lanes; requires C % 4 == 0
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int C,
                                                     float* __restrict__ partial, unsigned int* __restrict__ counter,
                                                     float* __restrict__ out) {
+  __shared__ float4 s_acc[4][64];
   __shared__ bool is_last;
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
   const int r0 = blockIdx.x * kColsumRows;
   const int r1 = min(R, r0 + kColsumRows);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int r = r0; r < r1; ++r) a += __ldg(x + (size_t)r * C + c);
-    partial[(size_t)blockIdx.x * C + c] = a;
+  const int C4 = C >> 2;
+  for (int c0 = 0; c0 < C4; c0 += 64) {
+    const int c = c0 + cx;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C4) {
+      for (int r = r0 + ry; r < r1; r += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * C) + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    }
+    s_acc[ry][cx] = a;
+    __syncthreads();
+    if (ry == 0 && c < C4) {
+      float4 t = s_acc[0][cx];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) { t.x += s_acc[k][cx].x; t.y += s_acc[k][cx].y; t.z += s_acc[k][cx].z; t.w += s_acc[k][cx].w; }
+      reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * C)[c] = t;
+    }
+    __syncthreads();
   }
   __threadfence();
   __syncthreads();
@@ -109,7 +127,7 @@ extern "C" int sgc_colsum_scratch_floats(int R, int C) {
 
 extern "C" int sgc_colsum(const float* x, int R, int C, float* out, float* scratch, unsigned int* counter,
                           void* stream) {
-  if (R <= 0 || C <= 0) return (int)cudaErrorInvalidValue;
+  if (R <= 0 || C <= 0 || (C & 3)) return (int)cudaErrorInvalidValue;
   const int blocks = (R + sgc::kColsumRows - 1) / sgc::kColsumRows;
   sgc::colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, R, C, scratch, counter, out);
   SGC_CUDA_CHECK_LAST();

@@ -87,6 +87,8 @@ def project_compact(proj: torch.Tensor, ref3d: torch.Tensor, sel: Optional[torch
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+import os as _os
+SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs with at most this many rows stay plain fp32
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -111,6 +113,8 @@ def split_rows(x: torch.Tensor, group: int, pattern: int) -> torch.Tensor:
 def mm_nt(a: torch.Tensor, w: torch.Tensor = None, ws: torch.Tensor = None) -> torch.Tensor:
     """a [R,K] @ w[N,K]^T -> [R,N] fp32, tensor cores with bf16 hi/lo split (hi*hi + lo*hi + hi*lo).
     ``ws`` = pre-split weight ``split_cols(w, 1)`` (computed once per step by ``LevelWeights``)."""
+    if a.shape[0] <= SMALL_ROWS and w is not None:
+        return a @ w.t()  # tiny problem: the plain fp32 GEMM is launch-bound either way, skip the two splits
     if ws is None:
         ws = split_cols(w, 1)
     return torch.mm(split_cols(a, 0), ws.t(), out_dtype=F32)
@@ -147,6 +151,8 @@ class LevelWeights:
 def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """g[Q,N]^T @ x[Q,K] -> [N,K] fp32 (reduction over the rows)."""
     Q = g.shape[0]
+    if Q <= SMALL_ROWS:
+        return g.t() @ x
     return torch.mm(split_rows(g, Q, 0)[0].t(), split_rows(x, Q, 1)[0], out_dtype=F32)
 
 
@@ -312,19 +318,27 @@ class CrossView(torch.autograd.Function):
         mean = torch.empty(Q, C, device=dev, dtype=F32)
         call('sgc_crossview_mean_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), stream())
         bq, bv = in_b[:C], in_b[2 * C:]
-        g = mm_nt(mean, ws=lw.w_out) + b_out
-        qv = mm_nt(g, ws=lw.wq) + bq
+        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
+        small = Q <= SMALL_ROWS
+        g = mm_nt(mean, w_out, lw.w_out) + b_out
+        qv = mm_nt(g, wq, lw.wq) + bq
         # qt[h] = qv_h @ (scale * Wk_h)   [8,Q,dh] x [8,dh,C]
-        qt = torch.bmm(_heads_cols(qv, 0), lw.wk_rows, out_dtype=F32)
+        if small:
+            qt = torch.bmm(qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C))
+        else:
+            qt = torch.bmm(_heads_cols(qv, 0), lw.wk_rows, out_dtype=F32)
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         call('sgc_crossview_attn_fwd', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), stream())
         # o[h] = t[h] @ Wv_h^T   [8,Q,C] x [8,C,dh]
-        o = torch.bmm(split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
-                      lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+        if small:
+            o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
+        else:
+            o = torch.bmm(split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
+                          lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         o2 = o.transpose(0, 1).reshape(Q, C) + bv
         has = (pl.count > 0).to(F32).unsqueeze(1)
-        out = (mm_nt(o2, ws=lw.wo) + bo) * has
+        out = (mm_nt(o2, wo, lw.wo) + bo) * has
         ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, w_out, in_w, wo)
         ctx.pl = pl
         return out
@@ -340,31 +354,46 @@ class CrossView(torch.autograd.Function):
         scale = 1.0 / math.sqrt(dh)
         dev = slots.device
         lw = ctx.lw
+        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
+        small = Q <= SMALL_ROWS
         gout = gout * has
         g_wo = mm_tn(gout, o2)
         g_bo = colsum(gout)
-        go2 = mm_nt(gout, ws=lw.wo_t)
+        go2 = mm_nt(gout, wo.t(), lw.wo_t)
         g_bv = colsum(go2)
         # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
-        gt = torch.bmm(_heads_cols(go2, 0), lw.wv_rows, out_dtype=F32)
+        go_h = go2.view(Q, H, dh).transpose(0, 1)
+        if small:
+            gt = torch.bmm(go_h, wv.view(H, dh, C))
+        else:
+            gt = torch.bmm(_heads_cols(go2, 0), lw.wv_rows, out_dtype=F32)
         # g_wv[h] = go_h^T @ t[h]   [8,dh,Q] x [8,Q,C]
-        g_wv = torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
+        if small:
+            g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
+        else:
+            g_wv = torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         call('sgc_crossview_attn_bwd_qt', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
              ptr(gqt), stream())
         # gqv[h] = gqt[h] @ (scale*Wk_h)^T   [8,Q,C] x [8,C,dh]
-        gqv_h = torch.bmm(split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
-                          lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+        if small:
+            gqv_h = torch.bmm(gqt, wk.view(H, dh, C).transpose(1, 2))
+        else:
+            gqv_h = torch.bmm(split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
+                              lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
         gqv = gqv_h.transpose(0, 1).reshape(Q, C)
         # g_wk[h] = scale * qv_h^T @ gqt[h]   [8,dh,Q] x [8,Q,C]
-        g_wk = torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
+        if small:
+            g_wk = torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
+        else:
+            g_wk = torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
         g_wq = mm_tn(gqv, g)
         g_bq = colsum(gqv)
-        gg = mm_nt(gqv, ws=lw.wq_t)
+        gg = mm_nt(gqv, wq.t(), lw.wq_t)
         g_wout = mm_tn(gg, mean)
         g_bout = colsum(gg)
-        gmean = mm_nt(gg, ws=lw.w_out_t)
+        gmean = mm_nt(gg, w_out.t(), lw.w_out_t)
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
@@ -386,7 +415,7 @@ class Linear3(torch.autograd.Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
-        gx = mm_nt(gy, ws=ctx.ws_t) if ctx.ws_t is not None else mm_nt(gy, w.t())
+        gx = mm_nt(gy, w.t(), ctx.ws_t)
         return gx, mm_tn(gy, x), colsum(gy), None, None
 
 
