@@ -1,0 +1,68 @@
+"""Generates tests/golden/plugin_level_*.pt by running the reference's OWN Python modules
+(/root/reference/mmdet3d_plugin/models/im2voxel/**, imported through tests/golden/ref_shims.py) on the CPU.
+
+    python tests/golden/make_golden_plugin.py          # in the build container (needs /root/reference)
+
+What runs: the reference AdaptiveSparseHead / DenseHead / PerceptionTransformer_DFA3D / VoxFormerEncoder_DFA3D /
+VoxFormerLayer / DeformCrossAttention_DFA3D / MSDeformableAttention3D_DFA3D classes, built from the same config
+dict a SGCDet_*.py file hands to build_head, eval() mode (FFN dropout off), weights = synthetic.make_state_dict
+loaded with strict=True.  The CUDA-only dfa3D._ext is replaced by the CPU oracle kernels (see ref_shims.py).
+The outputs pin oracle/path_ref.py (tests/test_oracle_cpu.py::test_module_oracle_matches_reference_plugin_golden)
+and, transitively, the product."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+import ref_shims  # noqa: E402
+from sgcdet_b200 import synthetic as syn  # noqa: E402
+
+
+def reference_head(cfg, mods):
+    C = cfg.embed_dims
+    cross_transformer = dict(
+        type='PerceptionTransformer_DFA3D', embed_dims=C,
+        encoder=dict(type='VoxFormerEncoder_DFA3D', num_layers=1, return_intermediate=False, dbound=list(cfg.dbound),
+                     transformerlayers=dict(
+                         type='VoxFormerLayer',
+                         attn_cfgs=[dict(type='DeformCrossAttention_DFA3D',
+                                         deformable_attention=dict(type='MSDeformableAttention3D_DFA3D', embed_dims=C,
+                                                                   num_heads=8, num_points=4, num_levels=1, im2col_step=128),
+                                         embed_dims=C, inter_view_aggregation='attn', dropout=0)],
+                         ffn_cfgs=dict(type='FFN', embed_dims=C, feedforward_channels=C * 2, num_fcs=2, ffn_drop=0.1,
+                                       act_cfg=dict(type='ReLU', inplace=True)),
+                         operation_order=('cross_attn', 'norm', 'ffn', 'norm'))))
+    heads = [dict(type='DenseHead', voxel_size=cfg.voxel_size_list[i], n_voxels=cfg.n_voxels_list[i], embed_dims=C,
+                  cross_transformer=cross_transformer) for i in range(cfg.num_levels)]
+    return mods['AdaptiveSparseHead'].AdaptiveSparseHead(
+        embed_dims=C, topk_list=list(cfg.topk_list), voxel_size_list=list(cfg.voxel_size_list),
+        n_voxels_list=list(cfg.n_voxels_list), base_head_configs=heads)
+
+
+def main():
+    mods = ref_shims.install()
+    for cfg_name, V, scene_seed, weight_seed in (('tiny', 9, 77, 4321),):
+        cfg = syn.CONFIGS[cfg_name]
+        head = reference_head(cfg, mods)
+        sd = syn.make_state_dict(cfg, seed=weight_seed)
+        print(head.load_state_dict(sd, strict=True))
+        head.eval()
+        sc = syn.make_scene(cfg, V, seed=scene_seed, shift_origin=True)
+        feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
+        vol, valid, occ = head(feats, sc.img_meta, sc.mlvl_dpt_dists)
+        loss = (vol * sc.grad_volume).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        loss.backward()
+        blob = dict(cfg=cfg_name, num_views=V, scene_seed=scene_seed, weight_seed=weight_seed,
+                    volume=vol.detach().contiguous(), valid=valid, occ_preds=occ.detach(), loss=float(loss),
+                    grad_feat2=feats[2].grad.clone(), torch=torch.__version__)
+        out = os.path.join(ROOT, 'tests', 'golden', f'plugin_level_{cfg_name}.pt')
+        torch.save(blob, out)
+        print('wrote', out, tuple(vol.shape), float(loss), int(valid.sum()))
+
+
+if __name__ == '__main__':
+    main()
