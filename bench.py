@@ -97,7 +97,7 @@ class ClockSampler:
 LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_crossview_mean_fwd=1,
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
-                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1)
+                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_fwd=1)
 
 
 class CallRecorder:
@@ -172,6 +172,9 @@ def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
         return float(args[1]) * args[2] * (4 + 6)   # fp32 read once, three bf16 slots written
     if name == 'sgc_colsum':
         return 4.0 * args[1] * args[2]
+    if name == 'sgc_project_tc_fwd':
+        V, C, S, N = args[3], args[4], args[5], args[7]
+        return 4.0 * V * S * (C + N) + 4.0 * N * C
     if name in ('sgc_scatter_add_rows', 'sgc_gather_rows'):
         return f * 3 * args[3] * args[4]
     return 0.0
@@ -196,24 +199,47 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     cfg = syn.CONFIGS[args.config]
     V = args.views
-    sc_cpu = syn.make_scene(cfg, V, seed=1234 + rank, shift_origin=True)
+    B = max(1, args.scenes_per_gpu)
     head = plugin.build_voxel_head(cfg)
     head.load_state_dict(syn.make_state_dict(cfg), strict=True)
     head = head.to(dev)
     head.train(not args.eval_mode)
     params = [p for p in head.parameters()]
-    sc = sc_cpu.to(dev)
     from sgcdet_b200 import functional as SF
-    sc.img_meta['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)  # static buffer for graph replay
-    feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats[:cfg.num_levels]]
-    dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists[:cfg.num_levels]]
-    gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)  # channels_last_3d, like the volume
+    scenes = []
+    for b in range(B):
+        sc_b = syn.make_scene(cfg, V, seed=1234 + rank * B + b, shift_origin=True).to(dev)
+        sc_b.img_meta['sgc_projection'] = SF.compute_projection(sc_b.img_meta).to(dev)  # static buffer for graph replay
+        scenes.append(dict(
+            sc=sc_b,
+            feats=[f.clone().requires_grad_(True) for f in sc_b.mlvl_feats[:cfg.num_levels]],
+            dists=[d.clone().requires_grad_(True) for d in sc_b.mlvl_dpt_dists[:cfg.num_levels]],
+            # channels_last_3d, like the returned volume
+            gvol=sc_b.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3),
+            stream=torch.cuda.Stream(device=dev) if B > 1 else None))
+    sc, feats, dists, gvol = scenes[0]['sc'], scenes[0]['feats'], scenes[0]['dists'], scenes[0]['gvol']
+    all_inputs = [t for s in scenes for t in s['feats'] + s['dists']]
     loss_buf = torch.zeros(1, device=dev)
-    flat_grads = None
+
+    def scene_loss(s):
+        vol, valid, occ = head(s['feats'], s['sc'].img_meta, s['dists'])
+        return (vol * s['gvol']).sum() + head.occ_loss(occ, None, s['sc'].geo_occ)['loss_occ']
 
     def step():
-        vol, valid, occ = head(feats, sc.img_meta, dists)
-        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        if B == 1:
+            loss = scene_loss(scenes[0])
+        else:
+            # B independent scenes in flight on B streams: the latency-bound per-voxel chains of different
+            # scenes overlap; one backward over the summed loss (autograd replays every node on its own stream)
+            main = torch.cuda.current_stream()
+            losses = []
+            for s in scenes:
+                s['stream'].wait_stream(main)
+                with torch.cuda.stream(s['stream']):
+                    losses.append(scene_loss(s))
+            for s in scenes:
+                main.wait_stream(s['stream'])
+            loss = torch.stack(losses).sum()
         loss.backward()
         loss_buf.copy_(loss.detach().view(1))
         if world > 1 and not args.no_grad_allreduce:
@@ -224,7 +250,7 @@ def run_ours(args):
             torch._foreach_copy_([p.grad.view(-1) for p in params], list(flat.split([p.numel() for p in params])))
 
     def zero_grads():
-        for t in params + feats + dists:
+        for t in params + all_inputs:
             t.grad = None
 
     # warm-up (eager) on a side stream, then capture fwd+bwd into one CUDA graph
@@ -283,8 +309,8 @@ def run_ours(args):
     loss_val = float(loss_buf.item())
 
     # ---- end to end: host buffers -> H2D -> step -> D2H of the loss, every step -------------------------
-    host_in = [t.detach().cpu().pin_memory() for t in feats + dists]
-    dev_in = feats + dists
+    host_in = [t.detach().cpu().pin_memory() for t in all_inputs]
+    dev_in = all_inputs
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     loss_host = torch.zeros(1).pin_memory()
 
@@ -322,12 +348,14 @@ def run_ours(args):
         agg = {}
         for name, a, e0, e1 in rec2.events:
             key = name
-            if name.startswith(('sgc_lift', 'sgc_crossview', 'sgc_project')):
+            if name.startswith(('sgc_lift', 'sgc_crossview')) or name == 'sgc_project_compact':
                 q = {'sgc_lift_fwd': 15, 'sgc_lift_bwd': 16, 'sgc_crossview_mean_fwd': 3, 'sgc_crossview_attn_fwd': 4,
                      'sgc_crossview_attn_bwd_qt': 4, 'sgc_crossview_attn_bwd_slots': 5, 'sgc_project_compact': 4}[name]
                 key = f'{name}[Q={a[q]}]'
             elif name.startswith('sgc_upsample'):
                 key = f'{name}[{a[1]}x{a[2]}x{a[3]}]'
+            elif name == 'sgc_project_tc_fwd':
+                key = f'{name}[V={a[3]},C={a[4]},S={a[5]},N={a[7]}]'
             elif name in ('sgc_split_bf16x3', 'sgc_colsum'):
                 key = f'{name}[{a[1]}x{a[2]}]'
             d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=kernel_algorithmic_bytes(name, a, pairs_by_q)))
@@ -350,8 +378,8 @@ def run_ours(args):
                     algorithmic_bytes_per_launch=int(d0['bytes']), avg_launch_ms=round(avg0, 4),
                     timing='CUDA events around each launch in an eager instrumented pass after the timed region')
         step_ms = total_ms / args.steps
-        path_roof = dict(algorithmic_bytes_fwd_bwd=int(ab['fwd_bwd']), achieved_gbs=round(ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9, 1),
-                         frac_of_hbm=round(ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4),
+        path_roof = dict(algorithmic_bytes_fwd_bwd=int(ab['fwd_bwd']), achieved_gbs=round(B * ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9, 1),
+                         frac_of_hbm=round(B * ab['fwd_bwd'] / (step_ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4),
                          own_kernels_ms_per_step=round(mine_ms, 3), pairs_per_level=[pairs_by_q[q][0] for q in sorted(pairs_by_q)])
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample --------
@@ -362,16 +390,17 @@ def run_ours(args):
     if rank == 0:
         step_ms = total_ms / args.steps
         line = {
-            'metric': METRIC, 'value': round(world * args.steps / (total_ms * 1e-3), 2), 'unit': UNIT,
+            'metric': METRIC, 'value': round(world * B * args.steps / (total_ms * 1e-3), 2), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(step_ms, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, 1 scene per GPU per step',
+            'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, {B} scene(s) per GPU per step',
+                       'scenes_per_gpu': B,
                        'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
                        'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else ' + NCCL weight-grad all-reduce'),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
-                       'cuda_graph': not args.no_graph, 'gemm': 'feature-map projections: bf16x3 operand split (own kernel) + library bf16 GEMM with fp32 accumulate; voxel-count GEMMs: library fp32'},
-            'e2e': {'value': None if args.skip_e2e else round(world * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                       'cuda_graph': not args.no_graph, 'gemm': 'forward feature projection: own tcgen05/TMEM/TMA kernel (bf16 hi/lo split in smem, fp32 accumulate); backward + voxel-count GEMMs: own bf16x3 split kernel + library bf16 GEMM, fp32 accumulate'},
+            'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': 4, 'steps': e2e_steps},
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),
@@ -472,6 +501,7 @@ def main():
     ap.add_argument('--config', default='SGCDet_ScanNet')
     ap.add_argument('--views', type=int, default=40)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--scenes-per-gpu', type=int, default=1, help='independent scenes in flight per GPU per step')
     ap.add_argument('--eval-mode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-grad-allreduce', action='store_true')

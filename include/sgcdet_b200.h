@@ -82,6 +82,14 @@ int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, i
 int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_stride, int rows_per_group, int pattern,
                      void* out, void* stream);
 
+/* Tensor-core (tcgen05/TMEM) feature projection, fused with the NCHW -> channel-last layout change and the bf16 hi/lo
+ * split: vg[v,s,n] = sum_c feat[v*view_stride + c*chan_stride + s] * W[n,c]  (value_proj + folded offset/weight rows,
+ * DCA:417-436; replaces the flatten/permute of transformer.py:151-170).  wpack = sgc_pack_weight_tc(W [N,C]) is
+ * 2*N*C bf16 (hi/lo slabs in the kernel's shared-memory image).  C % 32 == 0, N % 32 == 0, N <= 512. */
+int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream);
+int sgc_project_tc_fwd(const float* feat, long long view_stride, long long chan_stride, int V, int C, int S,
+                       const void* wpack, int N, float* vg, void* stream);
+
 /* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
  * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */
 int sgc_colsum_scratch_floats(int R, int C);

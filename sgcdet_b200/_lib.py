@@ -27,6 +27,8 @@ SIGNATURES = {
     'sgc_project_scratch_ints': [I, I],
     'sgc_project_compact': [P, P, P, I, I, F, F, F, F, F, F, F, F, F, P, P, P, P, P, P, P, P],
     'sgc_split_bf16x3': [P, LL, I, LL, I, I, P, P],
+    'sgc_pack_weight_tc': [P, I, I, P, P],
+    'sgc_project_tc_fwd': [P, LL, LL, I, I, I, P, I, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],

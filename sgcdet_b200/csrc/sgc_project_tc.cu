@@ -1,0 +1,408 @@
+// sgc_project_tc_fwd: the dense feature projection of one level on the 5th-gen tensor cores (tcgen05 / TMEM),
+// fused with the NCHW -> channel-last layout change and the fp32 -> bf16 hi/lo operand split.
+//
+//   vg[v, s, n] = sum_c feat[v, c, s] * Wcat[n, c]        (value_proj + the folded offset / depth-offset /
+//                                                          attention-weight rows, deformable_cross_attention.py:417-436;
+//                                                          replaces the flatten/permute copy of transformer.py:151-170)
+//
+// fp32-level accuracy from bf16 tensor cores: x = hi + lo, x*y ~= hi*hi' + lo*hi' + hi*lo' (fp32 accumulate in TMEM,
+// relative error ~1e-5).  Unlike the library path (sgc_split_bf16x3 + bf16 GEMM) the split never touches HBM:
+// the fp32 map is read once, converted in shared memory, and the fp32 result is written once.
+//
+// One persistent CTA per SM, 12 warps, warp-specialised; tile = 128 pixels x all N output channels:
+//   warp  5    F producer  : one thread issues TMA tile loads (cp.async.bulk.tensor.2d) of feat[c0..c0+31][s0..s0+127] fp32
+//   warps 0-3  A converters: fp32 staging tile -> bf16 hi/lo -> K-major core-matrix tiles (generic proxy + proxy fence)
+//   warp  4    B producer  : one thread issues cp.async.bulk (TMA bulk copy) of pre-packed weight slabs (L2 resident)
+//   warp  6    MMA issuer  : one thread issues tcgen05.mma (M=128, N=N/parts, K=16), accumulators in TMEM
+//   warp  7    TMEM alloc / dealloc
+//   warps 8-11 epilogue    : tcgen05.ld 32x32b.x32 -> registers -> 128B-swizzled smem tile -> TMA tensor store
+//                            (cp.async.bulk.tensor.3d) into the channel-last vg; rows beyond S are clipped by the map
+// Pipelines: A stages (a_full/a_empty), B stages (b_full/b_empty), one TMEM accumulator (tmem_full/tmem_empty),
+// all mbarrier based; tcgen05.commit releases the shared-memory stages.
+//
+// Shared-memory operand layout: canonical UMMA K-major, no swizzle: 8x8 bf16 core matrices (128 contiguous bytes),
+// LBO (next core matrix along K) = 128 B, SBO (next 8 rows) = (BK/8)*128 B.  The weight slabs are pre-packed into
+// exactly this image by sgc_pack_weight_tc so the B producer is a plain bulk copy.
+#include <cuda.h>
+#include <cstdlib>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace sgc {
+namespace tc {
+
+constexpr int BM = 128;      // pixels per tile (UMMA M)
+constexpr int BK = 32;       // channels per pipeline stage
+constexpr int NA = 2;        // A stages (hi+lo)
+constexpr int NB = 4;        // B stages (one of hi / lo per stage)
+constexpr int NF = 3;        // fp32 staging stages filled by TMA (BK x BM floats = 16 KB each)
+constexpr int NE = 2;        // epilogue staging buffers (BM rows x 32 floats, 128B-swizzled, TMA-stored)
+constexpr int kThreads = 384;
+constexpr uint32_t LBO = 128, SBO = (BK / 8) * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int y, int z, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y),
+               "r"(z), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Pipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  int n;
+  __device__ explicit Pipe(int n_) : n(n_) {}
+  __device__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
+};
+
+// shared memory carve-up (dynamic): [A stages: hi 8 KB | lo 8 KB] x NA, [B stages: N*BK*2 bytes] x NB, barriers
+struct Smem {
+  uint64_t f_full[NF], f_empty[NF], a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], tmem_full, tmem_empty;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+project_tc_fwd_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap omap, int V, int C, int S,
+                      const __nv_bfloat16* __restrict__ wpack, int N, float* __restrict__ vg, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_stage_bytes = 2 * BM * BK * 2;          // hi + lo
+  const int b_stage_bytes = N * BK * 2;
+  constexpr int f_stage_bytes = BK * BM * 4;
+  uint8_t* f_base = smem_raw;
+  uint8_t* a_base = f_base + NF * f_stage_bytes;
+  uint8_t* b_base = a_base + NA * a_stage_bytes;
+  uint8_t* e_base = b_base + NB * b_stage_bytes;  // 1024-byte aligned (all stage sizes are multiples of 1 KB)
+  Smem* sm = reinterpret_cast<Smem*>(e_base + NE * BM * 128);
+
+  const int n_parts = N > 256 ? 2 : 1;
+  const int n_mma = N / n_parts;                      // 192 (C=256) or 256 (C=128): multiple of 16, <= 256
+  const int k_slabs = C / BK;
+  const int m_tiles = (S + BM - 1) / BM;
+  const int tiles = V * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+    mbar_init(&sm->tmem_full, 1);
+    mbar_init(&sm->tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 7) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 5) {
+    // ===================== F producer: TMA tile loads of the fp32 NCHW map =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&fmap) : "memory");
+      Pipe pf(NF);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int v = tile / m_tiles, s0 = (tile - v * m_tiles) * BM;
+        for (int j = 0; j < k_slabs; ++j) {
+          mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
+          mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage_bytes);
+          tma_load_2d(f_base + pf.stage * f_stage_bytes, &fmap, s0, v * C + j * BK, &sm->f_full[pf.stage]);
+          pf.next();
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== A converters: fp32 staging -> bf16 hi/lo core-matrix tiles =====================
+    const int m = threadIdx.x;  // row of the tile (pixel)
+    Pipe pa(NA), pf(NF);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int j = 0; j < k_slabs; ++j) {
+        mbar_wait(&sm->f_full[pf.stage], pf.phase);
+        const float* src = reinterpret_cast<const float*>(f_base + pf.stage * f_stage_bytes) + m;
+        float x[BK];
+#pragma unroll
+        for (int k = 0; k < BK; ++k) x[k] = src[k * BM];
+        mbar_wait(&sm->a_empty[pa.stage], pa.phase ^ 1);
+        uint8_t* hi = a_base + pa.stage * a_stage_bytes;
+        uint8_t* lo = hi + BM * BK * 2;
+        const uint32_t off = (m >> 3) * SBO + (m & 7) * 16;
+#pragma unroll
+        for (int kc = 0; kc < ((dbg & 4) ? 0 : BK / 8); ++kc) {
+          __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            h[i] = __float2bfloat16_rn(x[kc * 8 + i]);
+            l[i] = __float2bfloat16_rn(x[kc * 8 + i] - __bfloat162float(h[i]));
+          }
+          *reinterpret_cast<uint4*>(hi + off + kc * LBO) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + off + kc * LBO) = *reinterpret_cast<const uint4*>(l);
+        }
+        // the staging slot is released only after every value read from it has been consumed by the conversion
+        // (an arrive right after the ld.shared could overtake the loads and let the next TMA tile land early)
+        mbar_arrive(&sm->f_empty[pf.stage]);
+        pf.next();
+        fence_proxy_async();
+        mbar_arrive(&sm->a_full[pa.stage]);
+        pa.next();
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== B producer: bulk copies of the pre-packed weight slabs =====================
+    if (lane == 0) {
+      Pipe pb(NB);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int q = 0; q < 2 * k_slabs; ++q) {  // q = 2*slab + (0: hi, 1: lo)
+          mbar_wait(&sm->b_empty[pb.stage], pb.phase ^ 1);
+          mbar_expect_tx(&sm->b_full[pb.stage], (uint32_t)b_stage_bytes);
+          bulk_g2s(b_base + pb.stage * b_stage_bytes, reinterpret_cast<const uint8_t*>(wpack) + (size_t)q * b_stage_bytes,
+                   (uint32_t)b_stage_bytes, &sm->b_full[pb.stage]);
+          pb.next();
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
+      // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      Pipe pa(NA), pb(NB);
+      uint32_t tphase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&sm->tmem_empty, tphase ^ 1);
+        tc_fence_after();
+        for (int j = 0; j < k_slabs; ++j) {
+          mbar_wait(&sm->a_full[pa.stage], pa.phase);
+          const uint32_t a_hi = smem_u32(a_base + pa.stage * a_stage_bytes);
+          const uint32_t a_lo = a_hi + BM * BK * 2;
+          // --- B_hi stage: hi*hi + lo*hi
+          mbar_wait(&sm->b_full[pb.stage], pb.phase);
+          tc_fence_after();
+          uint32_t b_s = smem_u32(b_base + pb.stage * b_stage_bytes);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (p < n_parts) {
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint64_t bd = umma_desc(b_s + p * (n_mma / 8) * SBO + ks * 2 * LBO);
+                if (!(dbg & 2)) {
+                  umma_bf16(tmem + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), bd, idesc, (j | ks) ? 1u : 0u);
+                  umma_bf16(tmem + p * n_mma, umma_desc(a_lo + ks * 2 * LBO), bd, idesc, 1u);
+                }
+              }
+            }
+          }
+          tc_commit(&sm->b_empty[pb.stage]);
+          pb.next();
+          // --- B_lo stage: hi*lo
+          mbar_wait(&sm->b_full[pb.stage], pb.phase);
+          tc_fence_after();
+          b_s = smem_u32(b_base + pb.stage * b_stage_bytes);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (p < n_parts) {
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks)
+                if (!(dbg & 2))
+                  umma_bf16(tmem + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), umma_desc(b_s + p * (n_mma / 8) * SBO + ks * 2 * LBO),
+                            idesc, 1u);
+            }
+          }
+          tc_commit(&sm->b_empty[pb.stage]);
+          pb.next();
+          tc_commit(&sm->a_empty[pa.stage]);
+          pa.next();
+        }
+        tc_commit(&sm->tmem_full);
+        tphase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;           // row of the tile == TMEM lane
+    const bool issuer = (threadIdx.x == 8 * 32);
+    uint32_t ephase = 0;
+    int chunk = 0;                               // running chunk counter -> staging buffer parity
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int v = tile / m_tiles, s0 = (tile - v * m_tiles) * BM;
+      mbar_wait(&sm->tmem_full, ephase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < N; c0 += 32, ++chunk) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint8_t* buf = e_base + (chunk & 1) * (BM * 128);
+        // the TMA store that read this buffer two chunks ago must have finished reading it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!(dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // 16-byte chunk i of the 128-byte row, CU_TENSOR_MAP_SWIZZLE_128B pattern
+            *reinterpret_cast<uint4*>(buf + row * 128 + ((i ^ (row & 7)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (!(dbg & 1)) tma_store_3d(&omap, c0, s0, v, buf);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm->tmem_empty);
+      ephase ^= 1;
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// Pack Wcat [N,C] fp32 into the shared-memory image the kernel above bulk-copies:
+//   out[(2*slab + part)][row-group n/8][k-chunk kc][n%8][8 k]  bf16, part 0 = hi, 1 = lo.
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int C, __nv_bfloat16* __restrict__ out) {
+  const int total = N * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    const float x = w[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    const int slab = c / BK, k = c - slab * BK;
+    const size_t stage_elems = (size_t)N * BK;
+    const size_t o = (size_t)(n >> 3) * (SBO / 2) + (size_t)(k >> 3) * (LBO / 2) + (n & 7) * 8 + (k & 7);
+    out[(size_t)(2 * slab) * stage_elems + o] = h;
+    out[(size_t)(2 * slab + 1) * stage_elems + o] = l;
+  }
+}
+
+}  // namespace tc
+}  // namespace sgc
+
+extern "C" int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream) {
+  if (N % 16 || C % sgc::tc::BK) return (int)cudaErrorInvalidValue;
+  sgc::tc::pack_weight_kernel<<<(N * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, N, C, (__nv_bfloat16*)out);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// feat: [V*C] channel planes of S_full floats each (element (v,c,s) at feat[(v*C+c)*chan_stride + s]); only s < S is used.
+// wpack: sgc_pack_weight_tc output (2*N*C bf16).  vg: [V,S,N] fp32, fully written.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+extern "C" int sgc_project_tc_fwd(const float* feat, long long view_stride, long long chan_stride, int V, int C, int S,
+                                  const void* wpack, int N, float* vg, void* stream) {
+  using namespace sgc::tc;
+  if (C % BK || N % 32 || N > 512 || (N > 256 && (N / 2) % 16) || V <= 0 || S <= 0) return (int)cudaErrorInvalidValue;
+  // the TMA descriptor needs a regular [V*C, chan_stride] matrix with a 16-byte aligned pitch
+  if (view_stride != (long long)C * chan_stride || (chan_stride * 4) % 16 || (reinterpret_cast<uintptr_t>(feat) & 15) ||
+      chan_stride < S)
+    return (int)cudaErrorInvalidValue;
+  static int sms = 0;
+  static PFN_encodeTiled encode = nullptr;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+    encode = (PFN_encodeTiled)fn;
+  }
+  CUtensorMap fmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)chan_stride, (cuuint64_t)V * C};
+  const cuuint64_t gstr[1] = {(cuuint64_t)chan_stride * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BM, (cuuint32_t)BK};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  CUtensorMap omap;
+  const cuuint64_t odim[3] = {(cuuint64_t)N, (cuuint64_t)S, (cuuint64_t)V};
+  const cuuint64_t ostr[2] = {(cuuint64_t)N * 4, (cuuint64_t)S * N * 4};
+  const cuuint32_t obox[3] = {32, (cuuint32_t)BM, 1};
+  const cuuint32_t oestr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(vg) & 15) ||
+      encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, vg, odim, ostr, obox, oestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  const size_t smem = (size_t)NF * BK * BM * 4 + (size_t)NA * 2 * BM * BK * 2 + (size_t)NB * N * BK * 2 + (size_t)NE * BM * 128 +
+                      sizeof(Smem) + 64;
+  cudaError_t e = cudaFuncSetAttribute(project_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int tiles = V * ((S + BM - 1) / BM);
+  const int grid = tiles < sms ? tiles : sms;
+  project_tc_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, omap, V, C, S, (const __nv_bfloat16*)wpack, N, vg,
+                                                                        getenv("SGC_TC_DBG") ? atoi(getenv("SGC_TC_DBG")) : 0);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

@@ -120,6 +120,14 @@ def mm_nt(a: torch.Tensor, w: torch.Tensor = None, ws: torch.Tensor = None) -> t
     return torch.mm(split_cols(a, 0), ws.t(), out_dtype=F32)
 
 
+def pack_weight_tc(w: torch.Tensor) -> torch.Tensor:
+    """[N,C] fp32 -> bf16 hi/lo slabs in the shared-memory image of sgc_project_tc_fwd (2*N*C bf16)."""
+    N, C = w.shape
+    out = torch.empty(2 * N * C, device=w.device, dtype=BF16)
+    call('sgc_pack_weight_tc', ptr(w.contiguous()), N, C, ptr(out), stream())
+    return out
+
+
 class LevelWeights:
     """Every bf16x3 split of one level's weights (both orientations), computed once per step -- normally on a
     side stream, off the critical path of the level.  Constants for the autograd Functions below (weight
@@ -132,6 +140,7 @@ class LevelWeights:
             scale = 1.0 / math.sqrt(dh)
             wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
             self.wcat = split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
+            self.wpack = pack_weight_tc(wcat) if (wcat.shape[1] % 32 == 0 and wcat.shape[0] % 32 == 0) else None
             self.wcat_t = split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
             self.w_out, self.w_out_t = split_cols(w_out, 1), split_cols(w_out.t(), 1)
             self.wq, self.wq_t = split_cols(wq, 1), split_cols(wq.t(), 1)
@@ -145,7 +154,8 @@ class LevelWeights:
 
     def record_stream(self, s):
         for t in self.__dict__.values():
-            t.record_stream(s)
+            if t is not None:
+                t.record_stream(s)
 
 
 def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -187,7 +197,7 @@ class ProjectFeatures(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
+    def _split_feat(feat, h, w):
         V, C, H0, W0 = feat.shape
         S = h * w
         src = feat
@@ -198,17 +208,39 @@ class ProjectFeatures(torch.autograd.Function):
             stride = H0 * W0  # row crop only: the first h*w elements of every channel plane
         acat = torch.empty(V, 3 * C, S, device=feat.device, dtype=BF16)  # (hi|lo|hi) along channels
         call('sgc_split_bf16x3', ptr(src), V * C, S, stride, C, 0, ptr(acat), stream())
+        return acat
+
+    @staticmethod
+    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
+        V, C, H0, W0 = feat.shape
+        S = h * w
+        N = wcat.shape[0]
+        ctx.dims = (V, C, H0, W0, h, w)
+        ctx.lw = lw
+        use_tc = (_os.environ.get('SGC_TC_PROJECT', '1') != '0' and w == W0 and feat.is_contiguous()
+                  and (H0 * W0 * 4) % 16 == 0 and C % 32 == 0 and N % 32 == 0 and N <= 512)
+        if use_tc:
+            # own tcgen05 kernel: TMA-loads the fp32 NCHW map, splits to bf16 hi/lo in shared memory, accumulates in
+            # TMEM and TMA-stores channel-last fp32 (csrc/sgc_project_tc.cu); the split never touches HBM
+            wpack = lw.wpack if lw is not None and getattr(lw, 'wpack', None) is not None else pack_weight_tc(wcat)
+            vg = torch.empty(V, S, N, device=feat.device, dtype=F32)
+            call('sgc_project_tc_fwd', ptr(feat), C * H0 * W0, H0 * W0, V, C, S, ptr(wpack), N, ptr(vg), stream())
+            ctx.save_for_backward(feat, wcat)
+            ctx.have_acat = False
+            return vg
+        acat = ProjectFeatures._split_feat(feat, h, w)
         bcat = lw.wcat if lw is not None else split_cols(wcat, 1)  # [N, 3C]
         vg = torch.bmm(acat.transpose(1, 2), bcat.t().unsqueeze(0).expand(V, -1, -1), out_dtype=F32)  # [V,S,N]
         ctx.save_for_backward(acat, wcat)
-        ctx.dims = (V, C, H0, W0, h, w)
-        ctx.lw = lw
+        ctx.have_acat = True
         return vg
 
     @staticmethod
     def backward(ctx, gvg: torch.Tensor):
         acat, wcat = ctx.saved_tensors
         V, C, H0, W0, h, w = ctx.dims
+        if not ctx.have_acat:
+            acat = ProjectFeatures._split_feat(acat, h, w) if ctx.needs_input_grad[3] else None
         S = h * w
         N = wcat.shape[0]
         gvg = gvg.contiguous()

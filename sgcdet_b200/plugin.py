@@ -291,11 +291,12 @@ class PerceptionTransformer_DFA3D(nn.Module):
 _STREAMS = {}
 
 
-def _side_streams(device, n: int):
-    key = torch.device(device)
+def _side_streams(device, n: int, main=None):
+    """n side streams private to (device, calling stream): concurrent scenes on different streams never share them."""
+    key = (torch.device(device), main.cuda_stream if main is not None else 0)
     pool = _STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=key))
+        pool.append(torch.cuda.Stream(device=torch.device(device)))
     return pool[:n]
 
 
@@ -447,7 +448,7 @@ class AdaptiveSparseHead(nn.Module):
         # selection-independent work of every level (weight splits, dense feature projection) goes to side
         # streams up front; level i joins its stream right before it needs the projected maps
         main = torch.cuda.current_stream(dev)
-        streams = _side_streams(dev, nl)
+        streams = _side_streams(dev, nl, main)
         prepared = []
         for i in range(nl):
             streams[i].wait_stream(main)
