@@ -167,6 +167,39 @@ def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 _COUNTERS = {}
+_GRAD_STREAMS = {}
+
+
+class _Side:
+    """Runs weight/bias-gradient work of a backward on a side stream private to the calling stream, so that it
+    overlaps the latency-bound activation-gradient chain; ``join()`` before the grads are handed to autograd."""
+
+    def __init__(self, dev):
+        self.main = torch.cuda.current_stream(dev)
+        key = (dev, self.main.cuda_stream)
+        s = _GRAD_STREAMS.get(key)
+        if s is None:
+            s = _GRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+        self.side = s
+        self.out = []
+        self.enabled = _os.environ.get('SGC_SIDE_GRADS', '1') != '0'
+
+    def run(self, fn, *inputs):
+        if not self.enabled:
+            return fn()
+        self.side.wait_stream(self.main)
+        for t in inputs:
+            t.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            r = fn()
+        self.out.append(r)
+        return r
+
+    def join(self):
+        if self.enabled and self.out:
+            self.main.wait_stream(self.side)
+            for t in self.out:
+                t.record_stream(self.main)
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:
@@ -388,11 +421,12 @@ class CrossView(torch.autograd.Function):
         lw = ctx.lw
         wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
         small = Q <= SMALL_ROWS
+        side = _Side(dev)
         gout = gout * has
-        g_wo = mm_tn(gout, o2)
-        g_bo = colsum(gout)
+        g_wo = side.run(lambda: mm_tn(gout, o2), gout, o2)
+        g_bo = side.run(lambda: colsum(gout), gout)
         go2 = mm_nt(gout, wo.t(), lw.wo_t)
-        g_bv = colsum(go2)
+        g_bv = side.run(lambda: colsum(go2), go2)
         # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
         go_h = go2.view(Q, H, dh).transpose(0, 1)
         if small:
@@ -403,7 +437,8 @@ class CrossView(torch.autograd.Function):
         if small:
             g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
         else:
-            g_wv = torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
+            g_wv = side.run(lambda: torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1),
+                                              out_dtype=F32).reshape(C, C), go2, t)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         call('sgc_crossview_attn_bwd_qt', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
@@ -419,16 +454,18 @@ class CrossView(torch.autograd.Function):
         if small:
             g_wk = torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
         else:
-            g_wk = torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
-        g_wq = mm_tn(gqv, g)
-        g_bq = colsum(gqv)
+            g_wk = side.run(lambda: torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1),
+                                              out_dtype=F32).reshape(C, C) * scale, qv, gqt)
+        g_wq = side.run(lambda: mm_tn(gqv, g), gqv, g)
+        g_bq = side.run(lambda: colsum(gqv), gqv)
         gg = mm_nt(gqv, wq.t(), lw.wq_t)
-        g_wout = mm_tn(gg, mean)
-        g_bout = colsum(gg)
+        g_wout = side.run(lambda: mm_tn(gg, mean), gg, mean)
+        g_bout = side.run(lambda: colsum(gg), gg)
         gmean = mm_nt(gg, w_out.t(), lw.w_out_t)
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
+        side.join()
         g_in_w = torch.cat([g_wq, g_wk, g_wv], dim=0)
         g_in_b = torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)
         return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None
@@ -447,8 +484,12 @@ class Linear3(torch.autograd.Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
+        side = _Side(gy.device)
+        gw = side.run(lambda: mm_tn(gy, x), gy, x)
+        gb = side.run(lambda: colsum(gy), gy)
         gx = mm_nt(gy, w.t(), ctx.ws_t)
-        return gx, mm_tn(gy, x), colsum(gy), None, None
+        side.join()
+        return gx, gw, gb, None, None
 
 
 # ----------------------------------------------------------------------------------------------
