@@ -242,8 +242,11 @@ def run_ours(args):
             loss = torch.stack(losses).sum()
         loss.backward()
         loss_buf.copy_(loss.detach().view(1))
+
+    def allreduce_grads():
+        # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks.  Issued on
+        # the compute stream right after the (graph-replayed) backward; NCCL is kept outside the CUDA graph.
         if world > 1 and not args.no_grad_allreduce:
-            # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
             flat.div_(world)
@@ -260,6 +263,7 @@ def run_ours(args):
         for _ in range(max(1, min(args.warmup, 3))):
             zero_grads()
             step()
+            allreduce_grads()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     rec = CallRecorder()
@@ -272,11 +276,15 @@ def run_ours(args):
             with torch.cuda.graph(graph):
                 step()
         launches_per_step = rec.count
-        run_step = graph.replay
+
+        def run_step():
+            graph.replay()
+            allreduce_grads()
     else:
         def run_step():
             zero_grads()
             step()
+            allreduce_grads()
         with rec:
             run_step()
         launches_per_step = rec.count
