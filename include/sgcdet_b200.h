@@ -125,6 +125,27 @@ int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const floa
                                  int V, int Q, int C, const float* grad_t, const float* grad_mean,
                                  float* grad_slots, void* stream);
 
+/* View-sharded cross-view fusion (config 5): the views are split over shards (GPUs) and every softmax
+ * statistic over views is (local partial) -> all-reduce on the host side (NCCL) -> (local finish):
+ *   sum_fwd   : sum_v slots (not divided)                       -> [SUM sum, count]  -> mean
+ *   scores    : scores [cap,8], local max m_loc [Q,8]           -> [MAX m]
+ *   accum     : e = exp(score - m) [cap,8], s_loc [Q,8], o_loc [8,Q,C] -> [SUM s, o] -> t = o / s
+ *   bwd_dot   : alpha = e/s, g_alpha [cap,8], D_loc [Q,8] = sum_v alpha g_alpha     -> [SUM D]
+ *   bwd_qt    : gscore = alpha (g_alpha - D) [cap,8], gqt_loc [8,Q,C]               -> [SUM gqt]
+ *   bwd_slots : as sgc_crossview_attn_bwd_slots with the GLOBAL view count in the mean term. */
+int sgc_crossview_sum_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* sum, void* stream);
+int sgc_cvs_scores(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C, float* scores,
+                   float* m_loc, void* stream);
+int sgc_cvs_accum(const float* scores, const float* m_glob, const float* slots, const int* pair_index, int V, int Q,
+                  int C, float* e_out, float* s_loc, float* o_loc, void* stream);
+int sgc_cvs_bwd_dot(const float* slots, const float* e_in, const float* s_glob, const int* pair_index, int V, int Q,
+                    int C, const float* grad_t, float* alpha, float* galpha, float* d_loc, void* stream);
+int sgc_cvs_bwd_qt(const float* slots, const float* alpha, const float* galpha, const float* d_glob,
+                   const int* pair_index, int V, int Q, int C, float* gscore, float* gqt_loc, void* stream);
+int sgc_cvs_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index, int V, int Q,
+                      int C, const float* grad_t, const float* grad_mean, const int* count_glob, float* grad_slots,
+                      void* stream);
+
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].
  * upsample: F.interpolate(x2, trilinear, align_corners=False) (ASH:64-69) fused with the occupancy head
  * Linear(C,1)+Sigmoid (ASH:37-39,71).  bwd: grad_in written; grad_w [C], grad_b [1] accumulated. */

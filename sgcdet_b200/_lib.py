@@ -38,6 +38,12 @@ SIGNATURES = {
     'sgc_crossview_attn_fwd': [P, P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_bwd_qt': [P, P, P, I, I, I, P, P, P, P],
     'sgc_crossview_attn_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P],
+    'sgc_crossview_sum_fwd': [P, P, I, I, I, P, P],
+    'sgc_cvs_scores': [P, P, P, I, I, I, P, P, P],
+    'sgc_cvs_accum': [P, P, P, P, I, I, I, P, P, P, P],
+    'sgc_cvs_bwd_dot': [P, P, P, P, I, I, I, P, P, P, P, P],
+    'sgc_cvs_bwd_qt': [P, P, P, P, P, I, I, I, P, P, P],
+    'sgc_cvs_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P, P],
     'sgc_upsample2x_occ_fwd': [P, I, I, I, I, P, P, P, P, P],
     'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
     'sgc_topk_select': [P, I, I, P, P, P],

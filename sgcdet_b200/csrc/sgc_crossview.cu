@@ -47,7 +47,7 @@ __device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, 
   return n;
 }
 
-template <int CPL>
+template <int CPL, bool DIVIDE = true>
 __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __restrict__ slots,
                                                                  const int* __restrict__ pair_index, int V, int Q,
                                                                  float* __restrict__ mean) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __
 #pragma unroll
     for (int j = 0; j < CPL; ++j) acc[j] += x[j];
   }
-  if (n > 0) {
+  if (DIVIDE && n > 0) {
     const float fn = (float)n;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) acc[j] = acc[j] / fn;  // DCA:826
@@ -247,7 +247,7 @@ template <int CPL>
 __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_slots_kernel(
     const float* __restrict__ qt, const float* __restrict__ alpha, const float* __restrict__ gscore,
     const int* __restrict__ pair_index, int V, int Q, const float* __restrict__ grad_t,
-    const float* __restrict__ grad_mean, float* __restrict__ grad_slots) {
+    const float* __restrict__ grad_mean, float* __restrict__ grad_slots, const int* __restrict__ count_override) {
   constexpr int C = CPL * 32;
   __shared__ int s_ids[kCvWarps][kMaxViews];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_slots_kernel(
   const size_t off = (size_t)q * C + lane * CPL;
   float gm[CPL];
   load_row_cv<CPL>(gm, grad_mean + off);
-  const float fn = (float)n;
+  // view-sharded mode: the mean is over the views of ALL shards
+  const float fn = (float)(count_override ? __ldg(count_override + q) : n);
 #pragma unroll
   for (int j = 0; j < CPL; ++j) gm[j] = gm[j] / fn;
   float gt[8][CPL], qv[8][CPL];
@@ -284,6 +285,189 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_slots_kernel(
       for (int j = 0; j < CPL; ++j) o[j] += a[h] * gt[h][j] + g[h] * qv[h][j];
     store_row_cv<CPL>(grad_slots + (size_t)ids[i] * C + lane * CPL, o);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// View-sharded variants: the views of a scene are split over shards (GPUs); every softmax
+// statistic over views becomes (local partial) -> all-reduce -> (local finish).  Exchange steps live on the host
+// (NCCL); these kernels are the local halves.
+//   fwd : scores -> [MAX m] -> accum (e = exp(sc - m), s_loc, o_loc) -> [SUM s, o] -> t = o / s
+//   bwd : dot (alpha = e/s, g_alpha, D_loc) -> [SUM D] -> qt (gscore, gqt_loc) -> [SUM gqt] -> slots (existing)
+constexpr float kNegBig = -3.0e38f;
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) cvs_scores_kernel(const float* __restrict__ qt,
+                                                                   const float* __restrict__ slots,
+                                                                   const int* __restrict__ pair_index, int V, int Q,
+                                                                   float* __restrict__ scores, float* __restrict__ mloc) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  float qv[8][CPL];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) load_row_cv<CPL>(qv[h], qt + h * hq + off);
+  float mx = kNegBig;  // lane h (< 8) tracks the running max of head h
+  for (int i = 0; i < n; ++i) {
+    float x[CPL];
+    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) p += qv[h][j] * x[j];
+      p = warp_sum(p);
+      if (lane == h) { scores[(size_t)ids[i] * 8 + h] = p; mx = fmaxf(mx, p); }
+    }
+  }
+  if (lane < 8) mloc[(size_t)q * 8 + lane] = mx;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) cvs_accum_kernel(const float* __restrict__ scores,
+                                                                  const float* __restrict__ mglob,
+                                                                  const float* __restrict__ slots,
+                                                                  const int* __restrict__ pair_index, int V, int Q,
+                                                                  float* __restrict__ e_out, float* __restrict__ sloc,
+                                                                  float* __restrict__ oloc) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  __shared__ float s_e[kCvWarps][kMaxViews][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  float(*e)[8] = s_e[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  {
+    const int h = lane & 7;
+    const float m = __ldg(mglob + (size_t)q * 8 + h);
+    float sum = 0.f;
+    for (int i = lane >> 3; i < n; i += 4) {
+      const float v = expf(__ldg(scores + (size_t)ids[i] * 8 + h) - m);
+      e[i][h] = v;
+      e_out[(size_t)ids[i] * 8 + h] = v;
+      sum += v;
+    }
+    sum += __shfl_xor_sync(SGC_FULL_MASK, sum, 8);
+    sum += __shfl_xor_sync(SGC_FULL_MASK, sum, 16);
+    if (lane < 8) sloc[(size_t)q * 8 + lane] = sum;
+  }
+  __syncwarp();
+  float t[8][CPL];
+#pragma unroll
+  for (int h = 0; h < 8; ++h)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) t[h][j] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float x[CPL];
+    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float a = e[i][h];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) t[h][j] += a * x[j];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) store_row_cv<CPL>(oloc + h * hq + off, t[h]);
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) cvs_bwd_dot_kernel(const float* __restrict__ slots,
+                                                                    const float* __restrict__ e_in,
+                                                                    const float* __restrict__ sglob,
+                                                                    const int* __restrict__ pair_index, int V, int Q,
+                                                                    const float* __restrict__ grad_t,
+                                                                    float* __restrict__ alpha, float* __restrict__ galpha,
+                                                                    float* __restrict__ dloc) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  float gt[8][CPL];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) load_row_cv<CPL>(gt[h], grad_t + h * hq + off);
+  const float sg = (lane < 8) ? __ldg(sglob + (size_t)q * 8 + lane) : 1.f;
+  float d = 0.f;  // lane h (< 8): partial of sum_v alpha[v,h] g_alpha[v,h]
+  for (int i = 0; i < n; ++i) {
+    float x[CPL];
+    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) p += gt[h][j] * x[j];
+      p = warp_sum(p);
+      if (lane == h) {
+        const float a = __ldg(e_in + (size_t)ids[i] * 8 + h) / sg;
+        alpha[(size_t)ids[i] * 8 + h] = a;
+        galpha[(size_t)ids[i] * 8 + h] = p;
+        d += a * p;
+      }
+    }
+  }
+  if (lane < 8) dloc[(size_t)q * 8 + lane] = d;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kCvWarps * 32) cvs_bwd_qt_kernel(const float* __restrict__ slots,
+                                                                   const float* __restrict__ alpha,
+                                                                   const float* __restrict__ galpha,
+                                                                   const float* __restrict__ dglob,
+                                                                   const int* __restrict__ pair_index, int V, int Q,
+                                                                   float* __restrict__ gscore, float* __restrict__ gqt) {
+  constexpr int C = CPL * 32;
+  __shared__ int s_ids[kCvWarps][kMaxViews];
+  __shared__ float s_gs[kCvWarps][kMaxViews][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * kCvWarps + wid;
+  if (q >= Q) return;
+  int* ids = s_ids[wid];
+  float(*gs)[8] = s_gs[wid];
+  const int n = gather_views(pair_index, V, Q, q, lane, ids);
+  const size_t hq = (size_t)Q * C;
+  const size_t off = (size_t)q * C + lane * CPL;
+  {
+    const int h = lane & 7;
+    const float d = __ldg(dglob + (size_t)q * 8 + h);
+    for (int i = lane >> 3; i < n; i += 4) {
+      const size_t o = (size_t)ids[i] * 8 + h;
+      const float g = __ldg(alpha + o) * (__ldg(galpha + o) - d);
+      gs[i][h] = g;
+      gscore[o] = g;
+    }
+  }
+  __syncwarp();
+  float gq[8][CPL];
+#pragma unroll
+  for (int h = 0; h < 8; ++h)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) gq[h][j] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float x[CPL];
+    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float g = gs[i][h];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) gq[h][j] += g * x[j];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) store_row_cv<CPL>(gqt + h * hq + off, gq[h]);
 }
 
 }  // namespace sgc
@@ -317,5 +501,55 @@ extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha,
 extern "C" int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const float* gscore,
                                             const int* pair_index, int V, int Q, int C, const float* grad_t,
                                             const float* grad_mean, float* grad_slots, void* stream) {
-  SGC_CV_LAUNCH(attn_bwd_slots_kernel, qt, alpha, gscore, pair_index, V, Q, grad_t, grad_mean, grad_slots);
+  SGC_CV_LAUNCH(attn_bwd_slots_kernel, qt, alpha, gscore, pair_index, V, Q, grad_t, grad_mean, grad_slots, nullptr);
+}
+
+// ---- view-sharded entry points (local halves; the exchange steps are host-side all-reduces) -------------------
+#define SGC_CV_LAUNCH2(KERNEL, ...)                                                             \
+  do {                                                                                          \
+    if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;                                \
+    if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;                                  \
+    const int grid = (Q + sgc::kCvWarps - 1) / sgc::kCvWarps;                                   \
+    if (C == 256) sgc::KERNEL<8><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
+    else sgc::KERNEL<4><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);    \
+    SGC_CUDA_CHECK_LAST();                                                                      \
+    return 0;                                                                                   \
+  } while (0)
+
+extern "C" int sgc_crossview_sum_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* sum,
+                                     void* stream) {
+  if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
+  if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;
+  const int grid = (Q + sgc::kCvWarps - 1) / sgc::kCvWarps;
+  if (C == 256) sgc::mean_fwd_kernel<8, false><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(slots, pair_index, V, Q, sum);
+  else sgc::mean_fwd_kernel<4, false><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(slots, pair_index, V, Q, sum);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_cvs_scores(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
+                              float* scores, float* m_loc, void* stream) {
+  SGC_CV_LAUNCH2(cvs_scores_kernel, qt, slots, pair_index, V, Q, scores, m_loc);
+}
+
+extern "C" int sgc_cvs_accum(const float* scores, const float* m_glob, const float* slots, const int* pair_index, int V,
+                             int Q, int C, float* e_out, float* s_loc, float* o_loc, void* stream) {
+  SGC_CV_LAUNCH2(cvs_accum_kernel, scores, m_glob, slots, pair_index, V, Q, e_out, s_loc, o_loc);
+}
+
+extern "C" int sgc_cvs_bwd_dot(const float* slots, const float* e_in, const float* s_glob, const int* pair_index, int V,
+                               int Q, int C, const float* grad_t, float* alpha, float* galpha, float* d_loc,
+                               void* stream) {
+  SGC_CV_LAUNCH2(cvs_bwd_dot_kernel, slots, e_in, s_glob, pair_index, V, Q, grad_t, alpha, galpha, d_loc);
+}
+
+extern "C" int sgc_cvs_bwd_qt(const float* slots, const float* alpha, const float* galpha, const float* d_glob,
+                              const int* pair_index, int V, int Q, int C, float* gscore, float* gqt_loc, void* stream) {
+  SGC_CV_LAUNCH2(cvs_bwd_qt_kernel, slots, alpha, galpha, d_glob, pair_index, V, Q, gscore, gqt_loc);
+}
+
+extern "C" int sgc_cvs_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index, int V,
+                                 int Q, int C, const float* grad_t, const float* grad_mean, const int* count_glob,
+                                 float* grad_slots, void* stream) {
+  SGC_CV_LAUNCH2(attn_bwd_slots_kernel, qt, alpha, gscore, pair_index, V, Q, grad_t, grad_mean, grad_slots, count_glob);
 }

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -448,7 +449,7 @@ class AdaptiveSparseHead(nn.Module):
         # selection-independent work of every level (weight splits, dense feature projection) goes to side
         # streams up front; level i joins its stream right before it needs the projected maps
         main = torch.cuda.current_stream(dev)
-        streams = _side_streams(dev, nl, main)
+        streams = _side_streams(dev, nl, main) if os.environ.get('SGC_SIDE_PREPARE', '1') != '0' else [main] * nl
         prepared = []
         for i in range(nl):
             streams[i].wait_stream(main)
