@@ -95,6 +95,11 @@ int sgc_project_tc_fwd(const float* feat, long long view_stride, long long chan_
 int sgc_colsum_scratch_floats(int R, int C);
 int sgc_colsum(const float* x, int R, int C, float* out, float* scratch, unsigned int* counter, void* stream);
 
+/* One pass over g [R,C]: the rows-split [3R,C] bf16 (slots per `pattern`) for the weight-gradient GEMM g^T x, and
+ * sums[c] = sum_r g[r,c] (the bias gradient).  scratch / counter as for sgc_colsum. */
+int sgc_split_rows_colsum(const float* x, int R, int C, int pattern, void* out, float* sums, float* scratch,
+                          unsigned int* counter, void* stream);
+
 /* Lift: reference-point sample (DCA:67-116) + offset/weight heads + softmax (DCA:423-436) + sampling
  * locations (DCA:445-461) + 8-head 4-point DFA3D (F3D:277-302) for every visible pair.
  * value [V,S,ldv] (no bias), G [V,S,ldg] (128 ch, [m][p][ox,oy,od,logit]), dist [V,S,D], vbias [C], gbias [128],

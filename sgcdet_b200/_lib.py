@@ -31,6 +31,7 @@ SIGNATURES = {
     'sgc_project_tc_fwd': [P, LL, LL, I, I, I, P, I, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
+    'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],
     'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],
     'sgc_lift_bwd_scratch_floats': [I, I],
     'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P],

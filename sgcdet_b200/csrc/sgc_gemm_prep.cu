@@ -75,7 +75,7 @@ extern "C" int sgc_split_bf16x3(const float* x, long long rows, int cols, long l
 // every CTA reduces a slab of rows into partial[b][:], the last CTA to finish (atomic ticket) adds the
 // partials in slab order.  `counter` must be zero on entry and is reset to zero on exit.
 namespace sgc {
-constexpr int kColsumRows = 64;
+constexpr int kColsumRows = 32;
 
 // block = 64 float4-column lanes x 4 row lanes; requires C % 4 == 0
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int C,
@@ -130,6 +130,73 @@ extern "C" int sgc_colsum(const float* x, int R, int C, float* out, float* scrat
   if (R <= 0 || C <= 0 || (C & 3)) return (int)cudaErrorInvalidValue;
   const int blocks = (R + sgc::kColsumRows - 1) / sgc::kColsumRows;
   sgc::colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, R, C, scratch, counter, out);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused: rows-split of g [R,C] (the three bf16 slots stacked along the reduction axis, [3R,C], slots per `pattern`)
+// AND the column sums of g (bias gradient) in one pass over g.  Same two-stage deterministic reduction as
+// sgc_colsum.  Used for every (weight, bias) gradient pair of the Linear layers: gW = g^T x needs the rows-split
+// of g, gb = colsum(g).
+namespace sgc {
+__global__ void __launch_bounds__(256) split_rows_colsum_kernel(const float* __restrict__ x, int R, int C, int pattern,
+                                                               __nv_bfloat16* __restrict__ out, float* __restrict__ partial,
+                                                               unsigned int* __restrict__ counter, float* __restrict__ sums) {
+  __shared__ float4 s_acc[4][64];
+  __shared__ bool is_last;
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int r0 = blockIdx.x * kColsumRows;
+  const int r1 = min(R, r0 + kColsumRows);
+  const int C4 = C >> 2;
+  const size_t slot = (size_t)R * C;
+  for (int c0 = 0; c0 < C4; c0 += 64) {
+    const int c = c0 + cx;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C4) {
+      for (int r = r0 + ry; r < r1; r += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * C) + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        __nv_bfloat16 h[4], l[4];
+        split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
+        const uint2 hv = *reinterpret_cast<uint2*>(h), lv = *reinterpret_cast<uint2*>(l);
+        const size_t o = (size_t)r * C + 4 * c;
+        *reinterpret_cast<uint2*>(out + o) = hv;
+        *reinterpret_cast<uint2*>(out + o + slot) = pattern ? hv : lv;
+        *reinterpret_cast<uint2*>(out + o + 2 * slot) = pattern ? lv : hv;
+      }
+    }
+    s_acc[ry][cx] = a;
+    __syncthreads();
+    if (ry == 0 && c < C4) {
+      float4 t = s_acc[0][cx];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) { t.x += s_acc[k][cx].x; t.y += s_acc[k][cx].y; t.z += s_acc[k][cx].z; t.w += s_acc[k][cx].w; }
+      reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * C)[c] = t;
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += partial[(size_t)b * C + c];
+    sums[c] = a;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+}  // namespace sgc
+
+extern "C" int sgc_split_rows_colsum(const float* x, int R, int C, int pattern, void* out, float* sums, float* scratch,
+                                     unsigned int* counter, void* stream) {
+  if (R <= 0 || C <= 0 || (C & 3)) return (int)cudaErrorInvalidValue;
+  const int blocks = (R + sgc::kColsumRows - 1) / sgc::kColsumRows;
+  sgc::split_rows_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, R, C, pattern, (__nv_bfloat16*)out, scratch,
+                                                                          counter, sums);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

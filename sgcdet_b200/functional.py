@@ -166,6 +166,31 @@ def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return torch.mm(split_rows(g, Q, 0)[0].t(), split_rows(x, Q, 1)[0], out_dtype=F32)
 
 
+def split_rows_colsum(g: torch.Tensor, pattern: int = 0):
+    """One pass over g [Q,N]: (rows-split [3Q,N] bf16, column sums [N])."""
+    g = g.contiguous()
+    R, C = g.shape
+    dev = g.device
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ctr = _COUNTERS.get(key)
+    if ctr is None:
+        ctr = _COUNTERS[key] = torch.zeros(1, device=dev, dtype=torch.int32)
+    out = torch.empty(3 * R, C, device=dev, dtype=BF16)
+    sums = torch.empty(C, device=dev, dtype=F32)
+    scratch = torch.empty(_lib.load().sgc_colsum_scratch_floats(R, C), device=dev, dtype=F32)
+    call('sgc_split_rows_colsum', ptr(g), R, C, pattern, ptr(out), ptr(sums), ptr(scratch), ptr(ctr), stream())
+    return out, sums
+
+
+def linear_grads(g: torch.Tensor, x: torch.Tensor):
+    """(gW, gb) of y = x W^T + b given g = dL/dy: gW = g^T x [N,K], gb = colsum(g); one fused pass over g."""
+    Q = g.shape[0]
+    if _os.environ.get('SGC_FUSED_COLSUM', '1') == '0':
+        return mm_tn(g, x), colsum(g)
+    gs, gb = split_rows_colsum(g, 0)
+    return torch.mm(gs.t(), split_rows(x, Q, 1)[0], out_dtype=F32), gb
+
+
 _COUNTERS = {}
 _GRAD_STREAMS = {}
 
@@ -192,7 +217,7 @@ class _Side:
             t.record_stream(self.side)
         with torch.cuda.stream(self.side):
             r = fn()
-        self.out.append(r)
+        self.out.extend(r if isinstance(r, tuple) else (r,))
         return r
 
     def join(self):
@@ -423,10 +448,9 @@ class CrossView(torch.autograd.Function):
         small = Q <= SMALL_ROWS
         side = _Side(dev)
         gout = gout * has
-        g_wo = side.run(lambda: mm_tn(gout, o2), gout, o2)
-        g_bo = side.run(lambda: colsum(gout), gout)
+        g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
         go2 = mm_nt(gout, wo.t(), lw.wo_t)
-        g_bv = side.run(lambda: colsum(go2), go2)
+
         # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
         go_h = go2.view(Q, H, dh).transpose(0, 1)
         if small:
@@ -436,9 +460,13 @@ class CrossView(torch.autograd.Function):
         # g_wv[h] = go_h^T @ t[h]   [8,dh,Q] x [8,Q,C]
         if small:
             g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
+            g_bv = colsum(go2)
         else:
-            g_wv = side.run(lambda: torch.bmm(_heads_rows_t(go2, 0), split_rows(t.view(H * Q, C), Q, 1),
-                                              out_dtype=F32).reshape(C, C), go2, t)
+            def _wv():
+                gs, gb = split_rows_colsum(go2, 0)  # [3Q,C] rows-split of go2 + the bias gradient of the value proj
+                a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
+                return torch.bmm(a, split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C), gb
+            g_wv, g_bv = side.run(_wv, go2, t)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         call('sgc_crossview_attn_bwd_qt', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
@@ -456,11 +484,9 @@ class CrossView(torch.autograd.Function):
         else:
             g_wk = side.run(lambda: torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1),
                                               out_dtype=F32).reshape(C, C) * scale, qv, gqt)
-        g_wq = side.run(lambda: mm_tn(gqv, g), gqv, g)
-        g_bq = side.run(lambda: colsum(gqv), gqv)
+        g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
         gg = mm_nt(gqv, wq.t(), lw.wq_t)
-        g_wout = side.run(lambda: mm_tn(gg, mean), gg, mean)
-        g_bout = side.run(lambda: colsum(gg), gg)
+        g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
         gmean = mm_nt(gg, w_out.t(), lw.w_out_t)
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
@@ -485,8 +511,7 @@ class Linear3(torch.autograd.Function):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
         side = _Side(gy.device)
-        gw = side.run(lambda: mm_tn(gy, x), gy, x)
-        gb = side.run(lambda: colsum(gy), gy)
+        gw, gb = side.run(lambda: linear_grads(gy, x), gy, x)
         gx = mm_nt(gy, w.t(), ctx.ws_t)
         side.join()
         return gx, gw, gb, None, None

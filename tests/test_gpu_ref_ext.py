@@ -104,3 +104,32 @@ def test_two_stage_product_exports_match_reference(ref_ext, cuda_lib):
     got = reference_fwd_bwd(ext, cu['value'], cu['dist'], cu['s3'], cu['lsi'], cu['loc'], cu['attn'], cu['gout'])
     for k in ref:
         torch.testing.assert_close(got[k], ref[k], rtol=RTOL, atol=2e-3 if k == 'g_loc' else ATOL, msg=lambda m: f'{k}: {m}')
+
+
+@pytest.mark.parametrize('V', [9, 20])
+def test_product_matches_reference_kernels_end_to_end(ref_ext, cuda_lib, V):
+    """Whole view transform: the reference's own DFA3D kernels under the restated reference glue (oracle/gpu_ref.py:
+    padded per-view rebatch, torch MHA, F.interpolate, torch.topk) vs the fused sgcdet_b200 path, same weights and scene.
+    The product is teacher-forced with the reference's selection."""
+    from oracle import gpu_ref
+    from sgcdet_b200 import plugin, synthetic as syn
+    cfg = syn.CONFIGS['tiny']
+    sc = syn.make_scene(cfg, V, shift_origin=True).to('cuda')
+    sd = syn.make_state_dict(cfg)
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        vol_r, valid_r, occ_r = gpu_ref.head_forward_gpu(sdg, sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, cfg, training=False)
+    head = plugin.build_voxel_head(cfg)
+    head.load_state_dict(sd)
+    head = head.cuda().eval()
+    n_mid = int(torch.tensor(cfg.n_voxels_list[1]).prod())
+    n_fine = int(torch.tensor(cfg.n_voxels_list[2]).prod())
+    # reference selections: finest from `valid`, middle from the top-k of its own occupancy
+    sel_fine = torch.nonzero(valid_r.view(-1)).view(-1).to(torch.int32)
+    occ_mid = occ_r[0, n_fine:n_fine + n_mid]
+    sel_mid = torch.sort(torch.topk(occ_mid, cfg.topk_list[0]).indices).values.to(torch.int32)
+    with torch.no_grad():
+        vol, valid, occ = head(sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, forced_selection=[None, sel_mid, sel_fine])
+    assert torch.equal(valid, valid_r)
+    torch.testing.assert_close(occ, occ_r, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(vol, vol_r, rtol=RTOL, atol=ATOL)
