@@ -256,6 +256,7 @@ class ProjectFeatures(torch.autograd.Function):
 
     @staticmethod
     def _split_feat(feat, h, w):
+        feat = feat.reshape(-1, *feat.shape[-3:])
         V, C, H0, W0 = feat.shape
         S = h * w
         src = feat
@@ -270,6 +271,10 @@ class ProjectFeatures(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
+        # feat is [V,C,H0,W0] or the reference's [1,V,C,H0,W0]; taking the 5-D leaf directly keeps autograd from
+        # materialising a zero-filled copy for the select() view on the way back
+        ctx.feat_shape = tuple(feat.shape)
+        feat = feat.reshape(-1, *feat.shape[-3:])
         V, C, H0, W0 = feat.shape
         S = h * w
         N = wcat.shape[0]
@@ -324,7 +329,10 @@ class ProjectFeatures(torch.autograd.Function):
                 gcat = split_cols(gvg.view(V * S, N), 0).view(V, S, 3 * N)
             x = torch.bmm(gcat[:, :, :N].transpose(1, 2), acat[:, :2 * C].transpose(1, 2), out_dtype=F32)  # [V,N,2C]
             y = torch.bmm(gcat[:, :, N:2 * N].transpose(1, 2), acat[:, :C].transpose(1, 2), out_dtype=F32)  # [V,N,C]
-            gw = (x[..., :C] + x[..., C:] + y).sum(0)
+            xs, ys = x.sum(0), y.sum(0)
+            gw = xs[:, :C] + xs[:, C:] + ys
+        if gfeat is not None:
+            gfeat = gfeat.view(ctx.feat_shape)
         return gfeat, None, None, gw, None
 
 
@@ -348,6 +356,7 @@ class Lift(torch.autograd.Function):
         ctx.save_for_backward(vg, dist, vbias, samp)
         ctx.pl, ctx.dims = pl, (S, H, W, D, C)
         ctx.mark_non_differentiable(samp)
+        ctx.set_materialize_grads(False)
         return slots, samp
 
     @staticmethod

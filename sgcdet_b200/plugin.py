@@ -355,7 +355,7 @@ class DenseHead(nn.Module):
         wcat, vbias, gbias = da.folded_weights()
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
                              ffn.layers[0][0].weight, ffn.layers[1].weight)
-        vg = SF.ProjectFeatures.apply(feat[0], h, w, wcat, lw)
+        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
         dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous(), gbias=gbias)
 

@@ -42,3 +42,9 @@ tot = sum(e.device_time_total for e in evs)
 print(f'GPU kernel time per step: {tot / N / 1e3:.3f} ms in {sum(e.count for e in evs) / N:.0f} launches')
 for e in sorted(evs, key=lambda e: -e.device_time_total)[:45]:
     print(f'{e.device_time_total / N / 1e3:8.3f} ms {e.count / N:6.1f}x  {e.key[:110]}')
+
+if os.environ.get('SGC_TRACE'):
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+        step()
+        torch.cuda.synchronize()
+    prof2.export_chrome_trace(os.environ['SGC_TRACE'])
