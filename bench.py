@@ -322,21 +322,43 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     loss_host = torch.zeros(1).pin_memory()
 
-    def e2e_step():
-        with torch.no_grad():
-            for h, d in zip(host_in, dev_in):
-                d.copy_(h, non_blocking=True)
-        run_step()
-        loss_host.copy_(loss_buf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Double-buffered pipeline: the H2D copy of step k+1 (copy stream, pinned host -> device staging) overlaps the
+    # compute of step k; every step still moves its own 270 MB of inputs and reads its own loss back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [[torch.empty_like(t) for t in dev_in] for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    losses_host = [torch.zeros(1).pin_memory() for _ in range(2)]
 
-    e2e_steps = max(3, min(args.steps, 10))
+    def issue_copy(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k % 2])          # staging slot free again
+            for h, s in zip(host_in, staging[k % 2]):
+                s.copy_(h, non_blocking=True)
+            copied[k % 2].record(copy_stream)
+
+    def e2e_run(n):
+        main = torch.cuda.current_stream()
+        for e in consumed:
+            e.record(main)
+        issue_copy(0)
+        for k in range(n):
+            if k + 1 < n:
+                issue_copy(k + 1)
+            main.wait_event(copied[k % 2])
+            with torch.no_grad():
+                torch._foreach_copy_(dev_in, staging[k % 2])   # device-side hand-off into the graph's static inputs
+            consumed[k % 2].record(main)
+            run_step()
+            losses_host[k % 2].copy_(loss_buf, non_blocking=True)
+        main.synchronize()
+
+    e2e_steps = max(4, min(args.steps, 12))
     if args.skip_e2e:
         e2e_ms = float('nan')
     else:
-        for _ in range(2):
-            e2e_step()
-        e2e_ms = timed(e2e_step, e2e_steps)
+        e2e_run(3)
+        e2e_ms = timed(lambda: e2e_run(e2e_steps), 1)
     clk = clocks.stop() if rank == 0 else None
 
     # ---- instrumented eager pass: per-kernel device time with CUDA events (not part of `value`) --------
@@ -409,7 +431,8 @@ def run_ours(args):
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
                        'cuda_graph': not args.no_graph, 'gemm': 'forward feature projection: own tcgen05/TMEM/TMA kernel (bf16 hi/lo split in smem, fp32 accumulate); backward + voxel-count GEMMs: own bf16x3 split kernel + library bf16 GEMM, fp32 accumulate'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': 4, 'steps': e2e_steps},
+                    'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                    'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),
             'clocks': clk, 'roofline': roof, 'path_roofline': path_roof, 'kernels': kernels, 'cpu_baseline': cpu,
