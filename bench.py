@@ -97,7 +97,7 @@ class ClockSampler:
 LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_crossview_mean_fwd=1,
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
-                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1)
+                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1)
 
 
 class CallRecorder:

@@ -90,6 +90,17 @@ int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream);
 int sgc_project_tc_fwd(const float* feat, long long view_stride, long long chan_stride, int V, int C, int S,
                        const void* wpack, int N, float* vg, void* stream);
 
+/* Data gradient of the projection on the tensor cores (same kernel family): gfeat[(v*C+c)*chan_stride + s] =
+ * sum_n gvg[v,s,n] W[n,c] for s < S (NCHW gradient written in place).  wpack_t = sgc_pack_weight_tc(W^T [C,N]). */
+int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, const void* wpack_t, int C, float* gfeat,
+                            long long chan_stride, void* stream);
+
+/* Weight gradient of the projection on the tensor cores: gw[n,c] = sum_{v,s} gvg[v,s,n] feat[(v*C+c)*chan_stride+s],
+ * both fp32 operands split to bf16 hi/lo in shared memory, split-K partials summed in a fixed order. */
+int sgc_project_tc_wgrad_scratch_floats(int N, int C);
+int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C, float* gw,
+                         float* scratch, void* stream);
+
 /* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
  * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */
 int sgc_colsum_scratch_floats(int R, int C);

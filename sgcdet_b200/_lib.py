@@ -29,6 +29,9 @@ SIGNATURES = {
     'sgc_split_bf16x3': [P, LL, I, LL, I, I, P, P],
     'sgc_pack_weight_tc': [P, I, I, P, P],
     'sgc_project_tc_fwd': [P, LL, LL, I, I, I, P, I, P, P],
+    'sgc_project_tc_bwd_data': [P, I, I, I, P, I, P, LL, P],
+    'sgc_project_tc_wgrad_scratch_floats': [I, I],
+    'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],

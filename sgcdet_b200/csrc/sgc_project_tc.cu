@@ -73,6 +73,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int y, int z, const void* src) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y),
                "r"(z), "r"(smem_u32(src))
@@ -111,9 +118,14 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+// BWD = false: forward projection   vg[v,s,n]    = sum_c feat[v,c,s] W[n,c]   (A tile arrives [k][m], TMA-store epilogue)
+// BWD = true : data gradient        gfeat[v,c,s] = sum_n gvg[v,s,n]  W[n,c]   (A tile arrives [m][k] 128B-swizzled,
+//              transposed epilogue: lanes = consecutive pixels -> coalesced NCHW rows).  In both cases "C" is the
+//              reduction length, "N" the output width, and wpack the [N x C] operand packed by sgc_pack_weight_tc.
+template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
-project_tc_fwd_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap omap, int V, int C, int S,
-                      const __nv_bfloat16* __restrict__ wpack, int N, float* __restrict__ vg, int dbg) {
+project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap omap, int V, int C, int S,
+                  const __nv_bfloat16* __restrict__ wpack, int N, float* __restrict__ vg, long long out_pitch, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_stage_bytes = 2 * BM * BK * 2;          // hi + lo
@@ -158,7 +170,8 @@ project_tc_fwd_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_con
         for (int j = 0; j < k_slabs; ++j) {
           mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
           mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage_bytes);
-          tma_load_2d(f_base + pf.stage * f_stage_bytes, &fmap, s0, v * C + j * BK, &sm->f_full[pf.stage]);
+          if (BWD) tma_load_3d(f_base + pf.stage * f_stage_bytes, &fmap, j * BK, s0, v, &sm->f_full[pf.stage]);
+          else tma_load_2d(f_base + pf.stage * f_stage_bytes, &fmap, s0, v * C + j * BK, &sm->f_full[pf.stage]);
           pf.next();
         }
       }
@@ -170,10 +183,19 @@ project_tc_fwd_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_con
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int j = 0; j < k_slabs; ++j) {
         mbar_wait(&sm->f_full[pf.stage], pf.phase);
-        const float* src = reinterpret_cast<const float*>(f_base + pf.stage * f_stage_bytes) + m;
         float x[BK];
+        if (BWD) {  // staging tile is [m][k], 128 B per row, 16-byte chunks XOR-swizzled with (m & 7)
+          const uint8_t* rowp = f_base + pf.stage * f_stage_bytes + m * 128;
 #pragma unroll
-        for (int k = 0; k < BK; ++k) x[k] = src[k * BM];
+          for (int i = 0; i < 8; ++i) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rowp + ((i ^ (m & 7)) << 4));
+            x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+          }
+        } else {    // staging tile is [k][m]
+          const float* src = reinterpret_cast<const float*>(f_base + pf.stage * f_stage_bytes) + m;
+#pragma unroll
+          for (int k = 0; k < BK; ++k) x[k] = src[k * BM];
+        }
         mbar_wait(&sm->a_empty[pa.stage], pa.phase ^ 1);
         uint8_t* hi = a_base + pa.stage * a_stage_bytes;
         uint8_t* lo = hi + BM * BK * 2;
@@ -292,6 +314,15 @@ project_tc_fwd_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_con
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (BWD) {
+          const int sg = s0 + row;
+          if (sg < S) {
+            float* dstc = vg + ((size_t)v * N + c0) * out_pitch + sg;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dstc[(size_t)i * out_pitch] = __uint_as_float(r[i]);
+          }
+          continue;
+        }
         uint8_t* buf = e_base + (chunk & 1) * (BM * 128);
         // the TMA store that read this buffer two chunks ago must have finished reading it
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -397,12 +428,319 @@ extern "C" int sgc_project_tc_fwd(const float* feat, long long view_stride, long
     return (int)cudaErrorInvalidValue;
   const size_t smem = (size_t)NF * BK * BM * 4 + (size_t)NA * 2 * BM * BK * 2 + (size_t)NB * N * BK * 2 + (size_t)NE * BM * 128 +
                       sizeof(Smem) + 64;
-  cudaError_t e = cudaFuncSetAttribute(project_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int tiles = V * ((S + BM - 1) / BM);
   const int grid = tiles < sms ? tiles : sms;
-  project_tc_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, omap, V, C, S, (const __nv_bfloat16*)wpack, N, vg,
-                                                                        getenv("SGC_TC_DBG") ? atoi(getenv("SGC_TC_DBG")) : 0);
+  project_tc_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, omap, V, C, S, (const __nv_bfloat16*)wpack, N, vg, 0,
+                                                                           getenv("SGC_TC_DBG") ? atoi(getenv("SGC_TC_DBG")) : 0);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// Data gradient of the projection on the tensor cores: gfeat[v,c,s] = sum_n gvg[v,s,n] * W[n,c], written straight into
+// the NCHW gradient (pitch chan_stride per channel plane; only s < S is written).  wpack_t = sgc_pack_weight_tc(W^T [C,N]).
+extern "C" int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, const void* wpack_t, int C, float* gfeat,
+                                       long long chan_stride, void* stream) {
+  using namespace sgc::tc;
+  if (N % BK || C % 32 || C > 256 || V <= 0 || S <= 0 || chan_stride < S) return (int)cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(gvg) & 15) || (N * 4) % 16) return (int)cudaErrorInvalidValue;
+  static int sms = 0;
+  static PFN_encodeTiled encode = nullptr;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+    encode = (PFN_encodeTiled)fn;
+  }
+  CUtensorMap fmap;
+  const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)S, (cuuint64_t)V};
+  const cuuint64_t gstr[2] = {(cuuint64_t)N * 4, (cuuint64_t)S * N * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (encode(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(gvg), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  const size_t smem = (size_t)NF * BK * BM * 4 + (size_t)NA * 2 * BM * BK * 2 + (size_t)NB * C * BK * 2 + (size_t)NE * BM * 128 +
+                      sizeof(Smem) + 64;
+  cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int tiles = V * ((S + BM - 1) / BM);
+  const int grid = tiles < sms ? tiles : sms;
+  // kernel convention: reduction length = N (channels of gvg), output width = C
+  project_tc_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, fmap, V, N, S, (const __nv_bfloat16*)wpack_t, C, gfeat,
+                                                                          chan_stride, 0);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// =====================================================================================================================
+// Weight gradient of the projection on the tensor cores:
+//     gw[n,c] = sum_{v,s} gvg[v,s,n] * feat[v,c,s]            (reduction over all pixels of all views)
+// Both operands are fp32 in HBM and are split to bf16 hi/lo in shared memory (no split round trip):
+//   A[m = n][k = s]  <- gvg tile  [32 s][128 n]  (TMA 3-D, rows = s)           -> "[k][m]" converter (as the forward)
+//   B[c][k = s]      <- feat tile [C rows][32 s] (TMA 2-D, 128B-swizzled rows) -> "[m][k]" converter (as the data grad)
+// Split-K: CTA (m-tile, k-chunk) accumulates its slab range in TMEM and writes a partial [128, C] tile; a second kernel
+// sums the partials in a fixed order (deterministic).
+namespace sgc {
+namespace tc {
+
+constexpr int WG_THREADS = 352;
+constexpr int WG_ST = 2;  // pipeline stages (staging and operand)
+
+struct SmemW {
+  uint64_t f_full[WG_ST], f_empty[WG_ST], op_full[WG_ST], op_empty[WG_ST], tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, int V, int S, int C,
+                int m_tiles, int slabs_per_cta, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_src = BK * BM * 4;              // 16 KB  [32 s][128 n] fp32
+  const int b_src = C * 128;                  // [C][32 s] fp32, swizzled
+  const int f_stage = a_src + b_src;
+  const int a_op = 2 * BM * BK * 2;           // hi + lo, 16 KB
+  const int b_op = 2 * C * BK * 2;            // hi + lo
+  const int op_stage = a_op + b_op;
+  uint8_t* f_base = smem_raw;
+  uint8_t* op_base = f_base + WG_ST * f_stage;
+  SmemW* sm = reinterpret_cast<SmemW*>(op_base + WG_ST * op_stage);
+
+  const int mt = blockIdx.x % m_tiles, kc = blockIdx.x / m_tiles;
+  const int spv = (S + BK - 1) / BK;          // slabs per view
+  const int total = V * spv;
+  const int s_begin = kc * slabs_per_cta;
+  const int s_end = min(total, s_begin + slabs_per_cta);
+  const int n_slabs = max(0, s_end - s_begin);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_ST; ++i) {
+      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 256);
+      mbar_init(&sm->op_full[i], 256); mbar_init(&sm->op_empty[i], 1);
+    }
+    mbar_init(&sm->tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      Pipe pf(WG_ST);
+      for (int i = 0; i < n_slabs; ++i) {
+        const int idx = s_begin + i, v = idx / spv, s0 = (idx - v * spv) * BK;
+        mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
+        mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage);
+        uint8_t* st = f_base + pf.stage * f_stage;
+        tma_load_3d(st, &amap, mt * BM, s0, v, &sm->f_full[pf.stage]);
+        tma_load_2d(st + a_src, &bmap, s0, v * C, &sm->f_full[pf.stage]);
+        pf.next();
+      }
+    }
+  } else if (warp < 8) {
+    // converters: warps 0-3 -> A (gvg, [k][m] tile), warps 4-7 -> B (feat, swizzled [row][k] tile)
+    const bool is_b = warp >= 4;
+    const int t = threadIdx.x & 127;
+    Pipe pf(WG_ST), po(WG_ST);
+    for (int i = 0; i < n_slabs; ++i) {
+      mbar_wait(&sm->f_full[pf.stage], pf.phase);
+      const uint8_t* st = f_base + pf.stage * f_stage;
+      mbar_wait(&sm->op_empty[po.stage], po.phase ^ 1);
+      uint8_t* op = op_base + po.stage * op_stage;
+      if (!is_b) {
+        const float* src = reinterpret_cast<const float*>(st) + t;
+        float x[BK];
+#pragma unroll
+        for (int k = 0; k < BK; ++k) x[k] = src[k * BM];
+        uint8_t* hi = op;
+        uint8_t* lo = op + BM * BK * 2;
+        const uint32_t off = (t >> 3) * SBO + (t & 7) * 16;
+#pragma unroll
+        for (int kcx = 0; kcx < BK / 8; ++kcx) {
+          __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            h[q] = __float2bfloat16_rn(x[kcx * 8 + q]);
+            l[q] = __float2bfloat16_rn(x[kcx * 8 + q] - __bfloat162float(h[q]));
+          }
+          *reinterpret_cast<uint4*>(hi + off + kcx * LBO) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + off + kcx * LBO) = *reinterpret_cast<const uint4*>(l);
+        }
+      } else {
+        uint8_t* hi = op + a_op;
+        uint8_t* lo = hi + C * BK * 2;
+        for (int r = t; r < C; r += 128) {
+          const uint8_t* rowp = st + a_src + r * 128;
+          const uint32_t off = (r >> 3) * SBO + (r & 7) * 16;
+#pragma unroll
+          for (int kcx = 0; kcx < BK / 8; ++kcx) {
+            const float4 u0 = *reinterpret_cast<const float4*>(rowp + (((2 * kcx) ^ (r & 7)) << 4));
+            const float4 u1 = *reinterpret_cast<const float4*>(rowp + (((2 * kcx + 1) ^ (r & 7)) << 4));
+            const float xv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              h[q] = __float2bfloat16_rn(xv[q]);
+              l[q] = __float2bfloat16_rn(xv[q] - __bfloat162float(h[q]));
+            }
+            *reinterpret_cast<uint4*>(hi + off + kcx * LBO) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(lo + off + kcx * LBO) = *reinterpret_cast<const uint4*>(l);
+          }
+        }
+      }
+      mbar_arrive(&sm->f_empty[pf.stage]);   // after the staged values were consumed (see the forward kernel)
+      pf.next();
+      fence_proxy_async();
+      mbar_arrive(&sm->op_full[po.stage]);
+      po.next();
+    }
+    if (!is_b) {
+      // epilogue by warps 0-3: partial[kc][mt*128 + row][0..C)
+      const int lane_base = (warp & 3) * 32;
+      const int row = lane_base + lane;
+      float* dst = partial + ((size_t)kc * m_tiles * BM + (size_t)mt * BM + row) * C;
+      if (n_slabs > 0) {
+        mbar_wait(&sm->tmem_full, 0);
+        tc_fence_after();
+      }
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+        if (n_slabs > 0) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      Pipe po(WG_ST);
+      for (int i = 0; i < n_slabs; ++i) {
+        mbar_wait(&sm->op_full[po.stage], po.phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(op_base + po.stage * op_stage);
+        const uint32_t a_lo = a_hi + BM * BK * 2;
+        const uint32_t b_hi = a_hi + a_op;
+        const uint32_t b_lo = b_hi + C * BK * 2;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          const uint32_t o = ks * 2 * LBO;
+          umma_bf16(tmem, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, (i | ks) ? 1u : 0u);
+          umma_bf16(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, 1u);
+          umma_bf16(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+        }
+        tc_commit(&sm->op_empty[po.stage]);
+        po.next();
+      }
+      if (n_slabs > 0) tc_commit(&sm->tmem_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+  }
+}
+
+// gw[i] = sum_k partial[k][i]   (fixed order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kch, int elems, float* __restrict__ gw) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= elems) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < kch; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * elems + i));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(gw + i) = a;
+}
+
+}  // namespace tc
+}  // namespace sgc
+
+extern "C" int sgc_project_tc_wgrad_scratch_floats(int N, int C) {
+  const int m_tiles = N / sgc::tc::BM;
+  const int kch = 148 / (m_tiles > 0 ? m_tiles : 1);
+  return kch * N * C;
+}
+
+// gw [N,C] = sum_{v,s} gvg[v,s,n] feat[(v*C+c)*chan_stride + s]; scratch: sgc_project_tc_wgrad_scratch_floats(N,C) floats.
+extern "C" int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C,
+                                    float* gw, float* scratch, void* stream) {
+  using namespace sgc::tc;
+  if (N % BM || C % 32 || C > 256 || V <= 0 || S <= 0 || chan_stride < S) return (int)cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(gvg) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15) || (chan_stride * 4) % 16)
+    return (int)cudaErrorInvalidValue;
+  static PFN_encodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int)cudaErrorNotSupported;
+    encode = (PFN_encodeTiled)fn;
+  }
+  CUtensorMap amap, bmap;
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)S, (cuuint64_t)V};
+    const cuuint64_t gstr[2] = {(cuuint64_t)N * 4, (cuuint64_t)S * N * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)BM, (cuuint32_t)BK, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(gvg), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)chan_stride, (cuuint64_t)V * C};
+    const cuuint64_t gstr[1] = {(cuuint64_t)chan_stride * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)C};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+  }
+  const int m_tiles = N / BM;
+  const int kch = 148 / m_tiles;
+  const int spv = (S + BK - 1) / BK;
+  const int total = V * spv;
+  const int slabs_per_cta = (total + kch - 1) / kch;
+  const size_t smem = (size_t)WG_ST * (BK * BM * 4 + C * 128) + (size_t)WG_ST * (2 * BM * BK * 2 + 2 * C * BK * 2) + sizeof(SmemW) + 64;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  wgrad_tc_kernel<<<m_tiles * kch, WG_THREADS, smem, (cudaStream_t)stream>>>(amap, bmap, V, S, C, m_tiles, slabs_per_cta, scratch);
+  SGC_CUDA_CHECK_LAST();
+  const int elems = N * C;
+  wgrad_reduce_kernel<<<(elems / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, kch, elems, gw);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

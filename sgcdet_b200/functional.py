@@ -140,7 +140,9 @@ class LevelWeights:
             scale = 1.0 / math.sqrt(dh)
             wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
             self.wcat = split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
-            self.wpack = pack_weight_tc(wcat) if (wcat.shape[1] % 32 == 0 and wcat.shape[0] % 32 == 0) else None
+            ok = wcat.shape[1] % 32 == 0 and wcat.shape[0] % 32 == 0
+            self.wpack = pack_weight_tc(wcat) if ok else None
+            self.wpack_t = pack_weight_tc(wcat.t().contiguous()) if ok else None
             self.wcat_t = split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
             self.w_out, self.w_out_t = split_cols(w_out, 1), split_cols(w_out.t(), 1)
             self.wq, self.wq_t = split_cols(wq, 1), split_cols(wq.t(), 1)
@@ -302,10 +304,29 @@ class ProjectFeatures(torch.autograd.Function):
     def backward(ctx, gvg: torch.Tensor):
         acat, wcat = ctx.saved_tensors
         V, C, H0, W0, h, w = ctx.dims
-        if not ctx.have_acat:
-            acat = ProjectFeatures._split_feat(acat, h, w) if ctx.needs_input_grad[3] else None
         S = h * w
         N = wcat.shape[0]
+        if (not ctx.have_acat) and _os.environ.get('SGC_TC_BWD', '1') != '0' and C <= 256 and N % 128 == 0:
+            # own tcgen05 kernels for both gradients: gvg and feat are read as fp32 and split in shared memory
+            feat = acat
+            gvg = gvg.contiguous()
+            gfeat = gw = None
+            lw = ctx.lw
+            if ctx.needs_input_grad[0]:
+                wpack_t = lw.wpack_t if lw is not None and getattr(lw, 'wpack_t', None) is not None \
+                    else pack_weight_tc(wcat.t().contiguous())
+                gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
+                if h != H0:
+                    gfeat[:, :, h:].zero_()
+                call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
+                gfeat = gfeat.view(ctx.feat_shape)
+            if ctx.needs_input_grad[3]:
+                gw = torch.empty(N, C, device=gvg.device, dtype=F32)
+                scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device=gvg.device, dtype=F32)
+                call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
+            return gfeat, None, None, gw, None
+        if not ctx.have_acat:
+            acat = ProjectFeatures._split_feat(acat, h, w) if ctx.needs_input_grad[3] else None
         gvg = gvg.contiguous()
         gfeat = gw = gcat = None
         if ctx.needs_input_grad[0]:
