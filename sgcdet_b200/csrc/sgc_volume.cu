@@ -313,6 +313,105 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(const float* __restri
   }
 }
 
+// Fast path for N <= 32768 (every level of the C=256 configs): the whole key set lives in registers (32 keys per thread),
+// 3 radix passes of 11/11/10 bits with a shared 2048-bin histogram and a parallel suffix scan, then the ordered
+// compaction from registers.  Same deterministic contract as topk_select_kernel.
+constexpr int kTopkKpt = 32;
+
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* warp_tot, int& total) {
+  // exclusive prefix of v over the 1024 threads of the block (thread order), total = sum
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(SGC_FULL_MASK, inc, o);
+    if (lane >= o) inc += y;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(SGC_FULL_MASK, t, o);
+      if (lane >= o) t += y;
+    }
+    warp_tot[lane] = t;
+  }
+  __syncthreads();
+  total = warp_tot[31];
+  return (wid ? warp_tot[wid - 1] : 0) + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) topk_select_small_kernel(const float* __restrict__ occ, int N, int k,
+                                                                int* __restrict__ sel, uint8_t* __restrict__ mask) {
+  __shared__ int hist[2048];
+  __shared__ int warp_tot[32];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need;
+  const int tid = threadIdx.x;
+  // thread t owns the CONTIGUOUS index range [t*per, (t+1)*per): the ordered compaction then needs one block scan
+  const int per = (N + 1023) / 1024;
+  uint32_t key[kTopkKpt];
+#pragma unroll
+  for (int j = 0; j < kTopkKpt; ++j) {
+    const int i = tid * per + j;
+    key[j] = (j < per && i < N) ? topk_key(__ldg(occ + i)) : 0u;
+  }
+  if (tid == 0) { s_prefix = 0u; s_need = k; }
+  const int shifts[3] = {21, 10, 0};
+  const int bits[3] = {11, 11, 10};
+  uint32_t pmask = 0u;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass], nb = 1 << bits[pass];
+    for (int b = tid; b < 2048; b += 1024) hist[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+#pragma unroll
+    for (int j = 0; j < kTopkKpt; ++j) {
+      const int i = tid * per + j;
+      if (j < per && i < N && (key[j] & pmask) == prefix) atomicAdd(&hist[(key[j] >> shift) & (nb - 1)], 1);
+    }
+    __syncthreads();
+    // suffix counts: thread t handles bins 2t, 2t+1 (descending order = ascending index in the reversed array)
+    const int b_hi = 2047 - 2 * tid, b_lo = b_hi - 1;      // reversed: position 2t <-> bin b_hi
+    const int c_hi = hist[b_hi], c_lo = hist[b_lo];
+    int total;
+    const int before = block_excl_scan_1024(c_hi + c_lo, warp_tot, total);  // count of keys in strictly higher bins
+    const int need = s_need;
+    __syncthreads();
+    // the threshold bin is the first (from the top) whose cumulative count reaches `need`
+    if (before < need && before + c_hi >= need) { s_prefix = prefix | ((uint32_t)b_hi << shift); s_need = need - before; }
+    else if (before + c_hi < need && before + c_hi + c_lo >= need) { s_prefix = prefix | ((uint32_t)b_lo << shift); s_need = need - before - c_hi; }
+    __syncthreads();
+    pmask |= (uint32_t)(nb - 1) << shift;
+  }
+  const uint32_t T = s_prefix;
+  const int need_eq = s_need;
+  int ngt = 0, neq = 0;
+#pragma unroll
+  for (int j = 0; j < kTopkKpt; ++j) {
+    const int i = tid * per + j;
+    if (j < per && i < N) { ngt += key[j] > T; neq += key[j] == T; }
+  }
+  int tot_gt, tot_eq;
+  int gt_before = block_excl_scan_1024(ngt, warp_tot, tot_gt);
+  int eq_before = block_excl_scan_1024(neq, warp_tot, tot_eq);
+#pragma unroll
+  for (int j = 0; j < kTopkKpt; ++j) {
+    const int i = tid * per + j;
+    if (j < per && i < N) {
+      const bool gt = key[j] > T, eq = key[j] == T;
+      const bool take = gt || (eq && eq_before < need_eq);
+      mask[i] = take ? 1 : 0;
+      if (take) sel[gt_before + (eq_before < need_eq ? eq_before : need_eq)] = i;
+      gt_before += gt;
+      eq_before += eq;
+    }
+  }
+}
+
 }  // namespace sgc
 
 extern "C" int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ,
@@ -375,7 +474,10 @@ extern "C" int sgc_gather_rows(const float* vol, const int* sel, float* y, int k
 
 extern "C" int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream) {
   if (k < 0 || k > N) return (int)cudaErrorInvalidValue;
-  sgc::topk_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
+  if (k > 0 && N <= 1024 * sgc::kTopkKpt)
+    sgc::topk_select_small_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
+  else
+    sgc::topk_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
