@@ -22,6 +22,8 @@
 // channels [lane*CPL, lane*CPL+CPL) (CPL = C/32 = Cm/4) in the gather stage.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace sgc {
 
 template <int CPL>
@@ -144,8 +146,8 @@ __device__ __forceinline__ void scatter_dist(float* gd_px, const Tap& t, int D, 
   if (t.d0 + 1 <= D - 1) red_add1(gd_px + t.d0 + 1, t.ld * gds);
 }
 
-template <int CPL>
-__global__ void __launch_bounds__(256) lift_bwd_kernel(
+template <int CPL, int MINB>
+__global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     const float* __restrict__ value, int ldv, const float* __restrict__ G, int ldg,
     const float* __restrict__ dist, const float* __restrict__ vbias,
     const int* __restrict__ pair_vq, const int* __restrict__ n_pairs_ptr, const float* __restrict__ ref_cam,
@@ -345,12 +347,16 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
-  if (C == 256)
-    sgc::lift_bwd_kernel<8><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp,
-                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist, scratch);
-  else
-    sgc::lift_bwd_kernel<4><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp,
-                                                  grad_slots, S, H, W, D, Q, grad_value, grad_G, grad_dist, scratch);
+#define SGC_LIFT_BWD_ARGS value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp, grad_slots, S, H, W, D, Q, \
+                          grad_value, grad_G, grad_dist, scratch
+  static const int minb = getenv("SGC_LIFT_MINB") ? atoi(getenv("SGC_LIFT_MINB")) : 2;
+  if (C == 256) {
+    if (minb == 2) sgc::lift_bwd_kernel<8, 2><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    else if (minb == 4) sgc::lift_bwd_kernel<8, 4><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    else sgc::lift_bwd_kernel<8, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+  } else {
+    sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+  }
   SGC_CUDA_CHECK_LAST();
   sgc::bias_reduce_kernel<<<(C + 128) / 32, 256, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
   SGC_CUDA_CHECK_LAST();
