@@ -87,6 +87,23 @@ int sgc_split_bf16x3(const float* x, long long rows, int cols, long long src_str
  * DCA:417-436; replaces the flatten/permute of transformer.py:151-170).  wpack = sgc_pack_weight_tc(W [N,C]) is
  * 2*N*C bf16 (hi/lo slabs in the kernel's shared-memory image).  C % 32 == 0, N % 32 == 0, N <= 512. */
 int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream);
+
+/* All per-step operand preparations of one level's weights in ONE launch (the nn.Linear weights of DCA:417-436,
+ * DCA:691-702 and the FFN, ENC:262-340, in the layouts the tensor-core GEMMs consume).  Each job reads a logical
+ * [rows, cols] fp32 matrix at src[r*row_stride + c*col_stride] (so transposed operands need no copy), multiplies by
+ * `scale` and writes kind 0: the sgc_split_bf16x3 image (rows_per_group, pattern as there), or kind 1: the
+ * sgc_pack_weight_tc image (rows = N, cols = C).  `jobs` is a HOST array of njobs <= SGC_MAX_WEIGHT_JOBS entries. */
+#define SGC_MAX_WEIGHT_JOBS 24
+typedef struct sgc_weight_job {
+  const float* src;
+  void* out;
+  long long row_stride, col_stride;
+  int rows, cols;
+  int rows_per_group, pattern;
+  float scale;
+  int kind;
+} sgc_weight_job;
+int sgc_prepare_weights(const sgc_weight_job* jobs, int njobs, void* stream);
 int sgc_project_tc_fwd(const float* feat, long long view_stride, long long chan_stride, int V, int C, int S,
                        const void* wpack, int N, float* vg, void* stream);
 
@@ -161,6 +178,15 @@ int sgc_cvs_bwd_qt(const float* slots, const float* alpha, const float* galpha, 
 int sgc_cvs_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index, int V, int Q,
                       int C, const float* grad_t, const float* grad_mean, const int* count_glob, float* grad_slots,
                       void* stream);
+
+/* nn.LayerNorm backward over voxel rows [R,C] (the two norms of VoxFormerLayer, ENC:262-340), C in {128, 256}:
+ * gx fully written; `partial` (sgc_layernorm_bwd_scratch_floats(R,C) floats) receives per-CTA sums that
+ * sgc_layernorm_bwd_params reduces in a fixed order into ggamma / gbeta (may run on another stream, after an event).
+ * mean / rstd are the [R] statistics of the forward (torch.native_layer_norm). */
+int sgc_layernorm_bwd_scratch_floats(int R, int C);
+int sgc_layernorm_bwd(const float* x, const float* gy, const float* mean, const float* rstd, const float* gamma,
+                      int R, int C, float* gx, float* partial, void* stream);
+int sgc_layernorm_bwd_params(const float* partial, int R, int C, float* ggamma, float* gbeta, void* stream);
 
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].
  * upsample: F.interpolate(x2, trilinear, align_corners=False) (ASH:64-69) fused with the occupancy head

@@ -28,6 +28,10 @@ SIGNATURES = {
     'sgc_project_compact': [P, P, P, I, I, F, F, F, F, F, F, F, F, F, P, P, P, P, P, P, P, P],
     'sgc_split_bf16x3': [P, LL, I, LL, I, I, P, P],
     'sgc_pack_weight_tc': [P, I, I, P, P],
+    'sgc_prepare_weights': [P, I, P],
+    'sgc_layernorm_bwd_scratch_floats': [I, I],
+    'sgc_layernorm_bwd': [P, P, P, P, P, I, I, P, P, P],
+    'sgc_layernorm_bwd_params': [P, I, I, P, P, P],
     'sgc_project_tc_fwd': [P, LL, LL, I, I, I, P, I, P, P],
     'sgc_project_tc_bwd_data': [P, I, I, I, P, I, P, LL, P],
     'sgc_project_tc_wgrad_scratch_floats': [I, I],
@@ -54,6 +58,16 @@ SIGNATURES = {
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],
 }
+
+
+class WeightJob(ctypes.Structure):
+    """``sgc_weight_job`` of include/sgcdet_b200.h."""
+    _fields_ = [('src', c_void_p), ('out', c_void_p), ('row_stride', c_longlong), ('col_stride', c_longlong),
+                ('rows', c_int), ('cols', c_int), ('rows_per_group', c_int), ('pattern', c_int),
+                ('scale', c_float), ('kind', c_int)]
+
+
+MAX_WEIGHT_JOBS = 24
 
 
 def lib_path() -> Path:

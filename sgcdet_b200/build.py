@@ -33,7 +33,8 @@ def sources():
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh'))):
+    hdr = CSRC.parent.parent / 'include' / 'sgcdet_b200.h'
+    for p in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh'))) + ([hdr] if hdr.exists() else []):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(' '.join(NVCC_FLAGS).encode())

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "../../include/sgcdet_b200.h"
 
 namespace sgc {
 namespace tc {
@@ -370,8 +371,60 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int C, __
   }
 }
 
+
+// One launch for ALL per-step operand preparations of a level's weights (replaces ~35 tiny launches):
+// every job reads a logical [rows, cols] fp32 matrix through (row_stride, col_stride) -- so transposed operands need
+// no copy --, multiplies by `scale`, and writes either the bf16x3 K-concatenated split of sgc_split_bf16x3 (kind 0)
+// or the tcgen05 slab image of pack_weight_kernel (kind 1, rows = N, cols = C).
+struct WeightJobs {
+  sgc_weight_job job[SGC_MAX_WEIGHT_JOBS];
+};
+
+__global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_constant__ WeightJobs jobs) {
+  const sgc_weight_job& j = jobs.job[blockIdx.y];
+  const int total = j.rows * j.cols;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(j.out);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / j.cols, c = i - r * j.cols;
+    const float x = __ldg(j.src + (long long)r * j.row_stride + (long long)c * j.col_stride) * j.scale;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    if (j.kind == 0) {
+      const int rpg = j.rows_per_group;
+      const size_t slot = (size_t)rpg * j.cols;
+      const size_t base = ((size_t)(r / rpg) * 3 * rpg + (r % rpg)) * j.cols + c;
+      out[base] = h;
+      out[base + slot] = j.pattern ? h : l;
+      out[base + 2 * slot] = j.pattern ? l : h;
+    } else {
+      const int slab = c / BK, k = c - slab * BK;
+      const size_t stage_elems = (size_t)j.rows * BK;
+      const size_t o = (size_t)(r >> 3) * (SBO / 2) + (size_t)(k >> 3) * (LBO / 2) + (r & 7) * 8 + (k & 7);
+      out[(size_t)(2 * slab) * stage_elems + o] = h;
+      out[(size_t)(2 * slab + 1) * stage_elems + o] = l;
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace sgc
+
+extern "C" int sgc_prepare_weights(const sgc_weight_job* jobs, int njobs, void* stream) {
+  if (njobs <= 0) return 0;
+  if (njobs > SGC_MAX_WEIGHT_JOBS) return (int)cudaErrorInvalidValue;
+  sgc::tc::WeightJobs wj;
+  for (int i = 0; i < njobs; ++i) {
+    const sgc_weight_job& j = jobs[i];
+    if (j.rows <= 0 || j.cols <= 0 || !j.src || !j.out) return (int)cudaErrorInvalidValue;
+    if (j.kind == 0 && (j.rows_per_group <= 0 || j.rows % j.rows_per_group)) return (int)cudaErrorInvalidValue;
+    if (j.kind == 1 && (j.rows % 16 || j.cols % sgc::tc::BK)) return (int)cudaErrorInvalidValue;
+    if (j.kind != 0 && j.kind != 1) return (int)cudaErrorInvalidValue;
+    wj.job[i] = j;
+  }
+  sgc::tc::prepare_weights_kernel<<<dim3(32, njobs), 256, 0, (cudaStream_t)stream>>>(wj);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
 
 extern "C" int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream) {
   if (N % 16 || C % sgc::tc::BK) return (int)cudaErrorInvalidValue;

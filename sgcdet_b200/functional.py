@@ -6,6 +6,7 @@ No function in this module has a CPU or eager fallback.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -128,31 +129,64 @@ def pack_weight_tc(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _WeightJobs:
+    """Collects the operand preparations of one level and issues them as ONE ``sgc_prepare_weights`` launch."""
+
+    def __init__(self, dev):
+        self.dev, self.jobs, self.keep = dev, [], []
+
+    def _add(self, x, out, rpg, pattern, scale, kind):
+        assert x.dim() == 2 and x.dtype == F32 and x.is_cuda
+        self.jobs.append(_lib.WeightJob(x.data_ptr(), out.data_ptr(), x.stride(0), x.stride(1), x.shape[0], x.shape[1],
+                                        rpg, pattern, scale, kind))
+        self.keep.append(x)
+        return out
+
+    def split_cols(self, x, pattern, scale=1.0):
+        return self._add(x, torch.empty(x.shape[0], 3 * x.shape[1], device=self.dev, dtype=BF16), 1, pattern, scale, 0)
+
+    def split_rows(self, x, group, pattern, scale=1.0):
+        out = torch.empty(x.shape[0] // group, 3 * group, x.shape[1], device=self.dev, dtype=BF16)
+        return self._add(x, out, group, pattern, scale, 0)
+
+    def pack(self, x):
+        return self._add(x, torch.empty(2 * x.numel(), device=self.dev, dtype=BF16), 1, 0, 1.0, 1)
+
+    def launch(self):
+        for i in range(0, len(self.jobs), _lib.MAX_WEIGHT_JOBS):
+            chunk = self.jobs[i:i + _lib.MAX_WEIGHT_JOBS]
+            arr = (_lib.WeightJob * len(chunk))(*chunk)
+            call('sgc_prepare_weights', ctypes.cast(arr, ctypes.c_void_p), len(chunk), stream())
+        self.jobs, self.keep = [], []
+
+
 class LevelWeights:
-    """Every bf16x3 split of one level's weights (both orientations), computed once per step -- normally on a
-    side stream, off the critical path of the level.  Constants for the autograd Functions below (weight
-    gradients are formed from the fp32 activations, not from these)."""
+    """Every bf16x3 split / tcgen05 slab image of one level's weights (both orientations), produced once per step by a
+    single launch -- normally on a side stream, off the critical path of the level.  Constants for the autograd
+    Functions below (weight gradients are formed from the fp32 activations, not from these)."""
 
     def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS):
         with torch.no_grad():
             C = w_out.shape[0]
             dh = C // num_heads
             scale = 1.0 / math.sqrt(dh)
-            wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
-            self.wcat = split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
+            wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
+            j = _WeightJobs(w_out.device)
+            self.wcat = j.split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
             ok = wcat.shape[1] % 32 == 0 and wcat.shape[0] % 32 == 0
-            self.wpack = pack_weight_tc(wcat) if ok else None
-            self.wpack_t = pack_weight_tc(wcat.t().contiguous()) if ok else None
-            self.wcat_t = split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
-            self.w_out, self.w_out_t = split_cols(w_out, 1), split_cols(w_out.t(), 1)
-            self.wq, self.wq_t = split_cols(wq, 1), split_cols(wq.t(), 1)
-            self.wo, self.wo_t = split_cols(wo, 1), split_cols(wo.t(), 1)
-            self.wk_rows = split_rows(wk, dh, 1)     # [8,3dh,C]  qv_h @ (scale Wk_h)
-            self.wk_cols = split_cols(wk, 1)         # [C,3C]     gqt[h] @ (scale Wk_h)^T
-            self.wv_rows = split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
-            self.wv_cols = split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
-            self.w1, self.w1_t = split_cols(w1, 1), split_cols(w1.t(), 1)
-            self.w2, self.w2_t = split_cols(w2, 1), split_cols(w2.t(), 1)
+            self.wpack = j.pack(wcat) if ok else None
+            self.wpack_t = j.pack(wcat.t()) if ok else None
+            self.wcat_t = j.split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
+            self.w_out, self.w_out_t = j.split_cols(w_out, 1), j.split_cols(w_out.t(), 1)
+            self.wq, self.wq_t = j.split_cols(wq, 1), j.split_cols(wq.t(), 1)
+            self.wo, self.wo_t = j.split_cols(wo, 1), j.split_cols(wo.t(), 1)
+            self.wk_rows = j.split_rows(wk, dh, 1, scale)  # [8,3dh,C]  qv_h @ (scale Wk_h)
+            self.wk_cols = j.split_cols(wk, 1, scale)      # [C,3C]     gqt[h] @ (scale Wk_h)^T
+            self.wv_rows = j.split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
+            self.wv_cols = j.split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
+            self.w1, self.w1_t = j.split_cols(w1, 1), j.split_cols(w1.t(), 1)
+            self.w2, self.w2_t = j.split_cols(w2, 1), j.split_cols(w2.t(), 1)
+            j.launch()
 
     def record_stream(self, s):
         for t in self.__dict__.values():
@@ -197,19 +231,40 @@ _COUNTERS = {}
 _GRAD_STREAMS = {}
 
 
-class _Side:
-    """Runs weight/bias-gradient work of a backward on a side stream private to the calling stream, so that it
-    overlaps the latency-bound activation-gradient chain; ``join()`` before the grads are handed to autograd."""
+class OnStream(torch.autograd.Function):
+    """Identity on parameters, applied under ``with torch.cuda.stream(wstream)``: the aliases' backward node (and the
+    AccumulateGrad behind it) belong to ``wstream``, so a backward that PRODUCES a weight gradient on ``wstream`` can
+    hand it to autograd without making the calling stream wait for it (autograd orders consumers after the
+    producing stream, and joins every leaf stream when the backward pass ends)."""
 
-    def __init__(self, dev):
+    @staticmethod
+    def forward(ctx, *ts):
+        return tuple(t.view_as(t) for t in ts)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        return gs
+
+
+class _Side:
+    """Runs the weight/bias-gradient work of a backward on a side stream so that it overlaps the latency-bound
+    activation-gradient chain.  With ``wstream`` (the stream the parameters were aliased on, see ``OnStream``) the
+    results are never joined into the calling stream; without it a private side stream is used and ``join()`` makes
+    the caller wait before the grads are handed to autograd."""
+
+    def __init__(self, dev, wstream=None):
         self.main = torch.cuda.current_stream(dev)
-        key = (dev, self.main.cuda_stream)
-        s = _GRAD_STREAMS.get(key)
-        if s is None:
-            s = _GRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
-        self.side = s
-        self.out = []
         self.enabled = _os.environ.get('SGC_SIDE_GRADS', '1') != '0'
+        self.detached = wstream is not None and self.enabled and wstream != self.main
+        if self.detached:
+            self.side = wstream
+        else:
+            key = (dev, self.main.cuda_stream)
+            s = _GRAD_STREAMS.get(key)
+            if s is None:
+                s = _GRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+            self.side = s
+        self.out = []
 
     def run(self, fn, *inputs):
         if not self.enabled:
@@ -223,7 +278,7 @@ class _Side:
         return r
 
     def join(self):
-        if self.enabled and self.out:
+        if self.enabled and self.out and not self.detached:
             self.main.wait_stream(self.side)
             for t in self.out:
                 t.record_stream(self.main)
@@ -365,7 +420,10 @@ class Lift(torch.autograd.Function):
     """sgc_lift_fwd / sgc_lift_bwd (see csrc/sgc_lift.cu)."""
 
     @staticmethod
-    def forward(ctx, vg, dist, vbias, gbias, pl: PairList, H: int, W: int):
+    def forward(ctx, vg, dist, vbias, gbias, pl: PairList, H: int, W: int, bwd_stream=None):
+        """``bwd_stream``: the stream the producers of vg / dist / vbias / gbias ran on (``DenseHead.prepare`` on a
+        side stream).  Autograd replays those producers' backward nodes on that stream, so the (large) backward kernel
+        is issued there as well and the main stream continues with the next level's per-voxel chain."""
         V, S, ld = vg.shape
         C = ld - G_CH
         D = dist.shape[-1]
@@ -376,6 +434,7 @@ class Lift(torch.autograd.Function):
              ptr(pl.n_pairs), pl.cap, ptr(pl.ref_cam), S, H, W, D, pl.Q, C, ptr(samp), ptr(slots), stream())
         ctx.save_for_backward(vg, dist, vbias, samp)
         ctx.pl, ctx.dims = pl, (S, H, W, D, C)
+        ctx.bwd_stream = bwd_stream if _os.environ.get('SGC_SIDE_LIFT_BWD', '1') != '0' else None
         ctx.mark_non_differentiable(samp)
         ctx.set_materialize_grads(False)
         return slots, samp
@@ -386,16 +445,26 @@ class Lift(torch.autograd.Function):
         pl = ctx.pl
         S, H, W, D, C = ctx.dims
         ld = vg.shape[-1]
-        gvg = torch.zeros_like(vg)
-        gdist = torch.zeros_like(dist)
-        gvb = torch.zeros_like(vbias)
-        ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
-        base, gbase = ptr(vg), ptr(gvg)
-        scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device, dtype=torch.float32)
-        call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
-             pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots.contiguous()), S, H, W, D, pl.Q, C,
-             gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
-        return gvg, gdist, gvb, ggb, None, None, None
+        gslots = gslots.contiguous()
+        cur = torch.cuda.current_stream(vg.device)
+        side = ctx.bwd_stream if ctx.bwd_stream is not None and ctx.bwd_stream != cur else None
+        if side is not None:
+            # every consumer of the four gradients is a backward node of the side stream, so main never waits
+            side.wait_stream(cur)
+            for t in (gslots, samp, pl.pair_vq, pl.n_pairs, pl.ref_cam):
+                t.record_stream(side)
+        with torch.cuda.stream(side if side is not None else cur):
+            gvg = torch.zeros_like(vg)
+            gdist = torch.zeros_like(dist)
+            gvb = torch.zeros_like(vbias)
+            ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
+            base, gbase = ptr(vg), ptr(gvg)
+            scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device,
+                                  dtype=torch.float32)
+            call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
+                 pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots), S, H, W, D, pl.Q, C,
+                 gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
+        return gvg, gdist, gvb, ggb, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -425,7 +494,8 @@ class CrossView(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, lw=None):
+    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, lw=None, wstream=None):
+        ctx.wstream = wstream
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
         H = NUM_HEADS
@@ -476,7 +546,7 @@ class CrossView(torch.autograd.Function):
         lw = ctx.lw
         wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
         small = Q <= SMALL_ROWS
-        side = _Side(dev)
+        side = _Side(dev, ctx.wstream)
         gout = gout * has
         g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
         go2 = mm_nt(gout, wo.t(), lw.wo_t)
@@ -522,29 +592,61 @@ class CrossView(torch.autograd.Function):
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
         side.join()
-        g_in_w = torch.cat([g_wq, g_wk, g_wv], dim=0)
-        g_in_b = torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)
-        return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None
+        g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
+                                           torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
+        side.join()
+        return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None, None
 
 
 class Linear3(torch.autograd.Function):
     """y = x W^T + b on the tensor cores with bf16x3-split operands (used for the FFN, encoder.py:335-338)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, ws=None, ws_t=None):
+    def forward(ctx, x, w, b, ws=None, ws_t=None, wstream=None):
         ctx.save_for_backward(x, w)
-        ctx.ws_t = ws_t
+        ctx.ws_t, ctx.wstream = ws_t, wstream
         return mm_nt(x, w, ws) + b
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gy = gy.contiguous()
-        side = _Side(gy.device)
+        side = _Side(gy.device, ctx.wstream)
         gw, gb = side.run(lambda: linear_grads(gy, x), gy, x)
         gx = mm_nt(gy, w.t(), ctx.ws_t)
         side.join()
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
+
+
+class LayerNormRows(torch.autograd.Function):
+    """nn.LayerNorm over voxel rows [R,C] (the norms of VoxFormerLayer, encoder.py:262-340): torch's forward kernel,
+    own backward (``sgc_layernorm_bwd``: one pass for gx, the gamma/beta reduction finishes on the weight stream)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, wstream=None):
+        x = x.contiguous()
+        y, mean, rstd = torch.native_layer_norm(x, (x.shape[1],), gamma, beta, eps)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.wstream = wstream
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        R, C = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        partial = torch.empty(_lib.load().sgc_layernorm_bwd_scratch_floats(R, C), device=x.device, dtype=F32)
+        call('sgc_layernorm_bwd', ptr(x), ptr(gy), ptr(mean), ptr(rstd), ptr(gamma), R, C, ptr(gx), ptr(partial), stream())
+        side = _Side(x.device, ctx.wstream)
+
+        def _params():
+            gg, gb = torch.empty(C, device=x.device, dtype=F32), torch.empty(C, device=x.device, dtype=F32)
+            call('sgc_layernorm_bwd_params', ptr(partial), R, C, ptr(gg), ptr(gb), stream())
+            return gg, gb
+        gg, gb = side.run(_params, partial)
+        side.join()
+        return gx, gg, gb, None, None
 
 
 # ----------------------------------------------------------------------------------------------

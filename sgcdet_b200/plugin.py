@@ -198,13 +198,15 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
         self.add_identity = add_identity
 
-    def forward(self, x, identity=None, lw=None):
+    def forward(self, x, identity=None, lw=None, params=None, wstream=None):
         if x.is_cuda and x.dim() == 2:
             # same arithmetic as ``self.layers`` with the two Linear layers on the tensor cores (bf16x3 split)
             l0, drop0 = self.layers[0][0], self.layers[0][2]
             w = (lw.w1, lw.w1_t, lw.w2, lw.w2_t) if lw is not None else (None,) * 4
-            hdn = drop0(F.relu(SF.Linear3.apply(x, l0.weight, l0.bias, w[0], w[1])))
-            out = self.layers[2](SF.Linear3.apply(hdn, self.layers[1].weight, self.layers[1].bias, w[2], w[3]))
+            w1, b1, w2, b2 = params if params is not None else (l0.weight, l0.bias, self.layers[1].weight,
+                                                                self.layers[1].bias)
+            hdn = drop0(F.relu(SF.Linear3.apply(x, w1, b1, w[0], w[1], wstream)))
+            out = self.layers[2](SF.Linear3.apply(hdn, w2, b2, w[2], w[3], wstream))
         else:
             out = self.layers(x)
         if not self.add_identity:
@@ -325,6 +327,7 @@ class DenseHead(nn.Module):
         vox_coords, ref_3d = self.get_voxel_indices()
         self.register_buffer('vox_coords', vox_coords)
         self.register_buffer('ref_3d', ref_3d)
+        self._wstream = None  # weight-gradient stream (created lazily on the inputs' device)
 
     def get_voxel_indices(self):
         """DenseHead.py:32-48 (voxel 'centres' are lower corners: idx*size - n/2*size)."""
@@ -357,7 +360,23 @@ class DenseHead(nn.Module):
                              ffn.layers[0][0].weight, ffn.layers[1].weight)
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
         dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
-        return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous(), gbias=gbias)
+        # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
+        # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
+        params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,
+                  mha.out_proj.weight, mha.out_proj.bias, ffn.layers[0][0].weight, ffn.layers[0][0].bias,
+                  ffn.layers[1].weight, ffn.layers[1].bias, layer.norms[0].weight, layer.norms[0].bias,
+                  layer.norms[1].weight, layer.norms[1].bias)
+        wstream = None
+        if torch.is_grad_enabled() and os.environ.get('SGC_WSTREAM', '1') != '0':
+            if self._wstream is None or self._wstream.device != feat.device:
+                self._wstream = torch.cuda.Stream(device=feat.device)
+            wstream = self._wstream
+            with torch.cuda.stream(wstream):
+                params = SF.OnStream.apply(*params)
+        # vbias is a leaf parameter: the view gives it a backward node that belongs to this stream like the
+        # producers of vg / dist / gbias (Lift issues its backward kernel on this stream, see functional.Lift)
+        return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
+                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None):
@@ -376,14 +395,14 @@ class DenseHead(nn.Module):
         if prepared is None:
             prepared = self.prepare(feat, dpt_dist, hw)
         lw = prepared['lw']
-        slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w)
-        mha = attn.attention_pooling
-        x = SF.CrossView.apply(slots, pl, attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight,
-                               mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lw)
+        slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w,
+                                    prepared.get('stream'))
+        pp, ws = prepared['params'], prepared['wstream']
+        x = SF.CrossView.apply(slots, pl, *pp[:6], lw, ws)
         x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
-        x = layer.norms[0](x)
-        x = layer.ffns[0](x, lw=lw)
-        x = layer.norms[1](x)
+        x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, ws)
+        x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=ws)
+        x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, ws)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
         return x

@@ -48,3 +48,30 @@ if os.environ.get('SGC_TRACE'):
         step()
         torch.cuda.synchronize()
     prof2.export_chrome_trace(os.environ['SGC_TRACE'])
+
+if os.environ.get('SGC_GRAPH_TRACE'):
+    from sgcdet_b200 import functional as SF
+    sc.img_meta['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)
+    # timeline of ONE CUDA-graph replay (true stream concurrency, no CPU launch gaps): feed to tools/graph_timeline.py
+    for t in list(head.parameters()) + feats + dists:
+        t.grad = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for t in list(head.parameters()) + feats + dists:
+        t.grad = None
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        vol, valid, occ = head(feats, sc.img_meta, dists)
+        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        loss.backward()
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof3:
+        g.replay()
+        torch.cuda.synchronize()
+    prof3.export_chrome_trace(os.environ['SGC_GRAPH_TRACE'])
