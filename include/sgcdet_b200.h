@@ -115,6 +115,10 @@ int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, const void* w
 /* Weight gradient of the projection on the tensor cores: gw[n,c] = sum_{v,s} gvg[v,s,n] feat[(v*C+c)*chan_stride+s],
  * both fp32 operands split to bf16 hi/lo in shared memory, split-K partials summed in a fixed order. */
 int sgc_project_tc_wgrad_scratch_floats(int N, int C);
+/* Cap on the SMs the three projection kernels occupy (0 = all; they run beside the latency-bound voxel chain). */
+int sgc_project_tc_set_max_ctas(int n);
+/* n > 0: the forward / data-gradient kernels run as short-lived CTAs of n tiles each instead of persistent ones. */
+int sgc_project_tc_set_tiles_per_cta(int n);
 int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C, float* gw,
                          float* scratch, void* stream);
 
@@ -154,6 +158,14 @@ int sgc_crossview_attn_fwd(const float* qt, const float* slots, const int* pair_
  *   _slots : grad_slots [#pairs,C] = grad_mean/n + sum_h (alpha grad_t[h] + gscore qt[h]), fully written. */
 int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q, int C,
                               const float* grad_t, float* gscore, float* grad_qt, void* stream);
+/* The same kernels additionally emitting the bf16x3 operand image (sgc_split_bf16x3 pattern 0) of their dense output
+ * for the tensor-core GEMM that follows: mean [Q,3C], t [8*Q,3C], grad_qt [8*Q,3C]. */
+int sgc_crossview_mean_fwd_split(const float* slots, const int* pair_index, int V, int Q, int C, float* mean, void* split,
+                                 void* stream);
+int sgc_crossview_attn_fwd_split(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
+                                 float* t_out, float* alpha, void* split, void* stream);
+int sgc_crossview_attn_bwd_qt_split(const float* slots, const float* alpha, const int* pair_index, int V, int Q, int C,
+                                    const float* grad_t, float* gscore, float* grad_qt, void* split, void* stream);
 int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index,
                                  int V, int Q, int C, const float* grad_t, const float* grad_mean,
                                  float* grad_slots, void* stream);
@@ -187,6 +199,52 @@ int sgc_layernorm_bwd_scratch_floats(int R, int C);
 int sgc_layernorm_bwd(const float* x, const float* gy, const float* mean, const float* rstd, const float* gamma,
                       int R, int C, float* gx, float* partial, void* stream);
 int sgc_layernorm_bwd_params(const float* partial, int R, int C, float* ggamma, float* gbeta, void* stream);
+
+/* Fused row epilogue / prologue around the tensor-core GEMMs of the encoder layer (output_proj + attention_pooling of
+ * DCA:815-837, the norms and the FFN of ENC:262-340): one warp per voxel row of N in {128,256,512} channels.
+ *   forward : v = x + bias; relu; v *= mask*mscale; v *= rowscale[r]; v += residual; [pre = v; v = LayerNorm(v)]
+ *             -> y (fp32) and ysplit (sgc_split_bf16x3 pattern-0 image of y: the operand of the next GEMM)
+ *   backward: v = g (+ g2); [LayerNorm backward; per-CTA (g*xhat, g) sums into partial, reduced by
+ *             sgc_layernorm_bwd_params]; gpre = v; v *= mask*mscale; v = gate > 0 ? v*gscale : 0; v *= rowscale[r]
+ *             -> gx (fp32), gxsplit (bf16x3 image)
+ * Every pointer except x / g may be NULL (= that stage is skipped).  in_heads = H: the input is head-major [H,R,N/H];
+ * split_heads = H: the bf16x3 image is per (row, head): [(r*H+h)][slot*dh + d] (operand of a per-head GEMM).
+ * partial needs sgc_layernorm_bwd_scratch_floats(R, N) floats. */
+typedef struct sgc_rowop_fwd_args {
+  const float* x;
+  const float* bias;
+  const unsigned char* mask;
+  const float* rowscale;
+  const float* residual;
+  const float* gamma;
+  const float* beta;
+  float* y;
+  void* ysplit;
+  float* pre;
+  float* mean;
+  float* rstd;
+  float mscale, eps;
+  int R, N, relu, in_heads, split_heads;
+} sgc_rowop_fwd_args;
+typedef struct sgc_rowop_bwd_args {
+  const float* g;
+  const float* g2;
+  const float* pre;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const unsigned char* mask;
+  const float* gate;
+  const float* rowscale;
+  float* partial;
+  float* gpre;
+  float* gx;
+  void* gxsplit;
+  float mscale, gscale;
+  int R, N, in_heads, split_heads;
+} sgc_rowop_bwd_args;
+int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
+int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);
 
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].
  * upsample: F.interpolate(x2, trilinear, align_corners=False) (ASH:64-69) fused with the occupancy head

@@ -3,6 +3,7 @@ tensor is not a contiguous CUDA tensor the call raises."""
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_float, c_int, c_longlong, c_void_p
 from pathlib import Path
 
@@ -29,12 +30,19 @@ SIGNATURES = {
     'sgc_split_bf16x3': [P, LL, I, LL, I, I, P, P],
     'sgc_pack_weight_tc': [P, I, I, P, P],
     'sgc_prepare_weights': [P, I, P],
+    'sgc_rowop_fwd': [P, P],
+    'sgc_rowop_bwd': [P, P],
+    'sgc_crossview_mean_fwd_split': [P, P, I, I, I, P, P, P],
+    'sgc_crossview_attn_fwd_split': [P, P, P, I, I, I, P, P, P, P],
+    'sgc_crossview_attn_bwd_qt_split': [P, P, P, I, I, I, P, P, P, P, P],
     'sgc_layernorm_bwd_scratch_floats': [I, I],
     'sgc_layernorm_bwd': [P, P, P, P, P, I, I, P, P, P],
     'sgc_layernorm_bwd_params': [P, I, I, P, P, P],
     'sgc_project_tc_fwd': [P, LL, LL, I, I, I, P, I, P, P],
     'sgc_project_tc_bwd_data': [P, I, I, I, P, I, P, LL, P],
     'sgc_project_tc_wgrad_scratch_floats': [I, I],
+    'sgc_project_tc_set_max_ctas': [I],
+    'sgc_project_tc_set_tiles_per_cta': [I],
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
@@ -70,6 +78,22 @@ class WeightJob(ctypes.Structure):
 MAX_WEIGHT_JOBS = 24
 
 
+class RowopFwdArgs(ctypes.Structure):
+    """``sgc_rowop_fwd_args`` of include/sgcdet_b200.h."""
+    _fields_ = [(n, c_void_p) for n in ('x', 'bias', 'mask', 'rowscale', 'residual', 'gamma', 'beta', 'y', 'ysplit',
+                                        'pre', 'mean', 'rstd')] + \
+               [('mscale', c_float), ('eps', c_float), ('R', c_int), ('N', c_int), ('relu', c_int),
+                ('in_heads', c_int), ('split_heads', c_int)]
+
+
+class RowopBwdArgs(ctypes.Structure):
+    """``sgc_rowop_bwd_args`` of include/sgcdet_b200.h."""
+    _fields_ = [(n, c_void_p) for n in ('g', 'g2', 'pre', 'mean', 'rstd', 'gamma', 'mask', 'gate', 'rowscale',
+                                        'partial', 'gpre', 'gx', 'gxsplit')] + \
+               [('mscale', c_float), ('gscale', c_float), ('R', c_int), ('N', c_int), ('in_heads', c_int),
+                ('split_heads', c_int)]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -86,6 +110,8 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = c_int
+        lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
+        lib.sgc_project_tc_set_tiles_per_cta(int(os.environ.get('SGC_TC_TILES_PER_CTA', '0')))
         _lib = lib
     return _lib
 

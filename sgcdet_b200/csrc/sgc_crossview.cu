@@ -11,6 +11,7 @@
 //
 // Layout: slots [cap,C] pair-major; pair_index [V,Q] (-1 = invisible); count [Q]; alpha [cap,8] saved for bwd.
 // Lane l owns channels [l*CPL, l*CPL+CPL), CPL = C/32.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace sgc {
@@ -32,6 +33,27 @@ __device__ __forceinline__ void store_row_cv(float* p, const float (&src)[CPL]) 
   for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(src[j], src[j + 1], src[j + 2], src[j + 3]);
 }
 
+// bf16x3 operand image of one row for the next tensor-core GEMM (pattern 0 of sgc_split_bf16x3: hi | lo | hi along K):
+// split[row][slot*C + c], written by the lane that owns channels [lane*CPL, lane*CPL + CPL)
+template <int CPL>
+__device__ __forceinline__ void store_split_cv(__nv_bfloat16* __restrict__ split, size_t row, int lane, const float (&v)[CPL]) {
+  constexpr int C = CPL * 32;
+  __align__(16) __nv_bfloat16 h[CPL], l[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    h[j] = __float2bfloat16_rn(v[j]);
+    l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+  }
+  __nv_bfloat16* o = split + row * 3 * C + lane * CPL;
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const uint2 hv = *reinterpret_cast<const uint2*>(h + j), lv = *reinterpret_cast<const uint2*>(l + j);
+    *reinterpret_cast<uint2*>(o + j) = hv;
+    *reinterpret_cast<uint2*>(o + C + j) = lv;
+    *reinterpret_cast<uint2*>(o + 2 * C + j) = hv;
+  }
+}
+
 // Collect the pair ids of the views that see voxel q into ids[] (warp-shared), return how many.
 __device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, int V, int Q, int q, int lane,
                                             int* ids) {
@@ -50,7 +72,8 @@ __device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, 
 template <int CPL, bool DIVIDE = true>
 __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __restrict__ slots,
                                                                  const int* __restrict__ pair_index, int V, int Q,
-                                                                 float* __restrict__ mean) {
+                                                                 float* __restrict__ mean,
+                                                                 __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
   __shared__ int s_ids[kCvWarps][kMaxViews];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -73,13 +96,15 @@ __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __
     for (int j = 0; j < CPL; ++j) acc[j] = acc[j] / fn;  // DCA:826
   }
   store_row_cv<CPL>(mean + (size_t)q * C + lane * CPL, acc);
+  if (split) store_split_cv<CPL>(split, (size_t)q, lane, acc);
 }
 
 template <int CPL>
 __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __restrict__ qt,
                                                                  const float* __restrict__ slots,
                                                                  const int* __restrict__ pair_index, int V, int Q,
-                                                                 float* __restrict__ t_out, float* __restrict__ alpha) {
+                                                                 float* __restrict__ t_out, float* __restrict__ alpha,
+                                                                 __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
   __shared__ int s_ids[kCvWarps][kMaxViews];
   __shared__ float s_sc[kCvWarps][kMaxViews][8];
@@ -96,7 +121,10 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
 #pragma unroll
     for (int j = 0; j < CPL; ++j) z[j] = 0.f;
 #pragma unroll
-    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(t_out + h * hq + off, z);
+    for (int h = 0; h < 8; ++h) {
+      store_row_cv<CPL>(t_out + h * hq + off, z);
+      if (split) store_split_cv<CPL>(split, (size_t)h * Q + q, lane, z);
+    }
     return;
   }
   {  // phase 1: scores
@@ -156,7 +184,10 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
       }
     }
 #pragma unroll
-    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(t_out + h * hq + off, t[h]);
+    for (int h = 0; h < 8; ++h) {
+      store_row_cv<CPL>(t_out + h * hq + off, t[h]);
+      if (split) store_split_cv<CPL>(split, (size_t)h * Q + q, lane, t[h]);
+    }
   }
 }
 
@@ -164,7 +195,8 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
 template <int CPL>
 __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_qt_kernel(
     const float* __restrict__ slots, const float* __restrict__ alpha, const int* __restrict__ pair_index, int V, int Q,
-    const float* __restrict__ grad_t, float* __restrict__ gscore, float* __restrict__ grad_qt) {
+    const float* __restrict__ grad_t, float* __restrict__ gscore, float* __restrict__ grad_qt,
+    __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
   __shared__ int s_ids[kCvWarps][kMaxViews];
   __shared__ float s_al[kCvWarps][kMaxViews][8];  // alpha
@@ -183,7 +215,10 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_qt_kernel(
 #pragma unroll
     for (int j = 0; j < CPL; ++j) z[j] = 0.f;
 #pragma unroll
-    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(grad_qt + h * hq + off, z);
+    for (int h = 0; h < 8; ++h) {
+      store_row_cv<CPL>(grad_qt + h * hq + off, z);
+      if (split) store_split_cv<CPL>(split, (size_t)h * Q + q, lane, z);
+    }
     return;
   }
   for (int i = lane >> 3; i < n; i += 4) al[i][lane & 7] = __ldg(alpha + (size_t)ids[i] * 8 + (lane & 7));
@@ -237,7 +272,10 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_qt_kernel(
       }
     }
 #pragma unroll
-    for (int h = 0; h < 8; ++h) store_row_cv<CPL>(grad_qt + h * hq + off, gq[h]);
+    for (int h = 0; h < 8; ++h) {
+      store_row_cv<CPL>(grad_qt + h * hq + off, gq[h]);
+      if (split) store_split_cv<CPL>(split, (size_t)h * Q + q, lane, gq[h]);
+    }
   }
 }
 
@@ -496,6 +534,22 @@ extern "C" int sgc_crossview_attn_fwd(const float* qt, const float* slots, const
 extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
                                          int C, const float* grad_t, float* gscore, float* grad_qt, void* stream) {
   SGC_CV_LAUNCH(attn_bwd_qt_kernel, slots, alpha, pair_index, V, Q, grad_t, gscore, grad_qt);
+}
+
+// Same three kernels, additionally emitting the bf16x3 operand image (sgc_split_bf16x3 pattern 0) of their dense output
+// for the tensor-core GEMM that follows: mean [Q,3C], t [8*Q,3C], grad_qt [8*Q,3C].
+extern "C" int sgc_crossview_mean_fwd_split(const float* slots, const int* pair_index, int V, int Q, int C, float* mean,
+                                            void* split, void* stream) {
+  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean, (__nv_bfloat16*)split);
+}
+extern "C" int sgc_crossview_attn_fwd_split(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
+                                            float* t_out, float* alpha, void* split, void* stream) {
+  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha, (__nv_bfloat16*)split);
+}
+extern "C" int sgc_crossview_attn_bwd_qt_split(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
+                                               int C, const float* grad_t, float* gscore, float* grad_qt, void* split,
+                                               void* stream) {
+  SGC_CV_LAUNCH(attn_bwd_qt_kernel, slots, alpha, pair_index, V, Q, grad_t, gscore, grad_qt, (__nv_bfloat16*)split);
 }
 
 extern "C" int sgc_crossview_attn_bwd_slots(const float* qt, const float* alpha, const float* gscore,

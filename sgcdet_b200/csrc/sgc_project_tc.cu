@@ -409,6 +409,30 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_const
 }  // namespace tc
 }  // namespace sgc
 
+// Upper bound on the CTAs (= SMs, the kernels are persistent with one CTA per SM) the tensor-core projection kernels
+// occupy; 0 = all SMs.  The kernels run on side streams next to the latency-bound per-voxel chain: leaving a few SMs
+// free lets the chain's kernels start immediately instead of waiting for a persistent CTA to retire.
+static int g_tc_max_ctas = 0;
+extern "C" int sgc_project_tc_set_max_ctas(int n) {
+  if (n < 0) return (int)cudaErrorInvalidValue;
+  g_tc_max_ctas = n;
+  return 0;
+}
+static int g_tc_tiles_per_cta = 0;  // 0 = persistent (grid = SM cap); n > 0: short-lived CTAs of n tiles each
+extern "C" int sgc_project_tc_set_tiles_per_cta(int n) {
+  if (n < 0) return (int)cudaErrorInvalidValue;
+  g_tc_tiles_per_cta = n;
+  return 0;
+}
+static inline int tc_grid(int tiles, int sms);
+static inline int tc_cta_cap(int sms) { return (g_tc_max_ctas > 0 && g_tc_max_ctas < sms) ? g_tc_max_ctas : sms; }
+
+static inline int tc_grid(int tiles, int sms) {
+  if (g_tc_tiles_per_cta > 0) return (tiles + g_tc_tiles_per_cta - 1) / g_tc_tiles_per_cta;
+  const int cap = tc_cta_cap(sms);
+  return tiles < cap ? tiles : cap;
+}
+
 extern "C" int sgc_prepare_weights(const sgc_weight_job* jobs, int njobs, void* stream) {
   if (njobs <= 0) return 0;
   if (njobs > SGC_MAX_WEIGHT_JOBS) return (int)cudaErrorInvalidValue;
@@ -421,7 +445,7 @@ extern "C" int sgc_prepare_weights(const sgc_weight_job* jobs, int njobs, void* 
     if (j.kind != 0 && j.kind != 1) return (int)cudaErrorInvalidValue;
     wj.job[i] = j;
   }
-  sgc::tc::prepare_weights_kernel<<<dim3(32, njobs), 256, 0, (cudaStream_t)stream>>>(wj);
+  sgc::tc::prepare_weights_kernel<<<dim3(96, njobs), 256, 0, (cudaStream_t)stream>>>(wj);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -484,7 +508,7 @@ extern "C" int sgc_project_tc_fwd(const float* feat, long long view_stride, long
   cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int tiles = V * ((S + BM - 1) / BM);
-  const int grid = tiles < sms ? tiles : sms;
+  const int grid = tc_grid(tiles, sms);
   project_tc_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, omap, V, C, S, (const __nv_bfloat16*)wpack, N, vg, 0,
                                                                            getenv("SGC_TC_DBG") ? atoi(getenv("SGC_TC_DBG")) : 0);
   SGC_CUDA_CHECK_LAST();
@@ -526,7 +550,7 @@ extern "C" int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, co
   cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int tiles = V * ((S + BM - 1) / BM);
-  const int grid = tiles < sms ? tiles : sms;
+  const int grid = tc_grid(tiles, sms);
   // kernel convention: reduction length = N (channels of gvg), output width = C
   project_tc_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, fmap, V, N, S, (const __nv_bfloat16*)wpack_t, C, gfeat,
                                                                           chan_stride, 0);
@@ -783,7 +807,7 @@ extern "C" int sgc_project_tc_wgrad(const float* gvg, const float* feat, long lo
       return (int)cudaErrorInvalidValue;
   }
   const int m_tiles = N / BM;
-  const int kch = 148 / m_tiles;
+  const int kch = tc_cta_cap(148) / m_tiles > 0 ? tc_cta_cap(148) / m_tiles : 1;
   const int spv = (S + BK - 1) / BK;
   const int total = V * spv;
   const int slabs_per_cta = (total + kch - 1) / kch;

@@ -5,6 +5,7 @@
 //   sgc_layernorm_bwd          gx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat))   (nn.LayerNorm backward,
 //                              encoder.py:325-338 norms) + per-CTA partial sums of (g*xhat, g) for gamma / beta
 //   sgc_layernorm_bwd_params   fixed-order reduction of those partials (deterministic; runs on the weight-gradient stream)
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/sgcdet_b200.h"
 
@@ -98,6 +99,203 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const float* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused row epilogue / prologue around the tensor-core GEMMs of the layer.  N = 32*CPL channels, lane owns channels
+// [lane*CPL, lane*CPL + CPL).
+//
+// forward:   v = x + bias;  relu;  v *= mask*mscale;  v *= rowscale[r];  v += residual;  [pre = v; v = LayerNorm(v)]
+//            -> y (fp32), ysplit (bf16x3 operand image of y for the next GEMM), pre / mean / rstd for the LN backward
+// backward:  v = g (+ g2);  [LN backward with pre/mean/rstd/gamma, partial sums for gamma/beta];  gpre = v;
+//            v *= mask*mscale;  v = gate > 0 ? v*gscale : 0;  v *= rowscale[r]   -> gx (fp32), gxsplit (bf16x3)
+template <int CPL>
+__device__ __forceinline__ void load_row(float (&dst)[CPL], const float* p) {
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const float4 t = ldg4(p + j);
+    dst[j] = t.x; dst[j + 1] = t.y; dst[j + 2] = t.z; dst[j + 3] = t.w;
+  }
+}
+template <int CPL>
+__device__ __forceinline__ void store_row(float* p, const float (&src)[CPL]) {
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(src[j], src[j + 1], src[j + 2], src[j + 3]);
+}
+template <int CPL>
+__device__ __forceinline__ void load_mask(float (&dst)[CPL], const uint8_t* p) {
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const uchar4 t = *reinterpret_cast<const uchar4*>(p + j);
+    dst[j] = t.x ? 1.f : 0.f; dst[j + 1] = t.y ? 1.f : 0.f; dst[j + 2] = t.z ? 1.f : 0.f; dst[j + 3] = t.w ? 1.f : 0.f;
+  }
+}
+// bf16x3 image (pattern 0: hi | lo | hi).  heads == 0: out[r][slot*N + c];  heads == H: out[(r*H + h)][slot*dh + d]
+template <int CPL>
+__device__ __forceinline__ void store_split(__nv_bfloat16* __restrict__ out, size_t r, int lane, int heads, const float (&v)[CPL]) {
+  constexpr int N = CPL * 32;
+  __align__(16) __nv_bfloat16 h[CPL], l[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    h[j] = __float2bfloat16_rn(v[j]);
+    l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+  }
+  __nv_bfloat16* o;
+  int slot;
+  if (heads == 0) {
+    o = out + r * 3 * N + lane * CPL;
+    slot = N;
+  } else {
+    const int dh = N / heads, c = lane * CPL, hd = c / dh;
+    o = out + (r * heads + hd) * 3 * dh + (c - hd * dh);
+    slot = dh;
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; j += 4) {
+    const uint2 hv = *reinterpret_cast<const uint2*>(h + j), lv = *reinterpret_cast<const uint2*>(l + j);
+    *reinterpret_cast<uint2*>(o + j) = hv;
+    *reinterpret_cast<uint2*>(o + slot + j) = lv;
+    *reinterpret_cast<uint2*>(o + 2 * slot + j) = hv;
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kRowWarps * 32) rowop_fwd_kernel(const sgc_rowop_fwd_args a) {
+  constexpr int N = 32 * CPL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * CPL;
+  float bias[CPL], gam[CPL], bet[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { bias[j] = 0.f; gam[j] = 1.f; bet[j] = 0.f; }
+  if (a.bias) load_row<CPL>(bias, a.bias + c0);
+  if (a.gamma) { load_row<CPL>(gam, a.gamma + c0); load_row<CPL>(bet, a.beta + c0); }
+  for (int r = blockIdx.x * kRowWarps + warp; r < a.R; r += gridDim.x * kRowWarps) {
+    float v[CPL];
+    if (a.in_heads) {  // x is [H, R, dh]
+      const int dh = N / a.in_heads, hd = c0 / dh;
+      load_row<CPL>(v, a.x + ((size_t)hd * a.R + r) * dh + (c0 - hd * dh));
+    } else {
+      load_row<CPL>(v, a.x + (size_t)r * N + c0);
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) v[j] += bias[j];
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (a.mask) {
+      float m[CPL];
+      load_mask<CPL>(m, a.mask + (size_t)r * N + c0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= m[j] * a.mscale;
+    }
+    if (a.rowscale) {
+      const float rsc = __ldg(a.rowscale + r);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= rsc;
+    }
+    if (a.residual) {
+      float t[CPL];
+      load_row<CPL>(t, a.residual + (size_t)r * N + c0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] += t[j];
+    }
+    if (a.gamma) {
+      if (a.pre) store_row<CPL>(a.pre + (size_t)r * N + c0, v);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) s += v[j];
+      const float mu = warp_sum(s) * (1.f / N);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { const float d = v[j] - mu; q += d * d; }
+      const float rs = rsqrtf(warp_sum(q) * (1.f / N) + a.eps);
+      if (lane == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] = (v[j] - mu) * rs * gam[j] + bet[j];
+    }
+    if (a.y) store_row<CPL>(a.y + (size_t)r * N + c0, v);
+    if (a.ysplit) store_split<CPL>(reinterpret_cast<__nv_bfloat16*>(a.ysplit), (size_t)r, lane, a.split_heads, v);
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kRowWarps * 32) rowop_bwd_kernel(const sgc_rowop_bwd_args a) {
+  constexpr int N = 32 * CPL;
+  __shared__ float s_part[kRowWarps][2 * N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * CPL;
+  const bool ln = a.gamma != nullptr;
+  float gam[CPL], agam[CPL], abet[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { gam[j] = 1.f; agam[j] = 0.f; abet[j] = 0.f; }
+  if (ln) load_row<CPL>(gam, a.gamma + c0);
+  for (int r = blockIdx.x * kRowWarps + warp; r < a.R; r += gridDim.x * kRowWarps) {
+    float v[CPL];
+    if (a.in_heads) {
+      const int dh = N / a.in_heads, hd = c0 / dh;
+      load_row<CPL>(v, a.g + ((size_t)hd * a.R + r) * dh + (c0 - hd * dh));
+    } else {
+      load_row<CPL>(v, a.g + (size_t)r * N + c0);
+    }
+    if (a.g2) {
+      float t[CPL];
+      load_row<CPL>(t, a.g2 + (size_t)r * N + c0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] += t[j];
+    }
+    if (ln) {
+      const float mu = __ldg(a.mean + r), rs = __ldg(a.rstd + r);
+      float xh[CPL];
+      load_row<CPL>(xh, a.pre + (size_t)r * N + c0);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        xh[j] = (xh[j] - mu) * rs;
+        agam[j] += v[j] * xh[j];
+        abet[j] += v[j];
+        v[j] *= gam[j];
+        s1 += v[j];
+        s2 += v[j] * xh[j];
+      }
+      s1 = warp_sum(s1) * (1.f / N);
+      s2 = warp_sum(s2) * (1.f / N);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] = rs * (v[j] - s1 - xh[j] * s2);
+    }
+    if (a.gpre) store_row<CPL>(a.gpre + (size_t)r * N + c0, v);
+    if (a.mask) {
+      float m[CPL];
+      load_mask<CPL>(m, a.mask + (size_t)r * N + c0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= m[j] * a.mscale;
+    }
+    if (a.gate) {
+      float t[CPL];
+      load_row<CPL>(t, a.gate + (size_t)r * N + c0);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] = t[j] > 0.f ? v[j] * a.gscale : 0.f;
+    }
+    if (a.rowscale) {
+      const float rsc = __ldg(a.rowscale + r);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= rsc;
+    }
+    if (a.gx) store_row<CPL>(a.gx + (size_t)r * N + c0, v);
+    if (a.gxsplit) store_split<CPL>(reinterpret_cast<__nv_bfloat16*>(a.gxsplit), (size_t)r, lane, a.split_heads, v);
+  }
+  if (ln) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { s_part[warp][c0 + j] = agam[j]; s_part[warp][N + c0 + j] = abet[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * N; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) t += s_part[w][c];
+      a.partial[(size_t)blockIdx.x * 2 * N + c] = t;
+    }
+  }
+}
+
 }  // namespace sgc
 
 extern "C" int sgc_layernorm_bwd_scratch_floats(int R, int C) { return sgc::rowop_blocks(R) * 2 * C; }
@@ -120,6 +318,42 @@ extern "C" int sgc_layernorm_bwd_params(const float* partial, int R, int C, floa
   if (R <= 0) return 0;
   const int blocks = sgc::rowop_blocks(R);
   sgc::layernorm_bwd_params_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, blocks, 2 * C, ggamma, gbeta);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream) {
+  const sgc_rowop_fwd_args a = *args;
+  if (a.R <= 0) return 0;
+  if (!a.x || (a.gamma && (!a.beta || !a.mean || !a.rstd))) return (int)cudaErrorInvalidValue;
+  if (a.in_heads && (a.N % a.in_heads || (a.N / a.in_heads) % (a.N / 32))) return (int)cudaErrorInvalidValue;
+  if (a.split_heads && (a.N % a.split_heads || (a.N / a.split_heads) % (a.N / 32))) return (int)cudaErrorInvalidValue;
+  const int blocks = sgc::rowop_blocks(a.R);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a.N) {
+    case 128: sgc::rowop_fwd_kernel<4><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 256: sgc::rowop_fwd_kernel<8><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 512: sgc::rowop_fwd_kernel<16><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream) {
+  const sgc_rowop_bwd_args a = *args;
+  if (a.R <= 0) return 0;
+  if (!a.g || (a.gamma && (!a.pre || !a.mean || !a.rstd || !a.partial))) return (int)cudaErrorInvalidValue;
+  if (a.in_heads && (a.N % a.in_heads || (a.N / a.in_heads) % (a.N / 32))) return (int)cudaErrorInvalidValue;
+  if (a.split_heads && (a.N % a.split_heads || (a.N / a.split_heads) % (a.N / 32))) return (int)cudaErrorInvalidValue;
+  const int blocks = sgc::rowop_blocks(a.R);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a.N) {
+    case 128: sgc::rowop_bwd_kernel<4><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 256: sgc::rowop_bwd_kernel<8><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 512: sgc::rowop_bwd_kernel<16><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -89,7 +89,8 @@ def project_compact(proj: torch.Tensor, ref3d: torch.Tensor, sel: Optional[torch
 BF16 = torch.bfloat16
 F32 = torch.float32
 import os as _os
-SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs with at most this many rows stay plain fp32
+HEADS_WGRAD_FP32 = _os.environ.get('SGC_HEADS_WGRAD_FP32', '0') != '0'  # per-head K/V weight grads as plain fp32 bmm
+SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '1000'))  # voxel-count GEMMs with at most this many rows stay plain fp32
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -561,6 +562,8 @@ class CrossView(torch.autograd.Function):
         if small:
             g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
             g_bv = colsum(go2)
+        elif HEADS_WGRAD_FP32:
+            g_wv, g_bv = side.run(lambda: (torch.bmm(go_h.transpose(1, 2), t).reshape(C, C), colsum(go2)), go2, t)
         else:
             def _wv():
                 gs, gb = split_rows_colsum(go2, 0)  # [3Q,C] rows-split of go2 + the bias gradient of the value proj
@@ -581,6 +584,8 @@ class CrossView(torch.autograd.Function):
         # g_wk[h] = scale * qv_h^T @ gqt[h]   [8,dh,Q] x [8,Q,C]
         if small:
             g_wk = torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
+        elif HEADS_WGRAD_FP32:
+            g_wk = side.run(lambda: torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale, qv, gqt)
         else:
             g_wk = side.run(lambda: torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1),
                                               out_dtype=F32).reshape(C, C) * scale, qv, gqt)
@@ -650,6 +655,176 @@ class LayerNormRows(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
+# fused encoder layer over voxel rows
+# ----------------------------------------------------------------------------------------------
+
+def rowop_fwd(x, R, N, *, bias=None, relu=False, mask=None, mscale=1.0, rowscale=None, residual=None, ln=None,
+              in_heads=0, split_heads=0, want_y=True, want_split=True):
+    """``sgc_rowop_fwd``: fused epilogue of a GEMM output ``x`` ([R,N], or head-major [H,R,N/H] with in_heads=H).
+    Returns (y [R,N] fp32 | None, ysplit bf16x3 | None, (pre, mean, rstd) | None)."""
+    dev = x.device
+    y = torch.empty(R, N, device=dev, dtype=F32) if want_y else None
+    ys = torch.empty(R, 3 * N, device=dev, dtype=BF16) if want_split else None
+    saved = None
+    a = _lib.RowopFwdArgs()
+    a.x, a.bias, a.mask, a.rowscale, a.residual = ptr(x), ptr(bias), ptr(mask), ptr(rowscale), ptr(residual)
+    if ln is not None:
+        gamma, beta, eps = ln
+        saved = (torch.empty(R, N, device=dev, dtype=F32), torch.empty(R, device=dev, dtype=F32),
+                 torch.empty(R, device=dev, dtype=F32))
+        a.gamma, a.beta, a.eps = ptr(gamma), ptr(beta), eps
+        a.pre, a.mean, a.rstd = ptr(saved[0]), ptr(saved[1]), ptr(saved[2])
+    a.y, a.ysplit = ptr(y), ptr(ys)
+    a.mscale, a.R, a.N, a.relu, a.in_heads, a.split_heads = mscale, R, N, int(relu), in_heads, split_heads
+    call('sgc_rowop_fwd', ctypes.byref(a), stream())
+    return y, ys, saved
+
+
+def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gscale=1.0, rowscale=None,
+              in_heads=0, split_heads=0, want_gpre=False, want_gx=True, want_split=True):
+    """``sgc_rowop_bwd``.  ``ln`` = (pre, mean, rstd, gamma).  Returns (gx, gxsplit, gpre, partial)."""
+    dev = g.device
+    gx = torch.empty(R, N, device=dev, dtype=F32) if want_gx else None
+    gs = torch.empty(R, 3 * N, device=dev, dtype=BF16) if want_split else None
+    gpre = torch.empty(R, N, device=dev, dtype=F32) if want_gpre else None
+    partial = None
+    a = _lib.RowopBwdArgs()
+    a.g, a.g2, a.mask, a.gate, a.rowscale = ptr(g), ptr(g2), ptr(mask), ptr(gate), ptr(rowscale)
+    if ln is not None:
+        pre, mean, rstd, gamma = ln
+        partial = torch.empty(_lib.load().sgc_layernorm_bwd_scratch_floats(R, N), device=dev, dtype=F32)
+        a.pre, a.mean, a.rstd, a.gamma, a.partial = ptr(pre), ptr(mean), ptr(rstd), ptr(gamma), ptr(partial)
+    a.gpre, a.gx, a.gxsplit = ptr(gpre), ptr(gx), ptr(gs)
+    a.mscale, a.gscale, a.R, a.N, a.in_heads, a.split_heads = mscale, gscale, R, N, in_heads, split_heads
+    call('sgc_rowop_bwd', ctypes.byref(a), stream())
+    return gx, gs, gpre, partial
+
+
+def _ln_params(partial, R, N):
+    gg, gb = torch.empty(N, device=partial.device, dtype=F32), torch.empty(N, device=partial.device, dtype=F32)
+    call('sgc_layernorm_bwd_params', ptr(partial), R, N, ptr(gg), ptr(gb), stream())
+    return gg, gb
+
+
+class EncoderLayerRows(torch.autograd.Function):
+    """One VoxFormerLayer over the selected voxel rows (encoder.py:262-340 with operation_order cross_attn, norm, ffn,
+    norm): masked mean over views -> output_proj -> 8-head attention pooling over views (DCA:815-837) -> LayerNorm ->
+    FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the tensor-core GEMMs (bf16x3 operands, fp32
+    accumulate) alternate with fused row kernels (``sgc_rowop_fwd/bwd``) that carry bias, ReLU, dropout mask, row
+    mask, residual, LayerNorm and the bf16x3 operand image of the next GEMM.  The backward is written out by hand;
+    weight / bias gradients are produced on ``wstream`` (see ``OnStream``).
+
+    ``masks`` = (mask_attn, mask_ffn1, mask_ffn2) uint8 keep-masks or None (eval / p = 0), ``drops`` the matching p."""
+
+    @staticmethod
+    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2,
+                lw, wstream, eps1, eps2, masks, drops):
+        Q, V = pl.Q, pl.V
+        C = slots.shape[1]
+        H = NUM_HEADS
+        dh = C // H
+        Fh = w1.shape[0]
+        dev = slots.device
+        bq, bv = in_b[:C], in_b[2 * C:]
+        m0, m1, m2 = masks if masks is not None else (None, None, None)
+        s0, s1, s2 = (1.0 / (1.0 - p) if m is not None else 1.0 for m, p in zip((m0, m1, m2), drops))
+        mean = torch.empty(Q, C, device=dev, dtype=F32)
+        mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16)
+        call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
+        g_raw = torch.mm(mean_s, lw.w_out.t(), out_dtype=F32)
+        g, g_s, _ = rowop_fwd(g_raw, Q, C, bias=b_out)
+        qv_raw = torch.mm(g_s, lw.wq.t(), out_dtype=F32)
+        qv, qv_hs, _ = rowop_fwd(qv_raw, Q, C, bias=bq, split_heads=H)
+        qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)       # [H,Q,C]
+        t = torch.empty(H, Q, C, device=dev, dtype=F32)
+        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16)
+        alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
+        call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
+             stream())
+        o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)  # [H,Q,dh]
+        o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H)
+        out_raw = torch.mm(o2_s, lw.wo.t(), out_dtype=F32)
+        has = (pl.count > 0).to(F32)
+        x1, x1_s, ln1 = rowop_fwd(out_raw, Q, C, bias=bo, mask=m0, mscale=s0, rowscale=has, ln=(g1, be1, eps1))
+        h_raw = torch.mm(x1_s, lw.w1.t(), out_dtype=F32)                                           # [Q,F]
+        hdn, hdn_s, _ = rowop_fwd(h_raw, Q, Fh, bias=b1, relu=True, mask=m1, mscale=s1)
+        f_raw = torch.mm(hdn_s, lw.w2.t(), out_dtype=F32)
+        y, _, ln2 = rowop_fwd(f_raw, Q, C, bias=b2, mask=m2, mscale=s2, residual=x1, ln=(g2, be2, eps2), want_split=False)
+        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, *ln1, *ln2, g1, g2)
+        ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
+        ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2) = \
+            ctx.saved_tensors
+        pl, lw = ctx.pl, ctx.lw
+        m0, m1, m2 = ctx.masks
+        s0, s1, s2 = ctx.scales
+        Q, V = pl.Q, pl.V
+        C = slots.shape[1]
+        H = NUM_HEADS
+        dh = C // H
+        Fh = hdn.shape[1]
+        dev = slots.device
+        scale = 1.0 / math.sqrt(dh)
+        side = _Side(dev, ctx.wstream)
+        gy = gy.contiguous()
+        # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
+        gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True)
+        g_g2, g_be2 = side.run(lambda: _ln_params(part2, Q, C), part2)
+        g_w2, g_b2 = side.run(lambda: linear_grads(gf, hdn), gf, hdn)
+        ghdn = torch.mm(gf_s, lw.w2_t.t(), out_dtype=F32)                                           # [Q,F]
+        # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
+        gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1)
+        g_w1, g_b1 = side.run(lambda: linear_grads(gh, x1), gh, x1)
+        gx1_raw = torch.mm(gh_s, lw.w1_t.t(), out_dtype=F32)                                        # [Q,C]
+        gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
+                                           rowscale=has)
+        g_g1, g_be1 = side.run(lambda: _ln_params(part1, Q, C), part1)
+        g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
+        go2 = torch.mm(gout_s, lw.wo_t.t(), out_dtype=F32)                                          # [Q,C]
+        _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
+        gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)        # [H,Q,C]
+
+        def _wv():
+            if HEADS_WGRAD_FP32:
+                return torch.bmm(go2.view(Q, H, dh).permute(1, 2, 0), t).reshape(C, C), colsum(go2)
+            gs, gb = split_rows_colsum(go2, 0)
+            a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
+            return torch.bmm(a, split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C), gb
+        g_wv, g_bv = side.run(_wv, go2, t)
+        gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
+        gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
+        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16)
+        call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
+             ptr(gqt), ptr(gqt_s), stream())
+        gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)  # [H,Q,dh]
+
+        def _wk():
+            if HEADS_WGRAD_FP32:
+                return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
+            return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
+        g_wk = side.run(_wk, qv, gqt)
+        gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H)
+        g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
+        gg = torch.mm(gqv_s, lw.wq_t.t(), out_dtype=F32)
+        gg_s = split_cols(gg, 0)
+        g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
+        gmean = torch.mm(gg_s, lw.w_out_t.t(), out_dtype=F32)
+        gslots = torch.empty_like(slots)
+        call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
+             ptr(gmean), ptr(gslots), stream())
+        side.join()
+        g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
+                                           torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
+        side.join()
+        return (gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2,
+                None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
 # sparse volume construction
 # ----------------------------------------------------------------------------------------------
 
@@ -692,7 +867,9 @@ def topk_select(occ: torch.Tensor, k: int):
 
 
 class ScatterAddRows(torch.autograd.Function):
-    """vol[sel] += y in place (DenseHead.py:80-81 + AdaptiveSparseHead.py:77)."""
+    """vol[sel] += y in place (DenseHead.py:80-81 + AdaptiveSparseHead.py:77).  ``vol`` is any contiguous [..., C]
+    tensor whose leading dims flatten to the voxel index; pass the tensor itself, not a view of it (in-place on a view
+    makes autograd copy the whole volume several times in the backward)."""
 
     @staticmethod
     def forward(ctx, vol, y, sel):

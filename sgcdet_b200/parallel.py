@@ -278,7 +278,7 @@ def forward_view_sharded(head, shards, group=None, forced_selection=None, use_di
             X, Y, Z = (int(v) for v in dh_.n_voxels)
             vol = x.view(X, Y, Z, head.embed_dims)
         else:
-            vol = SF.ScatterAddRows.apply(up.view(-1, head.embed_dims), x, sel).view_as(up)
+            vol = SF.ScatterAddRows.apply(up, x, sel)
     volume_out = vol.permute(3, 0, 1, 2).unsqueeze(0)
     occ_preds = torch.cat(occ_list[::-1], dim=1)
     valid = head.get_valid(masks[nl - 1]).unsqueeze(0).unsqueeze(0).detach()

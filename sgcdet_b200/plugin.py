@@ -292,6 +292,7 @@ class PerceptionTransformer_DFA3D(nn.Module):
 # ---------------------------------------------------------------------------------------------
 
 _STREAMS = {}
+_CHAIN_STREAMS = {}
 
 
 def _side_streams(device, n: int, main=None):
@@ -301,6 +302,12 @@ def _side_streams(device, n: int, main=None):
     while len(pool) < n:
         pool.append(torch.cuda.Stream(device=torch.device(device)))
     return pool[:n]
+
+
+def _dropout_masks(rows: int, widths, drops, device):
+    """uint8 keep-masks [rows, width] for every dropout with p > 0 (None otherwise)."""
+    return tuple(torch.empty(rows, w, device=device, dtype=torch.uint8).bernoulli_(1.0 - p) if p > 0 else None
+                 for w, p in zip(widths, drops))
 
 
 def projection_on_device(img_meta: dict, device) -> torch.Tensor:
@@ -344,7 +351,7 @@ class DenseHead(nn.Module):
     def num_voxels(self) -> int:
         return int(self.n_voxels.prod())
 
-    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw):
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
         map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
@@ -375,8 +382,14 @@ class DenseHead(nn.Module):
                 params = SF.OnStream.apply(*params)
         # vbias is a leaf parameter: the view gives it a backward node that belongs to this stream like the
         # producers of vg / dist / gbias (Lift issues its backward kernel on this stream, see functional.Lift)
+        masks = None
+        if self.training and n_rows:
+            # keep-masks of the layer's dropouts (nn.Dropout semantics: x * mask / (1-p)), drawn here -- off the
+            # critical path -- and applied inside the fused row kernels
+            masks = _dropout_masks(n_rows, (self.embed_dims, ffn.layers[0][0].out_features, self.embed_dims),
+                                   (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p), feat.device)
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
-                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream)
+                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream, masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None):
@@ -398,11 +411,24 @@ class DenseHead(nn.Module):
         slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w,
                                     prepared.get('stream'))
         pp, ws = prepared['params'], prepared['wstream']
-        x = SF.CrossView.apply(slots, pl, *pp[:6], lw, ws)
-        x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
-        x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, ws)
-        x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=ws)
-        x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, ws)
+        ffn = layer.ffns[0]
+        C = self.embed_dims
+        fused = (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and C in (128, 256) and ffn.add_identity
+                 and ffn.layers[0][0].out_features in (128, 256, 512))
+        if fused:
+            drops = (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p)
+            masks = prepared.get('masks') if self.training else None
+            if self.training and any(p > 0 for p in drops):
+                widths = (C, ffn.layers[0][0].out_features, C)
+                if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
+                    masks = _dropout_masks(pl.Q, widths, drops, feat.device)
+            x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops)
+        else:
+            x = SF.CrossView.apply(slots, pl, *pp[:6], lw, ws)
+            x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
+            x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, ws)
+            x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=ws)
+            x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, ws)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
         return x
@@ -455,7 +481,33 @@ class AdaptiveSparseHead(nn.Module):
         """-> (volume [1,C,X,Y,Z], valid [1,1,X,Y,Z] int64, occ_preds [1, sum N]).
 
         ``forced_selection[i]`` (int32 ascending voxel ids) overrides the top-k of level i (parity tests).
-        The returned volume is a channels_last_3d view of the internal [X,Y,Z,C] buffer."""
+        The returned volume is a channels_last_3d view of the internal [X,Y,Z,C] buffer.
+
+        The per-voxel chain (hundreds of small dependent kernels) is issued on a HIGH-priority stream forked from the
+        caller's stream, the large bandwidth-bound kernels (feature projection, lift backward, weight gradients) on
+        default-priority side streams: when a big kernel occupies every SM, the block scheduler hands freed slots to the
+        chain first, so the chain keeps its latency instead of queueing behind the big grid.  Autograd replays every
+        node on its forward stream, so the same holds for the backward."""
+        dev = mlvl_feats[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('sgcdet_b200 has no CPU implementation: inputs must be CUDA tensors')
+        if os.environ.get('SGC_CHAIN_PRIORITY', '1') == '0':
+            return self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+        caller = torch.cuda.current_stream(dev)
+        key = (torch.device(dev), caller.cuda_stream)
+        chain = _CHAIN_STREAMS.get(key)
+        if chain is None:
+            chain = _CHAIN_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
+        chain.wait_stream(caller)
+        with torch.cuda.stream(chain):
+            out = self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+        caller.wait_stream(chain)
+        for t in out[:3]:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(caller)
+        return out
+
+    def _forward_impl(self, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates):
         bs = mlvl_feats[0].shape[0]
         assert bs == 1
         nl = len(self.base_heads)
@@ -473,7 +525,16 @@ class AdaptiveSparseHead(nn.Module):
         for i in range(nl):
             streams[i].wait_stream(main)
             with torch.cuda.stream(streams[i]):
-                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i]))
+                if i == 0:
+                    n_rows = self.base_heads[i].num_voxels
+                elif forced_selection is not None and forced_selection[i] is not None:
+                    n_rows = int(forced_selection[i].numel())
+                elif (i - 1) < len(self.topk_list):
+                    n_rows = min(self.topk_list[i - 1], self.base_heads[i].num_voxels)
+                else:
+                    n_rows = self.base_heads[i].num_voxels
+                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i],
+                                                           n_rows))
         for i in range(nl):
             hw = hws[i]
             fi = nl - 1 - i
@@ -483,6 +544,9 @@ class AdaptiveSparseHead(nn.Module):
             for t in (pre['vg'], pre['dist'], pre['vbias'], pre['gbias']):
                 t.record_stream(main)
             pre['lw'].record_stream(main)
+            for t in (pre.get('masks') or ()):
+                if t is not None:
+                    t.record_stream(main)
             if i == 0:
                 r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, None, proj, return_intermediates, pre)
                 y, it = r if return_intermediates else (r, None)
@@ -507,7 +571,7 @@ class AdaptiveSparseHead(nn.Module):
                 if sel is None:
                     vol = up + y.view_as(up)
                 else:
-                    vol = SF.ScatterAddRows.apply(up.view(-1, self.embed_dims), y, sel).view_as(up)
+                    vol = SF.ScatterAddRows.apply(up, y, sel)  # in place on ``up`` itself (not on a view: no CopySlices)
             if it is not None:
                 it['sel'] = None if i == 0 else sel
             inters.append(it)

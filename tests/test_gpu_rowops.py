@@ -82,3 +82,116 @@ def test_detached_weight_stream_gradients_match(cuda_lib):
         res.append((x.grad.clone(), w.grad.clone(), b.grad.clone()))
     for a, b_ in zip(*res):
         assert torch.equal(a, b_)
+
+
+def _split_ref(x, heads=0):
+    """bf16x3 pattern-0 image computed with torch ops."""
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    if heads:
+        R, N = x.shape
+        dh = N // heads
+        h3, l3 = hi.view(R, heads, dh), lo.view(R, heads, dh)
+        return torch.cat([h3, l3, h3], dim=2).reshape(R * heads, 3 * dh)
+    return torch.cat([hi, lo, hi], dim=1)
+
+
+@pytest.mark.parametrize('R,N', [(5, 128), (400, 256), (801, 512), (6400, 256)])
+def test_rowop_fwd_bwd_match_torch(cuda_lib, R, N):
+    g = torch.Generator().manual_seed(R * 7 + N)
+    dev = 'cuda'
+    x = torch.randn(R, N, generator=g).to(dev)
+    bias, gamma, beta = (torch.randn(N, generator=g).to(dev) for _ in range(3))
+    mask = (torch.rand(R, N, generator=g) > 0.3).to(torch.uint8).to(dev)
+    rowscale = (torch.rand(R, generator=g) > 0.2).float().to(dev)
+    res = torch.randn(R, N, generator=g).to(dev)
+    gy = torch.randn(R, N, generator=g).to(dev)
+    ms = 1.0 / 0.7
+
+    xa = x.clone().double().requires_grad_(True)
+    ra = res.clone().double().requires_grad_(True)
+    ga, ba = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    pre = torch.relu(xa + bias.double()) * mask.double() * ms * rowscale.double()[:, None] + ra
+    ya = torch.nn.functional.layer_norm(pre, (N,), ga, ba, 1e-5)
+    ya.backward(gy.double())
+
+    y, ys, saved = SF.rowop_fwd(x, R, N, bias=bias, relu=True, mask=mask, mscale=ms, rowscale=rowscale, residual=res,
+                                ln=(gamma, beta, 1e-5))
+    torch.cuda.synchronize()
+    assert (y.double() - ya).abs().max().item() < 1e-4
+    assert torch.equal(ys.view(torch.int16), _split_ref(y).view(torch.int16))
+    assert (saved[0].double() - pre).abs().max().item() < 1e-5
+    # backward through LN, then mask / gate / rowscale (gate = relu output, as the FFN uses it)
+    hdn = torch.relu(x + bias)
+    gx, gs, gpre, partial = SF.rowop_bwd(gy, R, N, ln=(saved[0], saved[1], saved[2], gamma), mask=mask, mscale=ms,
+                                         gate=hdn, gscale=1.0, rowscale=rowscale, want_gpre=True)
+    gg, gb = SF._ln_params(partial, R, N)
+    torch.cuda.synchronize()
+    scale = max(xa.grad.abs().max().item(), 1e-6)
+    assert (gpre.double() - ra.grad).abs().max().item() <= 1e-4 + 1e-3 * scale
+    assert (gx.double() - xa.grad).abs().max().item() <= 1e-4 + 1e-3 * scale
+    assert torch.equal(gs.view(torch.int16), _split_ref(gx).view(torch.int16))
+    for got, ref in ((gg, ga.grad), (gb, ba.grad)):
+        sc = max(ref.abs().max().item(), 1e-6)
+        assert (got.double() - ref).abs().max().item() <= 1e-4 + 1e-3 * sc
+
+
+def test_rowop_head_layouts(cuda_lib):
+    g = torch.Generator().manual_seed(3)
+    R, N, H = 333, 256, 8
+    dh = N // H
+    xh = torch.randn(H, R, dh, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    y, ys, _ = SF.rowop_fwd(xh, R, N, bias=bias, in_heads=H, split_heads=H)
+    ref = xh.permute(1, 0, 2).reshape(R, N) + bias
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    assert torch.equal(ys.view(R * H, 3 * dh).view(torch.int16), _split_ref(ref, H).view(torch.int16))
+    gx, gs, _, _ = SF.rowop_bwd(xh, R, N, in_heads=H)
+    assert torch.equal(gx, xh.permute(1, 0, 2).reshape(R, N))
+    assert torch.equal(gs.view(torch.int16), _split_ref(gx).view(torch.int16))
+
+
+@pytest.mark.parametrize('train', [False, True])
+def test_fused_layer_matches_unfused_path(cuda_lib, train, monkeypatch):
+    """EncoderLayerRows (fused row kernels) against the op-by-op path on the tiny config: same outputs and gradients.
+    In train mode both paths get the same dropout keep-masks."""
+    from sgcdet_b200 import plugin, synthetic as syn
+    cfg = syn.CONFIGS['tiny']
+    sc = syn.make_scene(cfg, 6, shift_origin=True).to('cuda')
+    res = []
+    forced = None  # the second run is teacher-forced with the first run's selection (top-k ties flip at round-off)
+    for fused in ('1', '0'):
+        monkeypatch.setenv('SGC_FUSED_LAYER', fused)
+        head = plugin.build_voxel_head(cfg)
+        head.load_state_dict(syn.make_state_dict(cfg))
+        head = head.cuda().train(train)
+        if train:
+            for m in head.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0  # masks are compared through the eval-equivalent path: dropout off in both
+        feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats[:3]]
+        dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists[:3]]
+        vol, valid, occ, inters = head(feats, sc.img_meta, dists, forced_selection=forced, return_intermediates=True)
+        if forced is None:
+            forced = [it['sel'] for it in inters]
+        loss = (vol * sc.grad_volume).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((vol.detach(), occ.detach(), [f.grad for f in feats], [d.grad for d in dists],
+                    {n: p.grad for n, p in head.named_parameters() if p.grad is not None}))
+    a, b = res
+    assert (a[0] - b[0]).abs().max().item() <= 1e-4 + 1e-3 * b[0].abs().max().item()
+    assert (a[1] - b[1]).abs().max().item() <= 1e-5
+
+    def close(x, y, name):
+        # ReLU gates at round-off flip between the two paths, so single entries may differ: norm-wise check plus a
+        # loose bound on the worst entry
+        fro = ((x - y).norm() / y.norm().clamp_min(1e-12)).item()
+        worst = ((x - y).abs().max() / y.abs().max().clamp_min(1e-12)).item()
+        assert fro < 1e-2 and worst < 5e-2, (name, fro, worst)
+    for i, (ga, gb) in enumerate(zip(a[2] + a[3], b[2] + b[3])):
+        close(ga, gb, f'input{i}')
+    assert a[4].keys() == b[4].keys()
+    for n in a[4]:
+        close(a[4][n], b[4][n], n)
