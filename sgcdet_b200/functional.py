@@ -90,7 +90,7 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 import os as _os
 HEADS_WGRAD_FP32 = _os.environ.get('SGC_HEADS_WGRAD_FP32', '0') != '0'  # per-head K/V weight grads as plain fp32 bmm
-SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '1000'))  # voxel-count GEMMs with at most this many rows stay plain fp32
+SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs with at most this many rows stay plain fp32
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -709,10 +709,14 @@ def _ln_params(partial, R, N):
 class EncoderLayerRows(torch.autograd.Function):
     """One VoxFormerLayer over the selected voxel rows (encoder.py:262-340 with operation_order cross_attn, norm, ffn,
     norm): masked mean over views -> output_proj -> 8-head attention pooling over views (DCA:815-837) -> LayerNorm ->
-    FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the tensor-core GEMMs (bf16x3 operands, fp32
-    accumulate) alternate with fused row kernels (``sgc_rowop_fwd/bwd``) that carry bias, ReLU, dropout mask, row
-    mask, residual, LayerNorm and the bf16x3 operand image of the next GEMM.  The backward is written out by hand;
-    weight / bias gradients are produced on ``wstream`` (see ``OnStream``).
+    FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the dense GEMMs alternate with fused row kernels
+    (``sgc_rowop_fwd/bwd``) that carry bias, ReLU, dropout mask, row mask, residual, LayerNorm and the bf16x3 operand
+    image of the next GEMM.  The backward is written out by hand; weight / bias gradients are produced on ``wstream``
+    (see ``OnStream``).
+
+    GEMMs: tensor cores with bf16x3 operands and fp32 accumulation; levels with at most ``SMALL_ROWS`` voxels use plain
+    fp32 GEMMs instead (launch-bound either way, and the library's fp32 kernels need no thread-block cluster, so they
+    start at once next to the persistent projection kernels of the finer levels).
 
     ``masks`` = (mask_attn, mask_ffn1, mask_ffn2) uint8 keep-masks or None (eval / p = 0), ``drops`` the matching p."""
 
@@ -725,40 +729,53 @@ class EncoderLayerRows(torch.autograd.Function):
         dh = C // H
         Fh = w1.shape[0]
         dev = slots.device
+        small = Q <= SMALL_ROWS
+        sp = not small
+        scale = 1.0 / math.sqrt(dh)
         bq, bv = in_b[:C], in_b[2 * C:]
+        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         m0, m1, m2 = masks if masks is not None else (None, None, None)
         s0, s1, s2 = (1.0 / (1.0 - p) if m is not None else 1.0 for m, p in zip((m0, m1, m2), drops))
+
+        def lin(a, a_s, w, ws):  # a @ w^T
+            return a @ w.t() if small else torch.mm(a_s, ws.t(), out_dtype=F32)
+
         mean = torch.empty(Q, C, device=dev, dtype=F32)
-        mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16)
+        mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
         call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
-        g_raw = torch.mm(mean_s, lw.w_out.t(), out_dtype=F32)
-        g, g_s, _ = rowop_fwd(g_raw, Q, C, bias=b_out)
-        qv_raw = torch.mm(g_s, lw.wq.t(), out_dtype=F32)
-        qv, qv_hs, _ = rowop_fwd(qv_raw, Q, C, bias=bq, split_heads=H)
-        qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)       # [H,Q,C]
+        g, g_s, _ = rowop_fwd(lin(mean, mean_s, w_out, lw.w_out), Q, C, bias=b_out, want_split=sp)
+        qv, qv_hs, _ = rowop_fwd(lin(g, g_s, wq, lw.wq), Q, C, bias=bq, split_heads=H, want_split=sp)
+        if small:   # qt[h] = scale * qv_h @ Wk_h
+            qt = torch.empty(H, Q, C, device=dev, dtype=F32)
+            torch.baddbmm(qt, qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C), beta=0, alpha=scale, out=qt)
+        else:
+            qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)   # [H,Q,C]
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
-        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16)
+        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if sp else None
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
              stream())
-        o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)  # [H,Q,dh]
-        o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H)
-        out_raw = torch.mm(o2_s, lw.wo.t(), out_dtype=F32)
+        if small:   # o[h] = t[h] @ Wv_h^T   [H,Q,dh]
+            o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
+        else:
+            o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+        o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
         has = (pl.count > 0).to(F32)
-        x1, x1_s, ln1 = rowop_fwd(out_raw, Q, C, bias=bo, mask=m0, mscale=s0, rowscale=has, ln=(g1, be1, eps1))
-        h_raw = torch.mm(x1_s, lw.w1.t(), out_dtype=F32)                                           # [Q,F]
-        hdn, hdn_s, _ = rowop_fwd(h_raw, Q, Fh, bias=b1, relu=True, mask=m1, mscale=s1)
-        f_raw = torch.mm(hdn_s, lw.w2.t(), out_dtype=F32)
-        y, _, ln2 = rowop_fwd(f_raw, Q, C, bias=b2, mask=m2, mscale=s2, residual=x1, ln=(g2, be2, eps2), want_split=False)
-        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, *ln1, *ln2, g1, g2)
+        x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo), Q, C, bias=bo, mask=m0, mscale=s0, rowscale=has,
+                                  ln=(g1, be1, eps1), want_split=sp)
+        hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1), Q, Fh, bias=b1, relu=True, mask=m1, mscale=s1, want_split=sp)
+        y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2), Q, C, bias=b2, mask=m2, mscale=s2, residual=x1,
+                              ln=(g2, be2, eps2), want_split=False)
+        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, *ln1, *ln2, g1, g2,
+                              w_out, in_w, wo, w1, w2)
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
         ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        (slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2) = \
-            ctx.saved_tensors
+        (slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2,
+         w_out, in_w, wo, w1, w2) = ctx.saved_tensors
         pl, lw = ctx.pl, ctx.lw
         m0, m1, m2 = ctx.masks
         s0, s1, s2 = ctx.scales
@@ -769,27 +786,39 @@ class EncoderLayerRows(torch.autograd.Function):
         Fh = hdn.shape[1]
         dev = slots.device
         scale = 1.0 / math.sqrt(dh)
+        small = Q <= SMALL_ROWS
+        sp = not small
+        fp32_heads = small or HEADS_WGRAD_FP32
+        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         side = _Side(dev, ctx.wstream)
         gy = gy.contiguous()
+
+        def lin_t(a, a_s, w, ws_t):  # a @ w
+            return a @ w if small else torch.mm(a_s, ws_t.t(), out_dtype=F32)
+
         # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
-        gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True)
+        gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
+                                           want_split=sp)
         g_g2, g_be2 = side.run(lambda: _ln_params(part2, Q, C), part2)
         g_w2, g_b2 = side.run(lambda: linear_grads(gf, hdn), gf, hdn)
-        ghdn = torch.mm(gf_s, lw.w2_t.t(), out_dtype=F32)                                           # [Q,F]
+        ghdn = lin_t(gf, gf_s, w2, lw.w2_t)                                                         # [Q,F]
         # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
-        gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1)
+        gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
         g_w1, g_b1 = side.run(lambda: linear_grads(gh, x1), gh, x1)
-        gx1_raw = torch.mm(gh_s, lw.w1_t.t(), out_dtype=F32)                                        # [Q,C]
+        gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t)                                                      # [Q,C]
         gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
-                                           rowscale=has)
+                                           rowscale=has, want_split=sp)
         g_g1, g_be1 = side.run(lambda: _ln_params(part1, Q, C), part1)
         g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
-        go2 = torch.mm(gout_s, lw.wo_t.t(), out_dtype=F32)                                          # [Q,C]
-        _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
-        gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)        # [H,Q,C]
+        go2 = lin_t(gout, gout_s, wo, lw.wo_t)                                                      # [Q,C]
+        if small:   # gt[h] = go_h @ Wv_h
+            gt = torch.bmm(go2.view(Q, H, dh).transpose(0, 1), wv.view(H, dh, C))
+        else:
+            _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
+            gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)    # [H,Q,C]
 
         def _wv():
-            if HEADS_WGRAD_FP32:
+            if fp32_heads:
                 return torch.bmm(go2.view(Q, H, dh).permute(1, 2, 0), t).reshape(C, C), colsum(go2)
             gs, gb = split_rows_colsum(go2, 0)
             a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
@@ -797,22 +826,26 @@ class EncoderLayerRows(torch.autograd.Function):
         g_wv, g_bv = side.run(_wv, go2, t)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
-        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16)
+        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if sp else None
         call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
              ptr(gqt), ptr(gqt_s), stream())
-        gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)  # [H,Q,dh]
+        if small:   # gqv[h] = scale * gqt[h] @ Wk_h^T   [H,Q,dh]
+            gqv_h = torch.empty(H, Q, dh, device=dev, dtype=F32)
+            torch.baddbmm(gqv_h, gqt, wk.view(H, dh, C).transpose(1, 2), beta=0, alpha=scale, out=gqv_h)
+        else:
+            gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
 
         def _wk():
-            if HEADS_WGRAD_FP32:
+            if fp32_heads:
                 return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
             return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
         g_wk = side.run(_wk, qv, gqt)
-        gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H)
+        gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H, want_split=sp)
         g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
-        gg = torch.mm(gqv_s, lw.wq_t.t(), out_dtype=F32)
-        gg_s = split_cols(gg, 0)
+        gg = lin_t(gqv, gqv_s, wq, lw.wq_t)
+        gg_s = split_cols(gg, 0) if sp else None
         g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
-        gmean = torch.mm(gg_s, lw.w_out_t.t(), out_dtype=F32)
+        gmean = lin_t(gg, gg_s, w_out, lw.w_out_t)
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
