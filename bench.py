@@ -145,7 +145,23 @@ def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
         maps = f * V * S * (ldv + D)          # value + G + depth maps
         pairs = f * P * (C + 128) + P * 16    # slots + samp rows, pair id + ref point
         return maps + pairs if name == 'sgc_lift_fwd' else 2 * maps + pairs
+    if name in ('sgc_rowop_fwd', 'sgc_rowop_bwd'):
+        a = args[0]._obj   # ctypes.byref(struct)
+        rn = float(a.R) * a.N
+        if name == 'sgc_rowop_fwd':
+            n32 = sum(1 for p in (a.x, a.residual, a.y, a.pre) if p)
+            return rn * (4 * n32 + (1 if a.mask else 0) + (6 if a.ysplit else 0))
+        n32 = sum(1 for p in (a.g, a.g2, a.pre, a.gate, a.gpre, a.gx) if p)
+        return rn * (4 * n32 + (1 if a.mask else 0) + (6 if a.gxsplit else 0))
+    if name == 'sgc_layernorm_bwd':
+        return 3 * f * args[5] * args[6]
     if name.startswith('sgc_crossview'):
+        split = name.endswith('_split')
+        if split:
+            name = name[:-len('_split')]
+            extra = 6.0 * args[4 if name == 'sgc_crossview_mean_fwd' else 5] * \
+                (args[3] if name == 'sgc_crossview_mean_fwd' else 8 * args[4])
+            return extra + kernel_algorithmic_bytes(name, args, n_pairs_by_q)
         V, Q, C = (args[2], args[3], args[4]) if name == 'sgc_crossview_mean_fwd' else \
                   (args[3], args[4], args[5]) if name == 'sgc_crossview_attn_fwd' else \
                   (args[3], args[4], args[5]) if name == 'sgc_crossview_attn_bwd_qt' else (args[4], args[5], args[6])
@@ -368,19 +384,33 @@ def run_ours(args):
         rec2 = CallRecorder()
         rec2.timed = True
         n_inst = 3
-        with rec2:
-            for _ in range(n_inst):
-                zero_grads()
-                vol, valid, occ, its = head(feats, sc.img_meta, dists, return_intermediates=True)
-                ((vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']).backward()
-        torch.cuda.synchronize()
+        # every kernel timed ALONE: the side streams / priorities of the product path are switched off for this pass
+        serial = {k: '0' for k in ('SGC_SIDE_LIFT_BWD', 'SGC_WSTREAM', 'SGC_SIDE_PREPARE', 'SGC_CHAIN_PRIORITY',
+                                   'SGC_SIDE_GRADS')}
+        saved_env = {k: os.environ.get(k) for k in serial}
+        os.environ.update(serial)
+        try:
+            with rec2:
+                for _ in range(n_inst):
+                    zero_grads()
+                    vol, valid, occ, its = head(feats, sc.img_meta, dists, return_intermediates=True)
+                    ((vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']).backward()
+            torch.cuda.synchronize()
+        finally:
+            for k, v in saved_env.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
         pairs_by_q = {it['pairs'].Q: (int(it['pairs'].view_offsets[-1]), V) for it in its}
         agg = {}
         for name, a, e0, e1 in rec2.events:
             key = name
             if name.startswith(('sgc_lift', 'sgc_crossview')) or name == 'sgc_project_compact':
                 q = {'sgc_lift_fwd': 15, 'sgc_lift_bwd': 16, 'sgc_crossview_mean_fwd': 3, 'sgc_crossview_attn_fwd': 4,
-                     'sgc_crossview_attn_bwd_qt': 4, 'sgc_crossview_attn_bwd_slots': 5, 'sgc_project_compact': 4}[name]
+                     'sgc_crossview_attn_bwd_qt': 4, 'sgc_crossview_attn_bwd_slots': 5, 'sgc_project_compact': 4,
+                     'sgc_crossview_mean_fwd_split': 3, 'sgc_crossview_attn_fwd_split': 4,
+                     'sgc_crossview_attn_bwd_qt_split': 4}[name]
                 key = f'{name}[Q={a[q]}]'
             elif name.startswith('sgc_upsample'):
                 key = f'{name}[{a[1]}x{a[2]}x{a[3]}]'
@@ -388,6 +418,8 @@ def run_ours(args):
                 key = f'{name}[V={a[3]},C={a[4]},S={a[5]},N={a[7]}]'
             elif name in ('sgc_split_bf16x3', 'sgc_colsum'):
                 key = f'{name}[{a[1]}x{a[2]}]'
+            elif name in ('sgc_rowop_fwd', 'sgc_rowop_bwd'):
+                key = f'{name}[{a[0]._obj.R}x{a[0]._obj.N}]'
             d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=kernel_algorithmic_bytes(name, a, pairs_by_q)))
             d['ms'] += e0.elapsed_time(e1)
             d['n'] += 1

@@ -58,12 +58,14 @@ __device__ __forceinline__ float depth_score(const Tap& t, const float* __restri
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// Vector reduction into global memory (sm_90+: RED.E.ADD.F32x4).
+// Vector reduction into global memory (sm_90+: RED.E.ADD.F32x4).  No "memory" clobber on purpose: the gradient buffers
+// these accumulate into are never read by the issuing kernel, and the clobber would pin every later gather load behind
+// the reduction (the kernels that use them are latency-bound gathers).
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 __device__ __forceinline__ void red_add1(float* p, float a) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

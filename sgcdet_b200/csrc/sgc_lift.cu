@@ -198,20 +198,34 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     for (int p = 0; p < 4; ++p) {
       const int src = (lane & ~3) | p;
       const float a = __shfl_sync(SGC_FULL_MASK, sp.w, src);
+      int pk[4];
+      float wk[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int pk = __shfl_sync(SGC_FULL_MASK, px[k], src);
-        const float wk = __shfl_sync(SGC_FULL_MASK, cw[k], src);
-        float part = 0.f;
-        if (pk >= 0) {  // the corner exists: its value (plus bias) defines d out / d weight even when wk == 0
-          float x[CPL];
-          load_row<CPL>(x, vbase + (vS + pk) * ldv);
+        pk[k] = __shfl_sync(SGC_FULL_MASK, px[k], src);
+        wk[k] = __shfl_sync(SGC_FULL_MASK, cw[k], src);
+      }
+      // the four corner rows of this point are fetched together (4 independent gathers in flight per lane)
+      float x[4][CPL];
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) part += x[j] * g[j];
+      for (int k = 0; k < 4; ++k) {
+        if (pk[k] >= 0) {
+          load_row<CPL>(x[k], vbase + (vS + pk[k]) * ldv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) x[k][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float part = 0.f;
+        if (pk[k] >= 0) {  // the corner exists: its value (plus bias) defines d out / d weight even when wk == 0
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) part += x[k][j] * g[j];
           part += gb;
-          const float wa = wk * a;
+          const float wa = wk[k] * a;
           if (wa != 0.f) {
-            float* dst = gvbase + (vS + pk) * ldv;
+            float* dst = gvbase + (vS + pk[k]) * ldv;
 #pragma unroll
             for (int j = 0; j < CPL; j += 4) red_add4(dst + j, wa * g[j], wa * g[j + 1], wa * g[j + 2], wa * g[j + 3]);
             wsum += wa;
@@ -289,21 +303,22 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
 }
 
 // grad_vbias[c] += sum_rows partials[row][c] (c < C);  grad_gbias[c-C] += ... (c >= C).
-// block = 32 channels x 8 row-groups; fixed summation order -> deterministic.
-__global__ void __launch_bounds__(256) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
-                                                         float* __restrict__ grad_vbias,
-                                                         float* __restrict__ grad_gbias) {
-  __shared__ float s[8][32];
+// block = 32 channels x 32 row-lanes; fixed summation order -> deterministic.
+__global__ void __launch_bounds__(1024) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
+                                                          float* __restrict__ grad_vbias,
+                                                          float* __restrict__ grad_gbias) {
+  __shared__ float s[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   float a = 0.f;
-  for (int r = ry; r < rows; r += 8) a += __ldg(partials + (size_t)r * (C + 128) + c);
+#pragma unroll 4
+  for (int r = ry; r < rows; r += 32) a += __ldg(partials + (size_t)r * (C + 128) + c);
   s[ry][cx] = a;
   __syncthreads();
   if (ry == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += s[k][cx];
+    for (int k = 0; k < 32; ++k) t += s[k][cx];
     if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
   }
 }
@@ -358,7 +373,7 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
     sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   }
   SGC_CUDA_CHECK_LAST();
-  sgc::bias_reduce_kernel<<<(C + 128) / 32, 256, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
+  sgc::bias_reduce_kernel<<<(C + 128) / 32, 1024, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
