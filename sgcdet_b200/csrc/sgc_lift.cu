@@ -29,11 +29,19 @@ namespace sgc {
 template <int CPL>
 struct Vec { float v[CPL]; };
 
+// Channel ownership inside a row of C = 32*CPL channels (head m = lane >> 2 owns channels [m*4*CPL, (m+1)*4*CPL)):
+// register chunk j/4 of a lane is the float4 at  lane_base + (j/4)*16,  lane_base = m*4*CPL + (lane & 3)*4,
+// so the four lanes of a head cover 64 CONTIGUOUS bytes per instruction (whole 32-byte sectors for the gathers and,
+// above all, for the RED.v4 reductions of the backward: half the L2 atomic sector operations of a
+// "CPL contiguous channels per lane" layout).
+template <int CPL>
+__device__ __forceinline__ int lane_base(int lane) { return (lane >> 2) * (4 * CPL) + (lane & 3) * 4; }
+
 template <int CPL>
 __device__ __forceinline__ void load_row(float (&dst)[CPL], const float* p) {
 #pragma unroll
   for (int j = 0; j < CPL; j += 4) {
-    const float4 t = ldg4(p + j);
+    const float4 t = ldg4(p + j * 4);
     dst[j] = t.x; dst[j + 1] = t.y; dst[j + 2] = t.z; dst[j + 3] = t.w;
   }
 }
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(256) lift_fwd_kernel(
 #pragma unroll
     for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
     float wsum = 0.f;  // sum over the head's taps of attn * cw   (for the value_proj bias)
-    const float* vbase = value + lane * CPL;
+    const float* vbase = value + lane_base<CPL>(lane);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int src = (lane & ~3) | p;
@@ -128,14 +136,14 @@ __global__ void __launch_bounds__(256) lift_fwd_kernel(
       for (int j = 0; j < CPL; ++j) acc[j] += val[j] * a;
       wsum += ws * a;
     }
-    float* out = slots + (size_t)pair * C + lane * CPL;
+    float* out = slots + (size_t)pair * C + lane_base<CPL>(lane);
 #pragma unroll
     for (int j = 0; j < CPL; j += 4) {
-      const float4 b = ldg4(vbias + lane * CPL + j);
+      const float4 b = ldg4(vbias + lane_base<CPL>(lane) + j * 4);
       float4 o;
       o.x = acc[j] + b.x * wsum; o.y = acc[j + 1] + b.y * wsum;
       o.z = acc[j + 2] + b.z * wsum; o.w = acc[j + 3] + b.w * wsum;
-      *reinterpret_cast<float4*>(out + j) = o;
+      *reinterpret_cast<float4*>(out + j * 4) = o;
     }
   }
 }
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
   for (int j = 0; j < CPL; ++j) gvb[j] = 0.f;
   float4 ggb = make_float4(0.f, 0.f, 0.f, 0.f);  // per-warp partial of grad of the G bias
   float vb[CPL];
-  load_row<CPL>(vb, vbias + lane * CPL);
+  load_row<CPL>(vb, vbias + lane_base<CPL>(lane));
 
   for (int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < n_pairs;
        pair += gridDim.x * warps_per_block) {
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
       cw[k] = t.bw[k] * ds[k];
     }
     float g[CPL];
-    load_row<CPL>(g, grad_slots + (size_t)pair * C + lane * CPL);
+    load_row<CPL>(g, grad_slots + (size_t)pair * C + lane_base<CPL>(lane));
     float gb = 0.f;  // sum_j vbias[j] * g[j] over this lane's channels
 #pragma unroll
     for (int j = 0; j < CPL; ++j) gb += vb[j] * g[j];
@@ -192,8 +200,8 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     // d out / d (tap weight) for this lane's own point, gathered while the head walks its 4 points
     float dot[4] = {0.f, 0.f, 0.f, 0.f};
     float wsum = 0.f;
-    const float* vbase = value + lane * CPL;
-    float* gvbase = grad_value + lane * CPL;
+    const float* vbase = value + lane_base<CPL>(lane);
+    float* gvbase = grad_value + lane_base<CPL>(lane);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int src = (lane & ~3) | p;
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
           if (wa != 0.f) {
             float* dst = gvbase + (vS + pk[k]) * ldv;
 #pragma unroll
-            for (int j = 0; j < CPL; j += 4) red_add4(dst + j, wa * g[j], wa * g[j + 1], wa * g[j + 2], wa * g[j + 3]);
+            for (int j = 0; j < CPL; j += 4) red_add4(dst + j * 4, wa * g[j], wa * g[j + 1], wa * g[j + 2], wa * g[j + 3]);
             wsum += wa;
           }
         }
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
   // CTA stores one row of [C + 128] partials and bias_reduce_kernel sums the rows deterministically)
   const int wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) s_part[wid][lane * CPL + j] = gvb[j];
+  for (int j = 0; j < CPL; ++j) s_part[wid][lane_base<CPL>(lane) + (j >> 2) * 16 + (j & 3)] = gvb[j];
   s_part[wid][C + lane * 4 + 0] = ggb.x; s_part[wid][C + lane * 4 + 1] = ggb.y;
   s_part[wid][C + lane * 4 + 2] = ggb.z; s_part[wid][C + lane * 4 + 3] = ggb.w;
   __syncthreads();

@@ -36,7 +36,9 @@ constexpr int BM = 128;      // pixels per tile (UMMA M)
 constexpr int BK = 32;       // channels per pipeline stage
 constexpr int NA = 2;        // A stages (hi+lo)
 constexpr int NB = 4;        // B stages (one of hi / lo per stage)
-constexpr int NF = 3;        // fp32 staging stages filled by TMA (BK x BM floats = 16 KB each)
+constexpr int NF = 3;        // fp32 staging stages filled by TMA (BK x BM floats = 16 KB each), forward
+constexpr int NF_BWD = 5;    // data gradient: no epilogue staging buffers, so more loads can be in flight
+constexpr int NF_MAX = 6;
 constexpr int NE = 2;        // epilogue staging buffers (BM rows x 32 floats, 128B-swizzled, TMA-stored)
 constexpr int kThreads = 384;
 constexpr uint32_t LBO = 128, SBO = (BK / 8) * 128;
@@ -115,7 +117,7 @@ struct Pipe {
 
 // shared memory carve-up (dynamic): [A stages: hi 8 KB | lo 8 KB] x NA, [B stages: N*BK*2 bytes] x NB, barriers
 struct Smem {
-  uint64_t f_full[NF], f_empty[NF], a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], tmem_full, tmem_empty;
+  uint64_t f_full[NF_MAX], f_empty[NF_MAX], a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
 
@@ -133,23 +135,27 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
   const int b_stage_bytes = N * BK * 2;
   constexpr int f_stage_bytes = BK * BM * 4;
   uint8_t* f_base = smem_raw;
-  uint8_t* a_base = f_base + NF * f_stage_bytes;
+  constexpr int nf = BWD ? NF_BWD : NF;
+  constexpr int ne = BWD ? 0 : NE;
+  uint8_t* a_base = f_base + nf * f_stage_bytes;
   uint8_t* b_base = a_base + NA * a_stage_bytes;
   uint8_t* e_base = b_base + NB * b_stage_bytes;  // 1024-byte aligned (all stage sizes are multiples of 1 KB)
-  Smem* sm = reinterpret_cast<Smem*>(e_base + NE * BM * 128);
+  Smem* sm = reinterpret_cast<Smem*>(e_base + ne * BM * 128);
 
   const int n_parts = N > 256 ? 2 : 1;
   const int n_mma = N / n_parts;                      // 192 (C=256) or 256 (C=128): multiple of 16, <= 256
+  // two TMEM accumulators (columns [0,256) and [256,512)) whenever the output tile fits twice: the MMAs of tile i+1
+  // overlap the epilogue of tile i
+  const int n_bufs = N <= 256 ? 2 : 1;
   const int k_slabs = C / BK;
   const int m_tiles = (S + BM - 1) / BM;
   const int tiles = V * m_tiles;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
+    for (int i = 0; i < nf; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
     for (int i = 0; i < NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
-    mbar_init(&sm->tmem_full, 1);
-    mbar_init(&sm->tmem_empty, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 7) {
@@ -165,7 +171,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
     // ===================== F producer: TMA tile loads of the fp32 NCHW map =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&fmap) : "memory");
-      Pipe pf(NF);
+      Pipe pf(nf);
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int v = tile / m_tiles, s0 = (tile - v * m_tiles) * BM;
         for (int j = 0; j < k_slabs; ++j) {
@@ -180,7 +186,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
   } else if (warp < 4) {
     // ===================== A converters: fp32 staging -> bf16 hi/lo core-matrix tiles =====================
     const int m = threadIdx.x;  // row of the tile (pixel)
-    Pipe pa(NA), pf(NF);
+    Pipe pa(NA), pf(nf);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int j = 0; j < k_slabs; ++j) {
         mbar_wait(&sm->f_full[pf.stage], pf.phase);
@@ -242,9 +248,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
       // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       Pipe pa(NA), pb(NB);
-      uint32_t tphase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(&sm->tmem_empty, tphase ^ 1);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int buf = n_bufs == 2 ? (it & 1) : 0;
+        const uint32_t tphase = n_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+        const uint32_t acc = tmem + buf * 256;
+        mbar_wait(&sm->tmem_empty[buf], tphase ^ 1);
         tc_fence_after();
         for (int j = 0; j < k_slabs; ++j) {
           mbar_wait(&sm->a_full[pa.stage], pa.phase);
@@ -261,8 +270,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
               for (int ks = 0; ks < BK / 16; ++ks) {
                 const uint64_t bd = umma_desc(b_s + p * (n_mma / 8) * SBO + ks * 2 * LBO);
                 if (!(dbg & 2)) {
-                  umma_bf16(tmem + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), bd, idesc, (j | ks) ? 1u : 0u);
-                  umma_bf16(tmem + p * n_mma, umma_desc(a_lo + ks * 2 * LBO), bd, idesc, 1u);
+                  umma_bf16(acc + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), bd, idesc, (j | ks) ? 1u : 0u);
+                  umma_bf16(acc + p * n_mma, umma_desc(a_lo + ks * 2 * LBO), bd, idesc, 1u);
                 }
               }
             }
@@ -279,7 +288,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
 #pragma unroll
               for (int ks = 0; ks < BK / 16; ++ks)
                 if (!(dbg & 2))
-                  umma_bf16(tmem + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), umma_desc(b_s + p * (n_mma / 8) * SBO + ks * 2 * LBO),
+                  umma_bf16(acc + p * n_mma, umma_desc(a_hi + ks * 2 * LBO), umma_desc(b_s + p * (n_mma / 8) * SBO + ks * 2 * LBO),
                             idesc, 1u);
             }
           }
@@ -288,8 +297,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
           tc_commit(&sm->a_empty[pa.stage]);
           pa.next();
         }
-        tc_commit(&sm->tmem_full);
-        tphase ^= 1;
+        tc_commit(&sm->tmem_full[buf]);
       }
     }
   } else if (warp >= 8) {
@@ -297,11 +305,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;           // row of the tile == TMEM lane
     const bool issuer = (threadIdx.x == 8 * 32);
-    uint32_t ephase = 0;
     int chunk = 0;                               // running chunk counter -> staging buffer parity
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int v = tile / m_tiles, s0 = (tile - v * m_tiles) * BM;
-      mbar_wait(&sm->tmem_full, ephase);
+      const int buf = n_bufs == 2 ? (it & 1) : 0;
+      const uint32_t ephase = n_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+      const uint32_t acc = tmem + buf * 256;
+      mbar_wait(&sm->tmem_full[buf], ephase);
       tc_fence_after();
       for (int c0 = 0; c0 < N; c0 += 32, ++chunk) {
         uint32_t r[32];
@@ -313,7 +324,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
               "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
+            : "r"(acc + ((uint32_t)lane_base << 16) + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (BWD) {
           const int sg = s0 + row;
@@ -341,8 +352,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(&sm->tmem_empty);
-      ephase ^= 1;
+      mbar_arrive(&sm->tmem_empty[buf]);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -545,7 +555,7 @@ extern "C" int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, co
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return (int)cudaErrorInvalidValue;
-  const size_t smem = (size_t)NF * BK * BM * 4 + (size_t)NA * 2 * BM * BK * 2 + (size_t)NB * C * BK * 2 + (size_t)NE * BM * 128 +
+  const size_t smem = (size_t)NF_BWD * BK * BM * 4 + (size_t)NA * 2 * BM * BK * 2 + (size_t)NB * C * BK * 2 +
                       sizeof(Smem) + 64;
   cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

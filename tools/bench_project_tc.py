@@ -40,3 +40,34 @@ for name, fn in (('tcgen05 fused', tc), ('split + library bf16 GEMM', lib)):
     ms = e0.elapsed_time(e1) / 20
     by = 4.0 * V * S * (C + N)
     print(f'{name:28s} {ms * 1e3:8.1f} us   {by / ms / 1e6:8.1f} GB/s algorithmic   {2.0 * V * S * C * N / ms / 1e9:8.1f} TFLOP/s (fp32-equivalent)')
+
+# data gradient and weight gradient of the same level
+gvg = torch.randn(V, S, N, device='cuda')
+gfeat = torch.zeros(V, C, H0, W0, device='cuda')
+wpack_t = SF.pack_weight_tc(wcat.t().contiguous())
+gw = torch.empty(N, C, device='cuda')
+from sgcdet_b200 import _lib
+scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device='cuda')
+
+
+def bwd_data():
+    call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
+
+
+def wgrad():
+    call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
+
+
+for name, fn in (('tcgen05 data gradient', bwd_data), ('tcgen05 weight gradient', wgrad)):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    by = 4.0 * V * S * (C + N)
+    print(f'{name:28s} {ms * 1e3:8.1f} us   {by / ms / 1e6:8.1f} GB/s algorithmic')
