@@ -254,6 +254,10 @@ int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, cons
 int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ, const float* occ,
                            const float* grad_up, const float* grad_occ, float* gpre_scratch, float* grad_in,
                            float* grad_w, float* grad_b, void* stream);
+/* The weight-gradient part of the call above on its own (grad_w accumulated); pass grad_w = NULL above to skip it
+ * there and issue it on another stream. */
+int sgc_upsample2x_occ_gradw(const float* vol_in, int X, int Y, int Z, int C, const float* gpre, float* grad_w,
+                             void* stream);
 /* topk_wo_grad (ASH:9-13) + nonzero compaction (DH:66): k largest, ties -> lower index; sel ascending. */
 int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream);
 /* vol[sel[i],:] += y[i,:] (DH:80-81 + ASH:77) and y[i,:] = vol[sel[i],:] (its backward). */

@@ -62,6 +62,7 @@ SIGNATURES = {
     'sgc_cvs_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P, P],
     'sgc_upsample2x_occ_fwd': [P, I, I, I, I, P, P, P, P, P],
     'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
+    'sgc_upsample2x_occ_gradw': [P, I, I, I, I, P, P, P],
     'sgc_topk_select': [P, I, I, P, P, P],
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],

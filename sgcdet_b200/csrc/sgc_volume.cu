@@ -439,15 +439,29 @@ extern "C" int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, 
   if (grad_occ) {
     sgc::occ_gpre_kernel<<<(n_out + 1023) / 1024 < 148 ? (n_out + 1023) / 1024 : 148, 1024, 0, st>>>(occ, grad_occ, n_out, gpre, grad_b);
     SGC_CUDA_CHECK_LAST();
-    const int g2 = 148 * 2;
-    if (C == 256) sgc::occ_gradw_kernel<8><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
-    else sgc::occ_gradw_kernel<4><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
-    SGC_CUDA_CHECK_LAST();
+    if (grad_w) {  // NULL: the caller issues sgc_upsample2x_occ_gradw itself (e.g. on its weight-gradient stream)
+      const int g2 = 148 * 2;
+      if (C == 256) sgc::occ_gradw_kernel<8><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
+      else sgc::occ_gradw_kernel<4><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
+      SGC_CUDA_CHECK_LAST();
+    }
     gp = gpre;
   }
   const int grid = (n_in + sgc::kUpWarps - 1) / sgc::kUpWarps;
   if (C == 256) sgc::upsample_occ_bwd_kernel<8><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
   else sgc::upsample_occ_bwd_kernel<4><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// grad_w[c] += sum_o gpre[o] * up[o,c] (the occupancy Linear's weight gradient), up recomputed from vol_in.
+extern "C" int sgc_upsample2x_occ_gradw(const float* vol_in, int X, int Y, int Z, int C, const float* gpre, float* grad_w,
+                                        void* stream) {
+  if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
+  const int g2 = 148 * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 256) sgc::occ_gradw_kernel<8><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
+  else sgc::occ_gradw_kernel<4><<<g2, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, gpre, grad_w);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

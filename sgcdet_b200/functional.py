@@ -711,8 +711,8 @@ class EncoderLayerRows(torch.autograd.Function):
     norm): masked mean over views -> output_proj -> 8-head attention pooling over views (DCA:815-837) -> LayerNorm ->
     FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the dense GEMMs alternate with fused row kernels
     (``sgc_rowop_fwd/bwd``) that carry bias, ReLU, dropout mask, row mask, residual, LayerNorm and the bf16x3 operand
-    image of the next GEMM.  The backward is written out by hand; weight / bias gradients are produced on ``wstream``
-    (see ``OnStream``).
+    image of the next GEMM.  The backward is written out by hand; weight / bias gradients are produced on ``wstream`` =
+    (stream of the attention-block parameters, stream of the FFN / norm parameters), see ``OnStream``.
 
     GEMMs: tensor cores with bf16x3 operands and fp32 accumulation; levels with at most ``SMALL_ROWS`` voxels use plain
     fp32 GEMMs instead (launch-bound either way, and the library's fp32 kernels need no thread-block cluster, so they
@@ -790,7 +790,9 @@ class EncoderLayerRows(torch.autograd.Function):
         sp = not small
         fp32_heads = small or HEADS_WGRAD_FP32
         wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
-        side = _Side(dev, ctx.wstream)
+        ws_attn, ws_ffn = ctx.wstream if ctx.wstream is not None else (None, None)
+        side = _Side(dev, ws_attn)     # attention-block parameters
+        side_f = _Side(dev, ws_ffn)    # FFN + norms
         gy = gy.contiguous()
 
         def lin_t(a, a_s, w, ws_t):  # a @ w
@@ -799,16 +801,16 @@ class EncoderLayerRows(torch.autograd.Function):
         # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
         gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
                                            want_split=sp)
-        g_g2, g_be2 = side.run(lambda: _ln_params(part2, Q, C), part2)
-        g_w2, g_b2 = side.run(lambda: linear_grads(gf, hdn), gf, hdn)
+        g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
+        g_w2, g_b2 = side_f.run(lambda: linear_grads(gf, hdn), gf, hdn)
         ghdn = lin_t(gf, gf_s, w2, lw.w2_t)                                                         # [Q,F]
         # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
         gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
-        g_w1, g_b1 = side.run(lambda: linear_grads(gh, x1), gh, x1)
+        g_w1, g_b1 = side_f.run(lambda: linear_grads(gh, x1), gh, x1)
         gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t)                                                      # [Q,C]
         gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
                                            rowscale=has, want_split=sp)
-        g_g1, g_be1 = side.run(lambda: _ln_params(part1, Q, C), part1)
+        g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
         g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
         go2 = lin_t(gout, gout_s, wo, lw.wo_t)                                                      # [Q,C]
         if small:   # gt[h] = go_h @ Wv_h
@@ -850,6 +852,7 @@ class EncoderLayerRows(torch.autograd.Function):
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
         side.join()
+        side_f.join()
         g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
                                            torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
         side.join()
@@ -866,7 +869,8 @@ class UpsampleOcc(torch.autograd.Function):
     (AdaptiveSparseHead.py:64-71)."""
 
     @staticmethod
-    def forward(ctx, vol, w_occ, b_occ):
+    def forward(ctx, vol, w_occ, b_occ, wstream=None):
+        ctx.wstream = wstream
         X, Y, Z, C = vol.shape
         up = torch.empty(2 * X, 2 * Y, 2 * Z, C, device=vol.device, dtype=torch.float32)
         occ = torch.empty(8 * X * Y * Z, device=vol.device, dtype=torch.float32)
@@ -884,9 +888,18 @@ class UpsampleOcc(torch.autograd.Function):
         gw = torch.zeros(C, device=dev, dtype=torch.float32)
         gb = torch.zeros(1, device=dev, dtype=torch.float32)
         gpre = torch.empty_like(occ) if gocc is not None else None
+        side = _Side(dev, ctx.wstream)
+        detached = side.detached and gocc is not None
         call('sgc_upsample2x_occ_bwd', ptr(vol), X, Y, Z, C, ptr(w_occ), ptr(occ), ptr(gup),
-             ptr(gocc.contiguous()) if gocc is not None else None, ptr(gpre), ptr(gin), ptr(gw), ptr(gb), stream())
-        return gin, gw.view_as(w_occ), gb
+             ptr(gocc.contiguous()) if gocc is not None else None, ptr(gpre), ptr(gin),
+             None if detached else ptr(gw), ptr(gb), stream())
+        if detached:   # the weight gradient (a full pass over the upsampled volume) leaves the voxel chain
+            def _gw():
+                g = torch.zeros(C, device=dev, dtype=torch.float32)
+                call('sgc_upsample2x_occ_gradw', ptr(vol), X, Y, Z, C, ptr(gpre), ptr(g), stream())
+                return g
+            gw = side.run(_gw, vol, gpre)
+        return gin, gw.view_as(w_occ), gb, None
 
 
 def topk_select(occ: torch.Tensor, k: int):

@@ -375,13 +375,16 @@ class DenseHead(nn.Module):
                   layer.norms[1].weight, layer.norms[1].bias)
         wstream = None
         if torch.is_grad_enabled() and os.environ.get('SGC_WSTREAM', '1') != '0':
-            if self._wstream is None or self._wstream.device != feat.device:
-                self._wstream = torch.cuda.Stream(device=feat.device)
+            # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
+            # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
+            if self._wstream is None or self._wstream[0].device != feat.device:
+                self._wstream = (torch.cuda.Stream(device=feat.device), torch.cuda.Stream(device=feat.device))
             wstream = self._wstream
-            with torch.cuda.stream(wstream):
-                params = SF.OnStream.apply(*params)
-        # vbias is a leaf parameter: the view gives it a backward node that belongs to this stream like the
-        # producers of vg / dist / gbias (Lift issues its backward kernel on this stream, see functional.Lift)
+            with torch.cuda.stream(wstream[0]):
+                pa = SF.OnStream.apply(*params[:6])
+            with torch.cuda.stream(wstream[1]):
+                pf = SF.OnStream.apply(*params[6:])
+            params = tuple(pa) + tuple(pf)
         masks = None
         if self.training and n_rows:
             # keep-masks of the layer's dropouts (nn.Dropout semantics: x * mask / (1-p)), drawn here -- off the
@@ -424,11 +427,12 @@ class DenseHead(nn.Module):
                     masks = _dropout_masks(pl.Q, widths, drops, feat.device)
             x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops)
         else:
-            x = SF.CrossView.apply(slots, pl, *pp[:6], lw, ws)
+            wa, wf = ws if ws is not None else (None, None)
+            x = SF.CrossView.apply(slots, pl, *pp[:6], lw, wa)
             x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
-            x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, ws)
-            x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=ws)
-            x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, ws)
+            x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, wf)
+            x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=wf)
+            x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, wf)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
         return x
@@ -554,7 +558,12 @@ class AdaptiveSparseHead(nn.Module):
                 vol = y.view(X, Y, Z, self.embed_dims)
             else:
                 lin = self.occ_pred_heads[i - 1][0]
-                up, occ = SF.UpsampleOcc.apply(vol, lin.weight.view(-1), lin.bias)
+                ws = pre['wstream'][1] if pre['wstream'] is not None else None
+                w_occ, b_occ = lin.weight, lin.bias
+                if ws is not None:
+                    with torch.cuda.stream(ws):
+                        w_occ, b_occ = SF.OnStream.apply(w_occ, b_occ)
+                up, occ = SF.UpsampleOcc.apply(vol, w_occ, b_occ, ws)
                 occ_list.append(occ.view(1, -1))
                 if (i - 1) < len(self.topk_list):
                     if forced_selection is not None and forced_selection[i] is not None:
