@@ -1,6 +1,6 @@
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-for v in "A=1" "A=2"; do
-  env $v timeout 200 python bench.py --no-cpu-baseline --skip-e2e > gpurun_out/b_tmp.json 2>gpurun_out/b_tmp.err
-  echo "$v: $(python -c "import json;d=json.loads(open('gpurun_out/b_tmp.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['gpu_launches'])" 2>&1 | tail -1)"
-done
-tail -3 gpurun_out/b_tmp.err
+set -x
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 -c 900 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --no-graph --steps 2 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/ncu_bench_b.log 2>&1
+tail -c 300 gpurun_out/ncu_bench_b.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'lift_bwd|lift_fwd|project_tc_kernel|wgrad_tc_kernel|attn_fwd|attn_bwd_qt|rowop_fwd' -c 30 -o gpurun_out/prof_r1b_top python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/ncu_full_b.log 2>&1
+tail -c 300 gpurun_out/ncu_full_b.log
+ls -la gpurun_out/*.ncu-rep

@@ -50,5 +50,26 @@ else:
         name = re.sub(r'\(.*', '', d[idx['Kernel Name']]).replace('void ', '')
         vals = [f'{d[idx[w]]} {units[idx[w]]}'.strip() for w in want if w in idx]
         out.append(f'| {i} | `{name}` | ' + ' | '.join(vals) + ' |')
+if mode == 'full' and len(sys.argv) > 4:
+    # per-launch DRAM traffic of the finest-level (= longest) instance of each hot kernel, keyed like bench.py's
+    # `roofline.kernel` for the headline shape (SGCDet_ScanNet, V=40): read back by bench.py as `roofline.traffic`
+    import json
+    keys = {'lift_bwd_kernel': 'sgc_lift_bwd[Q=6400]', 'lift_fwd_kernel': 'sgc_lift_fwd[Q=6400]',
+            'project_tc_kernel<0>': 'sgc_project_tc_fwd[V=40,C=256,S=4720,N=384]'}
+    best = {}
+
+    def _bytes(v, u):
+        v = float(v.replace(',', ''))
+        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+    for d in data:
+        name = d[idx['Kernel Name']]
+        for frag, key in keys.items():
+            if frag in name.replace('false', '0').replace('true', '1'):
+                dur = float(d[idx['gpu__time_duration.sum']].replace(',', ''))
+                tr = _bytes(d[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + \
+                    _bytes(d[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
+                if key not in best or dur > best[key][0]:
+                    best[key] = (dur, int(tr))
+    json.dump({k: v[1] for k, v in best.items()}, open(sys.argv[4], 'w'), indent=1)
 open(dst, 'w').write('\n'.join(out) + '\n')
 print(open(dst).read()[:3000])
