@@ -467,7 +467,7 @@ def run_ours(args):
                        'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else ' + NCCL weight-grad all-reduce'),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
-                       'cuda_graph': not args.no_graph, 'gemm': 'forward feature projection: own tcgen05/TMEM/TMA kernel (bf16 hi/lo split in smem, fp32 accumulate); backward + voxel-count GEMMs: own bf16x3 split kernel + library bf16 GEMM, fp32 accumulate'},
+                       'cuda_graph': not args.no_graph, 'gemm': 'feature-map projection (forward, data gradient, weight gradient): own tcgen05/TMEM/TMA kernels, bf16 hi/lo split in shared memory, fp32 accumulate; voxel-count GEMMs: library bf16 GEMM with fp32 accumulate on bf16x3 operands emitted by the own fused row kernels', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                     'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},

@@ -1,6 +1,6 @@
-set -x
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 -c 900 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --no-graph --steps 2 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/ncu_bench_b.log 2>&1
-tail -c 300 gpurun_out/ncu_bench_b.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'lift_bwd|lift_fwd|project_tc_kernel|wgrad_tc_kernel|attn_fwd|attn_bwd_qt|rowop_fwd' -c 30 -o gpurun_out/prof_r1b_top python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/ncu_full_b.log 2>&1
-tail -c 300 gpurun_out/ncu_full_b.log
-ls -la gpurun_out/*.ncu-rep
+timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/bench_r1_n2.json 2>gpurun_out/bench_r1_n2.err
+tail -2 gpurun_out/bench_r1_n2.err
+python -c "
+import json;d=json.loads(open('gpurun_out/bench_r1_n2.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e'])"
+timeout -k 5 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_view_sharded.py > gpurun_out/view_sharded_n2.json 2>gpurun_out/view_sharded_n2.err
+tail -2 gpurun_out/view_sharded_n2.err; cat gpurun_out/view_sharded_n2.json | tail -3
