@@ -97,7 +97,8 @@ class ClockSampler:
 LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_crossview_mean_fwd=1,
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
-                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1)
+                sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1, sgc_rows_gemm_tc=1,
+                sgc_prepare_weights=1)
 
 
 class CallRecorder:
@@ -191,6 +192,9 @@ def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
     if name == 'sgc_project_tc_fwd':
         V, C, S, N = args[3], args[4], args[5], args[7]
         return 4.0 * V * S * (C + N) + 4.0 * N * C
+    if name == 'sgc_rows_gemm_tc':
+        R, K, B, N = args[3], args[4], args[5], args[12]
+        return 4.0 * B * R * (K + N) + 4.0 * B * N * K
     if name in ('sgc_scatter_add_rows', 'sgc_gather_rows'):
         return f * 3 * args[3] * args[4]
     return 0.0

@@ -93,7 +93,7 @@ int sgc_pack_weight_tc(const float* w, int N, int C, void* out, void* stream);
  * [rows, cols] fp32 matrix at src[r*row_stride + c*col_stride] (so transposed operands need no copy), multiplies by
  * `scale` and writes kind 0: the sgc_split_bf16x3 image (rows_per_group, pattern as there), or kind 1: the
  * sgc_pack_weight_tc image (rows = N, cols = C).  `jobs` is a HOST array of njobs <= SGC_MAX_WEIGHT_JOBS entries. */
-#define SGC_MAX_WEIGHT_JOBS 24
+#define SGC_MAX_WEIGHT_JOBS 48
 typedef struct sgc_weight_job {
   const float* src;
   void* out;
@@ -121,6 +121,21 @@ int sgc_project_tc_set_max_ctas(int n);
 int sgc_project_tc_set_tiles_per_cta(int n);
 int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C, float* gw,
                          float* scratch, void* stream);
+
+/* Voxel-count GEMMs of the encoder layer on the tensor cores (tcgen05/TMEM/TMA, csrc/sgc_rows_gemm_tc.cu): every
+ * nn.Linear applied to the selected voxel rows -- output_proj and the attention_pooling in/out projections (DCA:815-833;
+ * key / value projections per head), the FFN (ENC:335-338) -- and their data gradients:
+ *     y[b*batch_y + r*ldy + n] = sum_k x[b*batch_x + r*ldx + k] * W_b[n,k] (+ bias[b*bias_batch + n]),  r < R, n < N, b < B
+ * x, y fp32 (16-byte aligned, ld*4 and batch*4 multiples of 16; a batch stride smaller than ld addresses the heads of a
+ * [R, H*dh] matrix).  K % 32 == 0, N % 32 == 0.  The weights come packed by sgc_pack_weight_tc / sgc_prepare_weights
+ * (kind 1) as a [pack_rows, K] matrix: batch b uses rows [b*pack_batch_rows, +N) of the matrix at
+ * wpack + b*pack_batch_elems (bf16 elements; 0 = one matrix shared by all batches).  Both operands are split into bf16
+ * hi/lo in shared memory / at pack time and accumulate in fp32 (relative error ~1e-5).  n_cta = output columns per CTA
+ * (32/64/128/256, 0 = sgc_rows_gemm_tc_auto_ncta).  No cluster launch: starts as soon as one SM is free. */
+int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B);
+int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                     int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
+                     int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream);
 
 /* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
  * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */

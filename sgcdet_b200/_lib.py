@@ -44,6 +44,8 @@ SIGNATURES = {
     'sgc_project_tc_set_max_ctas': [I],
     'sgc_project_tc_set_tiles_per_cta': [I],
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
+    'sgc_rows_gemm_tc_auto_ncta': [I, I, I],
+    'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],
@@ -76,7 +78,7 @@ class WeightJob(ctypes.Structure):
                 ('scale', c_float), ('kind', c_int)]
 
 
-MAX_WEIGHT_JOBS = 24
+MAX_WEIGHT_JOBS = 48
 
 
 class RowopFwdArgs(ctypes.Structure):

@@ -1,0 +1,347 @@
+// sgc_rows_gemm_tc: the voxel-count GEMMs of one encoder layer on the 5th-gen tensor cores (tcgen05 / TMEM / TMA):
+//
+//   y[b, r, n] = sum_k x[b, r, k] * W_b[n, k]  (+ bias_b[n])        r < R voxel rows, b < B batches (attention heads)
+//
+// i.e. every nn.Linear applied to the selected voxel rows: output_proj and the in/out projections of attention_pooling
+// (deformable_cross_attention.py:815-833, per head for the key / value projections), the two FFN layers
+// (encoder.py:335-338), and the data gradients of all of them (the same product with the transposed weight).
+//
+// Same numerics as the pixel-count projection kernels (csrc/sgc_project_tc.cu): both operands are split into bf16
+// hi + lo, hi*hi' + lo*hi' + hi*lo' accumulates in fp32 in TMEM (relative error ~1e-5).  The fp32 activations are read
+// once with TMA (128B-swizzled [row][k] tiles) and split in shared memory; the weights come pre-packed
+// (sgc_pack_weight_tc / sgc_prepare_weights kind 1) and are streamed with bulk copies; the fp32 result leaves through a
+// 128B-swizzled staging tile and a TMA tensor store, which also clips the rows beyond R.  No bf16x3 operand image ever
+// touches HBM and -- unlike the library's small-GEMM kernels -- no thread-block cluster is needed, so a launch starts as
+// soon as ONE SM is free next to the persistent projection kernels.
+//
+// One CTA per SM, 12 warps, warp-specialised exactly like project_tc_kernel<true> + the forward kernel's epilogue:
+//   warp 5: TMA producer (fp32 x tiles)      warps 0-3: converters (fp32 -> bf16 hi/lo core-matrix tiles)
+//   warp 4: weight-slab producer             warp 6: MMA issuer          warp 7: TMEM alloc
+//   warps 8-11: epilogue (tcgen05.ld -> +bias -> swizzled smem -> TMA store)
+// Work item = (batch b, 128-row tile, column part of n_cta columns); column parts of the same row tile are adjacent in
+// the work order so that their x tile is shared through L2.  Two TMEM accumulators: the MMAs of work item i+1 overlap
+// the epilogue of item i.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/sgcdet_b200.h"
+
+namespace sgc {
+namespace tc {
+
+constexpr int RG_NF = 4;        // fp32 staging stages filled by TMA (BM x BK floats = 16 KB each)
+constexpr int RG_NA = 2;        // converted A stages (hi 8 KB + lo 8 KB)
+constexpr int RG_NB = 4;        // weight stages (one of hi / lo per stage, n_cta * 64 bytes)
+constexpr int RG_NE = 2;        // epilogue staging buffers (BM rows x 32 floats)
+constexpr int RG_THREADS = 384;
+
+struct SmemRG {
+  uint64_t f_full[RG_NF], f_empty[RG_NF], a_full[RG_NA], a_empty[RG_NA], b_full[RG_NB], b_empty[RG_NB], tmem_full[2],
+      tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct RowsGemmParams {
+  const uint8_t* wpack;
+  const float* bias;
+  long long pack_stage_bytes;   // bytes between consecutive (k-slab, hi/lo) stages of one packed matrix = pack_rows*BK*2
+  long long pack_batch_bytes;   // bytes between the packed matrices of consecutive batches (0: one matrix for all)
+  int pack_batch_rows;          // row offset of batch b inside a packed matrix: b * pack_batch_rows
+  int bias_batch;               // bias of batch b starts at bias + b * bias_batch
+  int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols;
+  int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
+};
+
+__global__ void __launch_bounds__(RG_THREADS, 1)
+rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap omap,
+                    const __grid_constant__ RowsGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int f_stage_bytes = BK * BM * 4;
+  constexpr int a_stage_bytes = 2 * BM * BK * 2;
+  const int b_stage_bytes = p.n_cta * BK * 2;
+  uint8_t* f_base = smem_raw;
+  uint8_t* a_base = f_base + RG_NF * f_stage_bytes;
+  uint8_t* b_base = a_base + RG_NA * a_stage_bytes;
+  uint8_t* e_base = b_base + RG_NB * b_stage_bytes;   // 1 KB aligned: every stage size is a multiple of 2 KB
+  SmemRG* sm = reinterpret_cast<SmemRG*>(e_base + RG_NE * BM * 128);
+  const int n_cta = p.n_cta, k_slabs = p.k_slabs, works = p.works;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RG_NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
+    for (int i = 0; i < RG_NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+    for (int i = 0; i < RG_NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 7) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
+                 "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 5) {
+    // ===================== producer: TMA loads of the fp32 activation tiles [128 rows][32 k] =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+      Pipe pf(RG_NF);
+      for (int w = blockIdx.x; w < works; w += gridDim.x) {
+        const int t = w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
+        for (int j = 0; j < k_slabs; ++j) {
+          mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
+          mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage_bytes);
+          if (p.a_swap) tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, j * BK, b, mt * BM, &sm->f_full[pf.stage]);
+          else tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, j * BK, mt * BM, b, &sm->f_full[pf.stage]);
+          pf.next();
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== converters: swizzled fp32 [m][k] tile -> bf16 hi/lo core-matrix tiles =====================
+    const int m = threadIdx.x;  // row of the tile
+    Pipe pa(RG_NA), pf(RG_NF);
+    for (int w = blockIdx.x; w < works; w += gridDim.x) {
+      for (int j = 0; j < k_slabs; ++j) {
+        mbar_wait(&sm->f_full[pf.stage], pf.phase);
+        float x[BK];
+        const uint8_t* rowp = f_base + pf.stage * f_stage_bytes + m * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {   // 16-byte chunk i of the 128-byte row sits at chunk (i ^ (m & 7))
+          const float4 t4 = *reinterpret_cast<const float4*>(rowp + ((i ^ (m & 7)) << 4));
+          x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+        }
+        mbar_wait(&sm->a_empty[pa.stage], pa.phase ^ 1);
+        uint8_t* hi = a_base + pa.stage * a_stage_bytes;
+        uint8_t* lo = hi + BM * BK * 2;
+        const uint32_t off = (m >> 3) * SBO + (m & 7) * 16;
+#pragma unroll
+        for (int kc = 0; kc < BK / 8; ++kc) {
+          __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            h[i] = __float2bfloat16_rn(x[kc * 8 + i]);
+            l[i] = __float2bfloat16_rn(x[kc * 8 + i] - __bfloat162float(h[i]));
+          }
+          *reinterpret_cast<uint4*>(hi + off + kc * LBO) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + off + kc * LBO) = *reinterpret_cast<const uint4*>(l);
+        }
+        // released only after every staged value has been consumed by the conversion (see project_tc_kernel)
+        mbar_arrive(&sm->f_empty[pf.stage]);
+        pf.next();
+        fence_proxy_async();
+        mbar_arrive(&sm->a_full[pa.stage]);
+        pa.next();
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== weight producer: bulk copies of n_cta rows of every packed (slab, hi/lo) stage =====================
+    if (lane == 0) {
+      Pipe pb(RG_NB);
+      for (int w = blockIdx.x; w < works; w += gridDim.x) {
+        const int np = w % p.nsplit, b = (w / p.nsplit) / p.m_tiles;
+        const uint8_t* src = p.wpack + (size_t)b * p.pack_batch_bytes +
+                             ((size_t)b * p.pack_batch_rows + (size_t)np * n_cta) * (BK * 2);
+        for (int q = 0; q < 2 * k_slabs; ++q) {  // q = 2*slab + (0: hi, 1: lo)
+          mbar_wait(&sm->b_empty[pb.stage], pb.phase ^ 1);
+          mbar_expect_tx(&sm->b_full[pb.stage], (uint32_t)b_stage_bytes);
+          bulk_g2s(b_base + pb.stage * b_stage_bytes, src + (size_t)q * p.pack_stage_bytes, (uint32_t)b_stage_bytes,
+                   &sm->b_full[pb.stage]);
+          pb.next();
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cta >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      Pipe pa(RG_NA), pb(RG_NB);
+      int it = 0;
+      for (int w = blockIdx.x; w < works; w += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        const uint32_t acc = tmem + buf * n_cta;
+        mbar_wait(&sm->tmem_empty[buf], tphase ^ 1);
+        tc_fence_after();
+        for (int j = 0; j < k_slabs; ++j) {
+          mbar_wait(&sm->a_full[pa.stage], pa.phase);
+          const uint32_t a_hi = smem_u32(a_base + pa.stage * a_stage_bytes);
+          const uint32_t a_lo = a_hi + BM * BK * 2;
+          // --- W_hi stage: hi*hi + lo*hi
+          mbar_wait(&sm->b_full[pb.stage], pb.phase);
+          tc_fence_after();
+          uint32_t b_s = smem_u32(b_base + pb.stage * b_stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t bd = umma_desc(b_s + ks * 2 * LBO);
+            umma_bf16(acc, umma_desc(a_hi + ks * 2 * LBO), bd, idesc, (j | ks) ? 1u : 0u);
+            umma_bf16(acc, umma_desc(a_lo + ks * 2 * LBO), bd, idesc, 1u);
+          }
+          tc_commit(&sm->b_empty[pb.stage]);
+          pb.next();
+          // --- W_lo stage: hi*lo
+          mbar_wait(&sm->b_full[pb.stage], pb.phase);
+          tc_fence_after();
+          b_s = smem_u32(b_base + pb.stage * b_stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks)
+            umma_bf16(acc, umma_desc(a_hi + ks * 2 * LBO), umma_desc(b_s + ks * 2 * LBO), idesc, 1u);
+          tc_commit(&sm->b_empty[pb.stage]);
+          pb.next();
+          tc_commit(&sm->a_empty[pa.stage]);
+          pa.next();
+        }
+        tc_commit(&sm->tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> registers (+bias) -> swizzled smem -> TMA store =====================
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;           // row of the tile == TMEM lane
+    const bool issuer = (threadIdx.x == 8 * 32);
+    int chunk = 0;                               // running chunk counter -> staging buffer parity
+    int it = 0;
+    for (int w = blockIdx.x; w < works; w += gridDim.x, ++it) {
+      const int np = w % p.nsplit, t = w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
+      const int buf = it & 1;
+      const uint32_t ephase = (it >> 1) & 1;
+      const uint32_t acc = tmem + buf * n_cta;
+      const float* bias = p.bias ? p.bias + (size_t)b * p.bias_batch + np * n_cta : nullptr;
+      mbar_wait(&sm->tmem_full[buf], ephase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < n_cta; c0 += 32, ++chunk) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(acc + ((uint32_t)lane_base << 16) + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bias + c0 + i));
+        }
+        uint8_t* ebuf = e_base + (chunk & 1) * (BM * 128);
+        // the TMA store that read this buffer two chunks ago must have finished reading it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // 16-byte chunk i of the 128-byte row, CU_TENSOR_MAP_SWIZZLE_128B pattern
+          *reinterpret_cast<uint4*>(ebuf + row * 128 + ((i ^ (row & 7)) << 4)) =
+              make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (p.o_swap) tma_store_3d(&omap, np * n_cta + c0, b, mt * BM, ebuf);
+          else tma_store_3d(&omap, np * n_cta + c0, mt * BM, b, ebuf);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm->tmem_empty[buf]);
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
+  }
+}
+
+// [cols, rows, batch] fp32 view with a [32, 128, 1] box (or [cols, batch, rows] with a [32, 1, 128] box when the batch
+// stride is the smaller one, e.g. the heads of a [R, H*dh] matrix): strides stay ascending for the descriptor.
+static inline bool make_rows_map(PFN_encodeTiled encode, CUtensorMap* map, const float* base, int cols, int rows, int batch,
+                                 long long ld, long long batch_stride, int* swapped) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || ld < cols) return false;
+  if (batch > 1 && ((batch_stride * 4) % 16 || batch_stride <= 0)) return false;
+  const bool swap = batch > 1 && batch_stride < ld;
+  *swapped = swap ? 1 : 0;
+  const cuuint64_t bs = batch > 1 ? (cuuint64_t)batch_stride * 4 : (cuuint64_t)ld * 4 * (cuuint64_t)rows;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t box[3];
+  const cuuint32_t estr[3] = {1, 1, 1};
+  gdim[0] = (cuuint64_t)cols;
+  box[0] = 32;
+  if (swap) {
+    gdim[1] = (cuuint64_t)batch; gdim[2] = (cuuint64_t)rows;
+    gstr[0] = bs; gstr[1] = (cuuint64_t)ld * 4;
+    box[1] = 1; box[2] = (cuuint32_t)BM;
+  } else {
+    gdim[1] = (cuuint64_t)rows; gdim[2] = (cuuint64_t)batch;
+    gstr[0] = (cuuint64_t)ld * 4; gstr[1] = bs;
+    box[1] = (cuuint32_t)BM; box[2] = 1;
+  }
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+}  // namespace sgc
+
+// Columns per CTA chosen by sgc_rows_gemm_tc for (R, N, B) when n_cta == 0: the widest of {256,128,64,32} dividing N that
+// still yields enough work items to spread over the SMs (the problems are latency-, not throughput-bound).
+extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
+  using namespace sgc::tc;
+  if (R <= 0 || N <= 0 || N % 32 || B <= 0) return 0;
+  const int m_tiles = (R + BM - 1) / BM;
+  int n_cta = 256;
+  while (n_cta > 32 && (N % n_cta || (long long)m_tiles * B * (N / n_cta) * 2 <= 148)) n_cta >>= 1;
+  while (N % n_cta) n_cta >>= 1;
+  return n_cta;
+}
+
+extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                                int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
+                                int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream) {
+  using namespace sgc::tc;
+  if (R <= 0 || B <= 0 || K <= 0 || K % BK || N <= 0 || N % 32 || !x || !y || !wpack) return (int)cudaErrorInvalidValue;
+  if (n_cta == 0) n_cta = sgc_rows_gemm_tc_auto_ncta(R, N, B);
+  if (n_cta < 32 || n_cta > 256 || (n_cta & (n_cta - 1)) || N % n_cta) return (int)cudaErrorInvalidValue;
+  if (pack_rows < N || pack_rows % 8 || pack_batch_rows % 8 || (reinterpret_cast<uintptr_t>(wpack) & 15) ||
+      (pack_batch_elems * 2) % 16 || pack_batch_elems < 0 || pack_batch_rows < 0)
+    return (int)cudaErrorInvalidValue;
+  if (pack_batch_elems == 0 && (long long)(B - 1) * pack_batch_rows + N > pack_rows) return (int)cudaErrorInvalidValue;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  PFN_encodeTiled encode = get_encode_tiled();
+  if (!encode) return (int)cudaErrorNotSupported;
+  CUtensorMap amap, omap;
+  RowsGemmParams p;
+  if (!make_rows_map(encode, &amap, x, K, R, B, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
+  if (!make_rows_map(encode, &omap, y, N, R, B, ldy, batch_y, &p.o_swap)) return (int)cudaErrorInvalidValue;
+  p.wpack = reinterpret_cast<const uint8_t*>(wpack);
+  p.bias = bias;
+  p.pack_stage_bytes = (long long)pack_rows * BK * 2;
+  p.pack_batch_bytes = pack_batch_elems * 2;
+  p.pack_batch_rows = pack_batch_rows;
+  p.bias_batch = bias_batch;
+  p.m_tiles = (R + BM - 1) / BM;
+  p.nsplit = N / n_cta;
+  p.works = p.m_tiles * p.nsplit * B;
+  p.k_slabs = K / BK;
+  p.n_cta = n_cta;
+  p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
+  const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * n_cta * BK * 2 +
+                      (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
+  cudaError_t e = cudaFuncSetAttribute(rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.works < sms ? p.works : sms;
+  rows_gemm_tc_kernel<<<grid, RG_THREADS, smem, (cudaStream_t)stream>>>(amap, omap, p);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

@@ -91,6 +91,9 @@ F32 = torch.float32
 import os as _os
 HEADS_WGRAD_FP32 = _os.environ.get('SGC_HEADS_WGRAD_FP32', '0') != '0'  # per-head K/V weight grads as plain fp32 bmm
 SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs with at most this many rows stay plain fp32
+# voxel-count GEMMs of the encoder layer on the own tcgen05 kernel (csrc/sgc_rows_gemm_tc.cu) instead of the library's
+# bf16 GEMM on bf16x3 operand images
+ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -122,6 +125,33 @@ def mm_nt(a: torch.Tensor, w: torch.Tensor = None, ws: torch.Tensor = None) -> t
     return torch.mm(split_cols(a, 0), ws.t(), out_dtype=F32)
 
 
+def rows_linear(x: torch.Tensor, wpack: torch.Tensor, N: int, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
+    """y [R,N] = x [R,K] @ W^T (+ bias) with ``wpack`` = the packed [N,K] weight (``sgc_rows_gemm_tc``)."""
+    R, K = x.shape
+    y = torch.empty(R, N, device=x.device, dtype=F32)
+    call('sgc_rows_gemm_tc', ptr(x), K, 0, R, K, 1, ptr(wpack), N, 0, 0, ptr(bias), 0, N, ptr(y), N, 0, n_cta, stream())
+    return y
+
+
+def rows_heads_in(x: torch.Tensor, wpack_heads: torch.Tensor, N: int, heads: int = NUM_HEADS, n_cta: int = 0):
+    """y [H,R,N]: y[h] = x[:, h*dh:(h+1)*dh] @ W_h^T with ``wpack_heads`` = H packed [N,dh] weights back to back."""
+    R, C = x.shape
+    dh = C // heads
+    y = torch.empty(heads, R, N, device=x.device, dtype=F32)
+    call('sgc_rows_gemm_tc', ptr(x), C, dh, R, dh, heads, ptr(wpack_heads), N, 2 * N * dh, 0, None, 0, N, ptr(y), N, R * N,
+         n_cta, stream())
+    return y
+
+
+def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
+    """y [R,H*dh]: y[:, h*dh:(h+1)*dh] = x[h] @ W[h*dh:(h+1)*dh]^T (+ bias) with ``wpack`` = the packed [H*dh,K] weight."""
+    H, R, K = x.shape
+    y = torch.empty(R, H * dh, device=x.device, dtype=F32)
+    call('sgc_rows_gemm_tc', ptr(x), K, R * K, R, K, H, ptr(wpack), H * dh, 0, dh, ptr(bias), dh, dh, ptr(y), H * dh, dh,
+         n_cta, stream())
+    return y
+
+
 def pack_weight_tc(w: torch.Tensor) -> torch.Tensor:
     """[N,C] fp32 -> bf16 hi/lo slabs in the shared-memory image of sgc_project_tc_fwd (2*N*C bf16)."""
     N, C = w.shape
@@ -150,8 +180,20 @@ class _WeightJobs:
         out = torch.empty(x.shape[0] // group, 3 * group, x.shape[1], device=self.dev, dtype=BF16)
         return self._add(x, out, group, pattern, scale, 0)
 
-    def pack(self, x):
-        return self._add(x, torch.empty(2 * x.numel(), device=self.dev, dtype=BF16), 1, 0, 1.0, 1)
+    def pack(self, x, scale=1.0):
+        return self._add(x, torch.empty(2 * x.numel(), device=self.dev, dtype=BF16), 1, 0, scale, 1)
+
+    def pack_heads_t(self, w, heads, scale=1.0):
+        """w [heads*dh, C] -> heads packed [C, dh] matrices (W_h^T, the operand of x_h @ W_h) back to back."""
+        assert w.dim() == 2 and w.dtype == F32 and w.is_cuda and w.stride(1) == 1
+        C = w.shape[1]
+        dh = w.shape[0] // heads
+        out = torch.empty(heads * 2 * C * dh, device=self.dev, dtype=BF16)
+        for h in range(heads):
+            self.jobs.append(_lib.WeightJob(w.data_ptr() + 4 * h * dh * w.stride(0), out.data_ptr() + 2 * h * 2 * C * dh,
+                                            1, w.stride(0), C, dh, 1, 0, scale, 1))
+        self.keep.append(w)
+        return out
 
     def launch(self):
         for i in range(0, len(self.jobs), _lib.MAX_WEIGHT_JOBS):
@@ -166,7 +208,9 @@ class LevelWeights:
     single launch -- normally on a side stream, off the critical path of the level.  Constants for the autograd
     Functions below (weight gradients are formed from the fp32 activations, not from these)."""
 
-    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS):
+    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS, images: bool = True):
+        """``images=False``: skip the bf16x3 images of the layer weights (operands of the library-GEMM path) wherever
+        the packed operands of the own voxel-count GEMM kernel replace them."""
         with torch.no_grad():
             C = w_out.shape[0]
             dh = C // num_heads
@@ -178,20 +222,39 @@ class LevelWeights:
             self.wpack = j.pack(wcat) if ok else None
             self.wpack_t = j.pack(wcat.t()) if ok else None
             self.wcat_t = j.split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
-            self.w_out, self.w_out_t = j.split_cols(w_out, 1), j.split_cols(w_out.t(), 1)
-            self.wq, self.wq_t = j.split_cols(wq, 1), j.split_cols(wq.t(), 1)
-            self.wo, self.wo_t = j.split_cols(wo, 1), j.split_cols(wo.t(), 1)
-            self.wk_rows = j.split_rows(wk, dh, 1, scale)  # [8,3dh,C]  qv_h @ (scale Wk_h)
-            self.wk_cols = j.split_cols(wk, 1, scale)      # [C,3C]     gqt[h] @ (scale Wk_h)^T
-            self.wv_rows = j.split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
-            self.wv_cols = j.split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
-            self.w1, self.w1_t = j.split_cols(w1, 1), j.split_cols(w1.t(), 1)
-            self.w2, self.w2_t = j.split_cols(w2, 1), j.split_cols(w2.t(), 1)
+            self.rows_tc = ROWS_TC and C % 32 == 0 and w1.shape[0] % 32 == 0
+            self.heads_tc = self.rows_tc and dh % 32 == 0
+            if self.rows_tc:
+                # packed operands of sgc_rows_gemm_tc: p_x for y = a @ x^T, p_x_t for the data gradient g @ x
+                self.p_w_out, self.p_w_out_t = j.pack(w_out), j.pack(w_out.t())
+                self.p_wq, self.p_wq_t = j.pack(wq), j.pack(wq.t())
+                self.p_wo, self.p_wo_t = j.pack(wo), j.pack(wo.t())
+                self.p_w1, self.p_w1_t = j.pack(w1), j.pack(w1.t())
+                self.p_w2, self.p_w2_t = j.pack(w2), j.pack(w2.t())
+            if self.heads_tc:
+                self.p_wk = j.pack(wk, scale)                          # gqv[:, h] = gqt[h] @ (scale Wk_h)^T
+                self.p_wv = j.pack(wv)                                 # o[:, h]   = t[h] @ Wv_h^T
+                self.p_wk_ht = j.pack_heads_t(wk, num_heads, scale)    # qt[h]     = qv_h @ (scale Wk_h)
+                self.p_wv_ht = j.pack_heads_t(wv, num_heads)           # gt[h]     = go_h @ Wv_h
+            for k in ('w_out', 'w_out_t', 'wq', 'wq_t', 'wo', 'wo_t', 'w1', 'w1_t', 'w2', 'w2_t', 'wk_rows', 'wk_cols',
+                      'wv_rows', 'wv_cols'):
+                setattr(self, k, None)
+            if images or not self.rows_tc:
+                self.w_out, self.w_out_t = j.split_cols(w_out, 1), j.split_cols(w_out.t(), 1)
+                self.wq, self.wq_t = j.split_cols(wq, 1), j.split_cols(wq.t(), 1)
+                self.wo, self.wo_t = j.split_cols(wo, 1), j.split_cols(wo.t(), 1)
+                self.w1, self.w1_t = j.split_cols(w1, 1), j.split_cols(w1.t(), 1)
+                self.w2, self.w2_t = j.split_cols(w2, 1), j.split_cols(w2.t(), 1)
+            if images or not self.heads_tc:
+                self.wk_rows = j.split_rows(wk, dh, 1, scale)  # [8,3dh,C]  qv_h @ (scale Wk_h)
+                self.wk_cols = j.split_cols(wk, 1, scale)      # [C,3C]     gqt[h] @ (scale Wk_h)^T
+                self.wv_rows = j.split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
+                self.wv_cols = j.split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
             j.launch()
 
     def record_stream(self, s):
         for t in self.__dict__.values():
-            if t is not None:
+            if isinstance(t, torch.Tensor):
                 t.record_stream(s)
 
 
@@ -449,16 +512,20 @@ class Lift(torch.autograd.Function):
         gslots = gslots.contiguous()
         cur = torch.cuda.current_stream(vg.device)
         side = ctx.bwd_stream if ctx.bwd_stream is not None and ctx.bwd_stream != cur else None
+        with torch.cuda.stream(side if side is not None else cur):
+            # the accumulation targets are zero-filled BEFORE the side stream joins the voxel chain: the fills (290 MB
+            # at the finest level) depend on nothing, so they run while the chain is still busy instead of in front of
+            # the kernel on the critical path
+            gvg = torch.zeros_like(vg)
+            gdist = torch.zeros_like(dist)
+            gvb = torch.zeros_like(vbias)
+            ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
         if side is not None:
             # every consumer of the four gradients is a backward node of the side stream, so main never waits
             side.wait_stream(cur)
             for t in (gslots, samp, pl.pair_vq, pl.n_pairs, pl.ref_cam):
                 t.record_stream(side)
         with torch.cuda.stream(side if side is not None else cur):
-            gvg = torch.zeros_like(vg)
-            gdist = torch.zeros_like(dist)
-            gvb = torch.zeros_like(vbias)
-            ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
             base, gbase = ptr(vg), ptr(gvg)
             scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device,
                                   dtype=torch.float32)
@@ -730,42 +797,60 @@ class EncoderLayerRows(torch.autograd.Function):
         Fh = w1.shape[0]
         dev = slots.device
         small = Q <= SMALL_ROWS
-        sp = not small
+        tc = (not small) and getattr(lw, 'rows_tc', False)      # own tcgen05 GEMM for the plain Linear layers
+        htc = tc and getattr(lw, 'heads_tc', False)             # ... and for the per-head key / value projections
+        sp = not small and not tc                               # bf16x3 operand images for the library GEMMs
+        hsp = not small and not htc
         scale = 1.0 / math.sqrt(dh)
         bq, bv = in_b[:C], in_b[2 * C:]
         wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         m0, m1, m2 = masks if masks is not None else (None, None, None)
         s0, s1, s2 = (1.0 / (1.0 - p) if m is not None else 1.0 for m, p in zip((m0, m1, m2), drops))
 
-        def lin(a, a_s, w, ws):  # a @ w^T
+        def lin(a, a_s, w, ws, pk, bias=None):  # a @ w^T (+ bias, own kernel only)
+            if tc:
+                return rows_linear(a, pk, w.shape[0], bias)
             return a @ w.t() if small else torch.mm(a_s, ws.t(), out_dtype=F32)
 
         mean = torch.empty(Q, C, device=dev, dtype=F32)
         mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
         call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
-        g, g_s, _ = rowop_fwd(lin(mean, mean_s, w_out, lw.w_out), Q, C, bias=b_out, want_split=sp)
-        qv, qv_hs, _ = rowop_fwd(lin(g, g_s, wq, lw.wq), Q, C, bias=bq, split_heads=H, want_split=sp)
+        if tc:   # biases ride in the GEMM epilogue, no row kernel in between
+            g = lin(mean, None, w_out, None, lw.p_w_out, b_out)
+            if htc:
+                qv, qv_hs = lin(g, None, wq, None, lw.p_wq, bq), None
+            else:
+                qv, qv_hs, _ = rowop_fwd(lin(g, None, wq, None, lw.p_wq), Q, C, bias=bq, split_heads=H)
+        else:
+            g, g_s, _ = rowop_fwd(lin(mean, mean_s, w_out, lw.w_out, None), Q, C, bias=b_out, want_split=sp)
+            qv, qv_hs, _ = rowop_fwd(lin(g, g_s, wq, lw.wq, None), Q, C, bias=bq, split_heads=H, want_split=sp)
         if small:   # qt[h] = scale * qv_h @ Wk_h
             qt = torch.empty(H, Q, C, device=dev, dtype=F32)
             torch.baddbmm(qt, qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C), beta=0, alpha=scale, out=qt)
+        elif htc:
+            qt = rows_heads_in(qv, lw.p_wk_ht, C, H)
         else:
             qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)   # [H,Q,C]
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
-        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if sp else None
+        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
              stream())
-        if small:   # o[h] = t[h] @ Wv_h^T   [H,Q,dh]
-            o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
+        if htc:     # o2[:, h] = t[h] @ Wv_h^T + bv_h, written straight into the [Q,C] layout
+            o2, o2_s = rows_heads_out(t, lw.p_wv, dh, bv), None
         else:
-            o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-        o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
+            if small:   # o[h] = t[h] @ Wv_h^T   [H,Q,dh]
+                o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
+            else:
+                o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+            o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
         has = (pl.count > 0).to(F32)
-        x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo), Q, C, bias=bo, mask=m0, mscale=s0, rowscale=has,
-                                  ln=(g1, be1, eps1), want_split=sp)
-        hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1), Q, Fh, bias=b1, relu=True, mask=m1, mscale=s1, want_split=sp)
-        y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2), Q, C, bias=b2, mask=m2, mscale=s2, residual=x1,
-                              ln=(g2, be2, eps2), want_split=False)
+        x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
+                                  rowscale=has, ln=(g1, be1, eps1), want_split=sp)
+        hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1, getattr(lw, 'p_w1', None)), Q, Fh, bias=b1, relu=True, mask=m1,
+                                  mscale=s1, want_split=sp)
+        y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2, getattr(lw, 'p_w2', None)), Q, C, bias=b2, mask=m2, mscale=s2,
+                              residual=x1, ln=(g2, be2, eps2), want_split=False)
         ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, *ln1, *ln2, g1, g2,
                               w_out, in_w, wo, w1, w2)
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
@@ -787,7 +872,10 @@ class EncoderLayerRows(torch.autograd.Function):
         dev = slots.device
         scale = 1.0 / math.sqrt(dh)
         small = Q <= SMALL_ROWS
-        sp = not small
+        tc = (not small) and getattr(lw, 'rows_tc', False)
+        htc = tc and getattr(lw, 'heads_tc', False)
+        sp = not small and not tc
+        hsp = not small and not htc
         fp32_heads = small or HEADS_WGRAD_FP32
         wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         ws_attn, ws_ffn = ctx.wstream if ctx.wstream is not None else (None, None)
@@ -795,7 +883,9 @@ class EncoderLayerRows(torch.autograd.Function):
         side_f = _Side(dev, ws_ffn)    # FFN + norms
         gy = gy.contiguous()
 
-        def lin_t(a, a_s, w, ws_t):  # a @ w
+        def lin_t(a, a_s, w, ws_t, pk_t):  # a @ w
+            if tc:
+                return rows_linear(a, pk_t, w.shape[1])
             return a @ w if small else torch.mm(a_s, ws_t.t(), out_dtype=F32)
 
         # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
@@ -803,18 +893,20 @@ class EncoderLayerRows(torch.autograd.Function):
                                            want_split=sp)
         g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
         g_w2, g_b2 = side_f.run(lambda: linear_grads(gf, hdn), gf, hdn)
-        ghdn = lin_t(gf, gf_s, w2, lw.w2_t)                                                         # [Q,F]
+        ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
         # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
         gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
         g_w1, g_b1 = side_f.run(lambda: linear_grads(gh, x1), gh, x1)
-        gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t)                                                      # [Q,C]
+        gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
         gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
                                            rowscale=has, want_split=sp)
         g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
         g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
-        go2 = lin_t(gout, gout_s, wo, lw.wo_t)                                                      # [Q,C]
+        go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
         if small:   # gt[h] = go_h @ Wv_h
             gt = torch.bmm(go2.view(Q, H, dh).transpose(0, 1), wv.view(H, dh, C))
+        elif htc:
+            gt = rows_heads_in(go2, lw.p_wv_ht, C, H)                                               # [H,Q,C]
         else:
             _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
             gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)    # [H,Q,C]
@@ -828,26 +920,29 @@ class EncoderLayerRows(torch.autograd.Function):
         g_wv, g_bv = side.run(_wv, go2, t)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
-        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if sp else None
+        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
         call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
              ptr(gqt), ptr(gqt_s), stream())
-        if small:   # gqv[h] = scale * gqt[h] @ Wk_h^T   [H,Q,dh]
-            gqv_h = torch.empty(H, Q, dh, device=dev, dtype=F32)
-            torch.baddbmm(gqv_h, gqt, wk.view(H, dh, C).transpose(1, 2), beta=0, alpha=scale, out=gqv_h)
+        if htc:     # gqv[:, h] = gqt[h] @ (scale Wk_h)^T, written straight into the [Q,C] layout
+            gqv, gqv_s = rows_heads_out(gqt, lw.p_wk, dh), None
         else:
-            gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+            if small:   # gqv[h] = scale * gqt[h] @ Wk_h^T   [H,Q,dh]
+                gqv_h = torch.empty(H, Q, dh, device=dev, dtype=F32)
+                torch.baddbmm(gqv_h, gqt, wk.view(H, dh, C).transpose(1, 2), beta=0, alpha=scale, out=gqv_h)
+            else:
+                gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
+            gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H, want_split=sp)
 
         def _wk():
             if fp32_heads:
                 return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
             return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
         g_wk = side.run(_wk, qv, gqt)
-        gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H, want_split=sp)
         g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
-        gg = lin_t(gqv, gqv_s, wq, lw.wq_t)
+        gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
         gg_s = split_cols(gg, 0) if sp else None
         g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
-        gmean = lin_t(gg, gg_s, w_out, lw.w_out_t)
+        gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())

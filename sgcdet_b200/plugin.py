@@ -351,6 +351,12 @@ class DenseHead(nn.Module):
     def num_voxels(self) -> int:
         return int(self.n_voxels.prod())
 
+    def _fused_layer(self) -> bool:
+        """Whether the VoxFormerLayer runs as ``functional.EncoderLayerRows`` (one autograd node, fused row kernels)."""
+        ffn = self.cross_transformer.encoder.layers[0].ffns[0]
+        return (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and self.embed_dims in (128, 256) and ffn.add_identity
+                and ffn.layers[0][0].out_features in (128, 256, 512))
+
     def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
@@ -363,8 +369,10 @@ class DenseHead(nn.Module):
         mha = attn.attention_pooling
         ffn = layer.ffns[0]
         wcat, vbias, gbias = da.folded_weights()
+        # the fused layer runs its GEMMs on the own tcgen05 kernel from packed weights; only the unfused fallback
+        # still needs the bf16x3 images of the layer weights
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
-                             ffn.layers[0][0].weight, ffn.layers[1].weight)
+                             ffn.layers[0][0].weight, ffn.layers[1].weight, images=not self._fused_layer())
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
         dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
@@ -416,9 +424,7 @@ class DenseHead(nn.Module):
         pp, ws = prepared['params'], prepared['wstream']
         ffn = layer.ffns[0]
         C = self.embed_dims
-        fused = (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and C in (128, 256) and ffn.add_identity
-                 and ffn.layers[0][0].out_features in (128, 256, 512))
-        if fused:
+        if self._fused_layer():
             drops = (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p)
             masks = prepared.get('masks') if self.training else None
             if self.training and any(p > 0 for p in drops):

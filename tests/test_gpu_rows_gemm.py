@@ -1,0 +1,128 @@
+"""Voxel-count GEMMs on the own tcgen05 kernel (csrc/sgc_rows_gemm_tc.cu) vs fp64 references of the same products.
+Tolerance: rtol 1e-3 / atol 1e-4 relative to the output scale (the bf16 hi/lo split gives ~1e-5)."""
+import math
+
+import pytest
+import torch
+
+from sgcdet_b200 import functional as SF
+from sgcdet_b200._lib import call, ptr, stream
+
+pytestmark = pytest.mark.gpu
+
+
+def pack(w):
+    N, K = w.shape
+    out = torch.empty(2 * N * K, device=w.device, dtype=torch.bfloat16)
+    call('sgc_pack_weight_tc', ptr(w.contiguous()), N, K, ptr(out), stream())
+    return out
+
+
+def check(got, ref):
+    assert torch.isfinite(got).all()
+    scale = ref.abs().max().item()
+    err = (got.double() - ref).abs().max().item() / scale
+    assert err < 1e-4, err
+    torch.testing.assert_close(got.double() / scale, ref / scale, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('R,K,N,n_cta,bias', [
+    (6400, 256, 256, 0, True),     # output_proj / attention in-projection at the finest level
+    (6400, 256, 512, 0, True),     # FFN layer 1
+    (6400, 512, 256, 0, False),    # FFN layer 2 (16 k-slabs)
+    (6400, 256, 256, 256, False),  # one column part per row tile
+    (6400, 256, 256, 32, True),    # eight column parts per row tile
+    (800, 256, 256, 0, True),      # 7 row tiles, the last one 32 rows
+    (400, 256, 512, 64, False),
+    (37, 256, 256, 0, True),       # fewer rows than one tile
+    (1, 128, 128, 0, True),
+    (3200, 128, 256, 128, True),   # "-L" shapes
+    (51200, 128, 128, 0, False),   # more work items than SMs: every pipeline wraps several times
+    (20000, 32, 64, 64, True),     # a single k-slab per work item
+])
+def test_rows_linear_matches_fp64(cuda_lib, R, K, N, n_cta, bias):
+    g = torch.Generator().manual_seed(R + 7 * K + 13 * N + n_cta)
+    x = torch.randn(R, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    y = SF.rows_linear(x, pack(w), N, b, n_cta)
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t()
+    if bias:
+        ref = ref + b.double()
+    check(y, ref)
+
+
+def test_rows_gemm_clips_rows_and_leaves_the_rest_untouched(cuda_lib):
+    """Rows >= R of the output allocation are never written (the TMA store clips), padding columns neither."""
+    g = torch.Generator().manual_seed(3)
+    R, K, N, ld = 200, 256, 128, 192
+    x = torch.randn(R, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / 16).cuda()
+    y = torch.full((R + 100, ld), 7.0, device='cuda')
+    call('sgc_rows_gemm_tc', ptr(x), K, 0, R, K, 1, ptr(pack(w)), N, 0, 0, None, 0, N, ptr(y), ld, 0, 0, stream())
+    torch.cuda.synchronize()
+    assert (y[R:] == 7.0).all() and (y[:, N:] == 7.0).all()
+    check(y[:R, :N], x.double() @ w.double().t())
+
+
+@pytest.mark.parametrize('R,C,N', [(6400, 256, 256), (800, 256, 256), (77, 256, 256)])
+def test_rows_heads_in_matches_fp64(cuda_lib, R, C, N):
+    """y[h] = x[:, h*dh:(h+1)*dh] @ W_h with the per-head packed transposes produced by sgc_prepare_weights."""
+    H = 8
+    dh = C // H
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g).cuda()
+    wk = (torch.randn(C, N, generator=g) / dh ** 0.5).cuda()      # rows h*dh.. are W_h [dh, N]
+    scale = 1.0 / math.sqrt(dh)
+    j = SF._WeightJobs(x.device)
+    p = j.pack_heads_t(wk, H, scale)
+    j.launch()
+    y = SF.rows_heads_in(x, p, N, H)
+    torch.cuda.synchronize()
+    ref = torch.einsum('rhd,hdn->hrn', x.double().view(R, H, dh), wk.double().view(H, dh, N)) * scale
+    check(y, ref)
+
+
+@pytest.mark.parametrize('R,C', [(6400, 256), (800, 256), (77, 256)])
+def test_rows_heads_out_matches_fp64(cuda_lib, R, C):
+    """y[:, h*dh:(h+1)*dh] = x[h] @ W[h*dh:(h+1)*dh]^T + bias, written straight into the [R,C] layout."""
+    H = 8
+    dh = C // H
+    g = torch.Generator().manual_seed(R * 3 + C)
+    x = torch.randn(H, R, C, generator=g).cuda()
+    wv = (torch.randn(C, C, generator=g) / C ** 0.5).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = SF.rows_heads_out(x, pack(wv), dh, b)
+    torch.cuda.synchronize()
+    ref = torch.einsum('hrk,hdk->rhd', x.double(), wv.double().view(H, dh, C)).reshape(R, C) + b.double()
+    check(y, ref)
+
+
+def test_level_weights_packs_match_single_kernel(cuda_lib):
+    """The packed operands LevelWeights prepares in one launch are bit-identical to sgc_pack_weight_tc of the same
+    (scaled / transposed) matrices."""
+    C, N, F = 256, 384, 512
+    g = torch.Generator().manual_seed(11)
+    dev = 'cuda'
+    wcat = torch.randn(N, C, generator=g).to(dev)
+    w_out, wo = torch.randn(C, C, generator=g).to(dev), torch.randn(C, C, generator=g).to(dev)
+    in_w = torch.randn(3 * C, C, generator=g).to(dev)
+    w1, w2 = torch.randn(F, C, generator=g).to(dev), torch.randn(C, F, generator=g).to(dev)
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
+    if not lw.rows_tc:
+        pytest.skip('SGC_ROWS_TC=0')
+    dh = C // 8
+    scale = 1.0 / math.sqrt(dh)
+    wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
+    ref = dict(p_w_out=pack(w_out), p_w_out_t=pack(w_out.t()), p_wq=pack(wq), p_wq_t=pack(wq.t()), p_wo=pack(wo),
+               p_wo_t=pack(wo.t()), p_w1=pack(w1), p_w1_t=pack(w1.t()), p_w2=pack(w2), p_w2_t=pack(w2.t()),
+               p_wk=pack(wk * scale), p_wv=pack(wv),
+               p_wk_ht=torch.cat([pack((wk[h * dh:(h + 1) * dh] * scale).t()) for h in range(8)]),
+               p_wv_ht=torch.cat([pack(wv[h * dh:(h + 1) * dh].t()) for h in range(8)]))
+    torch.cuda.synchronize()
+    for k, r in ref.items():
+        got = getattr(lw, k)
+        assert got.shape == r.shape, k
+        assert torch.equal(got.view(torch.int16), r.view(torch.int16)), k
+    assert lw.w_out is None and lw.wk_rows is None

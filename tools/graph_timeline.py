@@ -1,7 +1,7 @@
 """Timeline of one CUDA-graph replay from a torch-profiler chrome trace (tools/profile_step.py, SGC_GRAPH_TRACE):
 per-stream busy time, the union busy time, idle gaps, and the kernel sequence with start offsets.
 
-    python tools/graph_timeline.py trace.json [min_us_to_list]
+    python tools/graph_timeline.py trace.json [min_us_to_list] [all_events_out.txt]
 """
 import collections
 import json
@@ -47,3 +47,9 @@ for e in ev:
     gap = e['ts'] - prev if prev is not None else 0.0
     print(f'  {e["ts"] - t0:9.1f} {e["dur"]:7.1f} {gap:6.1f}  {e["name"][:64]}')
     prev = e['ts'] + e['dur']
+
+if len(sys.argv) > 3:
+    # every device activity: start, duration, stream, name (for dependency / overlap analysis offline)
+    with open(sys.argv[3], 'w') as f:
+        for e in ev:
+            f.write(f'{e["ts"] - t0:9.1f} {e["dur"]:7.1f} s{e["args"].get("stream")} {e["name"][:90]}\n')
