@@ -422,6 +422,8 @@ def run_ours(args):
                 key = f'{name}[V={a[3]},C={a[4]},S={a[5]},N={a[7]}]'
             elif name in ('sgc_split_bf16x3', 'sgc_colsum'):
                 key = f'{name}[{a[1]}x{a[2]}]'
+            elif name == 'sgc_rows_gemm_tc':
+                key = f'{name}[B={a[5]},R={a[3]},K={a[4]},N={a[12]}]'
             elif name in ('sgc_rowop_fwd', 'sgc_rowop_bwd'):
                 key = f'{name}[{a[0]._obj.R}x{a[0]._obj.N}]'
             d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=kernel_algorithmic_bytes(name, a, pairs_by_q)))

@@ -117,6 +117,9 @@ int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, const void* w
 int sgc_project_tc_wgrad_scratch_floats(int N, int C);
 /* Cap on the SMs the three projection kernels occupy (0 = all; they run beside the latency-bound voxel chain). */
 int sgc_project_tc_set_max_ctas(int n);
+/* The same cap for the forward projection alone (0 = the common cap): in the forward the projections of the finer levels
+ * only run beside the voxel chain of the coarser levels and may leave it more SMs. */
+int sgc_project_tc_set_max_ctas_fwd(int n);
 /* n > 0: the forward / data-gradient kernels run as short-lived CTAs of n tiles each instead of persistent ones. */
 int sgc_project_tc_set_tiles_per_cta(int n);
 int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C, float* gw,

@@ -42,6 +42,7 @@ SIGNATURES = {
     'sgc_project_tc_bwd_data': [P, I, I, I, P, I, P, LL, P],
     'sgc_project_tc_wgrad_scratch_floats': [I, I],
     'sgc_project_tc_set_max_ctas': [I],
+    'sgc_project_tc_set_max_ctas_fwd': [I],
     'sgc_project_tc_set_tiles_per_cta': [I],
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_rows_gemm_tc_auto_ncta': [I, I, I],
@@ -114,6 +115,7 @@ def load() -> ctypes.CDLL:
             fn.argtypes = argtypes
             fn.restype = c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
+        lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '0')))
         lib.sgc_project_tc_set_tiles_per_cta(int(os.environ.get('SGC_TC_TILES_PER_CTA', '0')))
         _lib = lib
     return _lib

@@ -354,6 +354,15 @@ extern "C" int sgc_project_tc_set_max_ctas(int n) {
   g_tc_max_ctas = n;
   return 0;
 }
+// Separate cap for the FORWARD projection only: in the forward the projections of the finer levels run beside the voxel
+// chain of the coarser ones and are far off the critical path, so they can leave more SMs to the chain than the backward
+// kernels (which ARE the critical path of the backward).  0 = use the common cap.
+static int g_tc_max_ctas_fwd = 0;
+extern "C" int sgc_project_tc_set_max_ctas_fwd(int n) {
+  if (n < 0) return (int)cudaErrorInvalidValue;
+  g_tc_max_ctas_fwd = n;
+  return 0;
+}
 static int g_tc_tiles_per_cta = 0;  // 0 = persistent (grid = SM cap); n > 0: short-lived CTAs of n tiles each
 extern "C" int sgc_project_tc_set_tiles_per_cta(int n) {
   if (n < 0) return (int)cudaErrorInvalidValue;
@@ -442,7 +451,8 @@ extern "C" int sgc_project_tc_fwd(const float* feat, long long view_stride, long
   cudaError_t e = cudaFuncSetAttribute(project_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int tiles = V * ((S + BM - 1) / BM);
-  const int grid = tc_grid(tiles, sms);
+  int grid = tc_grid(tiles, sms);
+  if (g_tc_tiles_per_cta == 0 && g_tc_max_ctas_fwd > 0 && grid > g_tc_max_ctas_fwd) grid = g_tc_max_ctas_fwd;
   project_tc_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(fmap, omap, V, C, S, (const __nv_bfloat16*)wpack, N, vg, 0,
                                                                            getenv("SGC_TC_DBG") ? atoi(getenv("SGC_TC_DBG")) : 0);
   SGC_CUDA_CHECK_LAST();

@@ -94,6 +94,7 @@ SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs wi
 # voxel-count GEMMs of the encoder layer on the own tcgen05 kernel (csrc/sgc_rows_gemm_tc.cu) instead of the library's
 # bf16 GEMM on bf16x3 operand images
 ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
+ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -129,6 +130,8 @@ def rows_linear(x: torch.Tensor, wpack: torch.Tensor, N: int, bias: Optional[tor
     """y [R,N] = x [R,K] @ W^T (+ bias) with ``wpack`` = the packed [N,K] weight (``sgc_rows_gemm_tc``)."""
     R, K = x.shape
     y = torch.empty(R, N, device=x.device, dtype=F32)
+    if n_cta == 0 and ROWS_NCTA and N % ROWS_NCTA == 0:
+        n_cta = ROWS_NCTA
     call('sgc_rows_gemm_tc', ptr(x), K, 0, R, K, 1, ptr(wpack), N, 0, 0, ptr(bias), 0, N, ptr(y), N, 0, n_cta, stream())
     return y
 
@@ -512,20 +515,24 @@ class Lift(torch.autograd.Function):
         gslots = gslots.contiguous()
         cur = torch.cuda.current_stream(vg.device)
         side = ctx.bwd_stream if ctx.bwd_stream is not None and ctx.bwd_stream != cur else None
+        def _zeros():
+            return (torch.zeros_like(vg), torch.zeros_like(dist), torch.zeros_like(vbias),
+                    torch.zeros(G_CH, device=vg.device, dtype=torch.float32))
+        prezero = _os.environ.get('SGC_PREZERO', '1') != '0'
         with torch.cuda.stream(side if side is not None else cur):
             # the accumulation targets are zero-filled BEFORE the side stream joins the voxel chain: the fills (290 MB
             # at the finest level) depend on nothing, so they run while the chain is still busy instead of in front of
             # the kernel on the critical path
-            gvg = torch.zeros_like(vg)
-            gdist = torch.zeros_like(dist)
-            gvb = torch.zeros_like(vbias)
-            ggb = torch.zeros(G_CH, device=vg.device, dtype=torch.float32)
+            if prezero:
+                gvg, gdist, gvb, ggb = _zeros()
         if side is not None:
             # every consumer of the four gradients is a backward node of the side stream, so main never waits
             side.wait_stream(cur)
             for t in (gslots, samp, pl.pair_vq, pl.n_pairs, pl.ref_cam):
                 t.record_stream(side)
         with torch.cuda.stream(side if side is not None else cur):
+            if not prezero:
+                gvg, gdist, gvb, ggb = _zeros()
             base, gbase = ptr(vg), ptr(gvg)
             scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device,
                                   dtype=torch.float32)

@@ -304,6 +304,21 @@ def _side_streams(device, n: int, main=None):
     return pool[:n]
 
 
+_LEVEL_STREAMS = {}
+
+
+def _level_chain_streams(device, n: int, main):
+    """One high-priority stream per level for that level's per-voxel chain.  In the forward the levels depend on each other
+    (level i needs the selection made from level i-1), but in the backward only through the small upsample / scatter
+    nodes: autograd replays every node on its forward stream, so with one stream per level the three voxel chains of the
+    backward run concurrently instead of back to back, each followed by its own large lift / projection gradient kernels."""
+    key = (torch.device(device), main.cuda_stream)
+    pool = _LEVEL_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=torch.device(device), priority=-1))
+    return pool[:n]
+
+
 def _dropout_masks(rows: int, widths, drops, device):
     """uint8 keep-masks [rows, width] for every dropout with p > 0 (None otherwise)."""
     return tuple(torch.empty(rows, w, device=device, dtype=torch.uint8).bernoulli_(1.0 - p) if p > 0 else None
@@ -373,8 +388,11 @@ class DenseHead(nn.Module):
         # still needs the bf16x3 images of the layer weights
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
                              ffn.layers[0][0].weight, ffn.layers[1].weight, images=not self._fused_layer())
-        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
+        # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
+        # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
+        # depth gradient's copies instead of queueing behind them on the same stream
         dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
+        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
         params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,
@@ -531,6 +549,23 @@ class AdaptiveSparseHead(nn.Module):
         # streams up front; level i joins its stream right before it needs the projected maps
         main = torch.cuda.current_stream(dev)
         streams = _side_streams(dev, nl, main) if os.environ.get('SGC_SIDE_PREPARE', '1') != '0' else [main] * nl
+        lvl_streams = _level_chain_streams(dev, nl, main) if os.environ.get('SGC_LEVEL_STREAMS', '1') != '0' else None
+
+        def level_rows(i, head, fi, hw, sel, pre):
+            """forward_rows of level i on that level's own chain stream (see _level_chain_streams)."""
+            if lvl_streams is None:
+                return head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre)
+            s = lvl_streams[i]
+            s.wait_stream(main)
+            for t in (sel, proj, pre['vg'], pre['dist'], pre['vbias'], pre['gbias']) + tuple(pre.get('masks') or ()):
+                if t is not None:
+                    t.record_stream(s)
+            pre['lw'].record_stream(s)
+            with torch.cuda.stream(s):
+                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre)
+            main.wait_stream(s)
+            (r[0] if return_intermediates else r).record_stream(main)
+            return r
         prepared = []
         for i in range(nl):
             streams[i].wait_stream(main)
@@ -558,7 +593,7 @@ class AdaptiveSparseHead(nn.Module):
                 if t is not None:
                     t.record_stream(main)
             if i == 0:
-                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, None, proj, return_intermediates, pre)
+                r = level_rows(i, head, fi, hw, None, pre)
                 y, it = r if return_intermediates else (r, None)
                 X, Y, Z = (int(v) for v in head.n_voxels)
                 vol = y.view(X, Y, Z, self.embed_dims)
@@ -581,7 +616,7 @@ class AdaptiveSparseHead(nn.Module):
                     masks[i] = mask
                 else:
                     sel = None
-                r = head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre)
+                r = level_rows(i, head, fi, hw, sel, pre)
                 y, it = r if return_intermediates else (r, None)
                 if sel is None:
                     vol = up + y.view_as(up)
