@@ -98,7 +98,7 @@ LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_cross
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
                 sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1, sgc_rows_gemm_tc=1,
-                sgc_prepare_weights=1)
+                sgc_prepare_weights=1, sgc_rows_wgrad_tc=2)
 
 
 class CallRecorder:
@@ -192,6 +192,9 @@ def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
     if name == 'sgc_project_tc_fwd':
         V, C, S, N = args[3], args[4], args[5], args[7]
         return 4.0 * V * S * (C + N) + 4.0 * N * C
+    if name == 'sgc_rows_wgrad_tc':
+        M, N, R, B = args[3], args[7], args[8], args[9]
+        return 4.0 * B * R * (M + N) + 4.0 * B * M * N
     if name == 'sgc_rows_gemm_tc':
         R, K, B, N = args[3], args[4], args[5], args[12]
         return 4.0 * B * R * (K + N) + 4.0 * B * N * K
@@ -422,6 +425,8 @@ def run_ours(args):
                 key = f'{name}[V={a[3]},C={a[4]},S={a[5]},N={a[7]}]'
             elif name in ('sgc_split_bf16x3', 'sgc_colsum'):
                 key = f'{name}[{a[1]}x{a[2]}]'
+            elif name == 'sgc_rows_wgrad_tc':
+                key = f'{name}[B={a[9]},R={a[8]},M={a[3]},N={a[7]}]'
             elif name == 'sgc_rows_gemm_tc':
                 key = f'{name}[B={a[5]},R={a[3]},K={a[4]},N={a[12]}]'
             elif name in ('sgc_rowop_fwd', 'sgc_rowop_bwd'):

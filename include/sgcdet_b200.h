@@ -140,6 +140,19 @@ int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, in
                      int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
                      int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream);
 
+/* Weight gradients of the same layers on the tensor cores (reduction over the voxel rows, csrc/sgc_rows_gemm_tc.cu):
+ *     out[b*out_b + m*out_m + n*out_n] = scale * sum_r a[b*batch_a + r*lda + m] * b[b*batch_b + r*ldb + n],  m < M, n < N
+ * For y = x W^T + bias with upstream gradient g: gW = g^T x (a = g, b = x).  bias_from = 1: bias_out[b*M + m] = sum_r a
+ * (the bias gradient), 2: bias_out[b*N + n] = sum_r b, 0: none.  M % 128 == 0, N % 32 == 0; a batch stride smaller than
+ * the leading dimension addresses the heads of a [R, H*dh] matrix (per-head key / value weights: a = t[h] or grad_qt[h],
+ * b = the head's columns, and the output strides write the transposed result into in_proj_weight's gradient).
+ * Both operands are split to bf16 hi/lo in shared memory; split-K partials in `scratch`
+ * (sgc_rows_wgrad_tc_scratch_floats floats) are summed in a fixed order (deterministic). */
+int sgc_rows_wgrad_tc_scratch_floats(int M, int N, int R, int B);
+int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_a, int M, const float* b, long long ldb,
+                      long long batch_b, int N, int R, int B, float* out, long long out_b, long long out_m,
+                      long long out_n, float scale, float* bias_out, int bias_from, float* scratch, void* stream);
+
 /* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
  * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */
 int sgc_colsum_scratch_floats(int R, int C);
@@ -243,6 +256,7 @@ typedef struct sgc_rowop_fwd_args {
   float* rstd;
   float mscale, eps;
   int R, N, relu, in_heads, split_heads;
+  const int* rowcount; /* optional [R] view counts: v *= (rowcount[r] > 0), applied where rowscale is */
 } sgc_rowop_fwd_args;
 typedef struct sgc_rowop_bwd_args {
   const float* g;
@@ -260,6 +274,7 @@ typedef struct sgc_rowop_bwd_args {
   void* gxsplit;
   float mscale, gscale;
   int R, N, in_heads, split_heads;
+  const int* rowcount; /* as in sgc_rowop_fwd_args */
 } sgc_rowop_bwd_args;
 int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
 int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);

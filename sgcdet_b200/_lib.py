@@ -47,6 +47,8 @@ SIGNATURES = {
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_rows_gemm_tc_auto_ncta': [I, I, I],
     'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
+    'sgc_rows_wgrad_tc_scratch_floats': [I, I, I, I],
+    'sgc_rows_wgrad_tc': [P, LL, LL, I, P, LL, LL, I, I, I, P, LL, LL, LL, F, P, I, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],
@@ -87,7 +89,7 @@ class RowopFwdArgs(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('x', 'bias', 'mask', 'rowscale', 'residual', 'gamma', 'beta', 'y', 'ysplit',
                                         'pre', 'mean', 'rstd')] + \
                [('mscale', c_float), ('eps', c_float), ('R', c_int), ('N', c_int), ('relu', c_int),
-                ('in_heads', c_int), ('split_heads', c_int)]
+                ('in_heads', c_int), ('split_heads', c_int), ('rowcount', c_void_p)]
 
 
 class RowopBwdArgs(ctypes.Structure):
@@ -95,7 +97,7 @@ class RowopBwdArgs(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('g', 'g2', 'pre', 'mean', 'rstd', 'gamma', 'mask', 'gate', 'rowscale',
                                         'partial', 'gpre', 'gx', 'gxsplit')] + \
                [('mscale', c_float), ('gscale', c_float), ('R', c_int), ('N', c_int), ('in_heads', c_int),
-                ('split_heads', c_int)]
+                ('split_heads', c_int), ('rowcount', c_void_p)]
 
 
 def lib_path() -> Path:

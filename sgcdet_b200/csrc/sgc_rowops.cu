@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) rowop_fwd_kernel(const sgc_row
 #pragma unroll
       for (int j = 0; j < CPL; ++j) v[j] *= rsc;
     }
+    if (a.rowcount) {  // rows no view sees are zeroed (DCA:819-835): scale 1 / 0 from the per-voxel view count
+      const float rsc = __ldg(a.rowcount + r) > 0 ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= rsc;
+    }
     if (a.residual) {
       float t[CPL];
       load_row<CPL>(t, a.residual + (size_t)r * N + c0);
@@ -277,6 +282,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) rowop_bwd_kernel(const sgc_row
     }
     if (a.rowscale) {
       const float rsc = __ldg(a.rowscale + r);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] *= rsc;
+    }
+    if (a.rowcount) {  // rows no view sees are zeroed (DCA:819-835): scale 1 / 0 from the per-voxel view count
+      const float rsc = __ldg(a.rowcount + r) > 0 ? 1.f : 0.f;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) v[j] *= rsc;
     }

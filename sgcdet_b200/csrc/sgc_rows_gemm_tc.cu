@@ -345,3 +345,312 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
+
+// =====================================================================================================================
+// sgc_rows_wgrad_tc: the weight gradients of the same layers (reduction over the voxel rows):
+//
+//     out_b[m, n] = scale * sum_r A_b[r, m] * B_b[r, n]          bias[m] = sum_r A[r, m]   (or over B's columns)
+//
+// For y = x W^T + b with upstream gradient g:  gW = g^T x  (A = g, B = x, bias gradient = column sums of A).  The per-head
+// key / value weights use the transposed product (A = t[h] / gqt[h] with M = C, B = the head's 32 columns of go / qv) and
+// the reduce kernel writes the result transposed, because a UMMA tile needs M = 128 rows.
+// Both operands are fp32 in HBM, TMA-loaded as [32 rows][cols] tiles and split to bf16 hi/lo in shared memory (the
+// "[k][m]" converter of wgrad_tc_kernel for both).  Split-K over the rows: CTA (m-tile, k-chunk, column part, batch)
+// accumulates its rows in TMEM and writes a partial tile; the reduce kernel sums the partials in a fixed order
+// (deterministic), applies `scale` and writes through arbitrary output strides (so gradients land directly inside
+// in_proj_weight's [3C,C] gradient).  Column sums are accumulated by the converter threads per CTA and reduced alike.
+namespace sgc {
+namespace tc {
+
+constexpr int RW_THREADS = 352;
+constexpr int RW_ST = 2;
+
+struct SmemRW {
+  uint64_t f_full[RW_ST], f_empty[RW_ST], op_full[RW_ST], op_empty[RW_ST], tmem_full;
+  uint32_t tmem_base;
+};
+
+struct RowsWgradParams {
+  float* partial;        // [kch][B][M][N]
+  float* bias_partial;   // [kch][B][M or N]
+  int M, N, n_cta, R, m_tiles, kch, slabs_per_cta, total_slabs;
+  int a_swap, b_swap, bias_from;
+};
+
+__global__ void __launch_bounds__(RW_THREADS, 1)
+rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                     const __grid_constant__ RowsWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cta = p.n_cta;
+  const int a_src = BK * BM * 4;              // 16 KB  [32 r][128 m] fp32
+  const int b_src = BK * n_cta * 4;           // [32 r][n_cta] fp32
+  const int f_stage = a_src + b_src;
+  const int a_op = 2 * BM * BK * 2;           // hi + lo, 16 KB
+  const int b_op = 2 * n_cta * BK * 2;        // hi + lo
+  const int op_stage = a_op + b_op;
+  uint8_t* f_base = smem_raw;
+  uint8_t* op_base = f_base + RW_ST * f_stage;
+  SmemRW* sm = reinterpret_cast<SmemRW*>(op_base + RW_ST * op_stage);
+
+  const int mt = blockIdx.x % p.m_tiles, kc = blockIdx.x / p.m_tiles;
+  const int np = blockIdx.y, bt = blockIdx.z, nb = gridDim.z;
+  const int s_begin = kc * p.slabs_per_cta;
+  const int s_end = min(p.total_slabs, s_begin + p.slabs_per_cta);
+  const int n_slabs = max(0, s_end - s_begin);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RW_ST; ++i) {
+      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 256);
+      mbar_init(&sm->op_full[i], 256); mbar_init(&sm->op_empty[i], 1);
+    }
+    mbar_init(&sm->tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      Pipe pf(RW_ST);
+      for (int i = 0; i < n_slabs; ++i) {
+        const int r0 = (s_begin + i) * BK;
+        mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
+        mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage);
+        uint8_t* st = f_base + pf.stage * f_stage;
+        if (p.a_swap) tma_load_3d(st, &amap, mt * BM, bt, r0, &sm->f_full[pf.stage]);
+        else tma_load_3d(st, &amap, mt * BM, r0, bt, &sm->f_full[pf.stage]);
+        if (p.b_swap) tma_load_3d(st + a_src, &bmap, np * n_cta, bt, r0, &sm->f_full[pf.stage]);
+        else tma_load_3d(st + a_src, &bmap, np * n_cta, r0, bt, &sm->f_full[pf.stage]);
+        pf.next();
+      }
+    }
+  } else if (warp < 8) {
+    // converters: warps 0-3 -> A tile [32 r][128 m], warps 4-7 -> B tile [32 r][n_cta]; thread = column(s) of the tile
+    const bool is_b = warp >= 4;
+    const int t = threadIdx.x & 127;
+    const int width = is_b ? n_cta : BM;
+    float csum0 = 0.f, csum1 = 0.f;     // column sums of this thread's column(s) over the CTA's rows
+    Pipe pf(RW_ST), po(RW_ST);
+    for (int i = 0; i < n_slabs; ++i) {
+      mbar_wait(&sm->f_full[pf.stage], pf.phase);
+      const uint8_t* st = f_base + pf.stage * f_stage + (is_b ? a_src : 0);
+      mbar_wait(&sm->op_empty[po.stage], po.phase ^ 1);
+      uint8_t* op = op_base + po.stage * op_stage + (is_b ? a_op : 0);
+      uint8_t* hi = op;
+      uint8_t* lo = op + width * BK * 2;
+#pragma unroll 1
+      for (int c = t, rep = 0; c < width; c += 128, ++rep) {
+        const float* src = reinterpret_cast<const float*>(st) + c;
+        float x[BK];
+#pragma unroll
+        for (int k = 0; k < BK; ++k) x[k] = src[k * width];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < BK; ++k) s += x[k];
+        if (rep == 0) csum0 += s; else csum1 += s;
+        const uint32_t off = (c >> 3) * SBO + (c & 7) * 16;
+#pragma unroll
+        for (int kcx = 0; kcx < BK / 8; ++kcx) {
+          __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            h[q] = __float2bfloat16_rn(x[kcx * 8 + q]);
+            l[q] = __float2bfloat16_rn(x[kcx * 8 + q] - __bfloat162float(h[q]));
+          }
+          *reinterpret_cast<uint4*>(hi + off + kcx * LBO) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + off + kcx * LBO) = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+      mbar_arrive(&sm->f_empty[pf.stage]);   // after the staged values were consumed
+      pf.next();
+      fence_proxy_async();
+      mbar_arrive(&sm->op_full[po.stage]);
+      po.next();
+    }
+    // column sums (bias gradients): one CTA per (k-chunk, batch, column) writes them
+    if (p.bias_from == 1 && !is_b && np == 0) {
+      p.bias_partial[((size_t)kc * nb + bt) * p.M + mt * BM + t] = csum0;
+    } else if (p.bias_from == 2 && is_b && mt == 0) {
+      float* dst = p.bias_partial + ((size_t)kc * nb + bt) * p.N + np * n_cta;
+      if (t < n_cta) dst[t] = csum0;
+      if (t + 128 < n_cta) dst[t + 128] = csum1;
+    }
+    if (!is_b) {
+      // epilogue by warps 0-3: partial[kc][bt][mt*128 + row][np*n_cta .. +n_cta)
+      const int lane_base = (warp & 3) * 32;
+      const int row = lane_base + lane;
+      float* dst = p.partial + (((size_t)kc * nb + bt) * p.M + (size_t)mt * BM + row) * p.N + np * n_cta;
+      if (n_slabs > 0) {
+        mbar_wait(&sm->tmem_full, 0);
+        tc_fence_after();
+      }
+      for (int c0 = 0; c0 < n_cta; c0 += 32) {
+        uint32_t r[32];
+        if (n_slabs > 0) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cta >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      Pipe po(RW_ST);
+      for (int i = 0; i < n_slabs; ++i) {
+        mbar_wait(&sm->op_full[po.stage], po.phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(op_base + po.stage * op_stage);
+        const uint32_t a_lo = a_hi + BM * BK * 2;
+        const uint32_t b_hi = a_hi + a_op;
+        const uint32_t b_lo = b_hi + n_cta * BK * 2;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          const uint32_t o = ks * 2 * LBO;
+          umma_bf16(tmem, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, (i | ks) ? 1u : 0u);
+          umma_bf16(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, 1u);
+          umma_bf16(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+        }
+        tc_commit(&sm->op_empty[po.stage]);
+        po.next();
+      }
+      if (n_slabs > 0) tc_commit(&sm->tmem_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+  }
+}
+
+// out[b*ob + m*om + n*on] = scale * sum_k partial[k][b][m][n]  and  bias_out[i] = sum_k bias_partial[k][i]   (fixed order)
+__global__ void __launch_bounds__(256)
+rows_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias_partial, int kch, int B, int M, int N,
+                         float scale, float* __restrict__ out, long long ob, long long om, long long on,
+                         float* __restrict__ bias_out, int bias_len) {
+  const long long elems = (long long)B * M * N;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < elems) {
+    float a = 0.f;
+    for (int k = 0; k < kch; ++k) a += __ldg(partial + (size_t)k * elems + i);
+    const int n = (int)(i % N);
+    const long long t = i / N;
+    const int m = (int)(t % M), b = (int)(t / M);
+    out[b * ob + m * om + n * on] = a * scale;
+  }
+  if (bias_out && i < bias_len) {
+    float a = 0.f;
+    for (int k = 0; k < kch; ++k) a += __ldg(bias_partial + (size_t)k * bias_len + i);
+    bias_out[i] = a;
+  }
+}
+
+// [cols, rows, batch] fp32 view with a [box_cols, 32, 1] box, no swizzle (or [cols, batch, rows] / [box_cols, 1, 32] when the
+// batch stride is the smaller one: the heads of a [R, H*dh] matrix).
+static inline bool make_wgrad_map(PFN_encodeTiled encode, CUtensorMap* map, const float* base, int cols, int rows, int batch,
+                                  long long ld, long long batch_stride, int box_cols, int* swapped) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || ld < cols || box_cols > 256 || (box_cols * 4) % 16) return false;
+  if (batch > 1 && ((batch_stride * 4) % 16 || batch_stride <= 0)) return false;
+  const bool swap = batch > 1 && batch_stride < ld;
+  *swapped = swap ? 1 : 0;
+  const cuuint64_t bs = batch > 1 ? (cuuint64_t)batch_stride * 4 : (cuuint64_t)ld * 4 * (cuuint64_t)rows;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t box[3];
+  const cuuint32_t estr[3] = {1, 1, 1};
+  gdim[0] = (cuuint64_t)cols;
+  box[0] = (cuuint32_t)box_cols;
+  if (swap) {
+    gdim[1] = (cuuint64_t)batch; gdim[2] = (cuuint64_t)rows;
+    gstr[0] = bs; gstr[1] = (cuuint64_t)ld * 4;
+    box[1] = 1; box[2] = (cuuint32_t)BK;
+  } else {
+    gdim[1] = (cuuint64_t)rows; gdim[2] = (cuuint64_t)batch;
+    gstr[0] = (cuuint64_t)ld * 4; gstr[1] = bs;
+    box[1] = (cuuint32_t)BK; box[2] = 1;
+  }
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline void rows_wgrad_plan(int M, int N, int R, int B, int* n_cta, int* kch) {
+  int nc = N <= 256 ? N : 256;
+  while (N % nc) nc >>= 1;
+  const int tiles = (M / BM) * (N / nc) * B;
+  const int total_slabs = (R + BK - 1) / BK;
+  int k = total_slabs / 8;                       // at least ~8 row slabs (256 rows) per CTA
+  const int cap = tiles < 148 ? 148 / tiles : 1;
+  if (k > cap) k = cap;
+  if (k < 1) k = 1;
+  *n_cta = nc;
+  *kch = k;
+}
+
+}  // namespace tc
+}  // namespace sgc
+
+extern "C" int sgc_rows_wgrad_tc_scratch_floats(int M, int N, int R, int B) {
+  if (M <= 0 || N <= 0 || R <= 0 || B <= 0 || M % sgc::tc::BM || N % 32) return 0;
+  int n_cta, kch;
+  sgc::tc::rows_wgrad_plan(M, N, R, B, &n_cta, &kch);
+  return (int)((long long)kch * B * ((long long)M * N + (M > N ? M : N)));
+}
+
+extern "C" int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_a, int M, const float* b, long long ldb,
+                                 long long batch_b, int N, int R, int B, float* out, long long out_b, long long out_m,
+                                 long long out_n, float scale, float* bias_out, int bias_from, float* scratch, void* stream) {
+  using namespace sgc::tc;
+  if (!a || !b || !out || !scratch || M <= 0 || M % BM || N <= 0 || N % 32 || R <= 0 || B <= 0) return (int)cudaErrorInvalidValue;
+  if (bias_from < 0 || bias_from > 2 || (bias_from && !bias_out)) return (int)cudaErrorInvalidValue;
+  PFN_encodeTiled encode = get_encode_tiled();
+  if (!encode) return (int)cudaErrorNotSupported;
+  RowsWgradParams p;
+  rows_wgrad_plan(M, N, R, B, &p.n_cta, &p.kch);
+  if (p.n_cta < 32 || p.n_cta % 16) return (int)cudaErrorInvalidValue;
+  CUtensorMap amap, bmap;
+  if (!make_wgrad_map(encode, &amap, a, M, R, B, lda, batch_a, BM, &p.a_swap)) return (int)cudaErrorInvalidValue;
+  if (!make_wgrad_map(encode, &bmap, b, N, R, B, ldb, batch_b, p.n_cta, &p.b_swap)) return (int)cudaErrorInvalidValue;
+  p.M = M; p.N = N; p.R = R;
+  p.m_tiles = M / BM;
+  p.total_slabs = (R + BK - 1) / BK;
+  p.slabs_per_cta = (p.total_slabs + p.kch - 1) / p.kch;
+  p.bias_from = bias_from;
+  p.partial = scratch;
+  p.bias_partial = scratch + (size_t)p.kch * B * M * N;
+  const size_t smem = (size_t)RW_ST * (BK * BM * 4 + BK * p.n_cta * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * p.n_cta * BK * 2) +
+                      sizeof(SmemRW) + 64;
+  cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(p.m_tiles * p.kch, N / p.n_cta, B);
+  rows_wgrad_tc_kernel<<<grid, RW_THREADS, smem, (cudaStream_t)stream>>>(amap, bmap, p);
+  SGC_CUDA_CHECK_LAST();
+  const long long elems = (long long)B * M * N;
+  const int bias_len = bias_from == 1 ? B * M : bias_from == 2 ? B * N : 0;
+  const long long work = elems > bias_len ? elems : bias_len;
+  rows_wgrad_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p.partial, p.bias_partial, p.kch, B, M, N, scale, out, out_b, out_m, out_n, bias_from ? bias_out : nullptr, bias_len);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

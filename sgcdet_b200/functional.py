@@ -94,6 +94,7 @@ SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs wi
 # voxel-count GEMMs of the encoder layer on the own tcgen05 kernel (csrc/sgc_rows_gemm_tc.cu) instead of the library's
 # bf16 GEMM on bf16x3 operand images
 ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
+ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and their weight gradients (sgc_rows_wgrad_tc)
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -153,6 +154,30 @@ def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional
     call('sgc_rows_gemm_tc', ptr(x), K, R * K, R, K, H, ptr(wpack), H * dh, 0, dh, ptr(bias), dh, dh, ptr(y), H * dh, dh,
          n_cta, stream())
     return y
+
+
+def rows_wgrad(a, b, M, N, R, out, out_strides, *, B=1, lda=None, batch_a=0, ldb=None, batch_b=0, scale=1.0,
+               bias_out=None, bias_from=0):
+    """``sgc_rows_wgrad_tc``: out[b*ob + m*om + n*on] = scale * sum_r a[b][r, m] * b[b][r, n] (+ column sums of a / b into
+    ``bias_out``).  ``out`` / ``bias_out`` may be slices of larger gradient tensors (they are written in place)."""
+    scratch = torch.empty(_lib.load().sgc_rows_wgrad_tc_scratch_floats(M, N, R, B), device=a.device, dtype=F32)
+    ob, om, on = out_strides
+    call('sgc_rows_wgrad_tc', ptr(a), M if lda is None else lda, batch_a, M, ptr(b), N if ldb is None else ldb, batch_b, N,
+         R, B, ptr(out), ob, om, on, scale, ptr(bias_out), bias_from, ptr(scratch), stream())
+    return out
+
+
+def linear_grads_tc(g: torch.Tensor, x: torch.Tensor, gw: Optional[torch.Tensor] = None, gb: Optional[torch.Tensor] = None):
+    """(gW [N,K], gb [N]) of y = x W^T + b given g = dL/dy [R,N] and x [R,K] on the own tensor-core kernel; ``gw`` /
+    ``gb`` (optional) are the destinations (e.g. row slices of in_proj_weight's gradient)."""
+    R, N = g.shape
+    K = x.shape[1]
+    if gw is None:
+        gw = torch.empty(N, K, device=g.device, dtype=F32)
+    if gb is None:
+        gb = torch.empty(N, device=g.device, dtype=F32)
+    rows_wgrad(g, x, N, K, R, gw, (0, K, 1), bias_out=gb, bias_from=1)
+    return gw, gb
 
 
 def pack_weight_tc(w: torch.Tensor) -> torch.Tensor:
@@ -733,7 +758,7 @@ class LayerNormRows(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 
 def rowop_fwd(x, R, N, *, bias=None, relu=False, mask=None, mscale=1.0, rowscale=None, residual=None, ln=None,
-              in_heads=0, split_heads=0, want_y=True, want_split=True):
+              in_heads=0, split_heads=0, want_y=True, want_split=True, rowcount=None):
     """``sgc_rowop_fwd``: fused epilogue of a GEMM output ``x`` ([R,N], or head-major [H,R,N/H] with in_heads=H).
     Returns (y [R,N] fp32 | None, ysplit bf16x3 | None, (pre, mean, rstd) | None)."""
     dev = x.device
@@ -742,6 +767,7 @@ def rowop_fwd(x, R, N, *, bias=None, relu=False, mask=None, mscale=1.0, rowscale
     saved = None
     a = _lib.RowopFwdArgs()
     a.x, a.bias, a.mask, a.rowscale, a.residual = ptr(x), ptr(bias), ptr(mask), ptr(rowscale), ptr(residual)
+    a.rowcount = ptr(rowcount)
     if ln is not None:
         gamma, beta, eps = ln
         saved = (torch.empty(R, N, device=dev, dtype=F32), torch.empty(R, device=dev, dtype=F32),
@@ -755,7 +781,7 @@ def rowop_fwd(x, R, N, *, bias=None, relu=False, mask=None, mscale=1.0, rowscale
 
 
 def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gscale=1.0, rowscale=None,
-              in_heads=0, split_heads=0, want_gpre=False, want_gx=True, want_split=True):
+              in_heads=0, split_heads=0, want_gpre=False, want_gx=True, want_split=True, rowcount=None):
     """``sgc_rowop_bwd``.  ``ln`` = (pre, mean, rstd, gamma).  Returns (gx, gxsplit, gpre, partial)."""
     dev = g.device
     gx = torch.empty(R, N, device=dev, dtype=F32) if want_gx else None
@@ -764,6 +790,7 @@ def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gs
     partial = None
     a = _lib.RowopBwdArgs()
     a.g, a.g2, a.mask, a.gate, a.rowscale = ptr(g), ptr(g2), ptr(mask), ptr(gate), ptr(rowscale)
+    a.rowcount = ptr(rowcount)
     if ln is not None:
         pre, mean, rstd, gamma = ln
         partial = torch.empty(_lib.load().sgc_layernorm_bwd_scratch_floats(R, N), device=dev, dtype=F32)
@@ -851,14 +878,14 @@ class EncoderLayerRows(torch.autograd.Function):
             else:
                 o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
             o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
-        has = (pl.count > 0).to(F32)
+        # rows no view sees are zeroed (DCA:819-835) straight from the per-voxel view count
         x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
-                                  rowscale=has, ln=(g1, be1, eps1), want_split=sp)
+                                  rowcount=pl.count, ln=(g1, be1, eps1), want_split=sp)
         hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1, getattr(lw, 'p_w1', None)), Q, Fh, bias=b1, relu=True, mask=m1,
                                   mscale=s1, want_split=sp)
         y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2, getattr(lw, 'p_w2', None)), Q, C, bias=b2, mask=m2, mscale=s2,
                               residual=x1, ln=(g2, be2, eps2), want_split=False)
-        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, *ln1, *ln2, g1, g2,
+        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2,
                               w_out, in_w, wo, w1, w2)
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
         ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
@@ -866,7 +893,7 @@ class EncoderLayerRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        (slots, mean, g, qv, qt, t, alpha, o2, has, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2,
+        (slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2,
          w_out, in_w, wo, w1, w2) = ctx.saved_tensors
         pl, lw = ctx.pl, ctx.lw
         m0, m1, m2 = ctx.masks
@@ -898,18 +925,30 @@ class EncoderLayerRows(torch.autograd.Function):
         # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
         gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
                                            want_split=sp)
+        wtc = tc and ROWS_WGRAD_TC and C % 128 == 0 and Fh % 128 == 0   # own kernel for the weight gradients too
+        hwtc = wtc and htc
+        lgrads = linear_grads_tc if wtc else linear_grads
         g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
-        g_w2, g_b2 = side_f.run(lambda: linear_grads(gf, hdn), gf, hdn)
+        g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
         ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
         # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
         gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
-        g_w1, g_b1 = side_f.run(lambda: linear_grads(gh, x1), gh, x1)
+        g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
         gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
         gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
-                                           rowscale=has, want_split=sp)
+                                           rowcount=pl.count, want_split=sp)
         g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
-        g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
+        g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
         go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
+        if hwtc:
+            # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients
+            # (rows [0,C) query, [C,2C) key, [2C,3C) value; the key bias gradient is identically zero)
+            def _alloc_in():
+                gw_ = torch.empty(3 * C, C, device=dev, dtype=F32)
+                gb_ = torch.empty(3 * C, device=dev, dtype=F32)
+                gb_[C:2 * C].zero_()
+                return gw_, gb_
+            g_in_w, g_in_b = side.run(_alloc_in)
         if small:   # gt[h] = go_h @ Wv_h
             gt = torch.bmm(go2.view(Q, H, dh).transpose(0, 1), wv.view(H, dh, C))
         elif htc:
@@ -919,6 +958,9 @@ class EncoderLayerRows(torch.autograd.Function):
             gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)    # [H,Q,C]
 
         def _wv():
+            if hwtc:   # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
+                return (rows_wgrad(t, go2, C, dh, Q, g_in_w[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C,
+                                   batch_b=dh, bias_out=g_in_b[2 * C:], bias_from=2), g_in_b[2 * C:])
             if fp32_heads:
                 return torch.bmm(go2.view(Q, H, dh).permute(1, 2, 0), t).reshape(C, C), colsum(go2)
             gs, gb = split_rows_colsum(go2, 0)
@@ -941,22 +983,29 @@ class EncoderLayerRows(torch.autograd.Function):
             gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H, want_split=sp)
 
         def _wk():
+            if hwtc:   # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
+                return rows_wgrad(gqt, qv, C, dh, Q, g_in_w[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C,
+                                  batch_b=dh, scale=scale)
             if fp32_heads:
                 return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
             return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
         g_wk = side.run(_wk, qv, gqt)
-        g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
+        if hwtc:
+            g_wq, g_bq = side.run(lambda: linear_grads_tc(gqv, g, g_in_w[:C], g_in_b[:C]), gqv, g)
+        else:
+            g_wq, g_bq = side.run(lambda: lgrads(gqv, g), gqv, g)
         gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
         gg_s = split_cols(gg, 0) if sp else None
-        g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
+        g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
         gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
         side.join()
         side_f.join()
-        g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
-                                           torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
+        if not hwtc:
+            g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
+                                               torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
         side.join()
         return (gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2,
                 None, None, None, None, None, None)

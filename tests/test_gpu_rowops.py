@@ -136,6 +136,25 @@ def test_rowop_fwd_bwd_match_torch(cuda_lib, R, N):
         assert (got.double() - ref).abs().max().item() <= 1e-4 + 1e-3 * sc
 
 
+def test_rowop_rowcount_equals_rowscale(cuda_lib):
+    """``rowcount`` (per-voxel view counts) zeroes exactly the rows a 0/1 ``rowscale`` built from it would."""
+    g = torch.Generator().manual_seed(9)
+    R, N = 777, 256
+    x, gy = torch.randn(R, N, generator=g).cuda(), torch.randn(R, N, generator=g).cuda()
+    bias, gamma, beta = (torch.randn(N, generator=g).cuda() for _ in range(3))
+    count = torch.randint(0, 3, (R,), generator=g).to(torch.int32).cuda()
+    has = (count > 0).float()
+    a = SF.rowop_fwd(x, R, N, bias=bias, rowscale=has, ln=(gamma, beta, 1e-5))
+    b = SF.rowop_fwd(x, R, N, bias=bias, rowcount=count, ln=(gamma, beta, 1e-5))
+    ga = SF.rowop_bwd(gy, R, N, ln=(a[2][0], a[2][1], a[2][2], gamma), rowscale=has)
+    gb = SF.rowop_bwd(gy, R, N, ln=(b[2][0], b[2][1], b[2][2], gamma), rowcount=count)
+    torch.cuda.synchronize()
+    assert (count == 0).any()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1].view(torch.int16), b[1].view(torch.int16))
+    assert torch.equal(ga[0], gb[0]) and torch.equal(ga[3], gb[3])
+    assert (gb[0][count == 0] == 0).all()
+
+
 def test_rowop_head_layouts(cuda_lib):
     g = torch.Generator().manual_seed(3)
     R, N, H = 333, 256, 8

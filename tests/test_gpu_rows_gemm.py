@@ -126,3 +126,58 @@ def test_level_weights_packs_match_single_kernel(cuda_lib):
         assert got.shape == r.shape, k
         assert torch.equal(got.view(torch.int16), r.view(torch.int16)), k
     assert lw.w_out is None and lw.wk_rows is None
+
+
+@pytest.mark.parametrize('R,N,K', [
+    (6400, 256, 256),    # output_proj / in-projection weight gradients at the finest level
+    (6400, 512, 256),    # FFN layer 1 (four 128-row tiles of the gradient)
+    (6400, 256, 512),    # FFN layer 2 (two column parts)
+    (800, 256, 256),
+    (400, 256, 512),     # a single k-chunk
+    (37, 128, 128),      # fewer rows than two slabs
+    (51200, 128, 256),   # "-L" finest level
+])
+def test_linear_grads_tc_matches_fp64(cuda_lib, R, N, K):
+    g = torch.Generator().manual_seed(R + 3 * N + 5 * K)
+    gy = torch.randn(R, N, generator=g).cuda()
+    x = torch.randn(R, K, generator=g).cuda()
+    gw, gb = SF.linear_grads_tc(gy, x)
+    torch.cuda.synchronize()
+    check(gw, gy.double().t() @ x.double())
+    check(gb, gy.double().sum(0))
+
+
+def test_linear_grads_tc_is_deterministic_and_writes_in_place(cuda_lib):
+    g = torch.Generator().manual_seed(21)
+    R, C = 3000, 256
+    gy, x = torch.randn(R, C, generator=g).cuda(), torch.randn(R, C, generator=g).cuda()
+    big_w = torch.full((3 * C, C), 5.0, device='cuda')
+    big_b = torch.full((3 * C,), 5.0, device='cuda')
+    SF.linear_grads_tc(gy, x, big_w[C:2 * C], big_b[C:2 * C])
+    a, _ = SF.linear_grads_tc(gy, x)
+    b, _ = SF.linear_grads_tc(gy, x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, big_w[C:2 * C])
+    assert (big_w[:C] == 5.0).all() and (big_w[2 * C:] == 5.0).all()
+    assert (big_b[:C] == 5.0).all() and (big_b[2 * C:] == 5.0).all()
+
+
+@pytest.mark.parametrize('R', [6400, 800, 77])
+def test_rows_wgrad_heads_matches_fp64(cuda_lib, R):
+    """Per-head key / value weight gradients: out[h*dh + d, c] = scale * sum_r a[h][r, c] * b[r, h*dh + d], written
+    transposed into a row slice of in_proj_weight's gradient; bias gradient = column sums of b."""
+    H, C = 8, 256
+    dh = C // H
+    g = torch.Generator().manual_seed(R)
+    a = torch.randn(H, R, C, generator=g).cuda()
+    b = torch.randn(R, C, generator=g).cuda()
+    gw = torch.full((3 * C, C), 9.0, device='cuda')
+    gb = torch.full((3 * C,), 9.0, device='cuda')
+    scale = 0.37
+    SF.rows_wgrad(a, b, C, dh, R, gw[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=R * C, ldb=C, batch_b=dh, scale=scale,
+                  bias_out=gb[2 * C:], bias_from=2)
+    torch.cuda.synchronize()
+    ref = torch.einsum('hrc,rhd->hdc', a.double(), b.double().view(R, H, dh)).reshape(C, C) * scale
+    check(gw[2 * C:], ref)
+    check(gb[2 * C:], b.double().sum(0))
+    assert (gw[:2 * C] == 9.0).all() and (gb[:2 * C] == 9.0).all()
