@@ -244,27 +244,41 @@ def run_ours(args):
     all_inputs = [t for s in scenes for t in s['feats'] + s['dists']]
     loss_buf = torch.zeros(1, device=dev)
 
-    def scene_loss(s):
+    loss_stream = torch.cuda.Stream(device=dev)
+
+    def scene_fwd(s):
+        """Forward of one scene.  loss = sum(volume * G) + occ_loss.  The gradient of the first term
+        w.r.t. the volume is G itself, so the backward is seeded with G directly and the VALUE of the first term (needed
+        only for the loss read-back) is evaluated beside the backward instead of in front of it."""
         vol, valid, occ = head(s['feats'], s['sc'].img_meta, s['dists'])
-        return (vol * s['gvol']).sum() + head.occ_loss(occ, None, s['sc'].geo_occ)['loss_occ']
+        return vol, head.occ_loss(occ, None, s['sc'].geo_occ)['loss_occ']
 
     def step():
+        main = torch.cuda.current_stream()
         if B == 1:
-            loss = scene_loss(scenes[0])
+            outs = [scene_fwd(scenes[0])]
         else:
             # B independent scenes in flight on B streams: the latency-bound per-voxel chains of different
-            # scenes overlap; one backward over the summed loss (autograd replays every node on its own stream)
-            main = torch.cuda.current_stream()
-            losses = []
+            # scenes overlap; one backward over all of them (autograd replays every node on its own stream)
+            outs = []
             for s in scenes:
                 s['stream'].wait_stream(main)
                 with torch.cuda.stream(s['stream']):
-                    losses.append(scene_loss(s))
+                    outs.append(scene_fwd(s))
             for s in scenes:
                 main.wait_stream(s['stream'])
-            loss = torch.stack(losses).sum()
-        loss.backward()
-        loss_buf.copy_(loss.detach().view(1))
+        # loss value on its own stream, concurrently with the backward
+        loss_stream.wait_stream(main)
+        with torch.cuda.stream(loss_stream):
+            with torch.no_grad():
+                val = outs[0][1].detach().new_zeros(())
+                for (vol, l_occ), s in zip(outs, scenes):
+                    vol.record_stream(loss_stream)
+                    val = val + (vol * s['gvol']).sum() + l_occ
+                loss_buf.copy_(val.view(1))
+        torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
+                                [g for s in scenes for g in (s['gvol'], None)])
+        main.wait_stream(loss_stream)
 
     def allreduce_grads():
         # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks (SURVEY.md 8e).  Issued on
@@ -477,6 +491,8 @@ def run_ours(args):
                        'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
                        'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else ' + NCCL weight-grad all-reduce'),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
+                       'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
+                               'and the loss value evaluated on a side stream beside the backward',
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
                        'cuda_graph': not args.no_graph, 'gemm': 'feature-map projection (forward, data gradient, weight gradient): own tcgen05/TMEM/TMA kernels, bf16 hi/lo split in shared memory, fp32 accumulate; voxel-count GEMMs: library bf16 GEMM with fp32 accumulate on bf16x3 operands emitted by the own fused row kernels', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),

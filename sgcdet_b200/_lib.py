@@ -117,7 +117,7 @@ def load() -> ctypes.CDLL:
             fn.argtypes = argtypes
             fn.restype = c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
-        lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '0')))
+        lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
         lib.sgc_project_tc_set_tiles_per_cta(int(os.environ.get('SGC_TC_TILES_PER_CTA', '0')))
         _lib = lib
     return _lib
