@@ -600,7 +600,7 @@ static inline void rows_wgrad_plan(int M, int N, int R, int B, int* n_cta, int* 
   while (N % nc) nc >>= 1;
   const int tiles = (M / BM) * (N / nc) * B;
   const int total_slabs = (R + BK - 1) / BK;
-  int k = total_slabs / 8;                       // at least ~8 row slabs (256 rows) per CTA
+  int k = total_slabs / 4;                       // at least ~4 row slabs (128 rows) per CTA
   const int cap = tiles < 148 ? 148 / tiles : 1;
   if (k > cap) k = cap;
   if (k < 1) k = 1;

