@@ -513,7 +513,8 @@ extern "C" int sgc_project_tc_bwd_data(const float* gvg, int V, int S, int N, co
 namespace sgc {
 namespace tc {
 
-constexpr int WG_THREADS = 352;
+constexpr int WG_THREADS = 480;  // warps 0-3: A converters (+ epilogue), 4-11: B converters, 12: TMA, 13: MMA, 14: TMEM
+constexpr int WG_CONV = 384;     // converter threads (arrivals on f_empty / op_full)
 constexpr int WG_ST = 2;  // pipeline stages (staging and operand)
 
 struct SmemW {
@@ -545,13 +546,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WG_ST; ++i) {
-      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 256);
-      mbar_init(&sm->op_full[i], 256); mbar_init(&sm->op_empty[i], 1);
+      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], WG_CONV);
+      mbar_init(&sm->op_full[i], WG_CONV); mbar_init(&sm->op_empty[i], 1);
     }
     mbar_init(&sm->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 10) {
+  if (warp == 14) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -560,7 +561,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       Pipe pf(WG_ST);
       for (int i = 0; i < n_slabs; ++i) {
@@ -573,10 +574,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
         pf.next();
       }
     }
-  } else if (warp < 8) {
-    // converters: warps 0-3 -> A (gvg, [k][m] tile), warps 4-7 -> B (feat, swizzled [row][k] tile)
+  } else if (warp < 12) {
+    // converters: warps 0-3 -> A (gvg, [k][m] tile), warps 4-11 -> B (feat, swizzled [row][k] tile; one row per thread
+    // for C = 256, so that the two operands take the same time per slab)
     const bool is_b = warp >= 4;
-    const int t = threadIdx.x & 127;
+    const int t = is_b ? (int)threadIdx.x - 128 : (int)threadIdx.x;   // A: 0..127, B: 0..255
     Pipe pf(WG_ST), po(WG_ST);
     for (int i = 0; i < n_slabs; ++i) {
       mbar_wait(&sm->f_full[pf.stage], pf.phase);
@@ -605,7 +607,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
       } else {
         uint8_t* hi = op + a_op;
         uint8_t* lo = hi + C * BK * 2;
-        for (int r = t; r < C; r += 128) {
+        for (int r = t; r < C; r += 256) {
           const uint8_t* rowp = st + a_src + r * 128;
           const uint32_t off = (r >> 3) * SBO + (r & 7) * 16;
 #pragma unroll
@@ -661,7 +663,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
           *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       Pipe po(WG_ST);
@@ -687,7 +689,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == 14) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
   }

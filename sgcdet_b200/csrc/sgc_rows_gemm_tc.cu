@@ -362,7 +362,8 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
 namespace sgc {
 namespace tc {
 
-constexpr int RW_THREADS = 352;
+constexpr int RW_THREADS = 480;  // warps 0-3: A converters (+ epilogue), 4-11: B converters, 12: TMA, 13: MMA, 14: TMEM
+constexpr int RW_CONV = 384;     // converter threads (arrivals on f_empty / op_full)
 constexpr int RW_ST = 2;
 
 struct SmemRW {
@@ -401,13 +402,13 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RW_ST; ++i) {
-      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 256);
-      mbar_init(&sm->op_full[i], 256); mbar_init(&sm->op_empty[i], 1);
+      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], RW_CONV);
+      mbar_init(&sm->op_full[i], RW_CONV); mbar_init(&sm->op_empty[i], 1);
     }
     mbar_init(&sm->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 10) {
+  if (warp == 14) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -416,7 +417,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       Pipe pf(RW_ST);
       for (int i = 0; i < n_slabs; ++i) {
@@ -431,12 +432,12 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
         pf.next();
       }
     }
-  } else if (warp < 8) {
-    // converters: warps 0-3 -> A tile [32 r][128 m], warps 4-7 -> B tile [32 r][n_cta]; thread = column(s) of the tile
+  } else if (warp < 12) {
+    // converters: warps 0-3 -> A tile [32 r][128 m], warps 4-11 -> B tile [32 r][n_cta <= 256]; thread = column of the tile
     const bool is_b = warp >= 4;
-    const int t = threadIdx.x & 127;
+    const int t = is_b ? (int)threadIdx.x - 128 : (int)threadIdx.x;   // A: 0..127, B: 0..255
     const int width = is_b ? n_cta : BM;
-    float csum0 = 0.f, csum1 = 0.f;     // column sums of this thread's column(s) over the CTA's rows
+    float csum0 = 0.f;                  // column sum of this thread's column over the CTA's rows
     Pipe pf(RW_ST), po(RW_ST);
     for (int i = 0; i < n_slabs; ++i) {
       mbar_wait(&sm->f_full[pf.stage], pf.phase);
@@ -445,8 +446,8 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
       uint8_t* op = op_base + po.stage * op_stage + (is_b ? a_op : 0);
       uint8_t* hi = op;
       uint8_t* lo = op + width * BK * 2;
-#pragma unroll 1
-      for (int c = t, rep = 0; c < width; c += 128, ++rep) {
+      if (t < width) {
+        const int c = t;
         const float* src = reinterpret_cast<const float*>(st) + c;
         float x[BK];
 #pragma unroll
@@ -454,7 +455,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < BK; ++k) s += x[k];
-        if (rep == 0) csum0 += s; else csum1 += s;
+        csum0 += s;
         const uint32_t off = (c >> 3) * SBO + (c & 7) * 16;
 #pragma unroll
         for (int kcx = 0; kcx < BK / 8; ++kcx) {
@@ -480,7 +481,6 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
     } else if (p.bias_from == 2 && is_b && mt == 0) {
       float* dst = p.bias_partial + ((size_t)kc * nb + bt) * p.N + np * n_cta;
       if (t < n_cta) dst[t] = csum0;
-      if (t + 128 < n_cta) dst[t + 128] = csum1;
     }
     if (!is_b) {
       // epilogue by warps 0-3: partial[kc][bt][mt*128 + row][np*n_cta .. +n_cta)
@@ -513,7 +513,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
           *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cta >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       Pipe po(RW_ST);
@@ -539,7 +539,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == 14) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
   }

@@ -419,7 +419,7 @@ class ProjectFeatures(torch.autograd.Function):
         return acat
 
     @staticmethod
-    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
+    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None, big_stream=None):
         # feat is [V,C,H0,W0] or the reference's [1,V,C,H0,W0]; taking the 5-D leaf directly keeps autograd from
         # materialising a zero-filled copy for the select() view on the way back
         ctx.feat_shape = tuple(feat.shape)
@@ -429,6 +429,7 @@ class ProjectFeatures(torch.autograd.Function):
         N = wcat.shape[0]
         ctx.dims = (V, C, H0, W0, h, w)
         ctx.lw = lw
+        ctx.big = big_stream   # optional dedicated stream for the two gradient kernels (see plugin._big_backward_streams)
         use_tc = (_os.environ.get('SGC_TC_PROJECT', '1') != '0' and w == W0 and feat.is_contiguous()
                   and (H0 * W0 * 4) % 16 == 0 and C % 32 == 0 and N % 32 == 0 and N <= 512)
         if use_tc:
@@ -459,19 +460,31 @@ class ProjectFeatures(torch.autograd.Function):
             gvg = gvg.contiguous()
             gfeat = gw = None
             lw = ctx.lw
-            if ctx.needs_input_grad[0]:
-                wpack_t = lw.wpack_t if lw is not None and getattr(lw, 'wpack_t', None) is not None \
-                    else pack_weight_tc(wcat.t().contiguous())
-                gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
-                if h != H0:
-                    gfeat[:, :, h:].zero_()
-                call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
-                gfeat = gfeat.view(ctx.feat_shape)
-            if ctx.needs_input_grad[3]:
-                gw = torch.empty(N, C, device=gvg.device, dtype=F32)
-                scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device=gvg.device, dtype=F32)
-                call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
-            return gfeat, None, None, gw, None
+            cur = torch.cuda.current_stream(gvg.device)
+            big = ctx.big if ctx.big is not None and ctx.big != cur else None
+            if big is not None:
+                big.wait_stream(cur)
+                for t_ in (gvg, feat):
+                    t_.record_stream(big)
+            with torch.cuda.stream(big if big is not None else cur):
+                if ctx.needs_input_grad[0]:
+                    wpack_t = lw.wpack_t if lw is not None and getattr(lw, 'wpack_t', None) is not None \
+                        else pack_weight_tc(wcat.t().contiguous())
+                    gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
+                    if h != H0:
+                        gfeat[:, :, h:].zero_()
+                    call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
+                    gfeat = gfeat.view(ctx.feat_shape)
+                if ctx.needs_input_grad[3]:
+                    gw = torch.empty(N, C, device=gvg.device, dtype=F32)
+                    scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device=gvg.device, dtype=F32)
+                    call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
+            if big is not None:
+                cur.wait_stream(big)
+                for t_ in (gfeat, gw):
+                    if t_ is not None:
+                        t_.record_stream(cur)
+            return gfeat, None, None, gw, None, None
         if not ctx.have_acat:
             acat = ProjectFeatures._split_feat(acat, h, w) if ctx.needs_input_grad[3] else None
         gvg = gvg.contiguous()
@@ -501,7 +514,7 @@ class ProjectFeatures(torch.autograd.Function):
             gw = xs[:, :C] + xs[:, C:] + ys
         if gfeat is not None:
             gfeat = gfeat.view(ctx.feat_shape)
-        return gfeat, None, None, gw, None
+        return gfeat, None, None, gw, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -512,7 +525,7 @@ class Lift(torch.autograd.Function):
     """sgc_lift_fwd / sgc_lift_bwd (see csrc/sgc_lift.cu)."""
 
     @staticmethod
-    def forward(ctx, vg, dist, vbias, gbias, pl: PairList, H: int, W: int, bwd_stream=None):
+    def forward(ctx, vg, dist, vbias, gbias, pl: PairList, H: int, W: int, bwd_stream=None, join_stream=None):
         """``bwd_stream``: the stream the producers of vg / dist / vbias / gbias ran on (``DenseHead.prepare`` on a
         side stream).  Autograd replays those producers' backward nodes on that stream, so the (large) backward kernel
         is issued there as well and the main stream continues with the next level's per-voxel chain."""
@@ -527,6 +540,9 @@ class Lift(torch.autograd.Function):
         ctx.save_for_backward(vg, dist, vbias, samp)
         ctx.pl, ctx.dims = pl, (S, H, W, D, C)
         ctx.bwd_stream = bwd_stream if _os.environ.get('SGC_SIDE_LIFT_BWD', '1') != '0' else None
+        # when bwd_stream is NOT the stream the producers of vg / dist ran on, that producer stream (join_stream) has to
+        # wait for the backward kernel before autograd replays the producers' backward nodes on it
+        ctx.join_stream = join_stream if ctx.bwd_stream is not None else None
         ctx.mark_non_differentiable(samp)
         ctx.set_materialize_grads(False)
         return slots, samp
@@ -564,7 +580,11 @@ class Lift(torch.autograd.Function):
             call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
                  pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots), S, H, W, D, pl.Q, C,
                  gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
-        return gvg, gdist, gvb, ggb, None, None, None, None
+        if side is not None and ctx.join_stream is not None and ctx.join_stream != side:
+            ctx.join_stream.wait_stream(side)
+            for t in (gvg, gdist, gvb, ggb):
+                t.record_stream(ctx.join_stream)
+        return gvg, gdist, gvb, ggb, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -314,9 +314,42 @@ def _level_chain_streams(device, n: int, main):
     backward run concurrently instead of back to back, each followed by its own large lift / projection gradient kernels."""
     key = (torch.device(device), main.cuda_stream)
     pool = _LEVEL_STREAMS.setdefault(key, [])
+    prio = _prio_list('SGC_CHAIN_PRIO', n, -1)
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=torch.device(device), priority=-1))
+        pool.append(torch.cuda.Stream(device=torch.device(device), priority=prio[len(pool)]))
     return pool[:n]
+
+
+def _prio_list(env: str, n: int, default):
+    """Per-level stream priorities from a comma list in the environment (coarsest level first; 'x' = ``default``)."""
+    vals = [v.strip() for v in os.environ.get(env, '').split(',') if v.strip()]
+    out = []
+    for i in range(n):
+        v = vals[i] if i < len(vals) else 'x'
+        out.append(default if v == 'x' else int(v))
+    return out
+
+
+_BIG_STREAMS = {}
+
+
+def _big_backward_streams(device, n: int, main):
+    """Optional dedicated streams (one per level, priorities from SGC_BIG_PRIO) for the large backward kernels of a level
+    (lift backward, the projection's data / weight gradients).  None for a level = they run on the level's prepare stream.
+    A dedicated high-priority stream for the finest level lets the kernels that end the step win the SMs over the coarser
+    levels' work, which has slack."""
+    prio = _prio_list('SGC_BIG_PRIO', n, None)
+    key = (torch.device(device), main.cuda_stream)
+    pool = _BIG_STREAMS.setdefault(key, {})
+    out = []
+    for i, p in enumerate(prio):
+        if p is None:
+            out.append(None)
+            continue
+        if (i, p) not in pool:
+            pool[(i, p)] = torch.cuda.Stream(device=torch.device(device), priority=p)
+        out.append(pool[(i, p)])
+    return out
 
 
 def _dropout_masks(rows: int, widths, drops, device):
@@ -372,7 +405,7 @@ class DenseHead(nn.Module):
         return (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and self.embed_dims in (128, 256) and ffn.add_identity
                 and ffn.layers[0][0].out_features in (128, 256, 512))
 
-    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None):
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None, big_stream=None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
         map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
@@ -392,7 +425,7 @@ class DenseHead(nn.Module):
         # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
         # depth gradient's copies instead of queueing behind them on the same stream
         dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
-        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
+        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw, big_stream)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
         params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,
@@ -417,8 +450,11 @@ class DenseHead(nn.Module):
             # critical path -- and applied inside the fused row kernels
             masks = _dropout_masks(n_rows, (self.embed_dims, ffn.layers[0][0].out_features, self.embed_dims),
                                    (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p), feat.device)
+        cur = torch.cuda.current_stream(feat.device)
+        if big_stream is not None:
+            big_stream.wait_stream(cur)   # forked here so that its backward work can start without joining the chain
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
-                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream, masks=masks)
+                    stream=cur, big=big_stream, params=params, wstream=wstream, masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None):
@@ -437,8 +473,10 @@ class DenseHead(nn.Module):
         if prepared is None:
             prepared = self.prepare(feat, dpt_dist, hw)
         lw = prepared['lw']
+        big = prepared.get('big')
         slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w,
-                                    prepared.get('stream'))
+                                    big if big is not None else prepared.get('stream'),
+                                    prepared.get('stream') if big is not None else None)
         pp, ws = prepared['params'], prepared['wstream']
         ffn = layer.ffns[0]
         C = self.embed_dims
@@ -566,6 +604,7 @@ class AdaptiveSparseHead(nn.Module):
             main.wait_stream(s)
             (r[0] if return_intermediates else r).record_stream(main)
             return r
+        big_streams = _big_backward_streams(dev, nl, main) if torch.is_grad_enabled() else [None] * nl
         prepared = []
         for i in range(nl):
             streams[i].wait_stream(main)
@@ -579,7 +618,7 @@ class AdaptiveSparseHead(nn.Module):
                 else:
                     n_rows = self.base_heads[i].num_voxels
                 prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i],
-                                                           n_rows))
+                                                           n_rows, big_streams[i]))
         for i in range(nl):
             hw = hws[i]
             fi = nl - 1 - i
