@@ -248,7 +248,8 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       tc_fence_before();
       mbar_arrive(&sm->tmem_empty[buf]);
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the staging buffers only have to outlive the stores' READS; the writes are complete (and visible) at kernel end
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();

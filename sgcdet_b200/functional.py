@@ -95,6 +95,10 @@ SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs wi
 # bf16 GEMM on bf16x3 operand images
 ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
 ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and their weight gradients (sgc_rows_wgrad_tc)
+# output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
+# (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
+# produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
+FUSE_QO = _os.environ.get('SGC_FUSE_QO', '1') != '0'
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -236,7 +240,8 @@ class LevelWeights:
     single launch -- normally on a side stream, off the critical path of the level.  Constants for the autograd
     Functions below (weight gradients are formed from the fp32 activations, not from these)."""
 
-    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS, images: bool = True):
+    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS, images: bool = True, b_out=None,
+                 in_b=None):
         """``images=False``: skip the bf16x3 images of the layer weights (operands of the library-GEMM path) wherever
         the packed operands of the own voxel-count GEMM kernel replace them."""
         with torch.no_grad():
@@ -252,6 +257,11 @@ class LevelWeights:
             self.wcat_t = j.split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
             self.rows_tc = ROWS_TC and C % 32 == 0 and w1.shape[0] % 32 == 0
             self.heads_tc = self.rows_tc and dh % 32 == 0
+            self.fuse_qo = self.rows_tc and FUSE_QO and b_out is not None and in_b is not None
+            if self.fuse_qo:
+                wqo = torch.mm(wq, w_out)                        # qv = mean @ (W_q W_out)^T + (W_q b_out + b_q)
+                self.bqo = torch.addmv(in_b[:C], wq, b_out)
+                self.p_wqo, self.p_wqo_t = j.pack(wqo), j.pack(wqo.t())
             if self.rows_tc:
                 # packed operands of sgc_rows_gemm_tc: p_x for y = a @ x^T, p_x_t for the data gradient g @ x
                 self.p_w_out, self.p_w_out_t = j.pack(w_out), j.pack(w_out.t())
@@ -869,7 +879,21 @@ class EncoderLayerRows(torch.autograd.Function):
         mean = torch.empty(Q, C, device=dev, dtype=F32)
         mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
         call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
-        if tc:   # biases ride in the GEMM epilogue, no row kernel in between
+        fqo = htc and getattr(lw, 'fuse_qo', False)
+        if fqo:  # one GEMM on the chain; g (an input of the weight gradients only) is produced beside it
+            qv, qv_hs = rows_linear(mean, lw.p_wqo, C, lw.bqo), None
+            g = None
+            if slots.requires_grad or w_out.requires_grad or in_w.requires_grad:
+                cur = torch.cuda.current_stream(dev)
+                gside = wstream[0] if wstream is not None and wstream[0] != cur else None
+                if gside is not None:
+                    gside.wait_stream(cur)
+                    mean.record_stream(gside)
+                with torch.cuda.stream(gside if gside is not None else cur):
+                    g = rows_linear(mean, lw.p_w_out, C, b_out)
+            else:
+                g = mean.new_empty(0)
+        elif tc:   # biases ride in the GEMM epilogue, no row kernel in between
             g = lin(mean, None, w_out, None, lw.p_w_out, b_out)
             if htc:
                 qv, qv_hs = lin(g, None, wq, None, lw.p_wq, bq), None
@@ -1014,10 +1038,16 @@ class EncoderLayerRows(torch.autograd.Function):
             g_wq, g_bq = side.run(lambda: linear_grads_tc(gqv, g, g_in_w[:C], g_in_b[:C]), gqv, g)
         else:
             g_wq, g_bq = side.run(lambda: lgrads(gqv, g), gqv, g)
-        gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
-        gg_s = split_cols(gg, 0) if sp else None
-        g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
-        gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
+        if htc and getattr(lw, 'fuse_qo', False):
+            # chain: gmean = gqv @ (W_q W_out) in one GEMM; gg = gqv @ W_q (an input of output_proj's weight gradient only)
+            # is produced on the weight-gradient stream
+            gmean = rows_linear(gqv, lw.p_wqo_t, C)
+            g_wout, g_bout = side.run(lambda: lgrads(rows_linear(gqv, lw.p_wq_t, C), mean), gqv, mean)
+        else:
+            gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
+            gg_s = split_cols(gg, 0) if sp else None
+            g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
+            gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())

@@ -420,7 +420,8 @@ class DenseHead(nn.Module):
         # the fused layer runs its GEMMs on the own tcgen05 kernel from packed weights; only the unfused fallback
         # still needs the bf16x3 images of the layer weights
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
-                             ffn.layers[0][0].weight, ffn.layers[1].weight, images=not self._fused_layer())
+                             ffn.layers[0][0].weight, ffn.layers[1].weight, images=not self._fused_layer(),
+                             b_out=attn.output_proj.bias, in_b=mha.in_proj_bias)
         # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
         # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
         # depth gradient's copies instead of queueing behind them on the same stream

@@ -27,8 +27,8 @@ if mode == 'launches':
     out.append('`ncu --metrics gpu__time_duration.sum --clock-control none` over a window of consecutive launches of '
                '`bench.py --no-graph` (cold-cache, serialised: compare SHARES, not absolutes).\n')
     out.append(f'window: {len(rows)} launches, {tot:.3f} ms total\n')
-    own = sum(ms for k, (n, ms) in agg.items() if k.startswith('sgc::') or 'sgc::' in k)
-    out.append(f'own kernels (sgc::*): {own:.3f} ms = {100 * own / tot:.1f} % of the window\n')
+    own = sum(ms for k, (n, ms) in agg.items() if k.startswith(('sgc::', 'tc::')) or 'sgc::' in k)
+    out.append(f'own kernels (sgc::*, sgc::tc::*): {own:.3f} ms = {100 * own / tot:.1f} % of the window\n')
     out.append('| share | total ms | launches | kernel |\n|---|---|---|---|')
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         out.append(f'| {100 * ms / tot:5.1f} % | {ms:.3f} | {n} | `{k}` |')
