@@ -98,7 +98,7 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
 # (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
-FUSE_QO = _os.environ.get('SGC_FUSE_QO', '1') != '0'
+FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs 550-572 volumes/s): off
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
