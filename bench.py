@@ -605,12 +605,32 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
-    if args.impl == 'reference':
-        run_reference(args)
-    elif args.impl == 'reference-gpu':
-        run_reference_gpu(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 themselves (NCCL prints its version
+    # there when NCCL_DEBUG is set in the environment) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    captured = []
+    builtin_print = print
+
+    def emit(*a, **k):
+        captured.append(' '.join(str(x) for x in a))
+    import builtins
+    builtins.print = emit
+    try:
+        if args.impl == 'reference':
+            run_reference(args)
+        elif args.impl == 'reference-gpu':
+            run_reference_gpu(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = builtin_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in captured:
+        print(line, flush=True)
 
 
 if __name__ == '__main__':

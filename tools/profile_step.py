@@ -25,8 +25,8 @@ def step():
     for t in list(head.parameters()) + feats + dists:
         t.grad = None
     vol, valid, occ = head(feats, sc.img_meta, dists)
-    loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
-    loss.backward()
+    # as bench.py: the backward is seeded with G (the gradient of sum(volume*G)); the loss value is not on its path
+    torch.autograd.backward([vol, head.occ_loss(occ, None, sc.geo_occ)['loss_occ']], [gvol, None])
 
 
 for _ in range(3):
@@ -65,9 +65,7 @@ if os.environ.get('SGC_GRAPH_TRACE'):
         t.grad = None
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        vol, valid, occ = head(feats, sc.img_meta, dists)
-        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
-        loss.backward()
+        step()
     for _ in range(5):
         g.replay()
     torch.cuda.synchronize()
