@@ -74,6 +74,11 @@ CONFIGS: Dict[str, PathConfig] = {
         'tiny', 128, ((4, 4, 2), (8, 8, 4), (16, 16, 8)),
         ((1.6, 1.6, 1.6), (.8, .8, .8), (.4, .4, .4)), (64, 512),
         (95, 128), (968, 1296), _SCANNET_K, feat_hw=((24, 32), (12, 16), (6, 8))),
+    # the tiny grids with the channel count of the C=256 configs (32-wide heads: the tensor-core per-head products)
+    'tiny256': PathConfig(
+        'tiny256', 256, ((4, 4, 2), (8, 8, 4), (16, 16, 8)),
+        ((1.6, 1.6, 1.6), (.8, .8, .8), (.4, .4, .4)), (64, 512),
+        (95, 128), (968, 1296), _SCANNET_K, feat_hw=((24, 32), (12, 16), (6, 8))),
 }
 
 

@@ -137,7 +137,7 @@ def _oracle_selection(inter, nl):
     return [None] + [torch.nonzero(inter['masks'][i]).view(-1).to(DEV, torch.int32) for i in range(1, nl)]
 
 
-@pytest.mark.parametrize('cfg_name,V', [('tiny', 12), ('tiny', 33)])
+@pytest.mark.parametrize('cfg_name,V', [('tiny', 12), ('tiny', 33), ('tiny256', 12)])
 def test_head_forward_matches_oracle_teacher_forced(cuda_lib, cfg_name, V):
     cfg = syn.CONFIGS[cfg_name]
     sc = syn.make_scene(cfg, V, shift_origin=True)
@@ -183,9 +183,14 @@ def test_head_free_running_selection_overlap(cuda_lib):
     assert int(valid.sum()) == cfg.topk_list[-1]
 
 
-def test_head_backward_matches_oracle(cuda_lib):
-    """Gradients of loss = sum(volume*G) + occ_loss w.r.t. every input map and every parameter."""
-    cfg = syn.CONFIGS['tiny']
+@pytest.mark.parametrize('cfg_name,legacy', [('tiny', False), ('tiny256', False), ('tiny256', True)])
+def test_head_backward_matches_oracle(cuda_lib, monkeypatch, cfg_name, legacy):
+    """Gradients of loss = sum(volume*G) + occ_loss w.r.t. every input map and every parameter.  'tiny256' has the 32-wide
+    heads of the C=256 configs (tensor-core per-head products and weight gradients); ``legacy`` runs the same through the
+    previous voxel-count GEMM path (own bf16x3 split kernels + library bf16 GEMM, SGC_ROWS_TC=0)."""
+    if legacy:
+        monkeypatch.setattr(SF, 'ROWS_TC', False)
+    cfg = syn.CONFIGS[cfg_name]
     V = 12
     sc = syn.make_scene(cfg, V, shift_origin=True)
     sd = syn.make_state_dict(cfg)
