@@ -293,6 +293,11 @@ int sgc_upsample2x_occ_gradw(const float* vol_in, int X, int Y, int Z, int C, co
                              void* stream);
 /* topk_wo_grad (ASH:9-13) + nonzero compaction (DH:66): k largest, ties -> lower index; sel ascending. */
 int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream);
+/* The same selection (same deterministic contract) spread over many CTAs for large N (the 204 800-voxel level of the "-L"
+ * configs): chunk histograms merged with integer atomics, one pick launch per radix round, then count + ordered compaction.
+ * scratch: sgc_topk_scratch_ints(N) ints, private to the call.  k >= 1. */
+int sgc_topk_scratch_ints(int N);
+int sgc_topk_select_mc(const float* occ, int N, int k, int* sel, uint8_t* mask, int* scratch, void* stream);
 /* vol[sel[i],:] += y[i,:] (DH:80-81 + ASH:77) and y[i,:] = vol[sel[i],:] (its backward). */
 int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
 int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);

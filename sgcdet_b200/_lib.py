@@ -69,6 +69,8 @@ SIGNATURES = {
     'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
     'sgc_upsample2x_occ_gradw': [P, I, I, I, I, P, P, P],
     'sgc_topk_select': [P, I, I, P, P, P],
+    'sgc_topk_scratch_ints': [I],
+    'sgc_topk_select_mc': [P, I, I, P, P, P, P],
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],
 }

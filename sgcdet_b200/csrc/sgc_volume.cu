@@ -436,6 +436,144 @@ __global__ void __launch_bounds__(1024) topk_select_small_kernel(const float* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------- top-k over many CTAs (N > 32 768)
+// The finest level of the "-L" configs selects 51 200 of 204 800 voxels; one CTA streaming over them four times took
+// ~0.4 ms on the critical path.  Same radix select (11 / 11 / 10 bits, MSB first) and the same deterministic contract, as
+// a short sequence of launches: every CTA histograms its 2048-key chunk in shared memory and adds it to a global
+// histogram with INTEGER atomics (order-independent, so the result is deterministic); one CTA picks the threshold bin;
+// after three rounds a count launch and an ordered-compaction launch write mask / sel.
+// scratch (ints): [0,2048) histogram, [2048] prefix, [2049] need, [2050] prefix mask, [2052, 2052+G) keys > T per chunk,
+// [2052+G, 2052+2G) keys == T per chunk.
+constexpr int kMcChunk = 2048;
+constexpr int kMcState = 2048;
+constexpr int kMcCounts = 2052;
+
+__global__ void __launch_bounds__(1024) topk_mc_init_kernel(int* __restrict__ scratch, int k) {
+  for (int b = threadIdx.x; b < 2048; b += 1024) scratch[b] = 0;
+  if (threadIdx.x == 0) { scratch[kMcState] = 0; scratch[kMcState + 1] = k; scratch[kMcState + 2] = 0; }
+}
+
+__global__ void __launch_bounds__(1024) topk_mc_hist_kernel(const float* __restrict__ occ, int N, int* __restrict__ scratch,
+                                                           int shift, int nb) {
+  __shared__ int hist[2048];
+  for (int b = threadIdx.x; b < 2048; b += 1024) hist[b] = 0;
+  __syncthreads();
+  const uint32_t prefix = (uint32_t)scratch[kMcState], pmask = (uint32_t)scratch[kMcState + 2];
+#pragma unroll
+  for (int j = 0; j < kMcChunk / 1024; ++j) {
+    const int i = blockIdx.x * kMcChunk + j * 1024 + threadIdx.x;
+    if (i < N) {
+      const uint32_t key = topk_key(__ldg(occ + i));
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += 1024) {
+    const int c = hist[b];
+    if (c) atomicAdd(scratch + b, c);
+  }
+}
+
+__global__ void __launch_bounds__(1024) topk_mc_pick_kernel(int* __restrict__ scratch, int shift, int nb) {
+  __shared__ int warp_tot[32];
+  const int tid = threadIdx.x;
+  // suffix counts over the (up to 2048) bins: thread t handles bins 2047-2t and 2046-2t, as in topk_select_small_kernel
+  const int b_hi = 2047 - 2 * tid, b_lo = b_hi - 1;
+  const int c_hi = b_hi < nb ? scratch[b_hi] : 0, c_lo = b_lo < nb ? scratch[b_lo] : 0;
+  int total;
+  const int before = block_excl_scan_1024(c_hi + c_lo, warp_tot, total);
+  const uint32_t prefix = (uint32_t)scratch[kMcState], pmask = (uint32_t)scratch[kMcState + 2];
+  const int need = scratch[kMcState + 1];
+  __syncthreads();   // every thread has read the state and its bins
+  if (before < need && before + c_hi >= need) {
+    scratch[kMcState] = (int)(prefix | ((uint32_t)b_hi << shift));
+    scratch[kMcState + 1] = need - before;
+  } else if (before + c_hi < need && before + c_hi + c_lo >= need) {
+    scratch[kMcState] = (int)(prefix | ((uint32_t)b_lo << shift));
+    scratch[kMcState + 1] = need - before - c_hi;
+  }
+  if (tid == 0) scratch[kMcState + 2] = (int)(pmask | ((uint32_t)(nb - 1) << shift));
+  scratch[b_hi] = 0;   // histogram cleared for the next round
+  scratch[b_lo] = 0;
+}
+
+__global__ void __launch_bounds__(1024) topk_mc_count_kernel(const float* __restrict__ occ, int N, int* __restrict__ scratch) {
+  __shared__ int warp_a[32], warp_b[32];
+  const uint32_t T = (uint32_t)scratch[kMcState];
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int j = 0; j < kMcChunk / 1024; ++j) {
+    const int i = blockIdx.x * kMcChunk + j * 1024 + threadIdx.x;
+    if (i < N) {
+      const uint32_t key = topk_key(__ldg(occ + i));
+      gt += key > T;
+      eq += key == T;
+    }
+  }
+  gt = __reduce_add_sync(SGC_FULL_MASK, gt);
+  eq = __reduce_add_sync(SGC_FULL_MASK, eq);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { warp_a[wid] = gt; warp_b[wid] = eq; }
+  __syncthreads();
+  if (wid == 0) {
+    const int a = __reduce_add_sync(SGC_FULL_MASK, warp_a[lane]), b = __reduce_add_sync(SGC_FULL_MASK, warp_b[lane]);
+    if (lane == 0) { scratch[kMcCounts + blockIdx.x] = a; scratch[kMcCounts + gridDim.x + blockIdx.x] = b; }
+  }
+}
+
+__global__ void __launch_bounds__(1024) topk_mc_write_kernel(const float* __restrict__ occ, int N, const int* __restrict__ scratch,
+                                                            int* __restrict__ sel, uint8_t* __restrict__ mask) {
+  __shared__ int warp_a[32], warp_b[32];
+  __shared__ int s_carry_sel, s_carry_eq;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t T = (uint32_t)scratch[kMcState];
+  const int need_eq = scratch[kMcState + 1];
+  // keys > T / == T in the chunks before this one (fixed order: deterministic)
+  int a = 0, b = 0;
+  for (int c = tid; c < (int)blockIdx.x; c += 1024) { a += scratch[kMcCounts + c]; b += scratch[kMcCounts + gridDim.x + c]; }
+  a = __reduce_add_sync(SGC_FULL_MASK, a);
+  b = __reduce_add_sync(SGC_FULL_MASK, b);
+  if (lane == 0) { warp_a[wid] = a; warp_b[wid] = b; }
+  __syncthreads();
+  if (wid == 0) {
+    const int ta = __reduce_add_sync(SGC_FULL_MASK, warp_a[lane]), tb = __reduce_add_sync(SGC_FULL_MASK, warp_b[lane]);
+    if (lane == 0) { s_carry_sel = ta; s_carry_eq = tb; }
+  }
+  __syncthreads();
+  for (int j = 0; j < kMcChunk / 1024; ++j) {
+    const int i = blockIdx.x * kMcChunk + j * 1024 + tid;
+    uint32_t key = 0;
+    if (i < N) key = topk_key(__ldg(occ + i));
+    const bool gt = (i < N) && key > T;
+    const bool eq = (i < N) && key == T;
+    const unsigned bg = __ballot_sync(SGC_FULL_MASK, gt), be = __ballot_sync(SGC_FULL_MASK, eq);
+    if (lane == 0) { warp_a[wid] = __popc(bg); warp_b[wid] = __popc(be); }
+    __syncthreads();
+    if (wid == 0) {
+      int x = warp_a[lane], y = warp_b[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int xa = __shfl_up_sync(SGC_FULL_MASK, x, o), yb = __shfl_up_sync(SGC_FULL_MASK, y, o);
+        if (lane >= o) { x += xa; y += yb; }
+      }
+      warp_a[lane] = x; warp_b[lane] = y;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+    const int gt_before = s_carry_sel + (wid ? warp_a[wid - 1] : 0) + __popc(bg & lt);
+    const int eq_before = s_carry_eq + (wid ? warp_b[wid - 1] : 0) + __popc(be & lt);
+    const bool take = gt || (eq && eq_before < need_eq);
+    if (i < N) {
+      mask[i] = take ? 1 : 0;
+      if (take) sel[gt_before + (eq_before < need_eq ? eq_before : need_eq)] = i;
+    }
+    __syncthreads();
+    if (tid == 1023) { s_carry_sel = gt_before + (gt ? 1 : 0); s_carry_eq = eq_before + (eq ? 1 : 0); }
+    __syncthreads();
+  }
+}
+
 }  // namespace sgc
 
 extern "C" int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ,
@@ -516,6 +654,34 @@ extern "C" int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t
     sgc::topk_select_small_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
   else
     sgc::topk_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_topk_scratch_ints(int N) {
+  if (N <= 0) return 0;
+  const int G = (N + sgc::kMcChunk - 1) / sgc::kMcChunk;
+  return sgc::kMcCounts + 2 * G;
+}
+
+// The same selection spread over many CTAs (meant for N > 32 768; any N works).  scratch: sgc_topk_scratch_ints(N) ints,
+// private to the call (concurrent calls on different streams need their own).
+extern "C" int sgc_topk_select_mc(const float* occ, int N, int k, int* sel, uint8_t* mask, int* scratch, void* stream) {
+  if (k < 0 || k > N || N <= 0 || !scratch) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = (N + sgc::kMcChunk - 1) / sgc::kMcChunk;
+  sgc::topk_mc_init_kernel<<<1, 1024, 0, st>>>(scratch, k);
+  SGC_CUDA_CHECK_LAST();
+  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    sgc::topk_mc_hist_kernel<<<G, 1024, 0, st>>>(occ, N, scratch, shifts[pass], 1 << bits[pass]);
+    SGC_CUDA_CHECK_LAST();
+    sgc::topk_mc_pick_kernel<<<1, 1024, 0, st>>>(scratch, shifts[pass], 1 << bits[pass]);
+    SGC_CUDA_CHECK_LAST();
+  }
+  sgc::topk_mc_count_kernel<<<G, 1024, 0, st>>>(occ, N, scratch);
+  SGC_CUDA_CHECK_LAST();
+  sgc::topk_mc_write_kernel<<<G, 1024, 0, st>>>(occ, N, scratch, sel, mask);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

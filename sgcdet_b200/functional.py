@@ -99,6 +99,7 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
 FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs 550-572 volumes/s): off
+TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -1109,7 +1110,12 @@ def topk_select(occ: torch.Tensor, k: int):
     N = occ.numel()
     sel = torch.empty(k, device=occ.device, dtype=torch.int32)
     mask = torch.empty(N, device=occ.device, dtype=torch.uint8)
-    call('sgc_topk_select', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), stream())
+    if N > TOPK_MC_MIN and k > 0:
+        # large levels ("-L" configs): many-CTA radix select instead of one CTA streaming over the scores
+        scratch = torch.empty(_lib.load().sgc_topk_scratch_ints(N), device=occ.device, dtype=torch.int32)
+        call('sgc_topk_select_mc', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), ptr(scratch), stream())
+    else:
+        call('sgc_topk_select', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), stream())
     return sel, mask
 
 

@@ -73,6 +73,20 @@ def test_topk_ties_broken_by_index(cuda_lib):
     _check_topk(occ, 150)
 
 
+def test_topk_many_cta_ties_and_small_sizes(cuda_lib, monkeypatch):
+    """The many-CTA top-k (used above 32 768 scores) under massive ties, +-0 and sizes around its 2048-key chunks."""
+    monkeypatch.setattr(SF, 'TOPK_MC_MIN', 0)
+    g = torch.Generator().manual_seed(1)
+    for N in (1, 5, 2047, 2048, 2049, 5000, 70000):
+        occ = torch.randint(0, 7, (N,), generator=g).float() / 7
+        for k in sorted({1, max(1, N // 3), N}):
+            _check_topk(occ, k)
+    _check_topk(torch.full((40000,), 0.5), 12345)   # all equal -> first k indices
+    occ = torch.cat([torch.zeros(3000), -torch.zeros(3000), torch.full((10,), -1.0)])
+    _check_topk(occ, 4500)
+    _check_topk(torch.sigmoid(torch.randn(204800, generator=g)), 51200)
+
+
 def _check_topk(occ, k):
     ref = path_ref.topk_mask(occ, k)
     sel, mask = SF.topk_select(occ.to(DEV), k)
