@@ -339,7 +339,11 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
   p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
   const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * n_cta * BK * 2 +
                       (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
-  cudaError_t e = cudaFuncSetAttribute(rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the opt-in limit is raised once to the widest configuration (n_cta = 256): launches captured into a CUDA graph with
+  // different column splits must not depend on which of them set the attribute last
+  const size_t smem_max = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * 256 * BK * 2 +
+                          (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
+  cudaError_t e = cudaFuncSetAttribute(rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.works < sms ? p.works : sms;
   rows_gemm_tc_kernel<<<grid, RG_THREADS, smem, (cudaStream_t)stream>>>(amap, omap, p);
@@ -642,7 +646,9 @@ extern "C" int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_
   p.bias_partial = scratch + (size_t)p.kch * B * M * N;
   const size_t smem = (size_t)RW_ST * (BK * BM * 4 + BK * p.n_cta * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * p.n_cta * BK * 2) +
                       sizeof(SmemRW) + 64;
-  cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem_max = (size_t)RW_ST * (BK * BM * 4 + BK * 256 * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * 256 * BK * 2) +
+                          sizeof(SmemRW) + 64;   // widest configuration, see sgc_rows_gemm_tc
+  cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(p.m_tiles * p.kch, N / p.n_cta, B);
   rows_wgrad_tc_kernel<<<grid, RW_THREADS, smem, (cudaStream_t)stream>>>(amap, bmap, p);
