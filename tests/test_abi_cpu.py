@@ -149,3 +149,38 @@ def test_algorithmic_bytes_match_baseline_table():
     assert abs(b['fwd'] / 1e9 - 0.84) < 0.01 and abs(b['fwd_bwd'] / 1e9 - 2.20) < 0.01
     b = syn.algorithmic_bytes('SGCDet_large_ScanNet200', 40)
     assert abs(b['fwd'] / 1e9 - 0.63) < 0.01 and abs(b['fwd_bwd'] / 1e9 - 1.53) < 0.01
+
+
+def test_host_side_planning_helpers():
+    """Host-only entry points of the C ABI (no device work): column split of the voxel-count GEMM kernel, scratch sizes of
+    the weight-gradient kernel and of the many-CTA top-k, and the argument checks that precede any launch."""
+    lib = _lib.load()
+    # the widest column part of {256,128,64,32} dividing N that still yields enough work items to spread over the SMs
+    assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 256, 1) == 128      # 50 row tiles x 2 parts
+    assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 512, 1) == 256      # 50 x 2
+    assert lib.sgc_rows_gemm_tc_auto_ncta(400, 256, 1) == 32        # 4 row tiles: split as far as possible
+    assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 256, 8) == 256      # 8 heads: 400 work items already
+    assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 32, 8) == 32        # per-head output of 32 columns
+    assert lib.sgc_rows_gemm_tc_auto_ncta(100, 96, 1) == 32         # 96 = 3 x 32
+    assert lib.sgc_rows_gemm_tc_auto_ncta(100, 48, 1) == 0          # N % 32 != 0 -> rejected
+    # split-K partials [kch][B][M][N] + column sums; kch <= 148 / tiles and >= 128 rows per CTA
+    assert lib.sgc_rows_wgrad_tc_scratch_floats(256, 256, 6400, 1) == 50 * (256 * 256 + 256)
+    assert lib.sgc_rows_wgrad_tc_scratch_floats(256, 256, 400, 1) == 3 * (256 * 256 + 256)
+    assert lib.sgc_rows_wgrad_tc_scratch_floats(256, 32, 6400, 8) == 9 * 8 * (256 * 32 + 256)
+    assert lib.sgc_rows_wgrad_tc_scratch_floats(100, 256, 6400, 1) == 0   # M % 128 != 0
+    assert lib.sgc_topk_scratch_ints(204800) == 2052 + 2 * 100
+    assert lib.sgc_topk_scratch_ints(1) == 2052 + 2
+    # argument errors are reported before anything is launched (cudaErrorInvalidValue = 1)
+    assert lib.sgc_rows_gemm_tc(None, 256, 0, 10, 256, 1, None, 256, 0, 0, None, 0, 256, None, 256, 0, 0, None) == 1
+    assert lib.sgc_rows_wgrad_tc(None, 256, 0, 256, None, 256, 0, 256, 10, 1, None, 0, 256, 1, 1.0, None, 0, None, None) == 1
+    assert lib.sgc_topk_select_mc(None, 10, 11, None, None, None, None) == 1
+
+
+def test_stream_priority_lists(monkeypatch):
+    monkeypatch.delenv('SGC_CHAIN_PRIO', raising=False)
+    assert plugin._prio_list('SGC_CHAIN_PRIO', 3, -1) == [-1, -1, -1]
+    monkeypatch.setenv('SGC_CHAIN_PRIO', '-1, x,-3')
+    assert plugin._prio_list('SGC_CHAIN_PRIO', 3, -1) == [-1, -1, -3]
+    monkeypatch.setenv('SGC_BIG_PRIO', 'x,x,-2')
+    assert plugin._prio_list('SGC_BIG_PRIO', 3, None) == [None, None, -2]
+    assert plugin._prio_list('SGC_BIG_PRIO', 4, None) == [None, None, -2, None]
