@@ -122,6 +122,12 @@ int sgc_project_tc_set_max_ctas(int n);
 int sgc_project_tc_set_max_ctas_fwd(int n);
 /* n > 0: the forward / data-gradient kernels run as short-lived CTAs of n tiles each instead of persistent ones. */
 int sgc_project_tc_set_tiles_per_cta(int n);
+/* Programmatic dependent launch (sm_90+) for the kernels of the per-voxel chain (projection / pair list, lift forward,
+ * cross-view kernels, row kernels, voxel-count GEMM, upsample / top-k / scatter / gather): with on != 0 they are launched
+ * with the programmatic-stream-serialization attribute and overlap their launch + prologue with the tail of their
+ * predecessor in the stream (every such kernel waits with griddepcontrol.wait before touching global data).  Off by
+ * default. */
+int sgc_set_pdl(int on);
 int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_stride, int V, int S, int N, int C, float* gw,
                          float* scratch, void* stream);
 

@@ -44,6 +44,7 @@ SIGNATURES = {
     'sgc_project_tc_set_max_ctas': [I],
     'sgc_project_tc_set_max_ctas_fwd': [I],
     'sgc_project_tc_set_tiles_per_cta': [I],
+    'sgc_set_pdl': [I],
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_rows_gemm_tc_auto_ncta': [I, I, I],
     'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
@@ -120,6 +121,7 @@ def load() -> ctypes.CDLL:
             fn.restype = c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
         lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
+        lib.sgc_set_pdl(int(os.environ.get('SGC_PDL', '0')))
         lib.sgc_project_tc_set_tiles_per_cta(int(os.environ.get('SGC_TC_TILES_PER_CTA', '0')))
         _lib = lib
     return _lib

@@ -92,6 +92,41 @@ __device__ __forceinline__ float quad_max(float v) {
 
 }  // namespace sgc
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+) for the latency-bound per-voxel chain: a kernel launched through
+// sgc::launch_chain() with the feature enabled (sgc_set_pdl) may start while its predecessor in the stream is still
+// running.  Device side, EVERY thread of such a kernel calls pdl_sync() before its first global read or write of data
+// another kernel touches: `launch_dependents` lets the successor's CTAs be scheduled (they then sit in their own wait),
+// `wait` blocks until the predecessor grid has completed and its memory is visible.  Without the launch attribute both
+// instructions are no-ops, so the same kernels run unchanged on ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+namespace sgc {
+int pdl_enabled();   // csrc/sgc_volume.cu (sgc_set_pdl)
+
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute when enabled.  Only for kernels
+// that call pdl_sync() / pdl_wait() as described above.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace sgc
+
 #define SGC_CUDA_CHECK_LAST() \
   do {                        \
     cudaError_t e__ = cudaGetLastError(); \

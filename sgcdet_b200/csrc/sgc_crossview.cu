@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __
                                                                  float* __restrict__ mean,
                                                                  __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   __shared__ int s_ids[kCvWarps][kMaxViews];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int q = blockIdx.x * kCvWarps + wid;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
                                                                  float* __restrict__ t_out, float* __restrict__ alpha,
                                                                  __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   __shared__ int s_ids[kCvWarps][kMaxViews];
   __shared__ float s_sc[kCvWarps][kMaxViews][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_qt_kernel(
     const float* __restrict__ grad_t, float* __restrict__ gscore, float* __restrict__ grad_qt,
     __nv_bfloat16* __restrict__ split = nullptr) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   __shared__ int s_ids[kCvWarps][kMaxViews];
   __shared__ float s_al[kCvWarps][kMaxViews][8];  // alpha
   __shared__ float s_gs[kCvWarps][kMaxViews][8];  // grad of the scores
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_bwd_slots_kernel(
     const int* __restrict__ pair_index, int V, int Q, const float* __restrict__ grad_t,
     const float* __restrict__ grad_mean, float* __restrict__ grad_slots, const int* __restrict__ count_override) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   __shared__ int s_ids[kCvWarps][kMaxViews];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int q = blockIdx.x * kCvWarps + wid;
@@ -515,25 +519,25 @@ __global__ void __launch_bounds__(kCvWarps * 32) cvs_bwd_qt_kernel(const float* 
     if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;                                \
     if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;                                  \
     const int grid = (Q + sgc::kCvWarps - 1) / sgc::kCvWarps;                                   \
-    if (C == 256) sgc::KERNEL<8><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
-    else sgc::KERNEL<4><<<grid, sgc::kCvWarps * 32, 0, (cudaStream_t)stream>>>(__VA_ARGS__);    \
+    if (C == 256) sgc::launch_chain(sgc::KERNEL<8>, dim3(grid), dim3(sgc::kCvWarps * 32), 0, (cudaStream_t)stream, __VA_ARGS__); \
+    else sgc::launch_chain(sgc::KERNEL<4>, dim3(grid), dim3(sgc::kCvWarps * 32), 0, (cudaStream_t)stream, __VA_ARGS__); \
     SGC_CUDA_CHECK_LAST();                                                                      \
     return 0;                                                                                   \
   } while (0)
 
 extern "C" int sgc_crossview_mean_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* mean,
                                       void* stream) {
-  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean);
+  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean, nullptr);
 }
 
 extern "C" int sgc_crossview_attn_fwd(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
                                       float* t_out, float* alpha, void* stream) {
-  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha);
+  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha, nullptr);
 }
 
 extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
                                          int C, const float* grad_t, float* gscore, float* grad_qt, void* stream) {
-  SGC_CV_LAUNCH(attn_bwd_qt_kernel, slots, alpha, pair_index, V, Q, grad_t, gscore, grad_qt);
+  SGC_CV_LAUNCH(attn_bwd_qt_kernel, slots, alpha, pair_index, V, Q, grad_t, gscore, grad_qt, nullptr);
 }
 
 // Same three kernels, additionally emitting the bf16x3 operand image (sgc_split_bf16x3 pattern 0) of their dense output

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) lift_fwd_kernel(
     const int* __restrict__ pair_vq, const int* __restrict__ n_pairs_ptr, const float* __restrict__ ref_cam,
     int S, int H, int W, int D, int Q, float* __restrict__ samp, float* __restrict__ slots) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int n_pairs = __ldg(n_pairs_ptr);
@@ -351,11 +352,11 @@ extern "C" int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
   if (C == 256)
-    sgc::lift_fwd_kernel<8><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs, ref_cam,
-                                                  S, H, W, D, Q, samp, slots);
+    sgc::launch_chain(sgc::lift_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
+                      ref_cam, S, H, W, D, Q, samp, slots);
   else
-    sgc::lift_fwd_kernel<4><<<grid, 256, 0, st>>>(value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs, ref_cam,
-                                                  S, H, W, D, Q, samp, slots);
+    sgc::launch_chain(sgc::lift_fwd_kernel<4>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
+                      ref_cam, S, H, W, D, Q, samp, slots);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kTile) project_kernel(const float* __restrict_
                                                        float* __restrict__ ref_cam, uint8_t* __restrict__ mask,
                                                        int* __restrict__ tile_counts, int* __restrict__ count) {
   __shared__ float P[12];
+  pdl_sync();
   const int v = blockIdx.y, tile = blockIdx.x;
   if (threadIdx.x < 12) P[threadIdx.x] = proj[v * 12 + threadIdx.x];
   __syncthreads();
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ tile
                                                    int* __restrict__ tile_offsets, int* __restrict__ view_offsets) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
+  pdl_sync();
   const int n = n_tiles_per_view * V;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(kTile) emit_kernel(const uint8_t* __restrict__
                                                     int Q, int* __restrict__ pair_index, int* __restrict__ pair_vq,
                                                     int* __restrict__ count) {
   __shared__ int warp_tot[32];
+  pdl_sync();
   const int v = blockIdx.y, tile = blockIdx.x;
   const int q = tile * kTile + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -160,12 +163,13 @@ extern "C" int sgc_project_compact(const float* proj, const float* ref3d, const 
   int* tile_counts = scratch;
   int* tile_offsets = scratch + V * tiles;
   dim3 grid(tiles, V);
-  sgc::project_kernel<<<grid, sgc::kTile, 0, st>>>(proj, ref3d, sel, Q, ox, oy, oz, eps, one_minus_eps, img_w, img_h, dbound0, dscale,
-                                                   ref_cam, mask, tile_counts, count);
+  sgc::launch_chain(sgc::project_kernel, grid, dim3(sgc::kTile), 0, st, proj, ref3d, sel, Q, ox, oy, oz, eps, one_minus_eps, img_w,
+                    img_h, dbound0, dscale, ref_cam, mask, tile_counts, count);
   SGC_CUDA_CHECK_LAST();
-  sgc::scan_kernel<<<1, 1024, 0, st>>>(tile_counts, tiles, V, tile_offsets, view_offsets);
+  sgc::launch_chain(sgc::scan_kernel, dim3(1), dim3(1024), 0, st, (const int*)tile_counts, tiles, V, tile_offsets, view_offsets);
   SGC_CUDA_CHECK_LAST();
-  sgc::emit_kernel<<<grid, sgc::kTile, 0, st>>>(mask, tile_offsets, Q, pair_index, pair_vq, count);
+  sgc::launch_chain(sgc::emit_kernel, grid, dim3(sgc::kTile), 0, st, (const uint8_t*)mask, (const int*)tile_offsets, Q, pair_index,
+                    pair_vq, count);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -161,6 +161,7 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* __restrict__ out, siz
 template <int CPL>
 __global__ void __launch_bounds__(kRowWarps * 32) rowop_fwd_kernel(const sgc_rowop_fwd_args a) {
   constexpr int N = 32 * CPL;
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * CPL;
   float bias[CPL], gam[CPL], bet[CPL];
@@ -227,6 +228,7 @@ template <int CPL>
 __global__ void __launch_bounds__(kRowWarps * 32) rowop_bwd_kernel(const sgc_rowop_bwd_args a) {
   constexpr int N = 32 * CPL;
   __shared__ float s_part[kRowWarps][2 * N];
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * CPL;
   const bool ln = a.gamma != nullptr;
@@ -341,9 +343,9 @@ extern "C" int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream) {
   const int blocks = sgc::rowop_blocks(a.R);
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.N) {
-    case 128: sgc::rowop_fwd_kernel<4><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
-    case 256: sgc::rowop_fwd_kernel<8><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
-    case 512: sgc::rowop_fwd_kernel<16><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 128: sgc::launch_chain(sgc::rowop_fwd_kernel<4>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
+    case 256: sgc::launch_chain(sgc::rowop_fwd_kernel<8>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
+    case 512: sgc::launch_chain(sgc::rowop_fwd_kernel<16>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
     default: return (int)cudaErrorInvalidValue;
   }
   SGC_CUDA_CHECK_LAST();
@@ -359,9 +361,9 @@ extern "C" int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream) {
   const int blocks = sgc::rowop_blocks(a.R);
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.N) {
-    case 128: sgc::rowop_bwd_kernel<4><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
-    case 256: sgc::rowop_bwd_kernel<8><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
-    case 512: sgc::rowop_bwd_kernel<16><<<blocks, sgc::kRowWarps * 32, 0, st>>>(a); break;
+    case 128: sgc::launch_chain(sgc::rowop_bwd_kernel<4>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
+    case 256: sgc::launch_chain(sgc::rowop_bwd_kernel<8>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
+    case 512: sgc::launch_chain(sgc::rowop_bwd_kernel<16>, dim3(blocks), dim3(sgc::kRowWarps * 32), 0, st, a); break;
     default: return (int)cudaErrorInvalidValue;
   }
   SGC_CUDA_CHECK_LAST();

@@ -80,10 +80,13 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
                  "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the successor may be scheduled from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
+  // barrier setup and the TMEM allocation above do not depend on the predecessor; everything below reads its output
+  pdl_wait();
 
   if (warp == 5) {
     // ===================== producer: TMA loads of the fp32 activation tiles [128 rows][32 k] =====================
@@ -346,7 +349,7 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
   cudaError_t e = cudaFuncSetAttribute(rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.works < sms ? p.works : sms;
-  rows_gemm_tc_kernel<<<grid, RG_THREADS, smem, (cudaStream_t)stream>>>(amap, omap, p);
+  sgc::launch_chain(rows_gemm_tc_kernel, dim3(grid), dim3(RG_THREADS), smem, (cudaStream_t)stream, amap, omap, p);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_fwd_kernel(const f
                                                                         float* __restrict__ out,
                                                                         float* __restrict__ occ) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
   const int n_out = X2 * Y2 * Z2;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_fwd_kernel(const f
 // per-voxel pre-activation gradient: gpre[n] = g_occ[n] * occ*(1-occ); also reduces grad_b
 __global__ void occ_gpre_kernel(const float* __restrict__ occ, const float* __restrict__ g_occ, int n_out,
                                 float* __restrict__ gpre, float* __restrict__ grad_b) {
+  pdl_sync();
   float local = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
     const float s = occ[i];
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_bwd_kernel(const f
                                                                         const float* __restrict__ w_occ, int X, int Y,
                                                                         int Z, float* __restrict__ grad_in) {
   constexpr int C = CPL * 32;
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int n_in = X * Y * Z;
   const int n = blockIdx.x * kUpWarps + (threadIdx.x >> 5);
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(kUpWarps * 32) upsample_occ_bwd_kernel(const f
 // out[sel[i], :] += y[i, :]   (sel entries are unique -> plain read-modify-write)
 __global__ void scatter_add_rows_kernel(float* __restrict__ vol, const int* __restrict__ sel, const float* __restrict__ y,
                                         int k, int C4) {
+  pdl_sync();
   const int total = k * C4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / C4, c = i - r * C4;
@@ -216,6 +220,7 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ vol, const int* __re
 }
 __global__ void gather_rows_kernel(const float* __restrict__ vol, const int* __restrict__ sel, float* __restrict__ y,
                                    int k, int C4) {
+  pdl_sync();
   const int total = k * C4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / C4, c = i - r * C4;
@@ -350,6 +355,7 @@ __global__ void __launch_bounds__(1024) topk_select_small_kernel(const float* __
   __shared__ int warp_tot[32];
   __shared__ uint32_t s_prefix;
   __shared__ int s_need;
+  pdl_sync();
   const int tid = threadIdx.x;
   // thread t owns the CONTIGUOUS index range [t*per, (t+1)*per): the ordered compaction then needs one block scan
   const int per = (N + 1023) / 1024;
@@ -576,14 +582,24 @@ __global__ void __launch_bounds__(1024) topk_mc_write_kernel(const float* __rest
 
 }  // namespace sgc
 
+// Programmatic dependent launch for the chain kernels (see common.cuh); off by default.
+static int g_sgc_pdl = 0;
+namespace sgc {
+int pdl_enabled() { return g_sgc_pdl; }
+}  // namespace sgc
+extern "C" int sgc_set_pdl(int on) {
+  g_sgc_pdl = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ,
                                       const float* b_occ, float* vol_out, float* occ, void* stream) {
   if (C != 256 && C != 128 && C != 64) return (int)cudaErrorInvalidValue;
   const int n_out = 8 * X * Y * Z;
   const int grid = (n_out + sgc::kUpWarps - 1) / sgc::kUpWarps;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 256) sgc::upsample_occ_fwd_kernel<8><<<grid, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
-  else if (C == 128) sgc::upsample_occ_fwd_kernel<4><<<grid, sgc::kUpWarps * 32, 0, st>>>(vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
+  if (C == 256) sgc::launch_chain(sgc::upsample_occ_fwd_kernel<8>, dim3(grid), dim3(sgc::kUpWarps * 32), 0, st, vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
+  else if (C == 128) sgc::launch_chain(sgc::upsample_occ_fwd_kernel<4>, dim3(grid), dim3(sgc::kUpWarps * 32), 0, st, vol_in, X, Y, Z, w_occ, b_occ, vol_out, occ);
   else return (int)cudaErrorInvalidValue;
   SGC_CUDA_CHECK_LAST();
   return 0;
@@ -599,7 +615,7 @@ extern "C" int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, 
   cudaStream_t st = (cudaStream_t)stream;
   const float* gp = nullptr;
   if (grad_occ) {
-    sgc::occ_gpre_kernel<<<(n_out + 1023) / 1024 < 148 ? (n_out + 1023) / 1024 : 148, 1024, 0, st>>>(occ, grad_occ, n_out, gpre, grad_b);
+    sgc::launch_chain(sgc::occ_gpre_kernel, dim3((n_out + 1023) / 1024 < 148 ? (n_out + 1023) / 1024 : 148), dim3(1024), 0, st, occ, grad_occ, n_out, gpre, grad_b);
     SGC_CUDA_CHECK_LAST();
     if (grad_w) {  // NULL: the caller issues sgc_upsample2x_occ_gradw itself (e.g. on its weight-gradient stream)
       const int g2 = 148 * 2;
@@ -610,8 +626,8 @@ extern "C" int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, 
     gp = gpre;
   }
   const int grid = (n_in + sgc::kUpWarps - 1) / sgc::kUpWarps;
-  if (C == 256) sgc::upsample_occ_bwd_kernel<8><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
-  else sgc::upsample_occ_bwd_kernel<4><<<grid, sgc::kUpWarps * 32, 0, st>>>(grad_up, gp, w_occ, X, Y, Z, grad_in);
+  if (C == 256) sgc::launch_chain(sgc::upsample_occ_bwd_kernel<8>, dim3(grid), dim3(sgc::kUpWarps * 32), 0, st, grad_up, gp, w_occ, X, Y, Z, grad_in);
+  else sgc::launch_chain(sgc::upsample_occ_bwd_kernel<4>, dim3(grid), dim3(sgc::kUpWarps * 32), 0, st, grad_up, gp, w_occ, X, Y, Z, grad_in);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -633,7 +649,7 @@ extern "C" int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, 
   const int total = k * (C / 4);
   if (total == 0) return 0;
   const int grid = (total + 255) / 256;
-  sgc::scatter_add_rows_kernel<<<grid < 148 * 8 ? grid : 148 * 8, 256, 0, (cudaStream_t)stream>>>(vol, sel, y, k, C / 4);
+  sgc::launch_chain(sgc::scatter_add_rows_kernel, dim3(grid < 148 * 8 ? grid : 148 * 8), dim3(256), 0, (cudaStream_t)stream, vol, sel, y, k, C / 4);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -643,7 +659,7 @@ extern "C" int sgc_gather_rows(const float* vol, const int* sel, float* y, int k
   const int total = k * (C / 4);
   if (total == 0) return 0;
   const int grid = (total + 255) / 256;
-  sgc::gather_rows_kernel<<<grid < 148 * 8 ? grid : 148 * 8, 256, 0, (cudaStream_t)stream>>>(vol, sel, y, k, C / 4);
+  sgc::launch_chain(sgc::gather_rows_kernel, dim3(grid < 148 * 8 ? grid : 148 * 8), dim3(256), 0, (cudaStream_t)stream, vol, sel, y, k, C / 4);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -651,7 +667,7 @@ extern "C" int sgc_gather_rows(const float* vol, const int* sel, float* y, int k
 extern "C" int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, void* stream) {
   if (k < 0 || k > N) return (int)cudaErrorInvalidValue;
   if (k > 0 && N <= 1024 * sgc::kTopkKpt)
-    sgc::topk_select_small_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
+    sgc::launch_chain(sgc::topk_select_small_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, occ, N, k, sel, mask);
   else
     sgc::topk_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(occ, N, k, sel, mask);
   SGC_CUDA_CHECK_LAST();
