@@ -45,20 +45,38 @@ def reference_head(cfg, mods):
 
 def main():
     mods = ref_shims.install()
-    for cfg_name, V, scene_seed, weight_seed in (('tiny', 9, 77, 4321),):
+    # 'tiny' (C = 128) is stored whole; 'tiny256' (the channel count and 32-wide heads of the C = 256 configs) is stored as
+    # strided samples (every 8th volume channel, every 4th gradient channel) to keep the fixture small
+    for cfg_name, V, scene_seed, weight_seed in (('tiny', 9, 77, 4321), ('tiny256', 7, 78, 4322)):
         cfg = syn.CONFIGS[cfg_name]
         head = reference_head(cfg, mods)
         sd = syn.make_state_dict(cfg, seed=weight_seed)
         print(head.load_state_dict(sd, strict=True))
         head.eval()
-        sc = syn.make_scene(cfg, V, seed=scene_seed, shift_origin=True)
-        feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
-        vol, valid, occ = head(feats, sc.img_meta, sc.mlvl_dpt_dists)
+        while True:
+            sc = syn.make_scene(cfg, V, seed=scene_seed, shift_origin=True)
+            feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
+            vol, valid, occ = head(feats, sc.img_meta, sc.mlvl_dpt_dists)
+            # torch.topk leaves the order of exactly tied scores unspecified (voxels no view sees share one occupancy
+            # value); a fixture must not depend on it: take the first scene seed without a tie at a selection threshold
+            sizes = [int(torch.tensor(n).prod()) for n in cfg.n_voxels_list[1:]][::-1]      # finest first, as in occ
+            ties, off = False, 0
+            for n_vox, k in zip(sizes, list(cfg.topk_list)[::-1]):
+                srt = torch.sort(occ.detach()[0, off:off + n_vox], descending=True).values
+                ties |= bool(srt[k - 1] - srt[k] < 1e-6)
+                off += n_vox
+            if not ties:
+                break
+            print(f'{cfg_name}: scene seed {scene_seed} has a tie at a top-k threshold, trying the next one')
+            scene_seed += 1
         loss = (vol * sc.grad_volume).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
         loss.backward()
+        sub = cfg_name != 'tiny'
+        vs, gs = (8, 4) if sub else (1, 1)
         blob = dict(cfg=cfg_name, num_views=V, scene_seed=scene_seed, weight_seed=weight_seed,
-                    volume=vol.detach().contiguous(), valid=valid, occ_preds=occ.detach(), loss=float(loss),
-                    grad_feat2=feats[2].grad.clone(), torch=torch.__version__)
+                    volume=vol.detach()[:, ::vs].contiguous(), valid=valid.to(torch.uint8) if sub else valid,
+                    occ_preds=occ.detach(), loss=float(loss), grad_feat2=feats[2].grad[:, :, ::gs].clone(),
+                    volume_stride=vs, grad_stride=gs, torch=torch.__version__)
         out = os.path.join(ROOT, 'tests', 'golden', f'plugin_level_{cfg_name}.pt')
         torch.save(blob, out)
         print('wrote', out, tuple(vol.shape), float(loss), int(valid.sum()))
