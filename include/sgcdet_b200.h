@@ -283,6 +283,43 @@ typedef struct sgc_rowop_bwd_args {
   const int* rowcount; /* as in sgc_rowop_fwd_args */
 } sgc_rowop_bwd_args;
 int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
+
+/* The row-local tail of one encoder layer (ENC:310-338 after the cross-view attention, DCA:827-837) in ONE launch: a CTA takes
+ * a 128-row tile through  x1 = LayerNorm1((o2 W_o^T + b_o) * mask0*mscale0 * [rowcount > 0]),
+ * hdn = relu(x1 W_1^T + b_1) * mask1*mscale1,  y = LayerNorm2((hdn W_2^T + b_2) * mask2*mscale2 + x1)  with the pipeline of
+ * sgc_rows_gemm_tc (csrc/sgc_rows_chain_tc.cu).  p_w* = sgc_pack_weight_tc images of W_o [C,C], W_1 [F,C], W_2 [C,F]; masks are
+ * uint8 keep-masks [R,C] / [R,F] / [R,C] or NULL; rowcount [R] int32 or NULL.  Outputs are what the separate launches write:
+ * x1, pre1, mean1, rstd1, hdn, y, pre2, mean2, rstd2.  C in {128, 256}, F in {256, 512}.
+ * Written at the end of round 1 without a GPU at hand: not yet used by the product path (see the file header). */
+typedef struct sgc_rows_chain_args {
+  const float* o2;
+  const void* p_wo;
+  const void* p_w1;
+  const void* p_w2;
+  const float* bo;
+  const float* b1;
+  const float* b2;
+  const float* g1;
+  const float* be1;
+  const float* g2;
+  const float* be2;
+  const unsigned char* mask0;
+  const unsigned char* mask1;
+  const unsigned char* mask2;
+  const int* rowcount;
+  float* x1;
+  float* pre1;
+  float* mean1;
+  float* rstd1;
+  float* hdn;
+  float* y;
+  float* pre2;
+  float* mean2;
+  float* rstd2;
+  float mscale0, mscale1, mscale2, eps1, eps2;
+  int R, C, F;
+} sgc_rows_chain_args;
+int sgc_rows_chain_tc(const sgc_rows_chain_args* args, void* stream);
 int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);
 
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].

@@ -32,6 +32,7 @@ SIGNATURES = {
     'sgc_prepare_weights': [P, I, P],
     'sgc_rowop_fwd': [P, P],
     'sgc_rowop_bwd': [P, P],
+    'sgc_rows_chain_tc': [P, P],
     'sgc_crossview_mean_fwd_split': [P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_fwd_split': [P, P, P, I, I, I, P, P, P, P],
     'sgc_crossview_attn_bwd_qt_split': [P, P, P, I, I, I, P, P, P, P, P],
@@ -101,6 +102,15 @@ class RowopBwdArgs(ctypes.Structure):
                                         'partial', 'gpre', 'gx', 'gxsplit')] + \
                [('mscale', c_float), ('gscale', c_float), ('R', c_int), ('N', c_int), ('in_heads', c_int),
                 ('split_heads', c_int), ('rowcount', c_void_p)]
+
+
+class RowsChainArgs(ctypes.Structure):
+    """``sgc_rows_chain_args`` of include/sgcdet_b200.h."""
+    _fields_ = [(n, c_void_p) for n in ('o2', 'p_wo', 'p_w1', 'p_w2', 'bo', 'b1', 'b2', 'g1', 'be1', 'g2', 'be2', 'mask0',
+                                        'mask1', 'mask2', 'rowcount', 'x1', 'pre1', 'mean1', 'rstd1', 'hdn', 'y', 'pre2',
+                                        'mean2', 'rstd2')] + \
+               [(n, c_float) for n in ('mscale0', 'mscale1', 'mscale2', 'eps1', 'eps2')] + \
+               [(n, c_int) for n in ('R', 'C', 'F')]
 
 
 def lib_path() -> Path:

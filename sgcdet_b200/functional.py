@@ -832,6 +832,31 @@ def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gs
     return gx, gs, gpre, partial
 
 
+def rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=None, masks=(None, None, None),
+                   scales=(1.0, 1.0, 1.0)):
+    """``sgc_rows_chain_tc``: W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> (+x1) LayerNorm over the voxel rows in one launch.
+    Returns (y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)) -- the tensors the separate launches of
+    ``EncoderLayerRows.forward`` produce.  Not used by the product path yet (written without a GPU at hand)."""
+    R, C = o2.shape
+    Fh = b1.numel()
+    dev = o2.device
+
+    def new(*shape):
+        return torch.empty(*shape, device=dev, dtype=F32)
+    x1, pre1, mean1, rstd1 = new(R, C), new(R, C), new(R), new(R)
+    hdn, y, pre2, mean2, rstd2 = new(R, Fh), new(R, C), new(R, C), new(R), new(R)
+    a = _lib.RowsChainArgs()
+    a.o2, a.p_wo, a.p_w1, a.p_w2 = ptr(o2), ptr(lw.p_wo), ptr(lw.p_w1), ptr(lw.p_w2)
+    a.bo, a.b1, a.b2, a.g1, a.be1, a.g2, a.be2 = ptr(bo), ptr(b1), ptr(b2), ptr(g1), ptr(be1), ptr(g2), ptr(be2)
+    a.mask0, a.mask1, a.mask2, a.rowcount = ptr(masks[0]), ptr(masks[1]), ptr(masks[2]), ptr(rowcount)
+    a.x1, a.pre1, a.mean1, a.rstd1 = ptr(x1), ptr(pre1), ptr(mean1), ptr(rstd1)
+    a.hdn, a.y, a.pre2, a.mean2, a.rstd2 = ptr(hdn), ptr(y), ptr(pre2), ptr(mean2), ptr(rstd2)
+    a.mscale0, a.mscale1, a.mscale2, a.eps1, a.eps2 = scales[0], scales[1], scales[2], eps1, eps2
+    a.R, a.C, a.F = R, C, Fh
+    call('sgc_rows_chain_tc', ctypes.byref(a), stream())
+    return y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)
+
+
 def _ln_params(partial, R, N):
     gg, gb = torch.empty(N, device=partial.device, dtype=F32), torch.empty(N, device=partial.device, dtype=F32)
     call('sgc_layernorm_bwd_params', ptr(partial), R, N, ptr(gg), ptr(gb), stream())

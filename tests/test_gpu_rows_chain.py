@@ -1,0 +1,53 @@
+"""The one-launch row-tile chain kernel (csrc/sgc_rows_chain_tc.cu) against the separate GEMM + row-kernel launches it is
+meant to replace, and against torch.  The kernel was written at the end of round 1 without a GPU at hand and is not used by
+the product path yet: these tests only run with SGC_TEST_CHAIN=1."""
+import os
+
+import pytest
+import torch
+
+from sgcdet_b200 import functional as SF
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('SGC_TEST_CHAIN', '0') == '0', reason='set SGC_TEST_CHAIN=1 (kernel not validated yet)')]
+
+
+@pytest.mark.parametrize('R,C,train', [(6400, 256, True), (800, 256, False), (400, 256, True), (77, 256, True),
+                                       (3200, 128, True), (130, 128, False)])
+def test_rows_chain_matches_separate_launches(cuda_lib, R, C, train):
+    g = torch.Generator().manual_seed(R + C)
+    dev = 'cuda'
+    Fh = 2 * C
+    o2 = torch.randn(R, C, generator=g).to(dev)
+    wcat = torch.randn(C + 128, C, generator=g).to(dev)
+    w_out, wo = (torch.randn(C, C, generator=g) / C ** 0.5).to(dev), (torch.randn(C, C, generator=g) / C ** 0.5).to(dev)
+    in_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(dev)
+    w1, w2 = (torch.randn(Fh, C, generator=g) / C ** 0.5).to(dev), (torch.randn(C, Fh, generator=g) / Fh ** 0.5).to(dev)
+    bo, b2, g1, be1, g2, be2 = (torch.randn(C, generator=g).to(dev) for _ in range(6))
+    b1 = torch.randn(Fh, generator=g).to(dev)
+    count = torch.randint(0, 3, (R,), generator=g).to(torch.int32).to(dev)
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
+    if not lw.rows_tc:
+        pytest.skip('SGC_ROWS_TC=0')
+    masks, scales = (None, None, None), (1.0, 1.0, 1.0)
+    if train:
+        masks = (None, (torch.rand(R, Fh, generator=g) > 0.1).to(torch.uint8).to(dev),
+                 (torch.rand(R, C, generator=g) > 0.1).to(torch.uint8).to(dev))
+        scales = (1.0, 1.0 / 0.9, 1.0 / 0.9)
+    # the separate launches (what EncoderLayerRows.forward issues today)
+    x1, _, ln1 = SF.rowop_fwd(SF.rows_linear(o2, lw.p_wo, C), R, C, bias=bo, mask=masks[0], mscale=scales[0], rowcount=count,
+                              ln=(g1, be1, 1e-5), want_split=False)
+    hdn, _, _ = SF.rowop_fwd(SF.rows_linear(x1, lw.p_w1, Fh), R, Fh, bias=b1, relu=True, mask=masks[1], mscale=scales[1],
+                             want_split=False)
+    y, _, ln2 = SF.rowop_fwd(SF.rows_linear(hdn, lw.p_w2, C), R, C, bias=b2, mask=masks[2], mscale=scales[2], residual=x1,
+                             ln=(g2, be2, 1e-5), want_split=False)
+    yc, x1c, hdnc, ln1c, ln2c = SF.rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, 1e-5, 1e-5, rowcount=count,
+                                                  masks=masks, scales=scales)
+    torch.cuda.synchronize()
+    for name, got, ref in (('x1', x1c, x1), ('hdn', hdnc, hdn), ('y', yc, y), ('pre1', ln1c[0], ln1[0]), ('mean1', ln1c[1], ln1[1]),
+                           ('rstd1', ln1c[2], ln1[2]), ('pre2', ln2c[0], ln2[0]), ('mean2', ln2c[1], ln2[1]),
+                           ('rstd2', ln2c[2], ln2[2])):
+        assert torch.isfinite(got).all(), name
+        scale = max(ref.abs().max().item(), 1e-6)
+        torch.testing.assert_close(got / scale, ref / scale, rtol=1e-3, atol=1e-4, msg=lambda m: f'{name}: {m}')
+    assert (x1c[count == 0] == be1).all()   # rows no view sees: LayerNorm of an all-zero row is beta
