@@ -100,6 +100,9 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
 FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs 550-572 volumes/s): off
 TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
+# W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> LayerNorm of the layer's forward as ONE launch (sgc_rows_chain_tc); parity-checked
+# on the GPU at the very end of round 1, not benchmarked yet: off by default
+ROWS_CHAIN = _os.environ.get('SGC_ROWS_CHAIN', '0') != '0'
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -948,6 +951,14 @@ class EncoderLayerRows(torch.autograd.Function):
             else:
                 o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
             o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
+        if tc and ROWS_CHAIN and C in (128, 256) and Fh in (256, 512):
+            y, x1, hdn, ln1, ln2 = rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=pl.count,
+                                                  masks=(m0, m1, m2), scales=(s0, s1, s2))
+            ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2,
+                                  w_out, in_w, wo, w1, w2)
+            ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
+            ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
+            return y
         # rows no view sees are zeroed (DCA:819-835) straight from the per-voxel view count
         x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
                                   rowcount=pl.count, ln=(g1, be1, eps1), want_split=sp)
