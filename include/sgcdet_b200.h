@@ -290,7 +290,7 @@ int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
  * sgc_rows_gemm_tc (csrc/sgc_rows_chain_tc.cu).  p_w* = sgc_pack_weight_tc images of W_o [C,C], W_1 [F,C], W_2 [C,F]; masks are
  * uint8 keep-masks [R,C] / [R,F] / [R,C] or NULL; rowcount [R] int32 or NULL.  Outputs are what the separate launches write:
  * x1, pre1, mean1, rstd1, hdn, y, pre2, mean2, rstd2.  C in {128, 256}, F in {256, 512}.
- * Written at the end of round 1 without a GPU at hand: not yet used by the product path (see the file header). */
+ * Parity-checked on the B200 but not benchmarked yet: used by the product path only with SGC_ROWS_CHAIN=1. */
 typedef struct sgc_rows_chain_args {
   const float* o2;
   const void* p_wo;

@@ -13,9 +13,9 @@
 // the stores have completed (an mbarrier per stage orders the producer warp behind them); everything the backward saves
 // (pre1, pre2, the row statistics, hdn) is written exactly as the unfused path writes it.
 //
-// STATUS: written at the end of round 1 without a GPU to run it on; NOT wired into the product path
-// (functional.EncoderLayerRows still issues the separate launches).  tests/test_gpu_rows_chain.py compares it with the
-// unfused sequence and only runs when SGC_TEST_CHAIN=1.
+// STATUS (end of round 1): parity-green on the B200 against the separate launches (tests/test_gpu_rows_chain.py, 6 shapes)
+// and at module level against the oracle with SGC_ROWS_CHAIN=1 (tests/test_gpu_path.py), but the GPU budget ran out before
+// it could be benchmarked: functional.EncoderLayerRows.forward uses it only when SGC_ROWS_CHAIN=1 (default 0).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"

@@ -839,7 +839,7 @@ def rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=No
                    scales=(1.0, 1.0, 1.0)):
     """``sgc_rows_chain_tc``: W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> (+x1) LayerNorm over the voxel rows in one launch.
     Returns (y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)) -- the tensors the separate launches of
-    ``EncoderLayerRows.forward`` produce.  Not used by the product path yet (written without a GPU at hand)."""
+    ``EncoderLayerRows.forward`` produce (used by it when SGC_ROWS_CHAIN=1)."""
     R, C = o2.shape
     Fh = b1.numel()
     dev = o2.device
