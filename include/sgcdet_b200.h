@@ -320,6 +320,42 @@ typedef struct sgc_rows_chain_args {
   int R, C, F;
 } sgc_rows_chain_args;
 int sgc_rows_chain_tc(const sgc_rows_chain_args* args, void* stream);
+
+/* The backward of that tail in one launch (csrc/sgc_rows_chain_bwd_tc.cu):
+ *   gf = LayerNorm2'(gy) * mask2*mscale2 (gpre2 = the unmasked value),  gh = hdn > 0 ? (gf W_2) * gscale1 : 0,
+ *   gx1 = gh W_1,  gout = LayerNorm1'(gx1 + gpre2) * mask0*mscale0 * [rowcount > 0],  go2 = gout W_o.
+ * p_w*_t = sgc_pack_weight_tc images of W_2^T [F,C], W_1^T [C,F], W_o^T [C,C].  gf / gh / gout are also the operands of the
+ * weight gradients; partial1 / partial2: [sgc_layernorm_bwd_scratch_floats(R,C)] floats, ZERO-FILLED by the caller, reduced
+ * by sgc_layernorm_bwd_params.  R <= 128 * 296.  Compiled but never run on a GPU yet (round 1 ran out of GPU budget). */
+typedef struct sgc_rows_chain_bwd_args {
+  const float* gy;
+  const void* p_w2_t;
+  const void* p_w1_t;
+  const void* p_wo_t;
+  const float* pre1;
+  const float* mean1;
+  const float* rstd1;
+  const float* g1;
+  const float* pre2;
+  const float* mean2;
+  const float* rstd2;
+  const float* g2;
+  const float* hdn;
+  const unsigned char* mask0;
+  const unsigned char* mask2;
+  const int* rowcount;
+  float* gf;
+  float* gpre2;
+  float* gh;
+  float* gx1;
+  float* gout;
+  float* go2;
+  float* partial1;
+  float* partial2;
+  float mscale0, mscale2, gscale1;
+  int R, C, F;
+} sgc_rows_chain_bwd_args;
+int sgc_rows_chain_bwd_tc(const sgc_rows_chain_bwd_args* args, void* stream);
 int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);
 
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].

@@ -33,6 +33,7 @@ SIGNATURES = {
     'sgc_rowop_fwd': [P, P],
     'sgc_rowop_bwd': [P, P],
     'sgc_rows_chain_tc': [P, P],
+    'sgc_rows_chain_bwd_tc': [P, P],
     'sgc_crossview_mean_fwd_split': [P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_fwd_split': [P, P, P, I, I, I, P, P, P, P],
     'sgc_crossview_attn_bwd_qt_split': [P, P, P, I, I, I, P, P, P, P, P],
@@ -111,6 +112,14 @@ class RowsChainArgs(ctypes.Structure):
                                         'mean2', 'rstd2')] + \
                [(n, c_float) for n in ('mscale0', 'mscale1', 'mscale2', 'eps1', 'eps2')] + \
                [(n, c_int) for n in ('R', 'C', 'F')]
+
+
+class RowsChainBwdArgs(ctypes.Structure):
+    """``sgc_rows_chain_bwd_args`` of include/sgcdet_b200.h."""
+    _fields_ = [(n, c_void_p) for n in ('gy', 'p_w2_t', 'p_w1_t', 'p_wo_t', 'pre1', 'mean1', 'rstd1', 'g1', 'pre2', 'mean2',
+                                        'rstd2', 'g2', 'hdn', 'mask0', 'mask2', 'rowcount', 'gf', 'gpre2', 'gh', 'gx1',
+                                        'gout', 'go2', 'partial1', 'partial2')] + \
+               [(n, c_float) for n in ('mscale0', 'mscale2', 'gscale1')] + [(n, c_int) for n in ('R', 'C', 'F')]
 
 
 def lib_path() -> Path:

@@ -860,6 +860,32 @@ def rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=No
     return y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)
 
 
+def rows_chain_bwd(gy, lw, hdn, ln1, ln2, g1, g2, rowcount=None, masks=(None, None, None), scales=(1.0, 1.0, 1.0)):
+    """``sgc_rows_chain_bwd_tc``: the backward of ``rows_chain_fwd`` in one launch.  ``ln1`` / ``ln2`` = (pre, mean, rstd) of
+    the two LayerNorms.  Returns (go2, gf, gh, gout, partial1, partial2): the chain's output gradient, the three operands of
+    the weight gradients and the gamma / beta partials for ``_ln_params``.  Not validated on a GPU yet."""
+    R, C = gy.shape
+    Fh = hdn.shape[1]
+    dev = gy.device
+
+    def new(*shape):
+        return torch.empty(*shape, device=dev, dtype=F32)
+    gf, gpre2, gh, gx1, gout, go2 = new(R, C), new(R, C), new(R, Fh), new(R, C), new(R, C), new(R, C)
+    nscr = _lib.load().sgc_layernorm_bwd_scratch_floats(R, C)
+    part1, part2 = torch.zeros(nscr, device=dev, dtype=F32), torch.zeros(nscr, device=dev, dtype=F32)
+    a = _lib.RowsChainBwdArgs()
+    a.gy, a.p_w2_t, a.p_w1_t, a.p_wo_t = ptr(gy), ptr(lw.p_w2_t), ptr(lw.p_w1_t), ptr(lw.p_wo_t)
+    a.pre1, a.mean1, a.rstd1, a.g1 = ptr(ln1[0]), ptr(ln1[1]), ptr(ln1[2]), ptr(g1)
+    a.pre2, a.mean2, a.rstd2, a.g2 = ptr(ln2[0]), ptr(ln2[1]), ptr(ln2[2]), ptr(g2)
+    a.hdn, a.mask0, a.mask2, a.rowcount = ptr(hdn), ptr(masks[0]), ptr(masks[2]), ptr(rowcount)
+    a.gf, a.gpre2, a.gh, a.gx1, a.gout, a.go2 = ptr(gf), ptr(gpre2), ptr(gh), ptr(gx1), ptr(gout), ptr(go2)
+    a.partial1, a.partial2 = ptr(part1), ptr(part2)
+    a.mscale0, a.mscale2, a.gscale1 = scales[0], scales[2], scales[1]
+    a.R, a.C, a.F = R, C, Fh
+    call('sgc_rows_chain_bwd_tc', ctypes.byref(a), stream())
+    return go2, gf, gh, gout, part1, part2
+
+
 def _ln_params(partial, R, N):
     gg, gb = torch.empty(N, device=partial.device, dtype=F32), torch.empty(N, device=partial.device, dtype=F32)
     call('sgc_layernorm_bwd_params', ptr(partial), R, N, ptr(gg), ptr(gb), stream())

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     build.build()
     lib = ctypes.CDLL(str(_lib.lib_path()))
     decls = _header_decls()
-    assert len(decls) == 56
+    assert len(decls) == 57
     for name in decls:
         assert hasattr(lib, name), f'{name} declared in include/sgcdet_b200.h but not exported'
 

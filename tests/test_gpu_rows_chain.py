@@ -48,3 +48,50 @@ def test_rows_chain_matches_separate_launches(cuda_lib, R, C, train):
         scale = max(ref.abs().max().item(), 1e-6)
         torch.testing.assert_close(got / scale, ref / scale, rtol=1e-3, atol=1e-4, msg=lambda m: f'{name}: {m}')
     assert (x1c[count == 0] == be1).all()   # rows no view sees: LayerNorm of an all-zero row is beta
+
+
+@pytest.mark.skipif(__import__('os').environ.get('SGC_TEST_CHAIN_BWD', '0') == '0',
+                    reason='sgc_rows_chain_bwd_tc has not run on a GPU yet: set SGC_TEST_CHAIN_BWD=1')
+@pytest.mark.parametrize('R,C,train', [(6400, 256, True), (800, 256, False), (77, 256, True), (3200, 128, True)])
+def test_rows_chain_bwd_matches_separate_launches(cuda_lib, R, C, train):
+    """The one-launch backward tail against the rowop_bwd + GEMM launches of EncoderLayerRows.backward."""
+    g = torch.Generator().manual_seed(2 * R + C)
+    dev = 'cuda'
+    Fh = 2 * C
+    wcat = torch.randn(C + 128, C, generator=g).to(dev)
+    w_out, wo = (torch.randn(C, C, generator=g) / C ** 0.5).to(dev), (torch.randn(C, C, generator=g) / C ** 0.5).to(dev)
+    in_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(dev)
+    w1, w2 = (torch.randn(Fh, C, generator=g) / C ** 0.5).to(dev), (torch.randn(C, Fh, generator=g) / Fh ** 0.5).to(dev)
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
+    if not lw.rows_tc:
+        pytest.skip('SGC_ROWS_TC=0')
+    gy = torch.randn(R, C, generator=g).to(dev)
+    pre1, pre2 = torch.randn(R, C, generator=g).to(dev) * 2 + 0.3, torch.randn(R, C, generator=g).to(dev) * 2 - 0.1
+    g1, g2 = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    hdn = torch.relu(torch.randn(R, Fh, generator=g)).to(dev)
+    count = torch.randint(0, 3, (R,), generator=g).to(torch.int32).to(dev)
+
+    def stats(x):
+        mu = x.mean(1)
+        return mu.contiguous(), torch.rsqrt(x.var(1, unbiased=False) + 1e-5).contiguous()
+    ln1, ln2 = (pre1, *stats(pre1)), (pre2, *stats(pre2))
+    masks, scales = (None, None, None), (1.0, 1.0, 1.0)
+    if train:
+        masks = (None, None, (torch.rand(R, C, generator=g) > 0.1).to(torch.uint8).to(dev))
+        scales = (1.0, 1.0 / 0.9, 1.0 / 0.9)
+    # the separate launches
+    gf, _, gpre2, part2 = SF.rowop_bwd(gy, R, C, ln=(*ln2, g2), mask=masks[2], mscale=scales[2], want_gpre=True, want_split=False)
+    gh, _, _, _ = SF.rowop_bwd(SF.rows_linear(gf, lw.p_w2_t, Fh), R, Fh, gate=hdn, gscale=scales[1], want_split=False)
+    gout, _, _, part1 = SF.rowop_bwd(SF.rows_linear(gh, lw.p_w1_t, C), R, C, g2=gpre2, ln=(*ln1, g1), mask=masks[0],
+                                     mscale=scales[0], rowcount=count, want_split=False)
+    go2 = SF.rows_linear(gout, lw.p_wo_t, C)
+    ref_p1, ref_p2 = SF._ln_params(part1, R, C), SF._ln_params(part2, R, C)
+    go2c, gfc, ghc, goutc, p1c, p2c = SF.rows_chain_bwd(gy, lw, hdn, ln1, ln2, g1, g2, rowcount=count, masks=masks, scales=scales)
+    got_p1, got_p2 = SF._ln_params(p1c, R, C), SF._ln_params(p2c, R, C)
+    torch.cuda.synchronize()
+    for name, got, ref in (('gf', gfc, gf), ('gh', ghc, gh), ('gout', goutc, gout), ('go2', go2c, go2),
+                           ('ggamma1', got_p1[0], ref_p1[0]), ('gbeta1', got_p1[1], ref_p1[1]),
+                           ('ggamma2', got_p2[0], ref_p2[0]), ('gbeta2', got_p2[1], ref_p2[1])):
+        assert torch.isfinite(got).all(), name
+        scale = max(ref.abs().max().item(), 1e-6)
+        torch.testing.assert_close(got / scale, ref / scale, rtol=1e-3, atol=1e-4, msg=lambda m: f'{name}: {m}')
