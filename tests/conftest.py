@@ -17,5 +17,6 @@ def cuda_lib():
     """The built C-ABI library; GPU tests must fail (not skip) when it is missing."""
     import torch
     assert torch.cuda.is_available(), 'GPU test selected but no CUDA device'
-    from sgcdet_b200 import _lib
+    from sgcdet_b200 import _lib, build
+    build.build()   # no-op when the in-tree library is up to date (it normally travels with the snapshot)
     return _lib.load()
