@@ -216,6 +216,9 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py (ours): no CUDA device -- sgcdet_b200 has no CPU path')
+    if world == 1:
+        from sgcdet_b200 import build
+        build.build()   # no-op when the in-tree library is up to date (it normally travels with the snapshot)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
