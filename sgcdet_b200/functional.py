@@ -103,6 +103,8 @@ TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with mo
 # W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> LayerNorm of the layer's forward as ONE launch (sgc_rows_chain_tc); parity-checked
 # on the GPU at the very end of round 1, not benchmarked yet: off by default
 ROWS_CHAIN = _os.environ.get('SGC_ROWS_CHAIN', '0') != '0'
+# ... and its backward mirror (sgc_rows_chain_bwd_tc): compiled but NEVER run on a GPU yet -- off
+ROWS_CHAIN_BWD = _os.environ.get('SGC_ROWS_CHAIN_BWD', '0') != '0'
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -1029,24 +1031,35 @@ class EncoderLayerRows(torch.autograd.Function):
                 return rows_linear(a, pk_t, w.shape[1])
             return a @ w if small else torch.mm(a_s, ws_t.t(), out_dtype=F32)
 
-        # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
-        gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
-                                           want_split=sp)
         wtc = tc and ROWS_WGRAD_TC and C % 128 == 0 and Fh % 128 == 0   # own kernel for the weight gradients too
         hwtc = wtc and htc
         lgrads = linear_grads_tc if wtc else linear_grads
-        g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
-        g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
-        ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
-        # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
-        gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
-        g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
-        gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
-        gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
-                                           rowcount=pl.count, want_split=sp)
-        g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
-        g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
-        go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
+        if tc and ROWS_CHAIN_BWD and C in (128, 256) and Fh in (256, 512) and Q <= 128 * 296:
+            # LayerNorm2' -> W_2 -> ReLU gate -> W_1 -> LayerNorm1' -> W_o as ONE launch (sgc_rows_chain_bwd_tc); the weight /
+            # bias / gamma / beta gradients are formed from its outputs on the weight-gradient streams as before
+            go2, gf, gh, gout, part1, part2 = rows_chain_bwd(gy, lw, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2), g1, g2,
+                                                             rowcount=pl.count, masks=(m0, m1, m2), scales=(s0, s1, s2))
+            g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
+            g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
+            g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
+            g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
+            g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
+        else:
+            # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
+            gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
+                                               want_split=sp)
+            g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
+            g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
+            ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
+            # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
+            gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
+            g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
+            gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
+            gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
+                                               rowcount=pl.count, want_split=sp)
+            g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
+            g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
+            go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
         if hwtc:
             # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients
             # (rows [0,C) query, [C,2C) key, [2C,3C) value; the key bias gradient is identically zero)
