@@ -497,7 +497,7 @@ def run_ours(args):
                        'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
                                'and the loss value evaluated on a side stream beside the backward',
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
-                       'cuda_graph': not args.no_graph, 'gemm': 'feature-map projection (forward, data gradient, weight gradient): own tcgen05/TMEM/TMA kernels, bf16 hi/lo split in shared memory, fp32 accumulate; voxel-count GEMMs: library bf16 GEMM with fp32 accumulate on bf16x3 operands emitted by the own fused row kernels', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
+                       'cuda_graph': not args.no_graph, 'gemm': 'all GEMMs of the path are own tcgen05/TMEM/TMA kernels with the bf16 hi/lo split in shared memory and fp32 accumulation: feature-map projection (forward, data gradient, weight gradient) and the voxel-count layers (forward, data and weight gradients; 16-wide heads of the -L configs keep a library bf16 GEMM for the per-head products)', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                     'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},
