@@ -480,8 +480,40 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample --------
     cpu = None
+    loss_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.config, V, volumes=1)
+        cpu = cpu_baseline(args.config, V, volumes=1, want_masks=True)
+        # one eval-mode, teacher-forced step of the product on the SAME scene the oracle just evaluated: the loss of the
+        # line's workload against the oracle's (the timed steps run in train mode, whose FFN dropout makes the loss random)
+        o_loss, o_masks = cpu.pop('_loss'), cpu.pop('_masks')
+        was_training = head.training
+        head.eval()
+        with torch.no_grad():
+            forced = [None] + [torch.nonzero(o_masks[i].view(-1) > 0).view(-1).to(dev, torch.int32)
+                               for i in range(1, cfg.num_levels)]
+            sc0 = syn.make_scene(cfg, V, shift_origin=True).to(dev)   # cpu_baseline's scene (default seed)
+            vol_e, _, occ_e = head(sc0.mlvl_feats[:cfg.num_levels], sc0.img_meta, sc0.mlvl_dpt_dists[:cfg.num_levels],
+                                   forced_selection=forced)
+            p_loss = float((vol_e * sc0.grad_volume).sum() + head.occ_loss(occ_e, None, sc0.geo_occ)['loss_occ'])
+        head.train(was_training)
+        loss_check = dict(product_eval_loss=round(p_loss, 4), oracle_loss=round(o_loss, 4),
+                          loss_vs_oracle_rel=abs(p_loss - o_loss) / max(abs(o_loss), 1e-12),
+                          how='eval mode, teacher-forced with the oracle selection, same scene and weights')
+
+    # ---- the reference's own kernels on the same GPU (rank 0, N == 1, after the timed region) ---------------
+    ref_gpu, op_bench = None, None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        try:
+            from oracle import gpu_ref
+            r = gpu_ref.bench(args.config, V, 3, 1)
+            ref_gpu = dict(value=r['value'], unit=UNIT, ms_per_step=r['ms_per_step'], kind='reference kernels',
+                           what=r['config']['what'])
+        except Exception as e:   # the checker must never break the product line
+            ref_gpu = dict(unavailable=f'{type(e).__name__}: {e}'[:200])
+        try:
+            op_bench = operator_bench(dev)
+        except Exception as e:
+            op_bench = dict(unavailable=f'{type(e).__name__}: {e}'[:200])
 
     if rank == 0:
         step_ms = total_ms / args.steps
@@ -504,7 +536,9 @@ def run_ours(args):
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),
             'clocks': clk, 'roofline': roof, 'path_roofline': path_roof, 'kernels': kernels, 'cpu_baseline': cpu,
-            'loss': round(loss_val, 4),
+            'loss': round(loss_val, 4), 'loss_check': loss_check,
+            'loss_vs_oracle_rel': None if loss_check is None else loss_check['loss_vs_oracle_rel'],
+            'reference_gpu': ref_gpu, 'operator_bench': op_bench,
         }
         print(json.dumps(line))
     if world > 1:
@@ -523,8 +557,9 @@ def load_peaks():
 # CPU arms
 # -------------------------------------------------------------------------------------------------
 
-def cpu_baseline(config: str, V: int, volumes: int = 1, warm: bool = False):
-    """The oracle port (torch CPU fp32, every host thread) on a bounded sample of the same workload."""
+def cpu_baseline(config: str, V: int, volumes: int = 1, warm: bool = False, want_masks: bool = False):
+    """The oracle port (torch CPU fp32, every host thread) on a bounded sample of the same workload.  With ``want_masks``
+    the dict also carries ``_loss`` / ``_masks`` of the (eval-mode) oracle pass for the loss cross-check of the line."""
     from oracle import path_ref
     from sgcdet_b200 import synthetic as syn
     cores = os.cpu_count() or 1
@@ -536,11 +571,15 @@ def cpu_baseline(config: str, V: int, volumes: int = 1, warm: bool = False):
     feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
     dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists]
 
+    keep = {}
+
     def one():
-        vol, valid, occ = path_ref.adaptive_sparse_head_forward(sdg, feats, sc.img_meta, dists, cfg)
+        vol, valid, occ, inter = path_ref.adaptive_sparse_head_forward(sdg, feats, sc.img_meta, dists, cfg,
+                                                                     return_intermediates=True)
         loss = (vol * sc.grad_volume).sum() + path_ref.occ_loss(occ, sc.geo_occ)
         loss.backward()
-        return float(loss)
+        keep['loss'], keep['masks'] = float(loss.detach()), inter['masks']
+        return keep['loss']
 
     if warm:
         one()
@@ -548,9 +587,87 @@ def cpu_baseline(config: str, V: int, volumes: int = 1, warm: bool = False):
     for _ in range(volumes):
         one()
     dt = time.perf_counter() - t0
-    return dict(value=round(volumes / dt, 4), unit=UNIT, cores=cores, kind='port',
-                sample=f'{volumes} volume(s) fwd+bwd of {cfg.name} V={V} on the CPU oracle port '
-                       f'(torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads), {dt:.1f} s')
+    out = dict(value=round(volumes / dt, 4), unit=UNIT, cores=cores, kind='port',
+               sample=f'{volumes} volume(s) fwd+bwd of {cfg.name} V={V} on the CPU oracle port '
+                      f'(torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads), {dt:.1f} s')
+    if want_masks:
+        out['_loss'], out['_masks'] = keep['loss'], keep['masks']
+    return out
+
+
+def operator_bench(dev, iters: int = 5):
+    """DFA3D operator boundary (B2) at the reference's own unit-test shapes (unittest_DFA3D.py:43-56): the reference's
+    two-stage kernels (oracle/_ref, unmodified, sm_100a) vs this library's fused one-stage kernels, forward and backward,
+    CUDA events, same tensors.  GB/s = algorithmic bytes (value + depth maps read once, per-query tensors once) / time."""
+    from oracle import build_ref
+    import sgcdet_b200
+    ext = build_ref.load()
+    if ext is None:
+        return {'unavailable': 'oracle/_ref/dfa3d_ref_ext.so not built'}
+    sgcdet_b200.install_dropin()
+    from dfa3D import ext_loader
+    mine = ext_loader.load_ext('_ext', ['wms_deform_attn_forward'])
+    B, M, Cm, D, Q, P = 6, 8, 32, 112, 9502, 8
+    shapes = [(116, 200), (58, 100), (29, 50), (15, 25)]
+    g = torch.Generator().manual_seed(5)
+    s3 = torch.tensor([[h, w, D] for h, w in shapes], dtype=torch.long)
+    sizes = s3[:, 0] * s3[:, 1]
+    lsi = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]]).to(dev)
+    S, L = int(sizes.sum()), len(shapes)
+    s3 = s3.to(dev)
+    value = torch.randn(B, S, M, Cm, generator=g).to(dev)
+    dist = torch.randn(B, S, M, D, generator=g).softmax(-1).to(dev)
+    loc = ((torch.rand(B, Q, M, L, P, 3, generator=g) - 0.5) * 1.2 + 0.5).to(dev)
+    attn = torch.rand(B, Q, M, L * P, generator=g).softmax(-1).view(B, Q, M, L, P).to(dev)
+    gout = torch.randn(B, Q, M * Cm, generator=g).to(dev)
+    s2, loc2 = s3[..., :2].contiguous(), loc[..., :2].contiguous()
+
+    def ref_fwd():
+        ds = ext.ms_depth_score_sample_forward(dist, s3, lsi, loc, im2col_step=64)
+        return ext.wms_deform_attn_forward(value, s2, lsi, loc2, attn, ds, im2col_step=64), ds
+
+    def ref_bwd(ds):
+        gv, gl2, ga, gds = torch.zeros_like(value), torch.zeros_like(loc2), torch.zeros_like(attn), torch.zeros_like(ds)
+        ext.wms_deform_attn_backward(value, s2, lsi, loc2, attn, ds, gout, gv, gl2, ga, gds, im2col_step=64)
+        gd, gl = torch.zeros_like(dist), torch.zeros_like(loc)
+        ext.ms_depth_score_sample_backward(dist, s3, lsi, loc, gds, gd, gl, im2col_step=64)
+        return gv, gd
+
+    def my_fwd():
+        return mine.dfa3d_fused_forward(value, dist, s3, lsi, loc, attn)
+
+    def my_bwd(_):
+        gv, gd, gl, ga = torch.zeros_like(value), torch.zeros_like(dist), torch.zeros_like(loc), torch.zeros_like(attn)
+        mine.dfa3d_fused_backward(value, dist, s3, lsi, loc, attn, gout, gv, gd, gl, ga)
+        return gv, gd
+
+    def t(fn, *a):
+        fn(*a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            r = fn(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, r
+
+    f = 4.0
+    maps = f * B * S * M * (Cm + D)
+    perq = f * B * Q * M * (Cm + L * P * 8)
+    r_f, (out_r, ds_r) = t(ref_fwd)
+    m_f, (out_m, ds_m) = t(my_fwd)
+    r_b, (gv_r, gd_r) = t(ref_bwd, ds_r)
+    m_b, (gv_m, gd_m) = t(my_bwd, None)
+    err = float((out_r - out_m).abs().max()), float((gv_r - gv_m).abs().max()), float((gd_r - gd_m).abs().max())
+    gbs = lambda ms, nbytes: round(nbytes / (ms * 1e-3) / 1e9, 1)
+    return {'shape': f'unittest_DFA3D.py:43-56  B={B} S={S} (4 levels) M={M} Cm={Cm} D={D} Q={Q} P={P}',
+            'fwd': {'reference_two_stage_ms': round(r_f, 3), 'ours_fused_ms': round(m_f, 3),
+                    'reference_gbs': gbs(r_f, maps + perq), 'ours_gbs': gbs(m_f, maps + perq)},
+            'bwd': {'reference_two_stage_ms': round(r_b, 3), 'ours_fused_ms': round(m_b, 3),
+                    'reference_gbs': gbs(r_b, 2 * maps + perq), 'ours_gbs': gbs(m_b, 2 * maps + perq),
+                    'note': 'both sides include the zero-fill of their gradient buffers (caller-zeroed contract, F3D:319-339)'},
+            'max_abs_diff': {'out': err[0], 'grad_value': err[1], 'grad_dist': err[2]}}
 
 
 def run_reference(args):
@@ -604,6 +721,7 @@ def main():
     ap.add_argument('--eval-mode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-grad-allreduce', action='store_true')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-kernel leg and the operator micro-bench')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the e2e and instrumented passes')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

@@ -168,7 +168,8 @@ def dense_head_forward_gpu(sd, level, feat, dpt_dist, img_meta, proposal, cfg, t
     return vol.reshape(*n_vox, C).permute(3, 0, 1, 2).unsqueeze(0)
 
 
-def head_forward_gpu(sd, mlvl_feats, img_meta, mlvl_dpt_dists, cfg, training=True):
+def head_forward_gpu(sd, mlvl_feats, img_meta, mlvl_dpt_dists, cfg, training=True, return_masks=False):
+    """``return_masks``: also return the per-level {0,1} proposal masks (what the parity tests teacher-force the product with)."""
     nl = cfg.num_levels
     volumes, occ_list, masks = [None] * nl, [], [None] * nl
     for i in range(nl):
@@ -192,6 +193,8 @@ def head_forward_gpu(sd, mlvl_feats, img_meta, mlvl_dpt_dists, cfg, training=Tru
     occ_preds = torch.cat(occ_list[::-1], dim=1)
     X, Y, Z = cfg.n_voxels_list[-1]
     valid = masks[-1].view(X, Y, Z).bool().long().unsqueeze(0).unsqueeze(0)
+    if return_masks:
+        return volumes[-1], valid, occ_preds, masks
     return volumes[-1], valid, occ_preds
 
 

@@ -133,6 +133,15 @@ def load() -> ctypes.CDLL:
             raise RuntimeError(
                 f'{_LIB_PATH} is missing: build it with `python -m sgcdet_b200.build` '
                 '(sgcdet_b200 has no CPU or PyTorch fallback)')
+        # a stale library (older argument structs / signatures than this tree declares) would be called through ctypes
+        # with mismatched layouts and corrupt memory silently: the build stamp must equal the digest of the sources
+        from . import build as _build
+        if os.environ.get('SGC_ALLOW_STALE_LIB', '0') == '0':
+            stamp = _build.STAMP.read_text().strip() if _build.STAMP.exists() else None
+            if stamp != _build._digest():
+                raise RuntimeError(
+                    f'{_LIB_PATH} was built from different sources than this tree (build.stamp mismatch): rebuild it with '
+                    '`python -m sgcdet_b200.build`')
         lib = ctypes.CDLL(str(_LIB_PATH))
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
@@ -157,8 +166,11 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """Raw handle of torch's current stream on ``device`` (default: the current device).  The module entry points
+    (``plugin.AdaptiveSparseHead.forward``, ``DenseHead.forward``, ``parallel.forward_view_sharded``, the dropin
+    ``_ext`` wrappers) make the tensors' device current around their launches, so the default is the tensors' device."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def call(name: str, *args):

@@ -3,6 +3,7 @@ signatures).  Gradient stitching follows the plugin's corrected copy
 (``multi_scale_3ddeformable_attn_function.py:303-351``), not the upstream file, whose backward drops the uv
 gradients (``multi_scale_3D_deform_attn.py:201``) and returns 8 grads for 7 inputs (``:220-221``)."""
 import torch
+from torch.amp import custom_bwd, custom_fwd
 from torch.autograd.function import Function, once_differentiable
 
 from dfa3D import ext_loader
@@ -64,6 +65,7 @@ class MultiScale3DDeformableAttnFunction(Function):
     (depth scores are still returned because the reference's callers read them, DCA:492)."""
 
     @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)   # F3D:276 (the _fp32 variant casts under autocast)
     def forward(ctx, value, value_dpt_dist, value_spatial_shapes, value_level_start_index, sampling_locations,
                 attention_weights, im2col_step):
         ctx.im2col_step = im2col_step
@@ -72,10 +74,15 @@ class MultiScale3DDeformableAttnFunction(Function):
             attention_weights)
         ctx.save_for_backward(value, value_dpt_dist, value_spatial_shapes, value_level_start_index,
                               sampling_locations, attention_weights)
+        # the reference raises NotImplementedError in backward when a gradient reaches depth_score (F3D:310-315, after a
+        # host sync on its sum); here the output is declared non-differentiable, so differentiating through it fails in
+        # autograd itself instead of silently dropping that gradient -- and without the sync
+        ctx.mark_non_differentiable(depth_score)
         return output, depth_score
 
     @staticmethod
     @once_differentiable
+    @custom_bwd(device_type='cuda')
     def backward(ctx, grad_output, grad_depth_score_):
         value, dist, shapes, lsi, loc, attn = ctx.saved_tensors
         grad_value = torch.zeros_like(value)

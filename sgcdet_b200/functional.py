@@ -20,6 +20,7 @@ from ._lib import call, ptr, stream
 NUM_HEADS = 8
 NUM_POINTS = 4
 G_CH = 4 * NUM_HEADS * NUM_POINTS  # channels of the folded offset/weight map
+MAX_VIEWS = 128   # csrc/sgc_crossview.cu kMaxViews
 
 
 # ----------------------------------------------------------------------------------------------

@@ -379,6 +379,16 @@ class DenseHead(nn.Module):
         self.n_voxels = torch.tensor(n_voxels)
         self.embed_dims = embed_dims
         self.cross_transformer = TRANSFORMER.build(cross_transformer)
+        da = self.cross_transformer.encoder.layers[0].attentions[0].deformable_attention
+        if (da.num_heads, da.num_points, da.num_levels) != (SF.NUM_HEADS, SF.NUM_POINTS, 1) or embed_dims not in (128, 256) \
+                or da.embed_dims != embed_dims:
+            # the fused level kernels fix the folded map's channel layout ([8 heads][4 points][ox,oy,od,logit]) and the
+            # head count of the attention pooling; every shipped SGCDet config uses exactly this
+            raise ValueError(
+                'sgcdet_b200.DenseHead supports the deformable attention of the shipped SGCDet configs only: '
+                f'num_heads={SF.NUM_HEADS}, num_points={SF.NUM_POINTS}, num_levels=1, embed_dims 128 or 256 '
+                f'(got num_heads={da.num_heads}, num_points={da.num_points}, num_levels={da.num_levels}, '
+                f'embed_dims={embed_dims}/{da.embed_dims})')
         vox_coords, ref_3d = self.get_voxel_indices()
         self.register_buffer('vox_coords', vox_coords)
         self.register_buffer('ref_3d', ref_3d)
@@ -470,6 +480,9 @@ class DenseHead(nn.Module):
         dbound = self.cross_transformer.encoder.dbound
         if proj is None:
             proj = projection_on_device(img_meta, feat.device)
+        if proj.shape[0] > SF.MAX_VIEWS:
+            raise ValueError(f'sgcdet_b200: at most {SF.MAX_VIEWS} views per scene (got {proj.shape[0]}); the cross-view '
+                             'kernels keep one score per view and head in shared memory (csrc/sgc_crossview.cu kMaxViews)')
         pl = SF.project_compact(proj, self.ref_3d, sel, img_meta, dbound)
         if prepared is None:
             prepared = self.prepare(feat, dpt_dist, hw)
@@ -508,11 +521,12 @@ class DenseHead(nn.Module):
         sel = None
         if proposal is not None:
             sel = torch.nonzero(proposal > 0).view(-1).to(torch.int32)
-        y = self.forward_rows(feat, dist, img_meta, feat.shape[-2:], sel)
-        if sel is None:
-            vol = y
-        else:
-            vol = SF.ScatterAddRows.apply(torch.zeros(N, C, device=y.device), y, sel)
+        with torch.cuda.device(feat.device):
+            y = self.forward_rows(feat, dist, img_meta, feat.shape[-2:], sel)
+            if sel is None:
+                vol = y
+            else:
+                vol = SF.ScatterAddRows.apply(torch.zeros(N, C, device=y.device), y, sel)
         X, Y, Z = (int(v) for v in self.n_voxels)
         return vol.view(X, Y, Z, C).permute(3, 0, 1, 2).unsqueeze(0)
 
@@ -558,6 +572,10 @@ class AdaptiveSparseHead(nn.Module):
         dev = mlvl_feats[0].device
         if dev.type != 'cuda':
             raise RuntimeError('sgcdet_b200 has no CPU implementation: inputs must be CUDA tensors')
+        with torch.cuda.device(dev):   # launches use the current device's current stream (_lib.stream)
+            return self._forward_streams(dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+
+    def _forward_streams(self, dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates):
         if os.environ.get('SGC_CHAIN_PRIORITY', '1') == '0':
             return self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
         caller = torch.cuda.current_stream(dev)
