@@ -377,6 +377,17 @@ int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, voi
  * scratch: sgc_topk_scratch_ints(N) ints, private to the call.  k >= 1. */
 int sgc_topk_scratch_ints(int N);
 int sgc_topk_select_mc(const float* occ, int N, int k, int* sel, uint8_t* mask, int* scratch, void* stream);
+/* The same selection as ONE launch for every level size up to sgc_topk_grid_max_n() (262 144) scores: a few CTAs, keys in
+ * registers, the threshold found 4 bits per step with the per-step counts merged through packed 64-bit atomics.
+ * scratch: sgc_topk_grid_scratch_bytes() bytes, zero-filled ONCE when allocated, then reused by every call issued on the
+ * same stream (calls on different streams need their own).  k >= 1. */
+int sgc_topk_grid_scratch_bytes(void);
+int sgc_topk_grid_max_n(void);
+int sgc_topk_select_grid(const float* occ, int N, int k, int* sel, uint8_t* mask, void* scratch, void* stream);
+/* AdaptiveSparseHead.occ_loss (ASH:100-103): loss[0] = 0.5 * mean(BCELoss(p, t)) (logs clamped at -100 like torch);
+ * bwd: grad_p[i] = g[0] * 0.5/N * (p-t)/max(p(1-p),1e-12), g = the upstream gradient (one float on the device). */
+int sgc_occ_loss_fwd(const float* p, const float* t, int N, float* loss, void* stream);
+int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, int N, float* grad_p, void* stream);
 /* vol[sel[i],:] += y[i,:] (DH:80-81 + ASH:77) and y[i,:] = vol[sel[i],:] (its backward). */
 int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
 int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);

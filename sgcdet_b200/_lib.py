@@ -74,6 +74,11 @@ SIGNATURES = {
     'sgc_topk_select': [P, I, I, P, P, P],
     'sgc_topk_scratch_ints': [I],
     'sgc_topk_select_mc': [P, I, I, P, P, P, P],
+    'sgc_topk_grid_scratch_bytes': [],
+    'sgc_topk_grid_max_n': [],
+    'sgc_topk_select_grid': [P, I, I, P, P, P, P],
+    'sgc_occ_loss_fwd': [P, P, I, P, P],
+    'sgc_occ_loss_bwd': [P, P, P, I, P, P],
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],
 }

@@ -312,22 +312,23 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
 }
 
 // grad_vbias[c] += sum_rows partials[row][c] (c < C);  grad_gbias[c-C] += ... (c >= C).
-// block = 32 channels x 32 row-lanes; fixed summation order -> deterministic.
-__global__ void __launch_bounds__(1024) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
-                                                          float* __restrict__ grad_vbias,
-                                                          float* __restrict__ grad_gbias) {
-  __shared__ float s[32][33];
+// block = 32 channels x 8 row-lanes (small CTAs: they have to fit next to whatever else is resident, this launch sits
+// between lift_bwd and the projection's gradient kernels on the backward's critical path); fixed summation order.
+__global__ void __launch_bounds__(256) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
+                                                         float* __restrict__ grad_vbias,
+                                                         float* __restrict__ grad_gbias) {
+  __shared__ float s[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   float a = 0.f;
 #pragma unroll 4
-  for (int r = ry; r < rows; r += 32) a += __ldg(partials + (size_t)r * (C + 128) + c);
+  for (int r = ry; r < rows; r += 8) a += __ldg(partials + (size_t)r * (C + 128) + c);
   s[ry][cx] = a;
   __syncthreads();
   if (ry == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) t += s[k][cx];
+    for (int k = 0; k < 8; ++k) t += s[k][cx];
     if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
   }
 }
@@ -382,7 +383,7 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
     sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   }
   SGC_CUDA_CHECK_LAST();
-  sgc::bias_reduce_kernel<<<(C + 128) / 32, 1024, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
+  sgc::bias_reduce_kernel<<<(C + 128) / 32, 256, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

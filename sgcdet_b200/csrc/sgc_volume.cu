@@ -580,6 +580,206 @@ __global__ void __launch_bounds__(1024) topk_mc_write_kernel(const float* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------- top-k over a few co-operating CTAs
+// One launch for every level size (N <= 262 144): G = ceil(N / 4096) CTAs of 512 threads, at most 8 keys per thread in
+// registers, thread g owning the CONTIGUOUS index range [g*per, (g+1)*per).  The threshold (the k-th largest key) is found
+// digit by digit, 4 bits per step from the top (8 steps): every thread counts, for its active keys (those matching the
+// prefix found so far), how many have a digit >= 1..15; the 15 counts are reduced over the warp, the CTA and -- for
+// G > 1 -- over the grid by ONE 64-bit atomicAdd per word that carries three 19-bit counts AND a 7-bit arrival counter,
+// so a step costs one atomic round trip plus a poll (no fence, no separate barrier).  No histogram, no shared-memory
+// atomics (sigmoid scores crowd the leading bits into a few bins), fully deterministic.  The ordered compaction publishes
+// each CTA's (#keys > T, #keys == T) in one flagged 64-bit word that the higher-ranked CTAs poll.
+// The CTAs spin on global memory, which needs every CTA of the (tiny) grid to become resident eventually: all other
+// kernels of the library are finite, so at worst the launch waits for SMs to free up; no cluster (a cluster launch next to
+// the persistent projection kernels waits for 8 free SMs in ONE GPC).
+// scratch (256 x u64, zero-initialised ONCE by the caller, private to a stream): [0] = parity; two halves of
+// kTkHalf words are used alternately, and every call clears the half the NEXT call will use.
+constexpr int kTkThreads = 512;
+constexpr int kTkKpt = 8;
+constexpr int kTkSteps = 8;
+constexpr int kTkWords = 5;        // 15 counts, three per word
+constexpr int kTkMaxG = 64;
+constexpr int kTkHalf = kTkSteps * kTkWords + kTkMaxG;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kTkThreads) topk_select_grid_kernel(const float* __restrict__ occ, int N, int k, int per,
+                                                                      int* __restrict__ sel, uint8_t* __restrict__ mask,
+                                                                      unsigned long long* __restrict__ scratch) {
+  __shared__ int s_warp[2][kTkThreads / 32][15];
+  __shared__ int s_tot[2][16];
+  __shared__ int s_scan[2][kTkThreads / 32];
+  __shared__ int s_carry[2];
+  pdl_sync();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.x;
+  const unsigned long long par = ld_volatile_u64(scratch) & 1ull;
+  unsigned long long* mine = scratch + 1 + par * kTkHalf;
+  unsigned long long* other = scratch + 1 + (par ^ 1ull) * kTkHalf;
+  if (blockIdx.x == 0)
+    for (int i = tid; i < kTkHalf; i += kTkThreads) other[i] = 0ull;   // nobody touches this half during this call
+  const int g = blockIdx.x * kTkThreads + tid;
+  uint32_t key[kTkKpt];
+#pragma unroll
+  for (int j = 0; j < kTkKpt; ++j) {
+    const long long i = (long long)g * per + j;
+    key[j] = (j < per && i < N) ? topk_key(__ldg(occ + i)) : 0u;   // unused slots: digit 0 everywhere, never counted
+  }
+  uint32_t prefix = 0u, pmask = 0u;
+  int need = k;
+  for (int s = 0; s < kTkSteps; ++s) {
+    const int shift = 28 - 4 * s;
+    int c[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) c[i] = 0;
+#pragma unroll
+    for (int j = 0; j < kTkKpt; ++j) {
+      const bool act = (key[j] & pmask) == prefix;
+      const int d = act ? (int)((key[j] >> shift) & 15u) : 0;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) c[i] += d > i ? 1 : 0;     // c[i] = #keys with digit >= i+1
+    }
+#pragma unroll
+    for (int i = 0; i < 15; ++i) c[i] = __reduce_add_sync(SGC_FULL_MASK, c[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 15; ++i) s_warp[s & 1][wid][i] = c[i];
+    }
+    __syncthreads();
+    if (tid < kTkWords) {
+      int n3[3] = {0, 0, 0};
+      for (int w = 0; w < kTkThreads / 32; ++w) {
+        n3[0] += s_warp[s & 1][w][3 * tid];
+        n3[1] += s_warp[s & 1][w][3 * tid + 1];
+        n3[2] += s_warp[s & 1][w][3 * tid + 2];
+      }
+      if (G > 1) {
+        unsigned long long* word = mine + s * kTkWords + tid;
+        const unsigned long long add = (1ull << 57) | ((unsigned long long)n3[2] << 38) | ((unsigned long long)n3[1] << 19) |
+                                       (unsigned long long)n3[0];
+        unsigned long long v = atomicAdd(word, add) + add;
+        while ((v >> 57) != (unsigned long long)G) v = ld_volatile_u64(word);
+        n3[0] = (int)(v & 0x7FFFFull); n3[1] = (int)((v >> 19) & 0x7FFFFull); n3[2] = (int)((v >> 38) & 0x7FFFFull);
+      }
+      s_tot[s & 1][3 * tid] = n3[0]; s_tot[s & 1][3 * tid + 1] = n3[1]; s_tot[s & 1][3 * tid + 2] = n3[2];
+    }
+    __syncthreads();
+    // the digit of the threshold: the largest d whose count of keys with digit >= d still reaches `need`
+    int d = 0;
+#pragma unroll
+    for (int i = 15; i >= 1; --i)
+      if (d == 0 && s_tot[s & 1][i - 1] >= need) d = i;
+    need -= d < 15 ? s_tot[s & 1][d] : 0;      // keys in strictly higher digits are all taken
+    prefix |= (uint32_t)d << shift;
+    pmask |= 15u << shift;
+  }
+  const uint32_t T = prefix;   // threshold key
+  const int need_eq = need;    // keys == T to take, lowest indices first
+  int ngt = 0, neq = 0;
+#pragma unroll
+  for (int j = 0; j < kTkKpt; ++j) {
+    const long long i = (long long)g * per + j;
+    if (j < per && i < N) { ngt += key[j] > T; neq += key[j] == T; }
+  }
+  // exclusive scan over the CTA's threads (thread order == index order)
+  int igt = ngt, ieq = neq;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(SGC_FULL_MASK, igt, o), b = __shfl_up_sync(SGC_FULL_MASK, ieq, o);
+    if (lane >= o) { igt += a; ieq += b; }
+  }
+  if (lane == 31) { s_scan[0][wid] = igt; s_scan[1][wid] = ieq; }
+  __syncthreads();
+  if (wid == 0) {
+    int a = lane < kTkThreads / 32 ? s_scan[0][lane] : 0, b = lane < kTkThreads / 32 ? s_scan[1][lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ya = __shfl_up_sync(SGC_FULL_MASK, a, o), yb = __shfl_up_sync(SGC_FULL_MASK, b, o);
+      if (lane >= o) { a += ya; b += yb; }
+    }
+    if (lane < kTkThreads / 32) { s_scan[0][lane] = a; s_scan[1][lane] = b; }
+  }
+  __syncthreads();
+  int gt_before = (wid ? s_scan[0][wid - 1] : 0) + igt - ngt;
+  int eq_before = (wid ? s_scan[1][wid - 1] : 0) + ieq - neq;
+  if (G > 1) {
+    unsigned long long* slots = mine + kTkSteps * kTkWords;
+    if (tid == 0) {
+      const unsigned long long v = (1ull << 63) | ((unsigned long long)s_scan[0][kTkThreads / 32 - 1] << 32) |
+                                   (unsigned long long)s_scan[1][kTkThreads / 32 - 1];
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slots + blockIdx.x), "l"(v) : "memory");
+    }
+    if (wid == 0) {   // totals of the lower-ranked CTAs (at most 63: two per lane)
+      int a = 0, b = 0;
+      for (int cta = lane; cta < (int)blockIdx.x; cta += 32) {
+        unsigned long long v = ld_volatile_u64(slots + cta);
+        while (!(v >> 63)) v = ld_volatile_u64(slots + cta);
+        a += (int)((v >> 32) & 0x7FFFFFFFull);
+        b += (int)(v & 0xFFFFFFFFull);
+      }
+      a = __reduce_add_sync(SGC_FULL_MASK, a);
+      b = __reduce_add_sync(SGC_FULL_MASK, b);
+      if (lane == 0) { s_carry[0] = a; s_carry[1] = b; }
+    }
+    __syncthreads();
+    gt_before += s_carry[0];
+    eq_before += s_carry[1];
+  }
+#pragma unroll
+  for (int j = 0; j < kTkKpt; ++j) {
+    const long long i = (long long)g * per + j;
+    if (j < per && i < N) {
+      const bool gt = key[j] > T, eq = key[j] == T;
+      const bool take = gt || (eq && eq_before < need_eq);
+      mask[i] = take ? 1 : 0;
+      if (take) sel[gt_before + (eq_before < need_eq ? eq_before : need_eq)] = (int)i;
+      gt_before += gt;
+      eq_before += eq;
+    }
+  }
+  // CTA 0 only gets here after every CTA arrived at the last step, i.e. after every CTA read the parity
+  if (blockIdx.x == 0 && tid == 0) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(scratch), "l"(par ^ 1ull) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------- occupancy loss
+// AdaptiveSparseHead.occ_loss (AdaptiveSparseHead.py:100-103): nn.BCELoss()(p, t).mean() * 0.5 with torch's clamp of
+// the logs at -100, as ONE CTA (N = 28 800 at the ScanNet shape): fixed summation order, no atomics.
+__global__ void __launch_bounds__(1024) occ_loss_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, int N,
+                                                            float* __restrict__ loss) {
+  __shared__ float s_part[32];
+  pdl_sync();
+  float a = 0.f;
+  for (int i = threadIdx.x; i < N; i += 1024) {
+    const float pi = __ldg(p + i), ti = __ldg(t + i);
+    const float l1 = fmaxf(logf(pi), -100.f), l0 = fmaxf(log1pf(-pi), -100.f);
+    a -= ti * l1 + (1.f - ti) * l0;
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float b = warp_sum(s_part[threadIdx.x]);
+    if (threadIdx.x == 0) loss[0] = b / (float)N * 0.5f;
+  }
+}
+
+// grad_p[i] = g * 0.5 / N * (p - t) / max(p (1 - p), 1e-12)   (ATen binary_cross_entropy_backward)
+__global__ void __launch_bounds__(256) occ_loss_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                           const float* __restrict__ g, int N, float* __restrict__ grad_p) {
+  pdl_sync();
+  const float gs = __ldg(g) * 0.5f / (float)N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float pi = __ldg(p + i), ti = __ldg(t + i);
+    grad_p[i] = gs * (pi - ti) / fmaxf((1.f - pi) * pi, 1e-12f);
+  }
+}
+
 }  // namespace sgc
 
 // Programmatic dependent launch for the chain kernels (see common.cuh); off by default.
@@ -698,6 +898,36 @@ extern "C" int sgc_topk_select_mc(const float* occ, int N, int k, int* sel, uint
   sgc::topk_mc_count_kernel<<<G, 1024, 0, st>>>(occ, N, scratch);
   SGC_CUDA_CHECK_LAST();
   sgc::topk_mc_write_kernel<<<G, 1024, 0, st>>>(occ, N, scratch, sel, mask);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// One launch for every level (see topk_select_grid_kernel).  scratch: sgc_topk_grid_scratch_bytes() bytes, zero-filled
+// ONCE when allocated and then reused by every call on the same stream (the kernel keeps it consistent itself).
+extern "C" int sgc_topk_grid_scratch_bytes() { return 8 * (1 + 2 * sgc::kTkHalf); }
+extern "C" int sgc_topk_grid_max_n() { return sgc::kTkMaxG * sgc::kTkThreads * sgc::kTkKpt; }
+
+extern "C" int sgc_topk_select_grid(const float* occ, int N, int k, int* sel, uint8_t* mask, void* scratch, void* stream) {
+  if (k <= 0 || k > N || N <= 0 || !scratch || N > sgc_topk_grid_max_n()) return (int)cudaErrorInvalidValue;
+  const int G = (N + sgc::kTkThreads * sgc::kTkKpt - 1) / (sgc::kTkThreads * sgc::kTkKpt);
+  const int per = (N + G * sgc::kTkThreads - 1) / (G * sgc::kTkThreads);
+  sgc::launch_chain(sgc::topk_select_grid_kernel, dim3(G), dim3(sgc::kTkThreads), 0, (cudaStream_t)stream, occ, N, k, per, sel, mask,
+                    reinterpret_cast<unsigned long long*>(scratch));
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// occ_loss (ASH:100-103): loss[0] = 0.5 * mean(BCE(p, t)); bwd: grad_p = g[0] * d loss / d p  (g: 1 float on the device).
+extern "C" int sgc_occ_loss_fwd(const float* p, const float* t, int N, float* loss, void* stream) {
+  if (N <= 0) return (int)cudaErrorInvalidValue;
+  sgc::launch_chain(sgc::occ_loss_fwd_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, p, t, N, loss);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+extern "C" int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, int N, float* grad_p, void* stream) {
+  if (N <= 0) return (int)cudaErrorInvalidValue;
+  const int grid = (N + 255) / 256;
+  sgc::launch_chain(sgc::occ_loss_bwd_kernel, dim3(grid < 296 ? grid : 296), dim3(256), 0, (cudaStream_t)stream, p, t, g, N, grad_p);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -101,6 +101,8 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
 FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs 550-572 volumes/s): off
 TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
+TOPK_GRID = _os.environ.get('SGC_TOPK_GRID', '1') != '0'   # one-launch grid top-k (round 2); 0 = the round-1 kernels
+_TOPK_SCRATCH = {}
 # W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> LayerNorm of the layer's forward as ONE launch (sgc_rows_chain_tc); parity-checked
 # on the GPU at the very end of round 1, not benchmarked yet: off by default
 ROWS_CHAIN = _os.environ.get('SGC_ROWS_CHAIN', '0') != '0'
@@ -1186,13 +1188,42 @@ def topk_select(occ: torch.Tensor, k: int):
     N = occ.numel()
     sel = torch.empty(k, device=occ.device, dtype=torch.int32)
     mask = torch.empty(N, device=occ.device, dtype=torch.uint8)
-    if N > TOPK_MC_MIN and k > 0:
+    lib = _lib.load()
+    if TOPK_GRID and 0 < k and N <= lib.sgc_topk_grid_max_n():
+        # one launch of a few co-operating CTAs (csrc/sgc_volume.cu topk_select_grid_kernel); its 2 KB of scratch is
+        # zero-filled once per (device, stream) and kept consistent by the kernel itself
+        dev = occ.device
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        scratch = _TOPK_SCRATCH.get(key)
+        if scratch is None:
+            scratch = _TOPK_SCRATCH[key] = torch.zeros(lib.sgc_topk_grid_scratch_bytes() // 8, device=dev, dtype=torch.int64)
+        call('sgc_topk_select_grid', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), ptr(scratch), stream())
+    elif N > TOPK_MC_MIN and k > 0:
         # large levels ("-L" configs): many-CTA radix select instead of one CTA streaming over the scores
         scratch = torch.empty(_lib.load().sgc_topk_scratch_ints(N), device=occ.device, dtype=torch.int32)
         call('sgc_topk_select_mc', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), ptr(scratch), stream())
     else:
         call('sgc_topk_select', ptr(occ.detach()), N, k, ptr(sel), ptr(mask), stream())
     return sel, mask
+
+
+class OccLoss(torch.autograd.Function):
+    """``AdaptiveSparseHead.occ_loss`` (AdaptiveSparseHead.py:100-103): 0.5 * mean(BCELoss(p, t)) as one launch each way."""
+
+    @staticmethod
+    def forward(ctx, p, t):
+        p, t = p.contiguous(), t.contiguous()
+        loss = torch.empty((), device=p.device, dtype=F32)
+        call('sgc_occ_loss_fwd', ptr(p), ptr(t), p.numel(), ptr(loss), stream())
+        ctx.save_for_backward(p, t)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        gp = torch.empty_like(p)
+        call('sgc_occ_loss_bwd', ptr(p), ptr(t), ptr(g.contiguous()), p.numel(), ptr(gp), stream())
+        return gp, None
 
 
 class ScatterAddRows(torch.autograd.Function):

@@ -625,8 +625,17 @@ class AdaptiveSparseHead(nn.Module):
             return r
         big_streams = _big_backward_streams(dev, nl, main) if torch.is_grad_enabled() else [None] * nl
         prepared = []
+        # The projections of the three levels are made to run back to back in level order (an event chain between the
+        # prepare streams, forward only): left to itself the graph executor started the finest level's projection -- the
+        # one big kernel the coarse levels' latency-bound chains are supposed to hide -- only ~250 us into the step, and
+        # the finest chain then waited ~100 us for it.  The streams stay separate, so the backward of each level (autograd
+        # replays it on the level's own stream) is not serialised behind the other levels.
+        chain_prepare = os.environ.get('SGC_CHAIN_PREPARE', '1') != '0'
+        prev_done = None
         for i in range(nl):
             streams[i].wait_stream(main)
+            if chain_prepare and prev_done is not None and streams[i] != main:
+                streams[i].wait_event(prev_done)
             with torch.cuda.stream(streams[i]):
                 if i == 0:
                     n_rows = self.base_heads[i].num_voxels
@@ -638,6 +647,9 @@ class AdaptiveSparseHead(nn.Module):
                     n_rows = self.base_heads[i].num_voxels
                 prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i],
                                                            n_rows, big_streams[i]))
+                if chain_prepare and streams[i] != main:
+                    prev_done = torch.cuda.Event()
+                    prev_done.record(streams[i])
         for i in range(nl):
             hw = hws[i]
             fi = nl - 1 - i
@@ -700,7 +712,11 @@ class AdaptiveSparseHead(nn.Module):
 
     def occ_loss(self, occ_pred, sem_occ_gt, geo_occ_gt):
         bs, N = occ_pred.shape
-        loss_occ = self.loss(occ_pred, geo_occ_gt[:, 0:N].float()).mean() * 0.5
+        gt = geo_occ_gt[:, 0:N].float()
+        if occ_pred.is_cuda and occ_pred.dtype == torch.float32:
+            with torch.cuda.device(occ_pred.device):
+                return {'loss_occ': SF.OccLoss.apply(occ_pred, gt)}
+        loss_occ = self.loss(occ_pred, gt).mean() * 0.5
         return {'loss_occ': loss_occ}
 
 

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     build.build()
     lib = ctypes.CDLL(str(_lib.lib_path()))
     decls = _header_decls()
-    assert len(decls) == 57
+    assert len(decls) >= 62   # grows with the library; every declared symbol is checked below
     for name in decls:
         assert hasattr(lib, name), f'{name} declared in include/sgcdet_b200.h but not exported'
 
@@ -34,7 +34,7 @@ def test_python_bindings_mirror_header():
     decls = _header_decls()
     assert set(decls) == set(_lib.SIGNATURES), set(decls) ^ set(_lib.SIGNATURES)
     for name, args in decls.items():
-        params = [a.strip() for a in args.split(',') if a.strip()]
+        params = [a.strip() for a in args.split(',') if a.strip() and a.strip() != 'void']
         sig = _lib.SIGNATURES[name]
         assert len(params) == len(sig), name
         for p, t in zip(params, sig):

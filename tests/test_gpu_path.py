@@ -302,3 +302,43 @@ def test_full_shape_properties(cuda_lib, cfg_name, V):
     vol4, _, occ4 = head(feats, sc.img_meta, dists)
     (2 * ((vol4 * sc.grad_volume).sum() + head.occ_loss(occ4, None, sc.geo_occ)['loss_occ'])).backward()
     torch.testing.assert_close(feats[0].grad, 2 * g1, rtol=1e-3, atol=1e-4 * g1.abs().max().item())
+
+
+def test_topk_round1_kernels_still_match(cuda_lib, monkeypatch):
+    """The single-CTA / many-CTA kernels of round 1 stay in the library behind SGC_TOPK_GRID=0."""
+    monkeypatch.setattr(SF, 'TOPK_GRID', False)
+    g = torch.Generator().manual_seed(3)
+    _check_topk(torch.sigmoid(torch.randn(25600, generator=g)), 6400)
+    _check_topk(torch.sigmoid(torch.randn(204800, generator=g)), 51200)
+
+
+def test_topk_grid_repeated_calls_and_sizes(cuda_lib):
+    """The grid top-k keeps its scratch consistent across calls of different sizes on one stream (parity halves),
+    including the single-CTA case (N <= 4096), CTA-boundary sizes and the largest supported level."""
+    g = torch.Generator().manual_seed(11)
+    for rep in range(3):
+        for N in (1, 7, 4095, 4096, 4097, 8192, 25600, 3200, 204800, 262144):
+            occ = torch.sigmoid(torch.randn(N, generator=g))
+            for k in sorted({1, max(1, N // 4), N}):
+                _check_topk(occ, k)
+    occ = torch.randint(0, 5, (30000,), generator=g).float() / 5   # massive ties across CTAs
+    for k in (1, 7000, 15000, 29999, 30000):
+        _check_topk(occ, k)
+
+
+@pytest.mark.parametrize('N', [28800, 5, 230400])
+def test_occ_loss_matches_torch_bce(cuda_lib, N):
+    """AdaptiveSparseHead.occ_loss (AdaptiveSparseHead.py:100-103) as own kernels vs nn.BCELoss (fp64), incl. the clamp."""
+    g = torch.Generator().manual_seed(N)
+    p = torch.sigmoid(3 * torch.randn(1, N, generator=g))
+    p[0, 0], p[0, -1] = 0.0, 1.0          # log clamped at -100 (torch semantics)
+    t = (torch.rand(1, N + 10, generator=g) < 0.2).float()
+    pg = p.to(DEV).requires_grad_(True)
+    head = plugin.AdaptiveSparseHead(embed_dims=128, base_head_configs=[])
+    loss = head.occ_loss(pg, None, t.to(DEV))['loss_occ']
+    (loss * 3.0).backward()
+    p64 = p.double().requires_grad_(True)
+    ref = torch.nn.BCELoss()(p64, t[:, :N].double()).mean() * 0.5
+    (ref * 3.0).backward()
+    torch.testing.assert_close(loss.item(), ref.item(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pg.grad.cpu().double(), p64.grad, rtol=1e-4, atol=1e-9)
