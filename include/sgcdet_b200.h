@@ -149,7 +149,7 @@ int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, in
 /* Weight gradients of the same layers on the tensor cores (reduction over the voxel rows, csrc/sgc_rows_gemm_tc.cu):
  *     out[b*out_b + m*out_m + n*out_n] = scale * sum_r a[b*batch_a + r*lda + m] * b[b*batch_b + r*ldb + n],  m < M, n < N
  * For y = x W^T + bias with upstream gradient g: gW = g^T x (a = g, b = x).  bias_from = 1: bias_out[b*M + m] = sum_r a
- * (the bias gradient), 2: bias_out[b*N + n] = sum_r b, 0: none.  M % 128 == 0, N % 32 == 0; a batch stride smaller than
+ * (the bias gradient), 2: bias_out[b*N + n] = sum_r b, 0: none.  M % 128 == 0, N % 16 == 0; a batch stride smaller than
  * the leading dimension addresses the heads of a [R, H*dh] matrix (per-head key / value weights: a = t[h] or grad_qt[h],
  * b = the head's columns, and the output strides write the transposed result into in_proj_weight's gradient).
  * Both operands are split to bf16 hi/lo in shared memory; split-K partials in `scratch`
@@ -158,6 +158,20 @@ int sgc_rows_wgrad_tc_scratch_floats(int M, int N, int R, int B);
 int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_a, int M, const float* b, long long ldb,
                       long long batch_b, int N, int R, int B, float* out, long long out_b, long long out_m,
                       long long out_n, float scale, float* bias_out, int bias_from, float* scratch, void* stream);
+/* The same for a TABLE of up to 8 products over the same R voxel rows in ONE launch (+ one reduce launch): all weight
+ * gradients of an encoder layer (output_proj, query / key / value in-projections, out_proj, both FFN layers).  Every job
+ * is one product of the call above (same operand / output conventions; N % 16 == 0 here, so the 16-wide heads of the
+ * C = 128 configs qualify).  scratch: sgc_rows_wgrad_group_scratch_floats(jobs, njobs, R) floats. */
+typedef struct sgc_wgrad_job {
+  const float* a; long long lda, batch_a; int M;
+  const float* b; long long ldb, batch_b; int N;
+  int B;
+  float* out; long long out_b, out_m, out_n;
+  float scale;
+  float* bias_out; int bias_from;
+} sgc_wgrad_job;
+long long sgc_rows_wgrad_group_scratch_floats(const sgc_wgrad_job* jobs, int njobs, int R);
+int sgc_rows_wgrad_group_tc(const sgc_wgrad_job* jobs, int njobs, int R, float* scratch, void* stream);
 
 /* out[c] = sum_r x[r,c] for a row-major [R,C] matrix (bias gradients), deterministic.  scratch:
  * sgc_colsum_scratch_floats(R,C) floats; counter: one uint32 that is zero on entry (reset to zero on exit). */
@@ -284,78 +298,6 @@ typedef struct sgc_rowop_bwd_args {
 } sgc_rowop_bwd_args;
 int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
 
-/* The row-local tail of one encoder layer (ENC:310-338 after the cross-view attention, DCA:827-837) in ONE launch: a CTA takes
- * a 128-row tile through  x1 = LayerNorm1((o2 W_o^T + b_o) * mask0*mscale0 * [rowcount > 0]),
- * hdn = relu(x1 W_1^T + b_1) * mask1*mscale1,  y = LayerNorm2((hdn W_2^T + b_2) * mask2*mscale2 + x1)  with the pipeline of
- * sgc_rows_gemm_tc (csrc/sgc_rows_chain_tc.cu).  p_w* = sgc_pack_weight_tc images of W_o [C,C], W_1 [F,C], W_2 [C,F]; masks are
- * uint8 keep-masks [R,C] / [R,F] / [R,C] or NULL; rowcount [R] int32 or NULL.  Outputs are what the separate launches write:
- * x1, pre1, mean1, rstd1, hdn, y, pre2, mean2, rstd2.  C in {128, 256}, F in {256, 512}.
- * Parity-checked on the B200 but not benchmarked yet: used by the product path only with SGC_ROWS_CHAIN=1. */
-typedef struct sgc_rows_chain_args {
-  const float* o2;
-  const void* p_wo;
-  const void* p_w1;
-  const void* p_w2;
-  const float* bo;
-  const float* b1;
-  const float* b2;
-  const float* g1;
-  const float* be1;
-  const float* g2;
-  const float* be2;
-  const unsigned char* mask0;
-  const unsigned char* mask1;
-  const unsigned char* mask2;
-  const int* rowcount;
-  float* x1;
-  float* pre1;
-  float* mean1;
-  float* rstd1;
-  float* hdn;
-  float* y;
-  float* pre2;
-  float* mean2;
-  float* rstd2;
-  float mscale0, mscale1, mscale2, eps1, eps2;
-  int R, C, F;
-} sgc_rows_chain_args;
-int sgc_rows_chain_tc(const sgc_rows_chain_args* args, void* stream);
-
-/* The backward of that tail in one launch (csrc/sgc_rows_chain_bwd_tc.cu):
- *   gf = LayerNorm2'(gy) * mask2*mscale2 (gpre2 = the unmasked value),  gh = hdn > 0 ? (gf W_2) * gscale1 : 0,
- *   gx1 = gh W_1,  gout = LayerNorm1'(gx1 + gpre2) * mask0*mscale0 * [rowcount > 0],  go2 = gout W_o.
- * p_w*_t = sgc_pack_weight_tc images of W_2^T [F,C], W_1^T [C,F], W_o^T [C,C].  gf / gh / gout are also the operands of the
- * weight gradients; partial1 / partial2: [sgc_layernorm_bwd_scratch_floats(R,C)] floats, ZERO-FILLED by the caller, reduced
- * by sgc_layernorm_bwd_params.  R <= 128 * 296.  Compiled but never run on a GPU yet (round 1 ran out of GPU budget). */
-typedef struct sgc_rows_chain_bwd_args {
-  const float* gy;
-  const void* p_w2_t;
-  const void* p_w1_t;
-  const void* p_wo_t;
-  const float* pre1;
-  const float* mean1;
-  const float* rstd1;
-  const float* g1;
-  const float* pre2;
-  const float* mean2;
-  const float* rstd2;
-  const float* g2;
-  const float* hdn;
-  const unsigned char* mask0;
-  const unsigned char* mask2;
-  const int* rowcount;
-  float* gf;
-  float* gpre2;
-  float* gh;
-  float* gx1;
-  float* gout;
-  float* go2;
-  float* partial1;
-  float* partial2;
-  float mscale0, mscale2, gscale1;
-  int R, C, F;
-} sgc_rows_chain_bwd_args;
-int sgc_rows_chain_bwd_tc(const sgc_rows_chain_bwd_args* args, void* stream);
 int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);
 
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].
@@ -377,7 +319,7 @@ int sgc_topk_select(const float* occ, int N, int k, int* sel, uint8_t* mask, voi
  * scratch: sgc_topk_scratch_ints(N) ints, private to the call.  k >= 1. */
 int sgc_topk_scratch_ints(int N);
 int sgc_topk_select_mc(const float* occ, int N, int k, int* sel, uint8_t* mask, int* scratch, void* stream);
-/* The same selection as ONE launch for every level size up to sgc_topk_grid_max_n() (262 144) scores: a few CTAs, keys in
+/* The same selection as ONE launch for every level size up to sgc_topk_grid_max_n() (229 376) scores: a few CTAs, keys in
  * registers, the threshold found 4 bits per step with the per-step counts merged through packed 64-bit atomics.
  * scratch: sgc_topk_grid_scratch_bytes() bytes, zero-filled ONCE when allocated, then reused by every call issued on the
  * same stream (calls on different streams need their own).  k >= 1. */

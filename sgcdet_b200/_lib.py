@@ -32,8 +32,6 @@ SIGNATURES = {
     'sgc_prepare_weights': [P, I, P],
     'sgc_rowop_fwd': [P, P],
     'sgc_rowop_bwd': [P, P],
-    'sgc_rows_chain_tc': [P, P],
-    'sgc_rows_chain_bwd_tc': [P, P],
     'sgc_crossview_mean_fwd_split': [P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_fwd_split': [P, P, P, I, I, I, P, P, P, P],
     'sgc_crossview_attn_bwd_qt_split': [P, P, P, I, I, I, P, P, P, P, P],
@@ -52,6 +50,8 @@ SIGNATURES = {
     'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
     'sgc_rows_wgrad_tc_scratch_floats': [I, I, I, I],
     'sgc_rows_wgrad_tc': [P, LL, LL, I, P, LL, LL, I, I, I, P, LL, LL, LL, F, P, I, P, P],
+    'sgc_rows_wgrad_group_scratch_floats': [P, I, I],
+    'sgc_rows_wgrad_group_tc': [P, I, I, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],
@@ -94,6 +94,19 @@ class WeightJob(ctypes.Structure):
 MAX_WEIGHT_JOBS = 48
 
 
+class WgradJob(ctypes.Structure):
+    """``sgc_wgrad_job`` of include/sgcdet_b200.h."""
+    _fields_ = [('a', c_void_p), ('lda', c_longlong), ('batch_a', c_longlong), ('M', c_int),
+                ('b', c_void_p), ('ldb', c_longlong), ('batch_b', c_longlong), ('N', c_int),
+                ('B', c_int),
+                ('out', c_void_p), ('out_b', c_longlong), ('out_m', c_longlong), ('out_n', c_longlong),
+                ('scale', c_float),
+                ('bias_out', c_void_p), ('bias_from', c_int)]
+
+
+MAX_WGRAD_JOBS = 8
+
+
 class RowopFwdArgs(ctypes.Structure):
     """``sgc_rowop_fwd_args`` of include/sgcdet_b200.h."""
     _fields_ = [(n, c_void_p) for n in ('x', 'bias', 'mask', 'rowscale', 'residual', 'gamma', 'beta', 'y', 'ysplit',
@@ -108,23 +121,6 @@ class RowopBwdArgs(ctypes.Structure):
                                         'partial', 'gpre', 'gx', 'gxsplit')] + \
                [('mscale', c_float), ('gscale', c_float), ('R', c_int), ('N', c_int), ('in_heads', c_int),
                 ('split_heads', c_int), ('rowcount', c_void_p)]
-
-
-class RowsChainArgs(ctypes.Structure):
-    """``sgc_rows_chain_args`` of include/sgcdet_b200.h."""
-    _fields_ = [(n, c_void_p) for n in ('o2', 'p_wo', 'p_w1', 'p_w2', 'bo', 'b1', 'b2', 'g1', 'be1', 'g2', 'be2', 'mask0',
-                                        'mask1', 'mask2', 'rowcount', 'x1', 'pre1', 'mean1', 'rstd1', 'hdn', 'y', 'pre2',
-                                        'mean2', 'rstd2')] + \
-               [(n, c_float) for n in ('mscale0', 'mscale1', 'mscale2', 'eps1', 'eps2')] + \
-               [(n, c_int) for n in ('R', 'C', 'F')]
-
-
-class RowsChainBwdArgs(ctypes.Structure):
-    """``sgc_rows_chain_bwd_args`` of include/sgcdet_b200.h."""
-    _fields_ = [(n, c_void_p) for n in ('gy', 'p_w2_t', 'p_w1_t', 'p_wo_t', 'pre1', 'mean1', 'rstd1', 'g1', 'pre2', 'mean2',
-                                        'rstd2', 'g2', 'hdn', 'mask0', 'mask2', 'rowcount', 'gf', 'gpre2', 'gh', 'gx1',
-                                        'gout', 'go2', 'partial1', 'partial2')] + \
-               [(n, c_float) for n in ('mscale0', 'mscale2', 'gscale1')] + [(n, c_int) for n in ('R', 'C', 'F')]
 
 
 def lib_path() -> Path:
@@ -151,7 +147,7 @@ def load() -> ctypes.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = c_int
+            fn.restype = c_longlong if name == 'sgc_rows_wgrad_group_scratch_floats' else c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
         lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
         lib.sgc_set_pdl(int(os.environ.get('SGC_PDL', '0')))

@@ -355,42 +355,59 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
 }
 
 // =====================================================================================================================
-// sgc_rows_wgrad_tc: the weight gradients of the same layers (reduction over the voxel rows):
+// sgc_rows_wgrad_tc / sgc_rows_wgrad_group_tc: the weight gradients of the same layers (reduction over the voxel rows):
 //
 //     out_b[m, n] = scale * sum_r A_b[r, m] * B_b[r, n]          bias[m] = sum_r A[r, m]   (or over B's columns)
 //
 // For y = x W^T + b with upstream gradient g:  gW = g^T x  (A = g, B = x, bias gradient = column sums of A).  The per-head
-// key / value weights use the transposed product (A = t[h] / gqt[h] with M = C, B = the head's 32 columns of go / qv) and
+// key / value weights use the transposed product (A = t[h] / gqt[h] with M = C, B = the head's dh columns of go / qv) and
 // the reduce kernel writes the result transposed, because a UMMA tile needs M = 128 rows.
 // Both operands are fp32 in HBM, TMA-loaded as [32 rows][cols] tiles and split to bf16 hi/lo in shared memory (the
 // "[k][m]" converter of wgrad_tc_kernel for both).  Split-K over the rows: CTA (m-tile, k-chunk, column part, batch)
 // accumulates its rows in TMEM and writes a partial tile; the reduce kernel sums the partials in a fixed order
 // (deterministic), applies `scale` and writes through arbitrary output strides (so gradients land directly inside
 // in_proj_weight's [3C,C] gradient).  Column sums are accumulated by the converter threads per CTA and reduced alike.
+//
+// Round 2: the kernel takes a TABLE of jobs, so ALL weight gradients of an encoder layer (output_proj, the three
+// in-projections incl. the per-head key / value products, out_proj, both FFN layers: 7 jobs) are ONE launch + ONE reduce
+// launch instead of 14 + 14.  The single launches were latency-bound (TMEM allocation, pipeline fill, 128 KB partial
+// tile per CTA after as little as 4 row slabs: ~0.5 ms of kernel time per step for ~35 GFLOP); in the grouped launch the
+// CTAs of all jobs fill the SMs together, so each CTA can own a long run of rows (few k-chunks, 8x less partial traffic).
 namespace sgc {
 namespace tc {
 
 constexpr int RW_THREADS = 480;  // warps 0-3: A converters (+ epilogue), 4-11: B converters, 12: TMA, 13: MMA, 14: TMEM
 constexpr int RW_CONV = 384;     // converter threads (arrivals on f_empty / op_full)
 constexpr int RW_ST = 2;
+constexpr int RW_MAX_JOBS = 8;
 
 struct SmemRW {
   uint64_t f_full[RW_ST], f_empty[RW_ST], op_full[RW_ST], op_empty[RW_ST], tmem_full;
   uint32_t tmem_base;
 };
 
-struct RowsWgradParams {
+struct alignas(64) RowsWgradJob {
+  CUtensorMap amap, bmap;
   float* partial;        // [kch][B][M][N]
   float* bias_partial;   // [kch][B][M or N]
-  int M, N, n_cta, R, m_tiles, kch, slabs_per_cta, total_slabs;
+  int M, N, n_cta, m_tiles, n_parts, nb, kch, slabs_per_cta, total_slabs;
   int a_swap, b_swap, bias_from;
+  int cta_begin;         // first CTA of the job in the grouped grid
+};
+
+struct RowsWgradJobs {
+  RowsWgradJob job[RW_MAX_JOBS];
+  int njobs;
 };
 
 __global__ void __launch_bounds__(RW_THREADS, 1)
-rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-                     const __grid_constant__ RowsWgradParams p) {
+rows_wgrad_tc_kernel(const __grid_constant__ RowsWgradJobs jobs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ji = 0;
+  for (int j = 1; j < jobs.njobs; ++j)
+    if ((int)blockIdx.x >= jobs.job[j].cta_begin) ji = j;
+  const RowsWgradJob& p = jobs.job[ji];
   const int n_cta = p.n_cta;
   const int a_src = BK * BM * 4;              // 16 KB  [32 r][128 m] fp32
   const int b_src = BK * n_cta * 4;           // [32 r][n_cta] fp32
@@ -402,8 +419,11 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   uint8_t* op_base = f_base + RW_ST * f_stage;
   SmemRW* sm = reinterpret_cast<SmemRW*>(op_base + RW_ST * op_stage);
 
-  const int mt = blockIdx.x % p.m_tiles, kc = blockIdx.x / p.m_tiles;
-  const int np = blockIdx.y, bt = blockIdx.z, nb = gridDim.z;
+  int w = (int)blockIdx.x - p.cta_begin;
+  const int mt = w % p.m_tiles; w /= p.m_tiles;
+  const int kc = w % p.kch; w /= p.kch;
+  const int np = w % p.n_parts;
+  const int bt = w / p.n_parts, nb = p.nb;
   const int s_begin = kc * p.slabs_per_cta;
   const int s_end = min(p.total_slabs, s_begin + p.slabs_per_cta);
   const int n_slabs = max(0, s_end - s_begin);
@@ -427,16 +447,18 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
 
   if (warp == 12) {
     if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.amap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.bmap) : "memory");
       Pipe pf(RW_ST);
       for (int i = 0; i < n_slabs; ++i) {
         const int r0 = (s_begin + i) * BK;
         mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
         mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage);
         uint8_t* st = f_base + pf.stage * f_stage;
-        if (p.a_swap) tma_load_3d(st, &amap, mt * BM, bt, r0, &sm->f_full[pf.stage]);
-        else tma_load_3d(st, &amap, mt * BM, r0, bt, &sm->f_full[pf.stage]);
-        if (p.b_swap) tma_load_3d(st + a_src, &bmap, np * n_cta, bt, r0, &sm->f_full[pf.stage]);
-        else tma_load_3d(st + a_src, &bmap, np * n_cta, r0, bt, &sm->f_full[pf.stage]);
+        if (p.a_swap) tma_load_3d(st, &p.amap, mt * BM, bt, r0, &sm->f_full[pf.stage]);
+        else tma_load_3d(st, &p.amap, mt * BM, r0, bt, &sm->f_full[pf.stage]);
+        if (p.b_swap) tma_load_3d(st + a_src, &p.bmap, np * n_cta, bt, r0, &sm->f_full[pf.stage]);
+        else tma_load_3d(st + a_src, &p.bmap, np * n_cta, r0, bt, &sm->f_full[pf.stage]);
         pf.next();
       }
     }
@@ -499,25 +521,22 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
         mbar_wait(&sm->tmem_full, 0);
         tc_fence_after();
       }
-      for (int c0 = 0; c0 < n_cta; c0 += 32) {
-        uint32_t r[32];
+      for (int c0 = 0; c0 < n_cta; c0 += 16) {
+        uint32_t r[16];
         if (n_slabs > 0) {
           asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
               : "r"(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) r[q] = 0u;
+          for (int q = 0; q < 16; ++q) r[q] = 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
+        for (int q = 0; q < 16; q += 4)
           *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
       }
     }
@@ -553,25 +572,41 @@ rows_wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   }
 }
 
-// out[b*ob + m*om + n*on] = scale * sum_k partial[k][b][m][n]  and  bias_out[i] = sum_k bias_partial[k][i]   (fixed order)
-__global__ void __launch_bounds__(256)
-rows_wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias_partial, int kch, int B, int M, int N,
-                         float scale, float* __restrict__ out, long long ob, long long om, long long on,
-                         float* __restrict__ bias_out, int bias_len) {
-  const long long elems = (long long)B * M * N;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// out[b*ob + m*om + n*on] = scale * sum_k partial[k][b][m][n]  and  bias_out[i] = sum_k bias_partial[k][i]   (fixed order),
+// for every job of the table; block -> job through block_begin.
+struct RowsWgradReduceJob {
+  const float* partial;
+  const float* bias_partial;
+  float* out;
+  float* bias_out;
+  long long ob, om, on;
+  int kch, B, M, N, bias_len, block_begin;
+  float scale;
+};
+struct RowsWgradReduceJobs {
+  RowsWgradReduceJob job[RW_MAX_JOBS];
+  int njobs;
+};
+
+__global__ void __launch_bounds__(256) rows_wgrad_reduce_kernel(const __grid_constant__ RowsWgradReduceJobs jobs) {
+  int ji = 0;
+  for (int j = 1; j < jobs.njobs; ++j)
+    if ((int)blockIdx.x >= jobs.job[j].block_begin) ji = j;
+  const RowsWgradReduceJob& q = jobs.job[ji];
+  const long long elems = (long long)q.B * q.M * q.N;
+  const long long i = (long long)((int)blockIdx.x - q.block_begin) * blockDim.x + threadIdx.x;
   if (i < elems) {
     float a = 0.f;
-    for (int k = 0; k < kch; ++k) a += __ldg(partial + (size_t)k * elems + i);
-    const int n = (int)(i % N);
-    const long long t = i / N;
-    const int m = (int)(t % M), b = (int)(t / M);
-    out[b * ob + m * om + n * on] = a * scale;
+    for (int k = 0; k < q.kch; ++k) a += __ldg(q.partial + (size_t)k * elems + i);
+    const int n = (int)(i % q.N);
+    const long long t = i / q.N;
+    const int m = (int)(t % q.M), b = (int)(t / q.M);
+    q.out[b * q.ob + m * q.om + n * q.on] = a * q.scale;
   }
-  if (bias_out && i < bias_len) {
+  if (q.bias_out && i < q.bias_len) {
     float a = 0.f;
-    for (int k = 0; k < kch; ++k) a += __ldg(bias_partial + (size_t)k * bias_len + i);
-    bias_out[i] = a;
+    for (int k = 0; k < q.kch; ++k) a += __ldg(q.bias_partial + (size_t)k * q.bias_len + i);
+    q.bias_out[i] = a;
   }
 }
 
@@ -603,64 +638,130 @@ static inline bool make_wgrad_map(PFN_encodeTiled encode, CUtensorMap* map, cons
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static inline void rows_wgrad_plan(int M, int N, int R, int B, int* n_cta, int* kch) {
+static inline int rows_wgrad_ncta(int N) {
   int nc = N <= 256 ? N : 256;
   while (N % nc) nc >>= 1;
-  const int tiles = (M / BM) * (N / nc) * B;
+  return nc;
+}
+
+// Split-K plan of a job table: every job gets the same number of k-chunks, chosen so that the CTAs of all jobs together
+// are about two per SM (the jobs differ in cost per row slab, two waves even that out) while a CTA keeps at least 8 row
+// slabs (256 rows) -- a single job is spread over the SMs once, with at least 4 slabs per CTA, as in round 1.
+static inline int rows_wgrad_group_kch(const sgc_wgrad_job* jobs, int njobs, int R) {
+  long long tiles = 0;
+  for (int j = 0; j < njobs; ++j) tiles += (long long)(jobs[j].M / BM) * (jobs[j].N / rows_wgrad_ncta(jobs[j].N)) * jobs[j].B;
   const int total_slabs = (R + BK - 1) / BK;
-  int k = total_slabs / 4;                       // at least ~4 row slabs (128 rows) per CTA
-  const int cap = tiles < 148 ? 148 / tiles : 1;
+  int k, cap;
+  if (njobs == 1) { k = total_slabs / 4; cap = tiles < 148 ? (int)(148 / tiles) : 1; }
+  else { k = total_slabs / 8; cap = tiles < 296 ? (int)(296 / tiles) : 1; }
   if (k > cap) k = cap;
   if (k < 1) k = 1;
-  *n_cta = nc;
-  *kch = k;
+  return k;
+}
+
+static inline bool rows_wgrad_job_ok(const sgc_wgrad_job& j) {
+  return j.a && j.b && j.out && j.M > 0 && j.M % BM == 0 && j.N > 0 && j.N % 16 == 0 && j.B > 0 && j.bias_from >= 0 &&
+         j.bias_from <= 2 && (!j.bias_from || j.bias_out);
 }
 
 }  // namespace tc
 }  // namespace sgc
 
-extern "C" int sgc_rows_wgrad_tc_scratch_floats(int M, int N, int R, int B) {
-  if (M <= 0 || N <= 0 || R <= 0 || B <= 0 || M % sgc::tc::BM || N % 32) return 0;
-  int n_cta, kch;
-  sgc::tc::rows_wgrad_plan(M, N, R, B, &n_cta, &kch);
-  return (int)((long long)kch * B * ((long long)M * N + (M > N ? M : N)));
+extern "C" long long sgc_rows_wgrad_group_scratch_floats(const sgc_wgrad_job* jobs, int njobs, int R) {
+  using namespace sgc::tc;
+  if (!jobs || njobs <= 0 || njobs > RW_MAX_JOBS || R <= 0) return 0;
+  for (int j = 0; j < njobs; ++j)
+    if (!rows_wgrad_job_ok(jobs[j])) return 0;
+  const long long kch = rows_wgrad_group_kch(jobs, njobs, R);
+  long long total = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const long long M = jobs[j].M, N = jobs[j].N, B = jobs[j].B;
+    total += kch * B * (M * N + (M > N ? M : N));
+  }
+  return total;
 }
 
-extern "C" int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_a, int M, const float* b, long long ldb,
-                                 long long batch_b, int N, int R, int B, float* out, long long out_b, long long out_m,
-                                 long long out_n, float scale, float* bias_out, int bias_from, float* scratch, void* stream) {
+extern "C" int sgc_rows_wgrad_group_tc(const sgc_wgrad_job* jobs, int njobs, int R, float* scratch, void* stream) {
   using namespace sgc::tc;
-  if (!a || !b || !out || !scratch || M <= 0 || M % BM || N <= 0 || N % 32 || R <= 0 || B <= 0) return (int)cudaErrorInvalidValue;
-  if (bias_from < 0 || bias_from > 2 || (bias_from && !bias_out)) return (int)cudaErrorInvalidValue;
+  if (!jobs || njobs <= 0 || njobs > RW_MAX_JOBS || R <= 0 || !scratch) return (int)cudaErrorInvalidValue;
   PFN_encodeTiled encode = get_encode_tiled();
   if (!encode) return (int)cudaErrorNotSupported;
-  RowsWgradParams p;
-  rows_wgrad_plan(M, N, R, B, &p.n_cta, &p.kch);
-  if (p.n_cta < 32 || p.n_cta % 16) return (int)cudaErrorInvalidValue;
-  CUtensorMap amap, bmap;
-  if (!make_wgrad_map(encode, &amap, a, M, R, B, lda, batch_a, BM, &p.a_swap)) return (int)cudaErrorInvalidValue;
-  if (!make_wgrad_map(encode, &bmap, b, N, R, B, ldb, batch_b, p.n_cta, &p.b_swap)) return (int)cudaErrorInvalidValue;
-  p.M = M; p.N = N; p.R = R;
-  p.m_tiles = M / BM;
-  p.total_slabs = (R + BK - 1) / BK;
-  p.slabs_per_cta = (p.total_slabs + p.kch - 1) / p.kch;
-  p.bias_from = bias_from;
-  p.partial = scratch;
-  p.bias_partial = scratch + (size_t)p.kch * B * M * N;
-  const size_t smem = (size_t)RW_ST * (BK * BM * 4 + BK * p.n_cta * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * p.n_cta * BK * 2) +
+  RowsWgradJobs tab;
+  RowsWgradReduceJobs red;
+  tab.njobs = red.njobs = njobs;
+  const int kch = rows_wgrad_group_kch(jobs, njobs, R);
+  int cta = 0, blocks = 0, max_ncta = 0;
+  float* sp = scratch;
+  for (int j = 0; j < njobs; ++j) {
+    const sgc_wgrad_job& in = jobs[j];
+    if (!rows_wgrad_job_ok(in)) return (int)cudaErrorInvalidValue;
+    RowsWgradJob& p = tab.job[j];
+    p.n_cta = rows_wgrad_ncta(in.N);
+    if (p.n_cta < 16 || p.n_cta % 16) return (int)cudaErrorInvalidValue;
+    if (!make_wgrad_map(encode, &p.amap, in.a, in.M, R, in.B, in.lda, in.batch_a, BM, &p.a_swap)) return (int)cudaErrorInvalidValue;
+    if (!make_wgrad_map(encode, &p.bmap, in.b, in.N, R, in.B, in.ldb, in.batch_b, p.n_cta, &p.b_swap)) return (int)cudaErrorInvalidValue;
+    p.M = in.M; p.N = in.N;
+    p.m_tiles = in.M / BM;
+    p.n_parts = in.N / p.n_cta;
+    p.nb = in.B;
+    p.kch = kch;
+    p.total_slabs = (R + BK - 1) / BK;
+    p.slabs_per_cta = (p.total_slabs + kch - 1) / kch;
+    p.bias_from = in.bias_from;
+    p.partial = sp;
+    sp += (size_t)kch * in.B * in.M * in.N;
+    p.bias_partial = sp;
+    sp += (size_t)kch * in.B * (in.M > in.N ? in.M : in.N);
+    p.cta_begin = cta;
+    cta += p.m_tiles * kch * p.n_parts * in.B;
+    if (p.n_cta > max_ncta) max_ncta = p.n_cta;
+    RowsWgradReduceJob& q = red.job[j];
+    q.partial = p.partial; q.bias_partial = p.bias_partial;
+    q.out = in.out; q.bias_out = in.bias_from ? in.bias_out : nullptr;
+    q.ob = in.out_b; q.om = in.out_m; q.on = in.out_n;
+    q.kch = kch; q.B = in.B; q.M = in.M; q.N = in.N;
+    q.bias_len = in.bias_from == 1 ? in.B * in.M : in.bias_from == 2 ? in.B * in.N : 0;
+    q.scale = in.scale;
+    q.block_begin = blocks;
+    const long long elems = (long long)in.B * in.M * in.N;
+    const long long work = elems > q.bias_len ? elems : q.bias_len;
+    blocks += (int)((work + 255) / 256);
+  }
+  const size_t smem = (size_t)RW_ST * (BK * BM * 4 + BK * max_ncta * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * max_ncta * BK * 2) +
                       sizeof(SmemRW) + 64;
   const size_t smem_max = (size_t)RW_ST * (BK * BM * 4 + BK * 256 * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * 256 * BK * 2) +
                           sizeof(SmemRW) + 64;   // widest configuration, see sgc_rows_gemm_tc
   cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(p.m_tiles * p.kch, N / p.n_cta, B);
-  rows_wgrad_tc_kernel<<<grid, RW_THREADS, smem, (cudaStream_t)stream>>>(amap, bmap, p);
+  rows_wgrad_tc_kernel<<<cta, RW_THREADS, smem, (cudaStream_t)stream>>>(tab);
   SGC_CUDA_CHECK_LAST();
-  const long long elems = (long long)B * M * N;
-  const int bias_len = bias_from == 1 ? B * M : bias_from == 2 ? B * N : 0;
-  const long long work = elems > bias_len ? elems : bias_len;
-  rows_wgrad_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p.partial, p.bias_partial, p.kch, B, M, N, scale, out, out_b, out_m, out_n, bias_from ? bias_out : nullptr, bias_len);
+  rows_wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(red);
   SGC_CUDA_CHECK_LAST();
   return 0;
+}
+
+static inline sgc_wgrad_job rows_wgrad_single_job(const float* a, long long lda, long long batch_a, int M, const float* b,
+                                                  long long ldb, long long batch_b, int N, int B, float* out, long long out_b,
+                                                  long long out_m, long long out_n, float scale, float* bias_out, int bias_from) {
+  sgc_wgrad_job j;
+  j.a = a; j.lda = lda; j.batch_a = batch_a; j.M = M;
+  j.b = b; j.ldb = ldb; j.batch_b = batch_b; j.N = N; j.B = B;
+  j.out = out; j.out_b = out_b; j.out_m = out_m; j.out_n = out_n;
+  j.scale = scale; j.bias_out = bias_out; j.bias_from = bias_from;
+  return j;
+}
+
+extern "C" int sgc_rows_wgrad_tc_scratch_floats(int M, int N, int R, int B) {
+  if (M <= 0 || N <= 0 || R <= 0 || B <= 0 || M % sgc::tc::BM || N % 16) return 0;
+  float dummy = 0.f;
+  const sgc_wgrad_job j = rows_wgrad_single_job(&dummy, M, 0, M, &dummy, N, 0, N, B, &dummy, 0, N, 1, 1.f, nullptr, 0);
+  return (int)sgc_rows_wgrad_group_scratch_floats(&j, 1, R);
+}
+
+extern "C" int sgc_rows_wgrad_tc(const float* a, long long lda, long long batch_a, int M, const float* b, long long ldb,
+                                 long long batch_b, int N, int R, int B, float* out, long long out_b, long long out_m,
+                                 long long out_n, float scale, float* bias_out, int bias_from, float* scratch, void* stream) {
+  const sgc_wgrad_job j = rows_wgrad_single_job(a, lda, batch_a, M, b, ldb, batch_b, N, B, out, out_b, out_m, out_n, scale,
+                                                bias_out, bias_from);
+  return sgc_rows_wgrad_group_tc(&j, 1, R, scratch, stream);
 }

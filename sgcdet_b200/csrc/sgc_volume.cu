@@ -582,10 +582,10 @@ __global__ void __launch_bounds__(1024) topk_mc_write_kernel(const float* __rest
 
 
 // ---------------------------------------------------------------------------------- top-k over a few co-operating CTAs
-// One launch for every level size (N <= 262 144): G = ceil(N / 4096) CTAs of 512 threads, at most 8 keys per thread in
+// One launch for every level size (N <= 229 376): G = ceil(N / 3584) CTAs of 512 threads, at most 7 keys per thread in
 // registers, thread g owning the CONTIGUOUS index range [g*per, (g+1)*per).  The threshold (the k-th largest key) is found
-// digit by digit, 4 bits per step from the top (8 steps): every thread counts, for its active keys (those matching the
-// prefix found so far), how many have a digit >= 1..15; the 15 counts are reduced over the warp, the CTA and -- for
+// digit by digit, 4 bits per step from the top (8 steps): every thread histograms the digit of its active keys (those
+// matching the prefix found so far) into 16 packed nibbles; the counts are reduced over the warp, the CTA and -- for
 // G > 1 -- over the grid by ONE 64-bit atomicAdd per word that carries three 19-bit counts AND a 7-bit arrival counter,
 // so a step costs one atomic round trip plus a poll (no fence, no separate barrier).  No histogram, no shared-memory
 // atomics (sigmoid scores crowd the leading bits into a few bins), fully deterministic.  The ordered compaction publishes
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(1024) topk_mc_write_kernel(const float* __rest
 // scratch (256 x u64, zero-initialised ONCE by the caller, private to a stream): [0] = parity; two halves of
 // kTkHalf words are used alternately, and every call clears the half the NEXT call will use.
 constexpr int kTkThreads = 512;
-constexpr int kTkKpt = 8;
+constexpr int kTkKpt = 7;        // keys per thread: a nibble of the packed digit histogram holds at most 7
 constexpr int kTkSteps = 8;
 constexpr int kTkWords = 5;        // 15 counts, three per word
 constexpr int kTkMaxG = 64;
@@ -611,7 +611,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __global__ void __launch_bounds__(kTkThreads) topk_select_grid_kernel(const float* __restrict__ occ, int N, int k, int per,
                                                                       int* __restrict__ sel, uint8_t* __restrict__ mask,
                                                                       unsigned long long* __restrict__ scratch) {
-  __shared__ int s_warp[2][kTkThreads / 32][15];
+  __shared__ int s_warp[2][kTkThreads / 32][4];
   __shared__ int s_tot[2][16];
   __shared__ int s_scan[2][kTkThreads / 32];
   __shared__ int s_carry[2];
@@ -634,29 +634,31 @@ __global__ void __launch_bounds__(kTkThreads) topk_select_grid_kernel(const floa
   int need = k;
   for (int s = 0; s < kTkSteps; ++s) {
     const int shift = 28 - 4 * s;
-    int c[15];
-#pragma unroll
-    for (int i = 0; i < 15; ++i) c[i] = 0;
+    // per-thread histogram of the digit over the active keys, one NIBBLE per digit value (at most 7 keys per thread), split
+    // into even / odd digits as bytes so that a warp sum (<= 224 per byte) cannot carry: 4 warp reductions per step
+    unsigned long long h = 0ull;
 #pragma unroll
     for (int j = 0; j < kTkKpt; ++j) {
       const bool act = (key[j] & pmask) == prefix;
-      const int d = act ? (int)((key[j] >> shift) & 15u) : 0;
-#pragma unroll
-      for (int i = 0; i < 15; ++i) c[i] += d > i ? 1 : 0;     // c[i] = #keys with digit >= i+1
+      h += act ? (1ull << (4 * ((key[j] >> shift) & 15u))) : 0ull;   // unused slots: digit 0, never looked at
     }
-#pragma unroll
-    for (int i = 0; i < 15; ++i) c[i] = __reduce_add_sync(SGC_FULL_MASK, c[i]);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < 15; ++i) s_warp[s & 1][wid][i] = c[i];
+    const unsigned long long ev = h & 0x0F0F0F0F0F0F0F0Full, od = (h >> 4) & 0x0F0F0F0F0F0F0F0Full;
+    const uint32_t r0 = __reduce_add_sync(SGC_FULL_MASK, (uint32_t)ev), r1 = __reduce_add_sync(SGC_FULL_MASK, (uint32_t)(ev >> 32));
+    const uint32_t r2 = __reduce_add_sync(SGC_FULL_MASK, (uint32_t)od), r3 = __reduce_add_sync(SGC_FULL_MASK, (uint32_t)(od >> 32));
+    if (lane == 0) {   // s_warp[.][wid][q]: bytes = digits (0,2,4,6) (8,10,12,14) (1,3,5,7) (9,11,13,15)
+      s_warp[s & 1][wid][0] = (int)r0; s_warp[s & 1][wid][1] = (int)r1; s_warp[s & 1][wid][2] = (int)r2; s_warp[s & 1][wid][3] = (int)r3;
     }
     __syncthreads();
     if (tid < kTkWords) {
+      // thread w merges the counts of digits 3w+1 .. 3w+3 over the CTA's warps and, for G > 1, over the grid
       int n3[3] = {0, 0, 0};
-      for (int w = 0; w < kTkThreads / 32; ++w) {
-        n3[0] += s_warp[s & 1][w][3 * tid];
-        n3[1] += s_warp[s & 1][w][3 * tid + 1];
-        n3[2] += s_warp[s & 1][w][3 * tid + 2];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int d = 3 * tid + 1 + q;                         // 1..15
+        const int word = ((d & 1) ? 2 : 0) + (d >> 3), byte = (d >> 1) & 3;
+        int a = 0;
+        for (int w = 0; w < kTkThreads / 32; ++w) a += (s_warp[s & 1][w][word] >> (8 * byte)) & 0xFF;
+        n3[q] = a;
       }
       if (G > 1) {
         unsigned long long* word = mine + s * kTkWords + tid;
@@ -669,12 +671,16 @@ __global__ void __launch_bounds__(kTkThreads) topk_select_grid_kernel(const floa
       s_tot[s & 1][3 * tid] = n3[0]; s_tot[s & 1][3 * tid + 1] = n3[1]; s_tot[s & 1][3 * tid + 2] = n3[2];
     }
     __syncthreads();
-    // the digit of the threshold: the largest d whose count of keys with digit >= d still reaches `need`
-    int d = 0;
+    // s_tot[.][i-1] = #active keys with digit == i.  The threshold's digit is the largest d whose count of keys with a digit
+    // >= d still reaches `need`; the keys in strictly higher digits are all taken.
+    int d = 0, above = 0, acc = 0;
 #pragma unroll
-    for (int i = 15; i >= 1; --i)
-      if (d == 0 && s_tot[s & 1][i - 1] >= need) d = i;
-    need -= d < 15 ? s_tot[s & 1][d] : 0;      // keys in strictly higher digits are all taken
+    for (int i = 15; i >= 1; --i) {
+      const int hi = s_tot[s & 1][i - 1];
+      if (d == 0 && acc + hi >= need) { d = i; above = acc; }
+      acc += hi;
+    }
+    need -= d ? above : acc;
     prefix |= (uint32_t)d << shift;
     pmask |= 15u << shift;
   }

@@ -96,6 +96,9 @@ SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs wi
 # bf16 GEMM on bf16x3 operand images
 ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
 ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and their weight gradients (sgc_rows_wgrad_tc)
+# all weight gradients of a layer as ONE grouped launch at the end of its backward (sgc_rows_wgrad_group_tc); 0 = one launch
+# per Linear layer as in round 1
+WGRAD_GROUP = _os.environ.get('SGC_WGRAD_GROUP', '1') != '0'
 # output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
 # (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
@@ -103,11 +106,6 @@ FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs
 TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
 TOPK_GRID = _os.environ.get('SGC_TOPK_GRID', '1') != '0'   # one-launch grid top-k (round 2); 0 = the round-1 kernels
 _TOPK_SCRATCH = {}
-# W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> LayerNorm of the layer's forward as ONE launch (sgc_rows_chain_tc); parity-checked
-# on the GPU at the very end of round 1, not benchmarked yet: off by default
-ROWS_CHAIN = _os.environ.get('SGC_ROWS_CHAIN', '0') != '0'
-# ... and its backward mirror (sgc_rows_chain_bwd_tc): compiled but NEVER run on a GPU yet -- off
-ROWS_CHAIN_BWD = _os.environ.get('SGC_ROWS_CHAIN_BWD', '0') != '0'
 ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
@@ -178,6 +176,42 @@ def rows_wgrad(a, b, M, N, R, out, out_strides, *, B=1, lda=None, batch_a=0, ldb
     call('sgc_rows_wgrad_tc', ptr(a), M if lda is None else lda, batch_a, M, ptr(b), N if ldb is None else ldb, batch_b, N,
          R, B, ptr(out), ob, om, on, scale, ptr(bias_out), bias_from, ptr(scratch), stream())
     return out
+
+
+class WgradGroup:
+    """Collects weight-gradient products over the same R voxel rows and issues them as ONE ``sgc_rows_wgrad_group_tc`` launch
+    (+ one reduce launch).  ``add`` has the conventions of ``rows_wgrad``; ``linear`` those of ``linear_grads_tc``."""
+
+    def __init__(self, R: int, dev):
+        self.R, self.dev, self.jobs, self.keep = R, dev, [], []
+
+    def add(self, a, b, M, N, out, out_strides, *, B=1, lda=None, batch_a=0, ldb=None, batch_b=0, scale=1.0, bias_out=None,
+            bias_from=0):
+        ob, om, on = out_strides
+        self.jobs.append(_lib.WgradJob(ptr(a), M if lda is None else lda, batch_a, M, ptr(b), N if ldb is None else ldb,
+                                       batch_b, N, B, ptr(out), ob, om, on, scale, ptr(bias_out), bias_from))
+        self.keep.extend((a, b, out, bias_out))
+        return out
+
+    def linear(self, g, x, gw=None, gb=None):
+        R, N = g.shape
+        K = x.shape[1]
+        gw = torch.empty(N, K, device=self.dev, dtype=F32) if gw is None else gw
+        gb = torch.empty(N, device=self.dev, dtype=F32) if gb is None else gb
+        self.add(g, x, N, K, gw, (0, K, 1), bias_out=gb, bias_from=1)
+        return gw, gb
+
+    def launch(self):
+        lib = _lib.load()
+        for i in range(0, len(self.jobs), _lib.MAX_WGRAD_JOBS):
+            chunk = self.jobs[i:i + _lib.MAX_WGRAD_JOBS]
+            arr = (_lib.WgradJob * len(chunk))(*chunk)
+            n = lib.sgc_rows_wgrad_group_scratch_floats(ctypes.cast(arr, ctypes.c_void_p), len(chunk), self.R)
+            if n <= 0:
+                raise RuntimeError('sgcdet_b200: invalid weight-gradient job table')
+            scratch = torch.empty(n, device=self.dev, dtype=F32)
+            call('sgc_rows_wgrad_group_tc', ctypes.cast(arr, ctypes.c_void_p), len(chunk), self.R, ptr(scratch), stream())
+        self.jobs, self.keep = [], []
 
 
 def linear_grads_tc(g: torch.Tensor, x: torch.Tensor, gw: Optional[torch.Tensor] = None, gb: Optional[torch.Tensor] = None):
@@ -840,57 +874,6 @@ def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gs
     return gx, gs, gpre, partial
 
 
-def rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=None, masks=(None, None, None),
-                   scales=(1.0, 1.0, 1.0)):
-    """``sgc_rows_chain_tc``: W_o -> LayerNorm -> W_1 -> ReLU -> W_2 -> (+x1) LayerNorm over the voxel rows in one launch.
-    Returns (y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)) -- the tensors the separate launches of
-    ``EncoderLayerRows.forward`` produce (used by it when SGC_ROWS_CHAIN=1)."""
-    R, C = o2.shape
-    Fh = b1.numel()
-    dev = o2.device
-
-    def new(*shape):
-        return torch.empty(*shape, device=dev, dtype=F32)
-    x1, pre1, mean1, rstd1 = new(R, C), new(R, C), new(R), new(R)
-    hdn, y, pre2, mean2, rstd2 = new(R, Fh), new(R, C), new(R, C), new(R), new(R)
-    a = _lib.RowsChainArgs()
-    a.o2, a.p_wo, a.p_w1, a.p_w2 = ptr(o2), ptr(lw.p_wo), ptr(lw.p_w1), ptr(lw.p_w2)
-    a.bo, a.b1, a.b2, a.g1, a.be1, a.g2, a.be2 = ptr(bo), ptr(b1), ptr(b2), ptr(g1), ptr(be1), ptr(g2), ptr(be2)
-    a.mask0, a.mask1, a.mask2, a.rowcount = ptr(masks[0]), ptr(masks[1]), ptr(masks[2]), ptr(rowcount)
-    a.x1, a.pre1, a.mean1, a.rstd1 = ptr(x1), ptr(pre1), ptr(mean1), ptr(rstd1)
-    a.hdn, a.y, a.pre2, a.mean2, a.rstd2 = ptr(hdn), ptr(y), ptr(pre2), ptr(mean2), ptr(rstd2)
-    a.mscale0, a.mscale1, a.mscale2, a.eps1, a.eps2 = scales[0], scales[1], scales[2], eps1, eps2
-    a.R, a.C, a.F = R, C, Fh
-    call('sgc_rows_chain_tc', ctypes.byref(a), stream())
-    return y, x1, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2)
-
-
-def rows_chain_bwd(gy, lw, hdn, ln1, ln2, g1, g2, rowcount=None, masks=(None, None, None), scales=(1.0, 1.0, 1.0)):
-    """``sgc_rows_chain_bwd_tc``: the backward of ``rows_chain_fwd`` in one launch.  ``ln1`` / ``ln2`` = (pre, mean, rstd) of
-    the two LayerNorms.  Returns (go2, gf, gh, gout, partial1, partial2): the chain's output gradient, the three operands of
-    the weight gradients and the gamma / beta partials for ``_ln_params``.  Not validated on a GPU yet."""
-    R, C = gy.shape
-    Fh = hdn.shape[1]
-    dev = gy.device
-
-    def new(*shape):
-        return torch.empty(*shape, device=dev, dtype=F32)
-    gf, gpre2, gh, gx1, gout, go2 = new(R, C), new(R, C), new(R, Fh), new(R, C), new(R, C), new(R, C)
-    nscr = _lib.load().sgc_layernorm_bwd_scratch_floats(R, C)
-    part1, part2 = torch.zeros(nscr, device=dev, dtype=F32), torch.zeros(nscr, device=dev, dtype=F32)
-    a = _lib.RowsChainBwdArgs()
-    a.gy, a.p_w2_t, a.p_w1_t, a.p_wo_t = ptr(gy), ptr(lw.p_w2_t), ptr(lw.p_w1_t), ptr(lw.p_wo_t)
-    a.pre1, a.mean1, a.rstd1, a.g1 = ptr(ln1[0]), ptr(ln1[1]), ptr(ln1[2]), ptr(g1)
-    a.pre2, a.mean2, a.rstd2, a.g2 = ptr(ln2[0]), ptr(ln2[1]), ptr(ln2[2]), ptr(g2)
-    a.hdn, a.mask0, a.mask2, a.rowcount = ptr(hdn), ptr(masks[0]), ptr(masks[2]), ptr(rowcount)
-    a.gf, a.gpre2, a.gh, a.gx1, a.gout, a.go2 = ptr(gf), ptr(gpre2), ptr(gh), ptr(gx1), ptr(gout), ptr(go2)
-    a.partial1, a.partial2 = ptr(part1), ptr(part2)
-    a.mscale0, a.mscale2, a.gscale1 = scales[0], scales[2], scales[1]
-    a.R, a.C, a.F = R, C, Fh
-    call('sgc_rows_chain_bwd_tc', ctypes.byref(a), stream())
-    return go2, gf, gh, gout, part1, part2
-
-
 def _ln_params(partial, R, N):
     gg, gb = torch.empty(N, device=partial.device, dtype=F32), torch.empty(N, device=partial.device, dtype=F32)
     call('sgc_layernorm_bwd_params', ptr(partial), R, N, ptr(gg), ptr(gb), stream())
@@ -982,14 +965,6 @@ class EncoderLayerRows(torch.autograd.Function):
             else:
                 o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
             o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
-        if tc and ROWS_CHAIN and C in (128, 256) and Fh in (256, 512):
-            y, x1, hdn, ln1, ln2 = rows_chain_fwd(o2, lw, bo, b1, b2, g1, be1, g2, be2, eps1, eps2, rowcount=pl.count,
-                                                  masks=(m0, m1, m2), scales=(s0, s1, s2))
-            ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2,
-                                  w_out, in_w, wo, w1, w2)
-            ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
-            ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
-            return y
         # rows no view sees are zeroed (DCA:819-835) straight from the per-voxel view count
         x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
                                   rowcount=pl.count, ln=(g1, be1, eps1), want_split=sp)
@@ -1035,33 +1010,29 @@ class EncoderLayerRows(torch.autograd.Function):
             return a @ w if small else torch.mm(a_s, ws_t.t(), out_dtype=F32)
 
         wtc = tc and ROWS_WGRAD_TC and C % 128 == 0 and Fh % 128 == 0   # own kernel for the weight gradients too
-        hwtc = wtc and htc
+        # all seven weight-gradient products of the layer as ONE grouped launch at the end of this backward (also the per-head
+        # key / value products of the 16-wide heads, which the per-layer launches leave to the library)
+        grouped = wtc and WGRAD_GROUP and not getattr(lw, 'fuse_qo', False) and dh % 16 == 0
+        hwtc = wtc and htc and not grouped
         lgrads = linear_grads_tc if wtc else linear_grads
-        if tc and ROWS_CHAIN_BWD and C in (128, 256) and Fh in (256, 512) and Q <= 128 * 296:
-            # LayerNorm2' -> W_2 -> ReLU gate -> W_1 -> LayerNorm1' -> W_o as ONE launch (sgc_rows_chain_bwd_tc); the weight /
-            # bias / gamma / beta gradients are formed from its outputs on the weight-gradient streams as before
-            go2, gf, gh, gout, part1, part2 = rows_chain_bwd(gy, lw, hdn, (pre1, mean1, rstd1), (pre2, mean2, rstd2), g1, g2,
-                                                             rowcount=pl.count, masks=(m0, m1, m2), scales=(s0, s1, s2))
-            g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
-            g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
-            g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
-            g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
-            g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
-        else:
+        if True:
             # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
             gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
                                                want_split=sp)
             g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
-            g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
+            if not grouped:
+                g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
             ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
             # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
             gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
-            g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
+            if not grouped:
+                g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
             gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
             gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
                                                rowcount=pl.count, want_split=sp)
             g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
-            g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
+            if not grouped:
+                g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
             go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
         if hwtc:
             # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients
@@ -1089,7 +1060,8 @@ class EncoderLayerRows(torch.autograd.Function):
             gs, gb = split_rows_colsum(go2, 0)
             a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
             return torch.bmm(a, split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C), gb
-        g_wv, g_bv = side.run(_wv, go2, t)
+        if not grouped:
+            g_wv, g_bv = side.run(_wv, go2, t)
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
@@ -1112,10 +1084,13 @@ class EncoderLayerRows(torch.autograd.Function):
             if fp32_heads:
                 return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
             return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
-        g_wk = side.run(_wk, qv, gqt)
-        if hwtc:
+        if grouped:
+            pass
+        elif hwtc:
+            g_wk = side.run(_wk, qv, gqt)
             g_wq, g_bq = side.run(lambda: linear_grads_tc(gqv, g, g_in_w[:C], g_in_b[:C]), gqv, g)
         else:
+            g_wk = side.run(_wk, qv, gqt)
             g_wq, g_bq = side.run(lambda: lgrads(gqv, g), gqv, g)
         if htc and getattr(lw, 'fuse_qo', False):
             # chain: gmean = gqv @ (W_q W_out) in one GEMM; gg = gqv @ W_q (an input of output_proj's weight gradient only)
@@ -1125,14 +1100,39 @@ class EncoderLayerRows(torch.autograd.Function):
         else:
             gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
             gg_s = split_cols(gg, 0) if sp else None
-            g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
+            if not grouped:
+                g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
             gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
         gslots = torch.empty_like(slots)
         call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
              ptr(gmean), ptr(gslots), stream())
+        if grouped:
+            def _group():
+                G = WgradGroup(Q, dev)
+                gw_in = torch.empty(3 * C, C, device=dev, dtype=F32)
+                gb_in = torch.zeros(3 * C, device=dev, dtype=F32)    # the key bias gradient is identically zero
+                w2g = G.linear(gf, hdn)
+                w1g = G.linear(gh, x1)
+                wog = G.linear(gout, o2)
+                # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
+                G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh,
+                      bias_out=gb_in[2 * C:], bias_from=2)
+                # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
+                G.add(gqt, qv, C, dh, gw_in[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh, scale=scale)
+                G.linear(gqv, g, gw_in[:C], gb_in[:C])
+                woutg = G.linear(gg, mean)
+                G.launch()
+                return w2g + w1g + wog + woutg + (gw_in, gb_in)
+            g_w2, g_b2, g_w1, g_b1, g_wo, g_bo, g_wout, g_bout, g_in_w, g_in_b = side.run(
+                _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean)
+            if side.detached and side_f.detached and side_f.side != side.side:
+                # the FFN parameters are aliased on the second weight stream: it only has to follow the grouped launch
+                side_f.side.wait_stream(side.side)
+                for t_ in (g_w2, g_b2, g_w1, g_b1):
+                    t_.record_stream(side_f.side)
         side.join()
         side_f.join()
-        if not hwtc:
+        if not hwtc and not grouped:
             g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
                                                torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
         side.join()

@@ -181,3 +181,47 @@ def test_rows_wgrad_heads_matches_fp64(cuda_lib, R):
     check(gw[2 * C:], ref)
     check(gb[2 * C:], b.double().sum(0))
     assert (gw[:2 * C] == 9.0).all() and (gb[:2 * C] == 9.0).all()
+
+
+@pytest.mark.parametrize('R,C', [(6400, 256), (800, 256), (400, 256), (37, 256), (51200, 128), (3200, 128)])
+def test_wgrad_group_matches_fp64(cuda_lib, R, C):
+    """All seven weight-gradient products of an encoder layer as ONE grouped launch (sgc_rows_wgrad_group_tc): plain Linear
+    layers, the per-head key / value products written transposed into in_proj_weight's gradient (32- and 16-wide heads),
+    bias gradients from either operand, scale; untouched rows of the destination stay untouched; deterministic."""
+    H, F = 8, 2 * C
+    dh = C // H
+    g = torch.Generator().manual_seed(R + C)
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()
+    gf, hdn, gh, x1, gout, o2 = rnd(R, C), rnd(R, F), rnd(R, F), rnd(R, C), rnd(R, C), rnd(R, C)
+    t, go2, gqt, qv, gqv, gg_, gmean_in, mean = rnd(H, R, C), rnd(R, C), rnd(H, R, C), rnd(R, C), rnd(R, C), rnd(R, C), rnd(R, C), rnd(R, C)
+    scale = 1.0 / math.sqrt(dh)
+
+    def run():
+        G = SF.WgradGroup(R, 'cuda')
+        gw_in = torch.full((3 * C, C), 9.0, device='cuda')
+        gb_in = torch.full((3 * C,), 9.0, device='cuda')
+        w2 = G.linear(gf, hdn)
+        w1 = G.linear(gh, x1)
+        wo = G.linear(gout, o2)
+        G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=R * C, ldb=C, batch_b=dh,
+              bias_out=gb_in[2 * C:], bias_from=2)
+        G.add(gqt, qv, C, dh, gw_in[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=R * C, ldb=C, batch_b=dh, scale=scale)
+        G.linear(gqv, gg_, gw_in[:C], gb_in[:C])
+        wout = G.linear(gmean_in, mean)
+        G.launch()
+        torch.cuda.synchronize()
+        return w2, w1, wo, wout, gw_in, gb_in
+
+    (g_w2, g_b2), (g_w1, g_b1), (g_wo, g_bo), (g_wout, g_bout), gw_in, gb_in = run()
+    d = lambda x: x.double()
+    check(g_w2, d(gf).t() @ d(hdn)); check(g_b2, d(gf).sum(0))
+    check(g_w1, d(gh).t() @ d(x1)); check(g_b1, d(gh).sum(0))
+    check(g_wo, d(gout).t() @ d(o2)); check(g_bo, d(gout).sum(0))
+    check(g_wout, d(gmean_in).t() @ d(mean)); check(g_bout, d(gmean_in).sum(0))
+    check(gw_in[2 * C:], torch.einsum('hrc,rhd->hdc', d(t), d(go2).view(R, H, dh)).reshape(C, C))
+    check(gb_in[2 * C:], d(go2).sum(0))
+    check(gw_in[C:2 * C], torch.einsum('hrc,rhd->hdc', d(gqt), d(qv).view(R, H, dh)).reshape(C, C) * scale)
+    assert (gb_in[C:2 * C] == 9.0).all()          # no bias job for the key projection: left untouched
+    check(gw_in[:C], d(gqv).t() @ d(gg_)); check(gb_in[:C], d(gqv).sum(0))
+    again = run()
+    assert torch.equal(again[4], gw_in) and torch.equal(again[0][0], g_w2) and torch.equal(again[3][1], g_bout)
