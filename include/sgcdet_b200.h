@@ -146,6 +146,15 @@ int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, in
                      int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
                      int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream);
 
+/* Folded projection weights of MSDeformableAttention3D_DFA3D (DCA:417-436): Wcat [C + 4MP, C] = value_proj.weight rows
+ * followed by the offset / depth-offset / attention-weight rows permuted to [head*P + point][off_x, off_y, off_d, logit];
+ * gbias [4MP] the same permutation of the three small biases.  unfold: the gradients of Wcat / gbias scattered back into
+ * seven contiguous parameter gradients (every element written). */
+int sgc_fold_wcat(const float* value_w, const float* off_w, const float* dep_w, const float* att_w, const float* off_b,
+                  const float* dep_b, const float* att_b, int C, int MP, float* wcat, float* gbias, void* stream);
+int sgc_unfold_wcat_grad(const float* gwcat, const float* ggbias, int C, int MP, float* g_value_w, float* g_off_w,
+                         float* g_dep_w, float* g_att_w, float* g_off_b, float* g_dep_b, float* g_att_b, void* stream);
+
 /* Weight gradients of the same layers on the tensor cores (reduction over the voxel rows, csrc/sgc_rows_gemm_tc.cu):
  *     out[b*out_b + m*out_m + n*out_n] = scale * sum_r a[b*batch_a + r*lda + m] * b[b*batch_b + r*ldb + n],  m < M, n < N
  * For y = x W^T + bias with upstream gradient g: gW = g^T x (a = g, b = x).  bias_from = 1: bias_out[b*M + m] = sum_r a
@@ -192,6 +201,16 @@ int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg, const flo
                  int S, int H, int W, int D, int Q, int C, float* samp, float* slots, void* stream);
 /* Backward of the above (F3D:303-351 + autograd of the Linear heads).  All grads ACCUMULATE (caller zeroes).
  * scratch: sgc_lift_bwd_scratch_floats(cap_pairs, C) floats (per-CTA bias partials, reduced deterministically). */
+/* The same backward as a GATHER over 4x8 pixel tiles (csrc/sgc_lift_tiles.cu): points are filed under the tiles their 2x2
+ * corner blocks touch; a CTA stages its tile's value rows in shared memory (bulk async copies), dots / accumulates the
+ * records of the tile there and writes every grad_value / grad_G row ONCE -- no zero fill of the two (grad_value / grad_G are
+ * fully overwritten), no reductions into them.  grad_dist is zero-filled inside; grad_vbias / grad_gbias are ASSIGNED.
+ * S == H*W.  workspace: sgc_lift_bwd_tiles_workspace_bytes() bytes, 256-byte aligned, private to the call. */
+long long sgc_lift_bwd_tiles_workspace_bytes(int cap_pairs, int V, int H, int W, int C);
+int sgc_lift_bwd_tiles(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
+                       const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam, const float* samp,
+                       const float* grad_slots, int V, int S, int H, int W, int D, int Q, int C, float* grad_value,
+                       float* grad_G, float* grad_dist, float* grad_vbias, float* grad_gbias, void* workspace, void* stream);
 int sgc_lift_bwd_scratch_floats(int cap_pairs, int C);
 int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg, const float* dist, const float* vbias,
                  const int* pair_vq, const int* n_pairs, int cap_pairs, const float* ref_cam, const float* samp,

@@ -50,12 +50,16 @@ SIGNATURES = {
     'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
     'sgc_rows_wgrad_tc_scratch_floats': [I, I, I, I],
     'sgc_rows_wgrad_tc': [P, LL, LL, I, P, LL, LL, I, I, I, P, LL, LL, LL, F, P, I, P, P],
+    'sgc_fold_wcat': [P, P, P, P, P, P, P, I, I, P, P, P],
+    'sgc_unfold_wcat_grad': [P, P, I, I, P, P, P, P, P, P, P, P],
     'sgc_rows_wgrad_group_scratch_floats': [P, I, I],
     'sgc_rows_wgrad_group_tc': [P, I, I, P, P],
     'sgc_colsum_scratch_floats': [I, I],
     'sgc_colsum': [P, I, I, P, P, P, P],
     'sgc_split_rows_colsum': [P, I, I, I, P, P, P, P, P],
     'sgc_lift_fwd': [P, I, P, I, P, P, P, P, P, I, P, I, I, I, I, I, I, P, P, P],
+    'sgc_lift_bwd_tiles_workspace_bytes': [I, I, I, I, I],
+    'sgc_lift_bwd_tiles': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     'sgc_lift_bwd_scratch_floats': [I, I],
     'sgc_lift_bwd': [P, I, P, I, P, P, P, P, I, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P],
     'sgc_crossview_mean_fwd': [P, P, I, I, I, P, P],
@@ -147,7 +151,7 @@ def load() -> ctypes.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = c_longlong if name == 'sgc_rows_wgrad_group_scratch_floats' else c_int
+            fn.restype = c_longlong if name in ('sgc_rows_wgrad_group_scratch_floats', 'sgc_lift_bwd_tiles_workspace_bytes') else c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
         lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
         lib.sgc_set_pdl(int(os.environ.get('SGC_PDL', '0')))

@@ -200,3 +200,85 @@ extern "C" int sgc_split_rows_colsum(const float* x, int R, int C, int pattern, 
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Folded projection weights of MSDeformableAttention3D_DFA3D (deformable_cross_attention.py:417-436): the level's dense
+// projection is ONE GEMM with  Wcat = [value_proj.weight ; G rows],  G row 4*(m*P + p) + j = sampling_offsets row
+// (m*P + p)*2 + j for j < 2, sampling_offsets_depth row m*P + p for j = 2, attention_weights row m*P + p for j = 3 (the
+// lift kernels read one float4 (off_x, off_y, off_d, logit) per (head, point)), and likewise for the biases.
+// fold: the four weights -> Wcat [C + 4MP, C], the three small biases -> gbias [4MP] (one launch instead of three cats);
+// unfold: the gradient of Wcat / gbias -> the seven parameter gradients, each its own contiguous tensor (one launch
+// instead of the cat's backward and eight strided copies at the very end of the step).
+namespace sgc {
+
+__device__ __forceinline__ void fold_row(int r, int C, const float* const (&w)[4], const float*& src) {
+  if (r < C) { src = w[0] + (size_t)r * C; return; }
+  const int g = r - C, mp = g >> 2, j = g & 3;
+  src = j < 2 ? w[1] + (size_t)(2 * mp + j) * C : j == 2 ? w[2] + (size_t)mp * C : w[3] + (size_t)mp * C;
+}
+
+__global__ void __launch_bounds__(256) fold_wcat_kernel(const float* __restrict__ wv, const float* __restrict__ wo,
+                                                        const float* __restrict__ wd, const float* __restrict__ wa,
+                                                        const float* __restrict__ bo, const float* __restrict__ bd,
+                                                        const float* __restrict__ ba, int C, int MP,
+                                                        float* __restrict__ wcat, float* __restrict__ gbias) {
+  const int N = C + 4 * MP, C4 = C / 4;
+  const float* const w[4] = {wv, wo, wd, wa};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * C4; i += gridDim.x * blockDim.x) {
+    const int r = i / C4, c = (i - r * C4) * 4;
+    const float* src;
+    fold_row(r, C, w, src);
+    *reinterpret_cast<float4*>(wcat + (size_t)r * C + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+  }
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < 4 * MP; g += gridDim.x * blockDim.x) {
+    const int mp = g >> 2, j = g & 3;
+    gbias[g] = j < 2 ? __ldg(bo + 2 * mp + j) : j == 2 ? __ldg(bd + mp) : __ldg(ba + mp);
+  }
+}
+
+__global__ void __launch_bounds__(256) unfold_wcat_grad_kernel(const float* __restrict__ gwcat, const float* __restrict__ ggbias,
+                                                               int C, int MP, float* __restrict__ gwv, float* __restrict__ gwo,
+                                                               float* __restrict__ gwd, float* __restrict__ gwa,
+                                                               float* __restrict__ gbo, float* __restrict__ gbd,
+                                                               float* __restrict__ gba) {
+  const int N = C + 4 * MP, C4 = C / 4;
+  float* const w[4] = {gwv, gwo, gwd, gwa};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * C4; i += gridDim.x * blockDim.x) {
+    const int r = i / C4, c = (i - r * C4) * 4;
+    float* dst;
+    if (r < C) dst = w[0] + (size_t)r * C;
+    else {
+      const int g = r - C, mp = g >> 2, j = g & 3;
+      dst = j < 2 ? w[1] + (size_t)(2 * mp + j) * C : j == 2 ? w[2] + (size_t)mp * C : w[3] + (size_t)mp * C;
+    }
+    *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(gwcat + (size_t)r * C + c));
+  }
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < 4 * MP; g += gridDim.x * blockDim.x) {
+    const int mp = g >> 2, j = g & 3;
+    const float v = __ldg(ggbias + g);
+    if (j < 2) gbo[2 * mp + j] = v; else if (j == 2) gbd[mp] = v; else gba[mp] = v;
+  }
+}
+
+}  // namespace sgc
+
+extern "C" int sgc_fold_wcat(const float* value_w, const float* off_w, const float* dep_w, const float* att_w,
+                             const float* off_b, const float* dep_b, const float* att_b, int C, int MP, float* wcat,
+                             float* gbias, void* stream) {
+  if (C <= 0 || C % 4 || MP <= 0) return (int)cudaErrorInvalidValue;
+  const int items = (C + 4 * MP) * (C / 4);
+  sgc::fold_wcat_kernel<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(value_w, off_w, dep_w, att_w, off_b, dep_b, att_b, C,
+                                                                             MP, wcat, gbias);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int sgc_unfold_wcat_grad(const float* gwcat, const float* ggbias, int C, int MP, float* g_value_w, float* g_off_w,
+                                    float* g_dep_w, float* g_att_w, float* g_off_b, float* g_dep_b, float* g_att_b, void* stream) {
+  if (C <= 0 || C % 4 || MP <= 0) return (int)cudaErrorInvalidValue;
+  const int items = (C + 4 * MP) * (C / 4);
+  sgc::unfold_wcat_grad_kernel<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gwcat, ggbias, C, MP, g_value_w, g_off_w, g_dep_w,
+                                                                                    g_att_w, g_off_b, g_dep_b, g_att_b);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

@@ -378,11 +378,12 @@ namespace tc {
 
 constexpr int RW_THREADS = 480;  // warps 0-3: A converters (+ epilogue), 4-11: B converters, 12: TMA, 13: MMA, 14: TMEM
 constexpr int RW_CONV = 384;     // converter threads (arrivals on f_empty / op_full)
-constexpr int RW_ST = 2;
+constexpr int RW_ST = 2;          // converted-operand stages
+constexpr int RW_MAX_F = 6;       // fp32 staging stages filled by TMA: as many as the job's tile width leaves room for
 constexpr int RW_MAX_JOBS = 8;
 
 struct SmemRW {
-  uint64_t f_full[RW_ST], f_empty[RW_ST], op_full[RW_ST], op_empty[RW_ST], tmem_full;
+  uint64_t f_full[RW_MAX_F], f_empty[RW_MAX_F], op_full[RW_ST], op_empty[RW_ST], tmem_full;
   uint32_t tmem_base;
 };
 
@@ -398,6 +399,7 @@ struct alignas(64) RowsWgradJob {
 struct RowsWgradJobs {
   RowsWgradJob job[RW_MAX_JOBS];
   int njobs;
+  int stage_bytes;       // shared memory available for the operand stages (the same for every CTA of the launch)
 };
 
 __global__ void __launch_bounds__(RW_THREADS, 1)
@@ -415,9 +417,13 @@ rows_wgrad_tc_kernel(const __grid_constant__ RowsWgradJobs jobs) {
   const int a_op = 2 * BM * BK * 2;           // hi + lo, 16 KB
   const int b_op = 2 * n_cta * BK * 2;        // hi + lo
   const int op_stage = a_op + b_op;
-  uint8_t* f_base = smem_raw;
-  uint8_t* op_base = f_base + RW_ST * f_stage;
-  SmemRW* sm = reinterpret_cast<SmemRW*>(op_base + RW_ST * op_stage);
+  // the TMA round trip (operands mostly come from HBM: they were produced many kernels ago) is hidden by as many fp32
+  // staging stages as fit beside the two converted-operand stages: 2 for 256-column tiles, 4 for 128, 6 for the heads' 16 / 32
+  int nf = (jobs.stage_bytes - RW_ST * op_stage) / f_stage;
+  nf = nf > RW_MAX_F ? RW_MAX_F : nf;
+  uint8_t* op_base = smem_raw;
+  uint8_t* f_base = op_base + RW_ST * op_stage;
+  SmemRW* sm = reinterpret_cast<SmemRW*>(smem_raw + jobs.stage_bytes);
 
   int w = (int)blockIdx.x - p.cta_begin;
   const int mt = w % p.m_tiles; w /= p.m_tiles;
@@ -429,10 +435,8 @@ rows_wgrad_tc_kernel(const __grid_constant__ RowsWgradJobs jobs) {
   const int n_slabs = max(0, s_end - s_begin);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RW_ST; ++i) {
-      mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], RW_CONV);
-      mbar_init(&sm->op_full[i], RW_CONV); mbar_init(&sm->op_empty[i], 1);
-    }
+    for (int i = 0; i < RW_MAX_F; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], RW_CONV); }
+    for (int i = 0; i < RW_ST; ++i) { mbar_init(&sm->op_full[i], RW_CONV); mbar_init(&sm->op_empty[i], 1); }
     mbar_init(&sm->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -449,7 +453,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ RowsWgradJobs jobs) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.amap) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.bmap) : "memory");
-      Pipe pf(RW_ST);
+      Pipe pf(nf);
       for (int i = 0; i < n_slabs; ++i) {
         const int r0 = (s_begin + i) * BK;
         mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
@@ -468,7 +472,7 @@ rows_wgrad_tc_kernel(const __grid_constant__ RowsWgradJobs jobs) {
     const int t = is_b ? (int)threadIdx.x - 128 : (int)threadIdx.x;   // A: 0..127, B: 0..255
     const int width = is_b ? n_cta : BM;
     float csum0 = 0.f;                  // column sum of this thread's column over the CTA's rows
-    Pipe pf(RW_ST), po(RW_ST);
+    Pipe pf(nf), po(RW_ST);
     for (int i = 0; i < n_slabs; ++i) {
       mbar_wait(&sm->f_full[pf.stage], pf.phase);
       const uint8_t* st = f_base + pf.stage * f_stage + (is_b ? a_src : 0);
@@ -638,8 +642,12 @@ static inline bool make_wgrad_map(PFN_encodeTiled encode, CUtensorMap* map, cons
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static inline int rows_wgrad_ncta(int N) {
-  int nc = N <= 256 ? N : 256;
+// column part of a job's gradient tile per CTA: 256 for a single job (round-1 behaviour), 128 in a grouped launch (4 instead
+// of 2 fp32 staging stages; the CTAs of the other jobs keep the SMs busy, so the wider tile's lower operand traffic matters
+// less than the latency it cannot hide)
+static inline int rows_wgrad_ncta(int N, int njobs) {
+  int nc = njobs > 1 ? 128 : 256;
+  if (N < nc) nc = N;
   while (N % nc) nc >>= 1;
   return nc;
 }
@@ -649,7 +657,7 @@ static inline int rows_wgrad_ncta(int N) {
 // slabs (256 rows) -- a single job is spread over the SMs once, with at least 4 slabs per CTA, as in round 1.
 static inline int rows_wgrad_group_kch(const sgc_wgrad_job* jobs, int njobs, int R) {
   long long tiles = 0;
-  for (int j = 0; j < njobs; ++j) tiles += (long long)(jobs[j].M / BM) * (jobs[j].N / rows_wgrad_ncta(jobs[j].N)) * jobs[j].B;
+  for (int j = 0; j < njobs; ++j) tiles += (long long)(jobs[j].M / BM) * (jobs[j].N / rows_wgrad_ncta(jobs[j].N, njobs)) * jobs[j].B;
   const int total_slabs = (R + BK - 1) / BK;
   int k, cap;
   if (njobs == 1) { k = total_slabs / 4; cap = tiles < 148 ? (int)(148 / tiles) : 1; }
@@ -696,7 +704,7 @@ extern "C" int sgc_rows_wgrad_group_tc(const sgc_wgrad_job* jobs, int njobs, int
     const sgc_wgrad_job& in = jobs[j];
     if (!rows_wgrad_job_ok(in)) return (int)cudaErrorInvalidValue;
     RowsWgradJob& p = tab.job[j];
-    p.n_cta = rows_wgrad_ncta(in.N);
+    p.n_cta = rows_wgrad_ncta(in.N, njobs);
     if (p.n_cta < 16 || p.n_cta % 16) return (int)cudaErrorInvalidValue;
     if (!make_wgrad_map(encode, &p.amap, in.a, in.M, R, in.B, in.lda, in.batch_a, BM, &p.a_swap)) return (int)cudaErrorInvalidValue;
     if (!make_wgrad_map(encode, &p.bmap, in.b, in.N, R, in.B, in.ldb, in.batch_b, p.n_cta, &p.b_swap)) return (int)cudaErrorInvalidValue;
@@ -727,11 +735,13 @@ extern "C" int sgc_rows_wgrad_group_tc(const sgc_wgrad_job* jobs, int njobs, int
     const long long work = elems > q.bias_len ? elems : q.bias_len;
     blocks += (int)((work + 255) / 256);
   }
-  const size_t smem = (size_t)RW_ST * (BK * BM * 4 + BK * max_ncta * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * max_ncta * BK * 2) +
-                      sizeof(SmemRW) + 64;
-  const size_t smem_max = (size_t)RW_ST * (BK * BM * 4 + BK * 256 * 4) + (size_t)RW_ST * (2 * BM * BK * 2 + 2 * 256 * BK * 2) +
-                          sizeof(SmemRW) + 64;   // widest configuration, see sgc_rows_gemm_tc
-  cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  // operand stages: two converted stages + at least two fp32 staging stages of the widest tile; always the full budget of
+  // the widest configuration, so that narrower jobs get their extra staging stages and graph-captured launches agree
+  const int stage_bytes = RW_ST * (2 * BM * BK * 2 + 2 * 256 * BK * 2) + 2 * (BK * BM * 4 + BK * 256 * 4);
+  (void)max_ncta;
+  tab.stage_bytes = stage_bytes;
+  const size_t smem = (size_t)stage_bytes + sizeof(SmemRW) + 64;
+  cudaError_t e = cudaFuncSetAttribute(rows_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   rows_wgrad_tc_kernel<<<cta, RW_THREADS, smem, (cudaStream_t)stream>>>(tab);
   SGC_CUDA_CHECK_LAST();

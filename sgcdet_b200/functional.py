@@ -99,6 +99,8 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # all weight gradients of a layer as ONE grouped launch at the end of its backward (sgc_rows_wgrad_group_tc); 0 = one launch
 # per Linear layer as in round 1
 WGRAD_GROUP = _os.environ.get('SGC_WGRAD_GROUP', '1') != '0'
+# backward of the lift as a gather over pixel tiles (csrc/sgc_lift_tiles.cu); 0 = the scatter kernel of round 1 (REDs)
+LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '1') != '0'
 # output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
 # (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
@@ -233,6 +235,36 @@ def pack_weight_tc(w: torch.Tensor) -> torch.Tensor:
     out = torch.empty(2 * N * C, device=w.device, dtype=BF16)
     call('sgc_pack_weight_tc', ptr(w.contiguous()), N, C, ptr(out), stream())
     return out
+
+
+class FoldWeights(torch.autograd.Function):
+    """(Wcat [C+128, C], gbias [128]) of a level from the four projection weights / three small biases of
+    ``MSDeformableAttention3D_DFA3D`` (``sgc_fold_wcat``); the backward hands every parameter its own contiguous gradient
+    (``sgc_unfold_wcat_grad``), so autograd's accumulation takes them as they are."""
+
+    @staticmethod
+    def forward(ctx, wv, wo, wd, wa, bo, bd, ba):
+        C = wv.shape[0]
+        MP = wd.shape[0]
+        wcat = torch.empty(C + 4 * MP, C, device=wv.device, dtype=F32)
+        gbias = torch.empty(4 * MP, device=wv.device, dtype=F32)
+        call('sgc_fold_wcat', ptr(wv), ptr(wo), ptr(wd), ptr(wa), ptr(bo), ptr(bd), ptr(ba), C, MP, ptr(wcat), ptr(gbias), stream())
+        ctx.dims = (C, MP)
+        return wcat, gbias
+
+    @staticmethod
+    def backward(ctx, gwcat, ggbias):
+        C, MP = ctx.dims
+        dev = gwcat.device if gwcat is not None else ggbias.device
+        if gwcat is None:
+            gwcat = torch.zeros(C + 4 * MP, C, device=dev, dtype=F32)
+        if ggbias is None:
+            ggbias = torch.zeros(4 * MP, device=dev, dtype=F32)
+        new = lambda *s: torch.empty(*s, device=dev, dtype=F32)
+        gwv, gwo, gwd, gwa, gbo, gbd, gba = new(C, C), new(2 * MP, C), new(MP, C), new(MP, C), new(2 * MP), new(MP), new(MP)
+        call('sgc_unfold_wcat_grad', ptr(gwcat.contiguous()), ptr(ggbias.contiguous()), C, MP, ptr(gwv), ptr(gwo), ptr(gwd),
+             ptr(gwa), ptr(gbo), ptr(gbd), ptr(gba), stream())
+        return gwv, gwo, gwd, gwa, gbo, gbd, gba
 
 
 class _WeightJobs:
@@ -609,14 +641,16 @@ class Lift(torch.autograd.Function):
         gslots = gslots.contiguous()
         cur = torch.cuda.current_stream(vg.device)
         side = ctx.bwd_stream if ctx.bwd_stream is not None and ctx.bwd_stream != cur else None
+        tiles = LIFT_TILES and S == H * W
+        lib = _lib.load()
+
         def _zeros():
             return (torch.zeros_like(vg), torch.zeros_like(dist), torch.zeros_like(vbias),
                     torch.zeros(G_CH, device=vg.device, dtype=torch.float32))
-        prezero = _os.environ.get('SGC_PREZERO', '1') != '0'
+        prezero = (not tiles) and _os.environ.get('SGC_PREZERO', '1') != '0'
         with torch.cuda.stream(side if side is not None else cur):
-            # the accumulation targets are zero-filled BEFORE the side stream joins the voxel chain: the fills (290 MB
-            # at the finest level) depend on nothing, so they run while the chain is still busy instead of in front of
-            # the kernel on the critical path
+            # scatter kernel only: the accumulation targets are zero-filled BEFORE the side stream joins the voxel chain (the
+            # fills, 290 MB at the finest level, depend on nothing); the tile kernel writes every row once and needs none
             if prezero:
                 gvg, gdist, gvb, ggb = _zeros()
         if side is not None:
@@ -625,14 +659,26 @@ class Lift(torch.autograd.Function):
             for t in (gslots, samp, pl.pair_vq, pl.n_pairs, pl.ref_cam):
                 t.record_stream(side)
         with torch.cuda.stream(side if side is not None else cur):
-            if not prezero:
-                gvg, gdist, gvb, ggb = _zeros()
-            base, gbase = ptr(vg), ptr(gvg)
-            scratch = torch.empty(_lib.load().sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device,
-                                  dtype=torch.float32)
-            call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
-                 pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots), S, H, W, D, pl.Q, C,
-                 gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
+            base = ptr(vg)
+            if tiles:
+                # gather over pixel tiles (csrc/sgc_lift_tiles.cu): no zero fill, no reductions into grad_vg
+                V = vg.shape[0]
+                gvg, gdist = torch.empty_like(vg), torch.empty_like(dist)
+                gvb = torch.empty_like(vbias)
+                ggb = torch.empty(G_CH, device=vg.device, dtype=torch.float32)
+                ws = torch.empty(lib.sgc_lift_bwd_tiles_workspace_bytes(pl.cap, V, H, W, C), device=vg.device, dtype=torch.uint8)
+                gbase = ptr(gvg)
+                call('sgc_lift_bwd_tiles', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
+                     pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots), V, S, H, W, D, pl.Q, C, gbase, gbase + 4 * C, ptr(gdist),
+                     ptr(gvb), ptr(ggb), ptr(ws), stream())
+            else:
+                if not prezero:
+                    gvg, gdist, gvb, ggb = _zeros()
+                gbase = ptr(gvg)
+                scratch = torch.empty(lib.sgc_lift_bwd_scratch_floats(pl.cap, C), device=vg.device, dtype=torch.float32)
+                call('sgc_lift_bwd', base, ld, base + 4 * C, ld, ptr(dist), ptr(vbias), ptr(pl.pair_vq), ptr(pl.n_pairs),
+                     pl.cap, ptr(pl.ref_cam), ptr(samp), ptr(gslots), S, H, W, D, pl.Q, C,
+                     gbase, gbase + 4 * C, ptr(gdist), ptr(gvb), ptr(ggb), ptr(scratch), stream())
         if side is not None and ctx.join_stream is not None and ctx.join_stream != side:
             ctx.join_stream.wait_stream(side)
             for t in (gvg, gdist, gvb, ggb):

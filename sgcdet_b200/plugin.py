@@ -142,6 +142,12 @@ class MSDeformableAttention3D_DFA3D(nn.Module):
     def folded_weights(self):
         """(Wcat [C+128,C], vbias [C], gbias [128]): value_proj rows followed by the offset / depth-offset /
         attention-weight rows permuted to the kernel's [m][p][ox,oy,od,logit] channel order."""
+        if self.value_proj.weight.is_cuda:
+            wcat, bg = SF.FoldWeights.apply(self.value_proj.weight, self.sampling_offsets.weight,
+                                            self.sampling_offsets_depth.weight, self.attention_weights.weight,
+                                            self.sampling_offsets.bias, self.sampling_offsets_depth.bias,
+                                            self.attention_weights.bias)
+            return wcat, self.value_proj.bias, bg
         M, P = self.num_heads, self.num_points
         C = self.embed_dims
         wo = self.sampling_offsets.weight.view(M, P, 2, C)
