@@ -98,7 +98,9 @@ LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=2, sgc_cross
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=3, sgc_topk_select=1, sgc_scatter_add_rows=1,
                 sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1, sgc_rows_gemm_tc=1,
-                sgc_prepare_weights=1, sgc_rows_wgrad_tc=2, sgc_topk_select_mc=9)
+                sgc_prepare_weights=1, sgc_rows_wgrad_tc=2, sgc_topk_select_mc=9, sgc_rows_wgrad_group_tc=2,
+                sgc_lift_bwd_tiles=7, sgc_topk_select_grid=1, sgc_fold_wcat=1, sgc_unfold_wcat_grad=1,
+                sgc_occ_loss_fwd=1, sgc_occ_loss_bwd=1)
 
 
 class CallRecorder:
@@ -136,9 +138,11 @@ class CallRecorder:
 def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
     """Unique bytes a launch has to move (DESIGN.md "Kernels"): inputs read once + outputs written once."""
     f = 4.0
-    if name in ('sgc_lift_fwd', 'sgc_lift_bwd'):
+    if name in ('sgc_lift_fwd', 'sgc_lift_bwd', 'sgc_lift_bwd_tiles'):
         if name == 'sgc_lift_fwd':
             ldv, S, H, W, D, Q, C = args[1], args[11], args[12], args[13], args[14], args[15], args[16]
+        elif name == 'sgc_lift_bwd_tiles':
+            ldv, S, H, W, D, Q, C = args[1], args[13], args[14], args[15], args[16], args[17], args[18]
         else:
             ldv, S, H, W, D, Q, C = args[1], args[12], args[13], args[14], args[15], args[16], args[17]
         V = n_pairs_by_q[Q][1]
@@ -431,7 +435,7 @@ def run_ours(args):
         for name, a, e0, e1 in rec2.events:
             key = name
             if name.startswith(('sgc_lift', 'sgc_crossview')) or name == 'sgc_project_compact':
-                q = {'sgc_lift_fwd': 15, 'sgc_lift_bwd': 16, 'sgc_crossview_mean_fwd': 3, 'sgc_crossview_attn_fwd': 4,
+                q = {'sgc_lift_fwd': 15, 'sgc_lift_bwd': 16, 'sgc_lift_bwd_tiles': 17, 'sgc_crossview_mean_fwd': 3, 'sgc_crossview_attn_fwd': 4,
                      'sgc_crossview_attn_bwd_qt': 4, 'sgc_crossview_attn_bwd_slots': 5, 'sgc_project_compact': 4,
                      'sgc_crossview_mean_fwd_split': 3, 'sgc_crossview_attn_fwd_split': 4,
                      'sgc_crossview_attn_bwd_qt_split': 4}[name]

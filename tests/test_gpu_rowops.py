@@ -214,3 +214,31 @@ def test_fused_layer_matches_unfused_path(cuda_lib, train, monkeypatch):
     assert a[4].keys() == b[4].keys()
     for n in a[4]:
         close(a[4][n], b[4][n], n)
+
+
+def test_fold_weights_matches_cat_and_unfolds_gradients(cuda_lib):
+    """sgc_fold_wcat / sgc_unfold_wcat_grad (the folded projection weights of MSDeformableAttention3D_DFA3D) against the torch
+    cat / view formulation (the CPU branch of ``folded_weights``): forward bit-exact, gradients bit-exact copies."""
+    import torch
+    from sgcdet_b200 import plugin
+    for C in (128, 256):
+        da_cpu = plugin.MSDeformableAttention3D_DFA3D(embed_dims=C, num_heads=8, num_levels=1, num_points=4)
+        g = torch.Generator().manual_seed(C)
+        with torch.no_grad():
+            for p in da_cpu.parameters():
+                p.copy_(torch.randn(p.shape, generator=g))
+        da = plugin.MSDeformableAttention3D_DFA3D(embed_dims=C, num_heads=8, num_levels=1, num_points=4)
+        da.load_state_dict(da_cpu.state_dict())
+        da = da.cuda()
+        wcat_r, vb_r, gb_r = da_cpu.folded_weights()
+        wcat, vb, gb = da.folded_weights()
+        assert torch.equal(wcat.cpu(), wcat_r) and torch.equal(gb.cpu(), gb_r) and torch.equal(vb.cpu(), vb_r)
+        gw = torch.randn(wcat.shape, generator=g)
+        gg = torch.randn(gb.shape, generator=g)
+        (wcat_r * gw).sum().add((gb_r * gg).sum()).backward()
+        (wcat * gw.cuda()).sum().add((gb * gg.cuda()).sum()).backward()
+        for (k, p), (_, q) in zip(da.named_parameters(), da_cpu.named_parameters()):
+            if k == 'value_proj.bias':
+                continue
+            assert p.grad is not None and p.grad.is_contiguous(), k
+            assert torch.equal(p.grad.cpu(), q.grad), k
