@@ -519,6 +519,14 @@ def run_ours(args):
         except Exception as e:
             op_bench = dict(unavailable=f'{type(e).__name__}: {e}'[:200])
 
+    # ---- config 5: view-sharded aggregation of ONE scene over the N ranks (every rank takes part) ---------
+    vs = None
+    if not args.no_view_sharded:
+        try:
+            vs = view_sharded_leg(args, rank, world, dev)
+        except Exception as e:   # an optional leg must never break the headline line
+            vs = dict(unavailable=f'{type(e).__name__}: {e}'[:300])
+
     if rank == 0:
         step_ms = total_ms / args.steps
         line = {
@@ -542,11 +550,86 @@ def run_ours(args):
             'clocks': clk, 'roofline': roof, 'path_roofline': path_roof, 'kernels': kernels, 'cpu_baseline': cpu,
             'loss': round(loss_val, 4), 'loss_check': loss_check,
             'loss_vs_oracle_rel': None if loss_check is None else loss_check['loss_vs_oracle_rel'],
-            'reference_gpu': ref_gpu, 'operator_bench': op_bench,
+            'reference_gpu': ref_gpu, 'operator_bench': op_bench, 'view_sharded': vs,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def view_sharded_leg(args, rank, world, dev):
+    """BASELINE.json configs[4]: ``SGCDet_large_ARKit`` with the V views of ONE scene split over the N ranks
+    (``sgcdet_b200.parallel.forward_view_sharded``): projection / lift local to a view's owner, the cross-view statistics
+    (sum + count, score max, partial-softmax sums -- the log-sum-exp merge -- and in the backward the softmax-normaliser dot
+    and the query gradient) all-reduced with NCCL, the voxel chain replicated.  Eager (NCCL stays outside CUDA graphs in this
+    stack), eval mode (the replicated chain must be identical on every rank), device-timed, max over ranks.  Rank 0 also times
+    the unsharded eager step of the same scene on its GPU for comparison."""
+    import torch.distributed as dist
+    from sgcdet_b200 import parallel, plugin, synthetic as syn
+    cfg = syn.CONFIGS['SGCDet_large_ARKit']
+    V = args.view_sharded_views
+    sc = syn.make_scene(cfg, V, shift_origin=True).to(dev)
+    head = plugin.build_voxel_head(cfg)
+    head.load_state_dict(syn.make_state_dict(cfg), strict=True)
+    head = head.to(dev).eval()
+    views = parallel.shard_views(V, world, rank)
+    f, m, d = parallel.shard_scene_inputs(sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, views)
+    f = [t.requires_grad_(True) for t in f[:cfg.num_levels]]
+    d = [t for t in d[:cfg.num_levels]]
+    gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+
+    def sharded():
+        for p in list(head.parameters()) + f:
+            p.grad = None
+        vol, valid, occ = parallel.forward_view_sharded(head, [(f, m, d)])
+        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+        loss.backward()
+        parallel.allreduce_view_sharded_gradients(head)
+        return vol, valid
+
+    def timed_eager(fn, warm, steps, sync_ranks):
+        for _ in range(warm):
+            out = fn()
+        torch.cuda.synchronize()
+        if sync_ranks and world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if sync_ranks and world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    ms, (vol, valid) = timed_eager(sharded, 3, 5, True)
+    chk = torch.stack([vol.detach().double().sum(), valid.double().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        feats = [t.clone().requires_grad_(True) for t in sc.mlvl_feats[:cfg.num_levels]]
+
+        def unsharded():
+            for p in list(head.parameters()) + feats:
+                p.grad = None
+            v_, _, o_ = head(feats, sc.img_meta, sc.mlvl_dpt_dists[:cfg.num_levels])
+            ((v_ * gvol).sum() + head.occ_loss(o_, None, sc.geo_occ)['loss_occ']).backward()
+            return v_, None
+        ms1, (vol_r, _) = timed_eager(unsharded, 3, 5, False)
+        out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(ms, 3),
+                   value=round(1e3 / ms, 2), unit=UNIT, unsharded_1gpu_eager_ms=round(ms1, 3),
+                   speedup_vs_unsharded_eager=round(ms1 / ms, 3), replicas_identical=bool(torch.allclose(lo, hi, rtol=1e-6)),
+                   volume_max_abs_diff_vs_unsharded=float((vol.detach() - vol_r.detach()).abs().max()),
+                   collective='NCCL all-reduce (sum, max) of the cross-view partial statistics' if world > 1 else 'none (1 rank)',
+                   mode='eager, eval, fwd+bwd, device-timed, max over ranks')
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 def load_peaks():
@@ -725,6 +808,8 @@ def main():
     ap.add_argument('--eval-mode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-grad-allreduce', action='store_true')
+    ap.add_argument('--no-view-sharded', action='store_true', help='skip the view-sharded leg (config 5)')
+    ap.add_argument('--view-sharded-views', type=int, default=40)
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-kernel leg and the operator micro-bench')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the e2e and instrumented passes')
     args = ap.parse_args()

@@ -145,6 +145,13 @@ int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B);
 int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
                      int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
                      int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream);
+/* The same with two more operand modes for attention heads narrower than a 32-column k-slab (the 16-wide heads of the
+ * C = 128 configs).  a_mode 1: the B batches share ONE x [R, K] (batch_x ignored): y[h] = x W_h^T with W_h the head's
+ * weights zero-extended over all K columns.  a_mode 2 (B == 1): y = sum_a x[a] W_a^T over a_batches matrices
+ * x[a] [R, K / a_batches] (batch stride batch_x), wpack = the packed [N, K] = [W_0 | W_1 | ...]. */
+int sgc_rows_gemm_tc_ex(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                        int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
+                        int N, float* y, long long ldy, long long batch_y, int n_cta, int a_mode, int a_batches, void* stream);
 
 /* Folded projection weights of MSDeformableAttention3D_DFA3D (DCA:417-436): Wcat [C + 4MP, C] = value_proj.weight rows
  * followed by the offset / depth-offset / attention-weight rows permuted to [head*P + point][off_x, off_y, off_d, logit];

@@ -91,6 +91,36 @@ def point_sampling_gpu(ref_3d, img_meta, dbound, device):
     return cam.permute(2, 1, 3, 0, 4), m.permute(2, 1, 3, 0, 4).squeeze(-1)  # [V,B,nq,D,3], [V,B,nq,D]
 
 
+def point_sampling_pinned_gpu(ref_3d, img_meta, dbound, device):
+    """``path_ref.point_sampling`` (the projection contract: explicit fp32 operation order, one rounding per operation) on
+    the device, in the layout of ``point_sampling_gpu``.  The reference's batched matmul leaves the accumulation order to the
+    library, so a handful of (view, voxel) pairs within round-off of a visibility bound flip between implementations; the
+    full-size parity tests pin the projection to compare everything downstream of it."""
+    ogfH, ogfW = img_meta['img_shape'][0], img_meta['img_shape'][1]
+    origin = torch.tensor(np.asarray(img_meta['lidar2img']['origin'], dtype=np.float32)).to(device)
+    p = ref_3d + origin
+    P = path_ref.compute_projection(img_meta, 1).to(device)
+    px, py, pz = p[:, 0][None], p[:, 1][None], p[:, 2][None]
+
+    def row(i):
+        a = P[:, i, 0:1] * px
+        a = a + P[:, i, 1:2] * py
+        a = a + P[:, i, 2:3] * pz
+        return a + P[:, i, 3:4]
+
+    x, y, z = row(0), row(1), row(2)
+    zc = torch.maximum(z, torch.full_like(z, path_ref.EPS))
+    u = (x / zc) / float(ogfW)
+    v = (y / zc) / float(ogfH)
+    d = (z - float(dbound[0])) / float(dbound[1] - dbound[0])
+    mask = (z > path_ref.EPS) & (u > path_ref.EPS) & (u < (1.0 - path_ref.EPS)) & (v > path_ref.EPS) & (v < (1.0 - path_ref.EPS))
+    cam = torch.stack([u, v, d], dim=-1)                      # [V,Q,3]
+    return cam[:, None, :, None, :], mask[:, None, :, None]   # [V,1,Q,1,3], [V,1,Q,1]
+
+
+PINNED_PROJECTION = False
+
+
 def dense_head_forward_gpu(sd, level, feat, dpt_dist, img_meta, proposal, cfg, training):
     dev = feat.device
     _, V, C, h, w = feat.shape
@@ -111,7 +141,8 @@ def dense_head_forward_gpu(sd, level, feat, dpt_dist, img_meta, proposal, cfg, t
     shapes = torch.as_tensor([[h, w]], dtype=torch.long, device=dev)
     shapes3d = torch.cat([shapes, shapes.new_ones(1, 1) * Dd], dim=-1).contiguous()
     lsi = torch.zeros(1, dtype=torch.long, device=dev)
-    ref_cam, bev_mask = point_sampling_gpu(ref_3d, img_meta, cfg.dbound, dev)   # [V,1,Q,1,3], [V,1,Q,1]
+    sampler = point_sampling_pinned_gpu if PINNED_PROJECTION else point_sampling_gpu
+    ref_cam, bev_mask = sampler(ref_3d, img_meta, cfg.dbound, dev)   # [V,1,Q,1,3], [V,1,Q,1]
     # DCA:758-773: per-view index lists + padded rebatch
     indexes = [bev_mask[i][0].sum(-1).nonzero().squeeze(-1) for i in range(V)]   # V host syncs
     max_len = max(len(e) for e in indexes)

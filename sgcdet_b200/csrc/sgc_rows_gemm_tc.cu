@@ -51,6 +51,8 @@ struct RowsGemmParams {
   int bias_batch;               // bias of batch b starts at bias + b * bias_batch
   int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols;
   int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
+  int a_bcast;                  // 1: every batch reads the SAME activation rows (batch coordinate 0)
+  int kpb;                      // > 0: the reduction runs over the batches of A too, kpb k-slabs per batch (K-concatenation)
 };
 
 __global__ void __launch_bounds__(RG_THREADS, 1)
@@ -98,8 +100,10 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
         for (int j = 0; j < k_slabs; ++j) {
           mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
           mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage_bytes);
-          if (p.a_swap) tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, j * BK, b, mt * BM, &sm->f_full[pf.stage]);
-          else tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, j * BK, mt * BM, b, &sm->f_full[pf.stage]);
+          int col = j * BK, bc = p.a_bcast ? 0 : b;
+          if (p.kpb) { bc = j / p.kpb; col = (j - bc * p.kpb) * BK; }
+          if (p.a_swap) tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, bc, mt * BM, &sm->f_full[pf.stage]);
+          else tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, mt * BM, bc, &sm->f_full[pf.stage]);
           pf.next();
         }
       }
@@ -305,11 +309,14 @@ extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
   return n_cta;
 }
 
-extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
-                                int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
-                                int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream) {
+static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                               int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
+                               int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, int a_mode,
+                               int a_batches, void* stream) {
   using namespace sgc::tc;
   if (R <= 0 || B <= 0 || K <= 0 || K % BK || N <= 0 || N % 32 || !x || !y || !wpack) return (int)cudaErrorInvalidValue;
+  if (a_mode < 0 || a_mode > 2) return (int)cudaErrorInvalidValue;
+  if (a_mode == 2 && (B != 1 || a_batches <= 0 || K % a_batches || (K / a_batches) % BK)) return (int)cudaErrorInvalidValue;
   if (n_cta == 0) n_cta = sgc_rows_gemm_tc_auto_ncta(R, N, B);
   if (n_cta < 32 || n_cta > 256 || (n_cta & (n_cta - 1)) || N % n_cta) return (int)cudaErrorInvalidValue;
   if (pack_rows < N || pack_rows % 8 || pack_batch_rows % 8 || (reinterpret_cast<uintptr_t>(wpack) & 15) ||
@@ -326,7 +333,13 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
   if (!encode) return (int)cudaErrorNotSupported;
   CUtensorMap amap, omap;
   RowsGemmParams p;
-  if (!make_rows_map(encode, &amap, x, K, R, B, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
+  p.a_bcast = a_mode == 1 ? 1 : 0;
+  p.kpb = a_mode == 2 ? (K / a_batches) / BK : 0;
+  if (a_mode == 1) {
+    if (!make_rows_map(encode, &amap, x, K, R, 1, ldx, 0, &p.a_swap)) return (int)cudaErrorInvalidValue;
+  } else if (a_mode == 2) {
+    if (!make_rows_map(encode, &amap, x, K / a_batches, R, a_batches, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
+  } else if (!make_rows_map(encode, &amap, x, K, R, B, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
   if (!make_rows_map(encode, &omap, y, N, R, B, ldy, batch_y, &p.o_swap)) return (int)cudaErrorInvalidValue;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack);
   p.bias = bias;
@@ -352,6 +365,25 @@ extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x
   sgc::launch_chain(rows_gemm_tc_kernel, dim3(grid), dim3(RG_THREADS), smem, (cudaStream_t)stream, amap, omap, p);
   SGC_CUDA_CHECK_LAST();
   return 0;
+}
+
+extern "C" int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                                int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
+                                int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, void* stream) {
+  return rows_gemm_tc_launch(x, ldx, batch_x, R, K, B, wpack, pack_rows, pack_batch_elems, pack_batch_rows, bias, bias_batch, N, y,
+                             ldy, batch_y, n_cta, 0, 0, stream);
+}
+
+// a_mode 1: the B batches share ONE activation matrix x [R, K] (batch_x ignored) -- per-head products whose heads are narrower
+// than a k-slab, with the head's weights zero-extended to all K columns.  a_mode 2: B == 1 and the reduction also runs over
+// the a_batches matrices x[a][R, K / a_batches] (batch stride batch_x): y = sum_a x[a] W_a^T with wpack the packed
+// [N, K] = [W_0 | W_1 | ...] -- the per-head output products of narrow heads as one K-concatenated GEMM.
+extern "C" int sgc_rows_gemm_tc_ex(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
+                                   int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
+                                   int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, int a_mode,
+                                   int a_batches, void* stream) {
+  return rows_gemm_tc_launch(x, ldx, batch_x, R, K, B, wpack, pack_rows, pack_batch_elems, pack_batch_rows, bias, bias_batch, N, y,
+                             ldy, batch_y, n_cta, a_mode, a_batches, stream);
 }
 
 // =====================================================================================================================

@@ -99,8 +99,10 @@ ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and thei
 # all weight gradients of a layer as ONE grouped launch at the end of its backward (sgc_rows_wgrad_group_tc); 0 = one launch
 # per Linear layer as in round 1
 WGRAD_GROUP = _os.environ.get('SGC_WGRAD_GROUP', '1') != '0'
-# backward of the lift as a gather over pixel tiles (csrc/sgc_lift_tiles.cu); 0 = the scatter kernel of round 1 (REDs)
-LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '1') != '0'
+# backward of the lift as a gather over pixel tiles (csrc/sgc_lift_tiles.cu) instead of the scatter kernel (REDs into a
+# zero-filled grad_vg).  Parity-green, but its first version is latency-bound per tile (830 us vs 195 + 58 us of fill at the
+# finest ScanNet level): off by default
+LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '0') != '0'
 # output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
 # (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
 # produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
@@ -167,6 +169,38 @@ def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional
     call('sgc_rows_gemm_tc', ptr(x), K, R * K, R, K, H, ptr(wpack), H * dh, 0, dh, ptr(bias), dh, dh, ptr(y), H * dh, dh,
          n_cta, stream())
     return y
+
+
+def rows_heads_in_exp(x: torch.Tensor, wpack_exp: torch.Tensor, heads: int = NUM_HEADS, n_cta: int = 0):
+    """y [H,R,C]: y[h] = x[:, head h] @ W_h for heads NARROWER than a k-slab (16 wide): every head reads the whole row and its
+    weights are zero-extended over all C columns (``wpack_exp`` = the packed [H*C, C] matrix, C rows per head)."""
+    R, C = x.shape
+    y = torch.empty(heads, R, C, device=x.device, dtype=F32)
+    call('sgc_rows_gemm_tc_ex', ptr(x), C, 0, R, C, heads, ptr(wpack_exp), heads * C, 0, C, None, 0, C, ptr(y), C, R * C, n_cta,
+         1, 0, stream())
+    return y
+
+
+def rows_heads_out_exp(x: torch.Tensor, wpack_cat: torch.Tensor, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
+    """y [R,C] = sum_h x[h] @ Wm_h^T with Wm_h the [C,C] weight masked to the output rows of head h (``wpack_cat`` = the packed
+    [C, H*C] concatenation along K): the per-head output products of narrow heads as ONE K-concatenated GEMM."""
+    H, R, C = x.shape
+    y = torch.empty(R, C, device=x.device, dtype=F32)
+    call('sgc_rows_gemm_tc_ex', ptr(x), C, R * C, R, H * C, 1, ptr(wpack_cat), C, 0, 0, ptr(bias), 0, C, ptr(y), C, 0, n_cta, 2, H,
+         stream())
+    return y
+
+
+_HEAD_MASKS = {}
+
+
+def _head_mask(dev, C: int, heads: int) -> torch.Tensor:
+    """[heads, C] 0/1: channel c belongs to head h."""
+    key = (dev, C, heads)
+    m = _HEAD_MASKS.get(key)
+    if m is None:
+        m = _HEAD_MASKS[key] = (torch.arange(C, device=dev) // (C // heads) == torch.arange(heads, device=dev).unsqueeze(1)).to(F32)
+    return m
 
 
 def rows_wgrad(a, b, M, N, R, out, out_strides, *, B=1, lda=None, batch_a=0, ldb=None, batch_b=0, scale=1.0,
@@ -344,6 +378,16 @@ class LevelWeights:
                 self.p_wo, self.p_wo_t = j.pack(wo), j.pack(wo.t())
                 self.p_w1, self.p_w1_t = j.pack(w1), j.pack(w1.t())
                 self.p_w2, self.p_w2_t = j.pack(w2), j.pack(w2.t())
+            # heads narrower than a 32-column k-slab (dh = 16 at C = 128): the per-head products run on the same kernel with
+            # zero-extended weights (rows_heads_in_exp / rows_heads_out_exp): 8x redundant MMA work on tiny matrices instead
+            # of bf16x3 operand images (315 MB each at Q = 51 200) + library GEMMs
+            self.heads_exp = self.rows_tc and not self.heads_tc and dh % 8 == 0 and _os.environ.get('SGC_HEADS_EXP', '1') != '0'
+            if self.heads_exp:
+                hm = _head_mask(w_out.device, C, num_heads)                                          # [H, C]
+                self.p_wk_in = j.pack(((wk.t() * scale).unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
+                self.p_wv_in = j.pack((wv.t().unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
+                self.p_wv_out = j.pack((wv.unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
+                self.p_wk_out = j.pack(((wk * scale).unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
             if self.heads_tc:
                 self.p_wk = j.pack(wk, scale)                          # gqv[:, h] = gqt[h] @ (scale Wk_h)^T
                 self.p_wv = j.pack(wv)                                 # o[:, h]   = t[h] @ Wv_h^T
@@ -358,7 +402,7 @@ class LevelWeights:
                 self.wo, self.wo_t = j.split_cols(wo, 1), j.split_cols(wo.t(), 1)
                 self.w1, self.w1_t = j.split_cols(w1, 1), j.split_cols(w1.t(), 1)
                 self.w2, self.w2_t = j.split_cols(w2, 1), j.split_cols(w2.t(), 1)
-            if images or not self.heads_tc:
+            if images or not (self.heads_tc or self.heads_exp):
                 self.wk_rows = j.split_rows(wk, dh, 1, scale)  # [8,3dh,C]  qv_h @ (scale Wk_h)
                 self.wk_cols = j.split_cols(wk, 1, scale)      # [C,3C]     gqt[h] @ (scale Wk_h)^T
                 self.wv_rows = j.split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
@@ -952,8 +996,9 @@ class EncoderLayerRows(torch.autograd.Function):
         small = Q <= SMALL_ROWS
         tc = (not small) and getattr(lw, 'rows_tc', False)      # own tcgen05 GEMM for the plain Linear layers
         htc = tc and getattr(lw, 'heads_tc', False)             # ... and for the per-head key / value projections
+        hexp = tc and getattr(lw, 'heads_exp', False)           # ... of heads narrower than a k-slab (zero-extended weights)
         sp = not small and not tc                               # bf16x3 operand images for the library GEMMs
-        hsp = not small and not htc
+        hsp = not small and not (htc or hexp)
         scale = 1.0 / math.sqrt(dh)
         bq, bv = in_b[:C], in_b[2 * C:]
         wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
@@ -984,7 +1029,7 @@ class EncoderLayerRows(torch.autograd.Function):
                 g = mean.new_empty(0)
         elif tc:   # biases ride in the GEMM epilogue, no row kernel in between
             g = lin(mean, None, w_out, None, lw.p_w_out, b_out)
-            if htc:
+            if htc or hexp:
                 qv, qv_hs = lin(g, None, wq, None, lw.p_wq, bq), None
             else:
                 qv, qv_hs, _ = rowop_fwd(lin(g, None, wq, None, lw.p_wq), Q, C, bias=bq, split_heads=H)
@@ -996,6 +1041,8 @@ class EncoderLayerRows(torch.autograd.Function):
             torch.baddbmm(qt, qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C), beta=0, alpha=scale, out=qt)
         elif htc:
             qt = rows_heads_in(qv, lw.p_wk_ht, C, H)
+        elif hexp:
+            qt = rows_heads_in_exp(qv, lw.p_wk_in, H)
         else:
             qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)   # [H,Q,C]
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
@@ -1005,6 +1052,8 @@ class EncoderLayerRows(torch.autograd.Function):
              stream())
         if htc:     # o2[:, h] = t[h] @ Wv_h^T + bv_h, written straight into the [Q,C] layout
             o2, o2_s = rows_heads_out(t, lw.p_wv, dh, bv), None
+        elif hexp:
+            o2, o2_s = rows_heads_out_exp(t, lw.p_wv_out, bv), None
         else:
             if small:   # o[h] = t[h] @ Wv_h^T   [H,Q,dh]
                 o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
@@ -1041,8 +1090,9 @@ class EncoderLayerRows(torch.autograd.Function):
         small = Q <= SMALL_ROWS
         tc = (not small) and getattr(lw, 'rows_tc', False)
         htc = tc and getattr(lw, 'heads_tc', False)
+        hexp = tc and getattr(lw, 'heads_exp', False)
         sp = not small and not tc
-        hsp = not small and not htc
+        hsp = not small and not (htc or hexp)
         fp32_heads = small or HEADS_WGRAD_FP32
         wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         ws_attn, ws_ffn = ctx.wstream if ctx.wstream is not None else (None, None)
@@ -1093,6 +1143,8 @@ class EncoderLayerRows(torch.autograd.Function):
             gt = torch.bmm(go2.view(Q, H, dh).transpose(0, 1), wv.view(H, dh, C))
         elif htc:
             gt = rows_heads_in(go2, lw.p_wv_ht, C, H)                                               # [H,Q,C]
+        elif hexp:
+            gt = rows_heads_in_exp(go2, lw.p_wv_in, H)
         else:
             _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
             gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)    # [H,Q,C]
@@ -1115,6 +1167,8 @@ class EncoderLayerRows(torch.autograd.Function):
              ptr(gqt), ptr(gqt_s), stream())
         if htc:     # gqv[:, h] = gqt[h] @ (scale Wk_h)^T, written straight into the [Q,C] layout
             gqv, gqv_s = rows_heads_out(gqt, lw.p_wk, dh), None
+        elif hexp:
+            gqv, gqv_s = rows_heads_out_exp(gqt, lw.p_wk_out), None
         else:
             if small:   # gqv[h] = scale * gqt[h] @ Wk_h^T   [H,Q,dh]
                 gqv_h = torch.empty(H, Q, dh, device=dev, dtype=F32)

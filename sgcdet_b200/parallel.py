@@ -262,7 +262,8 @@ def forward_view_sharded(head, shards, group=None, forced_selection=None, use_di
             masks[i] = mask
         pls, slots_list, lw = [], [], None
         for (feats, meta, dists), proj in zip(shards, projs):
-            pre = dh_.prepare(feats[fi], dists[fi], hws[i])
+            # the sharded cross-view block runs its voxel-count GEMMs on the library path, which needs the bf16x3 images
+            pre = dh_.prepare(feats[fi], dists[fi], hws[i], images=True)
             lw = pre['lw']
             pl = SF.project_compact(proj, dh_.ref_3d, sel, meta, dbound)
             slots, _ = SF.Lift.apply(pre['vg'], pre['dist'], pre['vbias'], pre['gbias'], pl, hws[i][0], hws[i][1])

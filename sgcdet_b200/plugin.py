@@ -421,7 +421,8 @@ class DenseHead(nn.Module):
         return (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and self.embed_dims in (128, 256) and ffn.add_identity
                 and ffn.layers[0][0].out_features in (128, 256, 512))
 
-    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None, big_stream=None):
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None, big_stream=None,
+                images: Optional[bool] = None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
         map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
@@ -436,7 +437,8 @@ class DenseHead(nn.Module):
         # the fused layer runs its GEMMs on the own tcgen05 kernel from packed weights; only the unfused fallback
         # still needs the bf16x3 images of the layer weights
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
-                             ffn.layers[0][0].weight, ffn.layers[1].weight, images=not self._fused_layer(),
+                             ffn.layers[0][0].weight, ffn.layers[1].weight,
+                             images=(not self._fused_layer()) if images is None else images,
                              b_out=attn.output_proj.bias, in_b=mha.in_proj_bias)
         # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
         # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the

@@ -225,3 +225,34 @@ def test_wgrad_group_matches_fp64(cuda_lib, R, C):
     check(gw_in[:C], d(gqv).t() @ d(gg_)); check(gb_in[:C], d(gqv).sum(0))
     again = run()
     assert torch.equal(again[4], gw_in) and torch.equal(again[0][0], g_w2) and torch.equal(again[3][1], g_bout)
+
+
+@pytest.mark.parametrize('R,C', [(3200, 128), (51200, 128), (77, 128), (400, 256)])
+def test_narrow_head_products_match_fp64(cuda_lib, R, C):
+    """Per-head key / value products for heads narrower than a k-slab (16 wide at C = 128; also valid for 32): the head's
+    weights zero-extended over all C columns (a_mode 1: one shared activation matrix) and the per-head output products as one
+    K-concatenated GEMM (a_mode 2), as LevelWeights packs them."""
+    H = 8
+    dh = C // H
+    g = torch.Generator().manual_seed(R + C)
+    w_out, wo = torch.randn(C, C, generator=g).cuda(), torch.randn(C, C, generator=g).cuda()
+    in_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).cuda()
+    w1, w2 = torch.randn(2 * C, C, generator=g).cuda(), torch.randn(C, 2 * C, generator=g).cuda()
+    wcat = torch.randn(C + 128, C, generator=g).cuda()
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
+    if not getattr(lw, 'heads_exp', False):
+        pytest.skip('32-wide heads use the per-head tensor maps (heads_tc)')
+    scale = 1.0 / math.sqrt(dh)
+    wk, wv = in_w[C:2 * C].double(), in_w[2 * C:].double()
+    qv = torch.randn(R, C, generator=g).cuda()
+    t = torch.randn(H, R, C, generator=g).cuda()
+    bv = torch.randn(C, generator=g).cuda()
+    qt = SF.rows_heads_in_exp(qv, lw.p_wk_in, H)
+    gt = SF.rows_heads_in_exp(qv, lw.p_wv_in, H)
+    o2 = SF.rows_heads_out_exp(t, lw.p_wv_out, bv)
+    gqv = SF.rows_heads_out_exp(t, lw.p_wk_out)
+    torch.cuda.synchronize()
+    check(qt, torch.einsum('rhd,hdc->hrc', qv.double().view(R, H, dh), wk.view(H, dh, C)) * scale)
+    check(gt, torch.einsum('rhd,hdc->hrc', qv.double().view(R, H, dh), wv.view(H, dh, C)))
+    check(o2, torch.einsum('hrk,hdk->rhd', t.double(), wv.view(H, dh, C)).reshape(R, C) + bv.double())
+    check(gqv, torch.einsum('hrk,hdk->rhd', t.double(), wk.view(H, dh, C)).reshape(R, C) * scale)

@@ -11,9 +11,9 @@ RTOL, ATOL = 1e-3, 1e-4
 DEV = 'cuda'
 
 
-@pytest.mark.parametrize('V,parts', [(12, 2), (13, 3), (9, 9)])
-def test_view_sharded_matches_unsharded(cuda_lib, V, parts):
-    cfg = syn.CONFIGS['tiny']
+@pytest.mark.parametrize('cfg_name,V,parts', [('tiny', 12, 2), ('tiny', 13, 3), ('tiny', 9, 9), ('tiny256', 12, 2)])
+def test_view_sharded_matches_unsharded(cuda_lib, cfg_name, V, parts):
+    cfg = syn.CONFIGS[cfg_name]
     sc = syn.make_scene(cfg, V, shift_origin=True).to(DEV)
     head = plugin.build_voxel_head(cfg)
     head.load_state_dict(syn.make_state_dict(cfg))
