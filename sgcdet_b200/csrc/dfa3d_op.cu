@@ -237,6 +237,180 @@ __global__ void __launch_bounds__(256) wms_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// ---- one-stage operator, lane-parallel points (Cm % 4 == 0) -----------------------------------------
+// The generic kernels above resolve every sampling point in ALL 32 lanes (make_tap + 8 depth loads, serially over the
+// L*P points) and gather one float per lane.  Here a warp still owns one (b, q, m), but the points are spread over the
+// lanes for the parameter stage (lane = point: tap, depth scores, weights -- 32 points resolved at once), and the gather
+// stage walks the points with the lanes split as 4 corners x 8 four-channel groups: one 16-byte load per lane and point
+// covers all four corners of a 32-channel slice, the weights arrive by shuffle.  Backward: vector reductions
+// (red.global.add.v4.f32) into grad_value instead of scalar ones.
+struct PointTaps {
+  long long row[4];   // (b*S + level start + pixel) of the corner, or -1
+  float w[4];         // attention weight * bilinear weight * depth score
+};
+
+__device__ __forceinline__ void lanes_point(const float* __restrict__ dist, const int64_t* __restrict__ shapes3d,
+                                            const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                                            const float* __restrict__ attn, long long it, int pt, int npts, int b, int m, int S,
+                                            int M, int Dch, int P, Tap& t, LevelInfo& li, float (&ds)[4], float (&dlo)[4],
+                                            float (&dhi)[4], float& a, PointTaps& pt_out) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { ds[k] = 0.f; dlo[k] = 0.f; dhi[k] = 0.f; pt_out.row[k] = -1; pt_out.w[k] = 0.f; }
+  a = 0.f;
+  t.in2d = t.in3d = false;
+  li.H = li.W = li.D = 1; li.start = 0;
+  if (pt >= npts) return;
+  const int l = pt / P;
+  li = level_info(shapes3d, 3, lsi, l);
+  const long long sp = it * npts + pt;
+  const float* lp = loc + sp * 3;
+  t = make_tap(__ldg(lp), __ldg(lp + 1), __ldg(lp + 2), li.H, li.W, li.D);
+  a = __ldg(attn + sp);
+  if (!t.in2d) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.pix[k] >= 0) {
+      const long long row = (long long)b * S + li.start + t.pix[k];
+      pt_out.row[k] = row;
+      if (t.in3d) ds[k] = depth_score(t, dist + ((size_t)row * M + m) * Dch, li.D, dlo[k], dhi[k]);
+      pt_out.w[k] = a * (t.bw[k] * ds[k]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fused_fwd_lanes_kernel(const float* __restrict__ value, const float* __restrict__ dist,
+                                                              const int64_t* __restrict__ shapes3d,
+                                                              const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                                                              const float* __restrict__ attn, float* __restrict__ ds_out, int B,
+                                                              int S, int M, int Cm, int Dch, int L, int Q, int P,
+                                                              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, k = lane >> 3, cg = lane & 7;
+  const int npts = L * P;
+  const long long items = (long long)B * Q * M;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long it = w0; it < items; it += wstride) {
+    const int m = (int)(it % M);
+    const int b = (int)(it / ((long long)M * Q));
+    for (int c0 = 0; c0 < Cm; c0 += 32) {
+      const int c = c0 + cg * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p0 = 0; p0 < npts; p0 += 32) {
+        Tap t; LevelInfo li; float ds[4], dlo[4], dhi[4], a; PointTaps pt;
+        lanes_point(dist, shapes3d, lsi, loc, attn, it, p0 + lane, npts, b, m, S, M, Dch, P, t, li, ds, dlo, dhi, a, pt);
+        if (ds_out && c0 == 0 && p0 + lane < npts)
+          reinterpret_cast<float4*>(ds_out)[it * npts + p0 + lane] = make_float4(ds[0], ds[1], ds[2], ds[3]);
+        const int n = min(32, npts - p0);
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+          // corner k of point j: row and weight from the lane that resolved the point
+          long long row = -1;
+          float w = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const long long r = __shfl_sync(SGC_FULL_MASK, pt.row[kk], j);
+            const float ww = __shfl_sync(SGC_FULL_MASK, pt.w[kk], j);
+            if (kk == k) { row = r; w = ww; }
+          }
+          if (row >= 0 && w != 0.f && c < Cm) {
+            const float4 x = ldg4(value + ((size_t)row * M + m) * Cm + c);
+            acc.x += w * x.x; acc.y += w * x.y; acc.z += w * x.z; acc.w += w * x.w;
+          }
+        }
+      }
+      // sum over the four corner groups
+#pragma unroll
+      for (int o = 8; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(SGC_FULL_MASK, acc.x, o); acc.y += __shfl_xor_sync(SGC_FULL_MASK, acc.y, o);
+        acc.z += __shfl_xor_sync(SGC_FULL_MASK, acc.z, o); acc.w += __shfl_xor_sync(SGC_FULL_MASK, acc.w, o);
+      }
+      if (k == 0 && c < Cm) *reinterpret_cast<float4*>(out + it * Cm + c) = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fused_bwd_lanes_kernel(const float* __restrict__ value, const float* __restrict__ dist,
+                                                              const int64_t* __restrict__ shapes3d,
+                                                              const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                                                              const float* __restrict__ attn, const float* __restrict__ grad_out,
+                                                              int B, int S, int M, int Cm, int Dch, int L, int Q, int P,
+                                                              float* __restrict__ grad_value, float* __restrict__ grad_dist,
+                                                              float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  const int lane = threadIdx.x & 31, k = lane >> 3, cg = lane & 7;
+  const int npts = L * P;
+  const long long items = (long long)B * Q * M;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long it = w0; it < items; it += wstride) {
+    const int m = (int)(it % M);
+    const int b = (int)(it / ((long long)M * Q));
+    for (int p0 = 0; p0 < npts; p0 += 32) {
+      Tap t; LevelInfo li; float ds[4], dlo[4], dhi[4], a; PointTaps pt;
+      lanes_point(dist, shapes3d, lsi, loc, attn, it, p0 + lane, npts, b, m, S, M, Dch, P, t, li, ds, dlo, dhi, a, pt);
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};   // of THIS lane's point, filled while the warp walks the points
+      const int n = min(32, npts - p0);
+      for (int c0 = 0; c0 < Cm; c0 += 32) {
+        const int c = c0 + cg * 4;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < Cm) g = ldg4(grad_out + it * Cm + c);
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+          long long row = -1;
+          float w = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const long long r = __shfl_sync(SGC_FULL_MASK, pt.row[kk], j);
+            const float ww = __shfl_sync(SGC_FULL_MASK, pt.w[kk], j);
+            if (kk == k) { row = r; w = ww; }
+          }
+          float d = 0.f;
+          if (row >= 0 && c < Cm) {
+            const size_t o = ((size_t)row * M + m) * Cm + c;
+            const float4 x = ldg4(value + o);
+            d = x.x * g.x + x.y * g.y + x.z * g.z + x.w * g.w;
+            if (w != 0.f) red_add4(grad_value + o, w * g.x, w * g.y, w * g.z, w * g.w);
+          }
+          d += __shfl_xor_sync(SGC_FULL_MASK, d, 1);
+          d += __shfl_xor_sync(SGC_FULL_MASK, d, 2);
+          d += __shfl_xor_sync(SGC_FULL_MASK, d, 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float dk = __shfl_sync(SGC_FULL_MASK, d, kk * 8);
+            if (lane == j) dot[kk] += dk;
+          }
+        }
+      }
+      if (p0 + lane < npts) {
+        const long long sp = it * npts + p0 + lane;
+        float g_attn = 0.f, g_w = 0.f, g_h = 0.f, g_d = 0.f;
+        if (t.in2d) {
+          const float hh = 1.f - t.lh, hw = 1.f - t.lw;
+          const float e0 = ds[0] * dot[0], e1 = ds[1] * dot[1], e2 = ds[2] * dot[2], e3 = ds[3] * dot[3];
+          g_attn = t.bw[0] * e0 + t.bw[1] * e1 + t.bw[2] * e2 + t.bw[3] * e3;
+          g_w = (float)li.W * a * (-hh * e0 + hh * e1 + t.lh * e2 - t.lh * e3);
+          g_h = (float)li.H * a * (-hw * e0 - t.lw * e1 + t.lw * e2 + hw * e3);
+          if (t.in3d) {
+            float gz = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (t.pix[kk] >= 0) {
+                const float gds = a * t.bw[kk] * dot[kk];
+                const size_t o = ((size_t)pt.row[kk] * M + m) * Dch;
+                gz += gds * (dhi[kk] - dlo[kk]);
+                if (t.d0 >= 0) red_add1(grad_dist + o + t.d0, t.hd * gds);
+                if (t.d0 + 1 <= li.D - 1) red_add1(grad_dist + o + t.d0 + 1, t.ld * gds);
+              }
+            }
+            g_d = (float)li.D * gz;
+          }
+        }
+        grad_loc[sp * 3 + 0] = g_w; grad_loc[sp * 3 + 1] = g_h; grad_loc[sp * 3 + 2] = g_d;
+        grad_attn[sp] = g_attn;
+      }
+    }
+  }
+}
+
 static inline int op_grid(long long warps_needed) {
   long long blocks = (warps_needed + 7) / 8;
   const long long cap = 148LL * 16;
@@ -300,8 +474,12 @@ extern "C" int dfa3d_fused_fwd(const float* value, const float* dist, const int6
                                int P, float* out, float* depth_score_out, void* stream) {
   const long long items = (long long)B * Q * M;
   if (items == 0) return 0;
-  sgc::wms_fwd_kernel<true><<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(
-      value, dist, shapes3d, lsi, loc, attn, depth_score_out, B, S, M, Cm, D, L, Q, P, out);
+  if (Cm % 4 == 0 && (reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    sgc::fused_fwd_lanes_kernel<<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(value, dist, shapes3d, lsi, loc, attn,
+                                                                                      depth_score_out, B, S, M, Cm, D, L, Q, P, out);
+  else
+    sgc::wms_fwd_kernel<true><<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(
+        value, dist, shapes3d, lsi, loc, attn, depth_score_out, B, S, M, Cm, D, L, Q, P, out);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -312,9 +490,14 @@ extern "C" int dfa3d_fused_bwd(const float* value, const float* dist, const int6
                                float* grad_attn, void* stream) {
   const long long items = (long long)B * Q * M;
   if (items == 0) return 0;
-  sgc::wms_bwd_kernel<true><<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(
-      value, dist, shapes3d, lsi, loc, attn, nullptr, grad_out, B, S, M, Cm, D, L, Q, P, grad_value, grad_dist,
-      grad_loc, grad_attn, nullptr);
+  if (Cm % 4 == 0 && (reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(grad_value) & 15) == 0)
+    sgc::fused_bwd_lanes_kernel<<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(
+        value, dist, shapes3d, lsi, loc, attn, grad_out, B, S, M, Cm, D, L, Q, P, grad_value, grad_dist, grad_loc, grad_attn);
+  else
+    sgc::wms_bwd_kernel<true><<<sgc::op_grid(items), 256, 0, (cudaStream_t)stream>>>(
+        value, dist, shapes3d, lsi, loc, attn, nullptr, grad_out, B, S, M, Cm, D, L, Q, P, grad_value, grad_dist,
+        grad_loc, grad_attn, nullptr);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -163,9 +163,11 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     const float* __restrict__ samp, const float* __restrict__ grad_slots,
     int S, int H, int W, int D, int Q,
     float* __restrict__ grad_value, float* __restrict__ grad_G, float* __restrict__ grad_dist,
-    float* __restrict__ bias_partials) {
+    float* __restrict__ bias_partials, unsigned int* __restrict__ done_counter, float* __restrict__ grad_vbias,
+    float* __restrict__ grad_gbias) {
   constexpr int C = CPL * 32;
   __shared__ float s_part[8][C + 128];
+  __shared__ unsigned int s_ticket;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int n_pairs = __ldg(n_pairs_ptr);
@@ -309,27 +311,29 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     for (int w = 0; w < warps_per_block; ++w) a += s_part[w][c];
     bias_partials[(size_t)blockIdx.x * (C + 128) + c] = a;
   }
-}
-
-// grad_vbias[c] += sum_rows partials[row][c] (c < C);  grad_gbias[c-C] += ... (c >= C).
-// block = 32 channels x 8 row-lanes (small CTAs: they have to fit next to whatever else is resident, this launch sits
-// between lift_bwd and the projection's gradient kernels on the backward's critical path); fixed summation order.
-__global__ void __launch_bounds__(256) bias_reduce_kernel(const float* __restrict__ partials, int rows, int C,
-                                                         float* __restrict__ grad_vbias,
-                                                         float* __restrict__ grad_gbias) {
-  __shared__ float s[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float a = 0.f;
-#pragma unroll 4
-  for (int r = ry; r < rows; r += 8) a += __ldg(partials + (size_t)r * (C + 128) + c);
-  s[ry][cx] = a;
+  // The CTA that finishes LAST sums the per-CTA rows in a fixed order (deterministic) -- in here rather than in a launch of
+  // its own: that launch sat between this kernel and the projection's gradient kernels on the critical path of the
+  // backward and waited ~70 us for a free SM slot behind the coarser levels' kernels.
+  __threadfence();
   __syncthreads();
-  if (ry == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += s[k][cx];
-    if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(done_counter, 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1) {
+    __threadfence();
+    const int rows = gridDim.x;
+    for (int c = threadIdx.x; c < C + 128; c += blockDim.x) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int r = 0;
+      for (; r + 3 < rows; r += 4) {
+        a0 += __ldcg(bias_partials + (size_t)r * (C + 128) + c);
+        a1 += __ldcg(bias_partials + (size_t)(r + 1) * (C + 128) + c);
+        a2 += __ldcg(bias_partials + (size_t)(r + 2) * (C + 128) + c);
+        a3 += __ldcg(bias_partials + (size_t)(r + 3) * (C + 128) + c);
+      }
+      for (; r < rows; ++r) a0 += __ldcg(bias_partials + (size_t)r * (C + 128) + c);
+      const float t = (a0 + a1) + (a2 + a3);
+      if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
+    }
   }
 }
 
@@ -372,8 +376,12 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
+  // scratch: [grid][C + 128] partial rows, then one unsigned completion counter
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)grid * (C + 128));
+  cudaError_t me = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+  if (me != cudaSuccess) return (int)me;
 #define SGC_LIFT_BWD_ARGS value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp, grad_slots, S, H, W, D, Q, \
-                          grad_value, grad_G, grad_dist, scratch
+                          grad_value, grad_G, grad_dist, scratch, counter, grad_vbias, grad_gbias
   static const int minb = getenv("SGC_LIFT_MINB") ? atoi(getenv("SGC_LIFT_MINB")) : 2;
   if (C == 256) {
     if (minb == 2) sgc::lift_bwd_kernel<8, 2><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
@@ -383,10 +391,8 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
     sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   }
   SGC_CUDA_CHECK_LAST();
-  sgc::bias_reduce_kernel<<<(C + 128) / 32, 256, 0, st>>>(scratch, grid, C, grad_vbias, grad_gbias);
-  SGC_CUDA_CHECK_LAST();
   return 0;
 }
 
 // floats of scratch sgc_lift_bwd needs for a given pair capacity
-extern "C" int sgc_lift_bwd_scratch_floats(int cap_pairs, int C) { return lift_grid(cap_pairs) * (C + 128); }
+extern "C" int sgc_lift_bwd_scratch_floats(int cap_pairs, int C) { return lift_grid(cap_pairs) * (C + 128) + 4; }
