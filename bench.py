@@ -286,14 +286,19 @@ def run_ours(args):
         torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
                                 [g for s in scenes for g in (s['gvol'], None)])
         main.wait_stream(loss_stream)
+        if ar_in_graph:
+            allreduce_grads()      # captured with the step: no CPU launch gap between the backward and the collective
+
+    ar_in_graph = world > 1 and not args.no_grad_allreduce and not args.no_graph and args.allreduce_in_graph
+    avg_op = dist.ReduceOp.AVG if world > 1 else None
 
     def allreduce_grads():
-        # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks.  Issued on
-        # the compute stream right after the (graph-replayed) backward; NCCL is kept outside the CUDA graph.
+        # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks: one flattened
+        # NCCL all-reduce (ncclAvg) right after the backward -- captured INTO the step's CUDA graph (--allreduce-in-graph,
+        # the communicator is initialised by the eager warm-up steps first) or issued after the graph replay.
         if world > 1 and not args.no_grad_allreduce:
             flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
+            dist.all_reduce(flat, op=avg_op)
             torch._foreach_copy_([p.grad.view(-1) for p in params], list(flat.split([p.numel() for p in params])))
 
     def zero_grads():
@@ -323,7 +328,8 @@ def run_ours(args):
 
         def run_step():
             graph.replay()
-            allreduce_grads()
+            if not ar_in_graph:
+                allreduce_grads()
     else:
         def run_step():
             zero_grads()
@@ -544,7 +550,8 @@ def run_ours(args):
             'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, {B} scene(s) per GPU per step',
                        'scenes_per_gpu': B,
                        'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
-                       'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else ' + NCCL weight-grad all-reduce'),
+                       'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else
+                                                                  ' + NCCL weight-grad all-reduce' + (' (inside the CUDA graph)' if ar_in_graph else '')),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
                        'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
                                'and the loss value evaluated on a side stream beside the backward',
@@ -625,6 +632,8 @@ def view_sharded_leg(args, rank, world, dev):
     head = head.to(dev).eval()
     views = parallel.shard_views(V, world, rank)
     f, m, d = parallel.shard_scene_inputs(sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, views)
+    from sgcdet_b200 import functional as SF
+    m['sgc_projection'] = SF.compute_projection(m).to(dev)    # static device buffer: no H2D copy inside the step
     f = [t.requires_grad_(True) for t in f[:cfg.num_levels]]
     d = [t for t in d[:cfg.num_levels]]
     gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
@@ -656,6 +665,23 @@ def view_sharded_leg(args, rank, world, dev):
         return float(ms.item()), out
 
     ms, (vol, valid) = timed_eager(sharded, 3, 5, True)
+    ms_graph = None
+    if args.view_sharded_graph:
+        # the same step as ONE CUDA graph with the NCCL all-reduces captured inside (communicator warmed up above)
+        try:
+            for p in list(head.parameters()) + f:
+                p.grad = None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    vol_g, valid_g = sharded()
+            torch.cuda.current_stream().wait_stream(side)
+            ms_graph, _ = timed_eager(lambda: (g.replay(), (vol_g, valid_g))[1], 3, 10, True)
+            vol, valid = vol_g, valid_g
+        except Exception as e:
+            ms_graph = f'capture failed: {type(e).__name__}: {e}'[:200]
     chk = torch.stack([vol.detach().double().sum(), valid.double().sum()])
     lo, hi = chk.clone(), chk.clone()
     if world > 1:
@@ -672,8 +698,10 @@ def view_sharded_leg(args, rank, world, dev):
             ((v_ * gvol).sum() + head.occ_loss(o_, None, sc.geo_occ)['loss_occ']).backward()
             return v_, None
         ms1, (vol_r, _) = timed_eager(unsharded, 3, 5, False)
-        out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(ms, 3),
-                   value=round(1e3 / ms, 2), unit=UNIT, unsharded_1gpu_eager_ms=round(ms1, 3),
+        best = ms_graph if isinstance(ms_graph, float) else ms
+        out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(best, 3),
+                   ms_per_step_eager=round(ms, 3), ms_per_step_graph=round(ms_graph, 3) if isinstance(ms_graph, float) else ms_graph,
+                   value=round(1e3 / best, 2), unit=UNIT, unsharded_1gpu_eager_ms=round(ms1, 3),
                    speedup_vs_unsharded_eager=round(ms1 / ms, 3), replicas_identical=bool(torch.allclose(lo, hi, rtol=1e-6)),
                    volume_max_abs_diff_vs_unsharded=float((vol.detach() - vol_r.detach()).abs().max()),
                    collective='NCCL all-reduce (sum, max) of the cross-view partial statistics' if world > 1 else 'none (1 rank)',
@@ -859,9 +887,13 @@ def main():
     ap.add_argument('--eval-mode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-grad-allreduce', action='store_true')
+    ap.add_argument('--allreduce-in-graph', type=int, default=int(os.environ.get('SGC_ALLREDUCE_IN_GRAPH', '0')),
+                    help='1: capture the NCCL gradient all-reduce into the step graph')
     ap.add_argument('--no-view-sharded', action='store_true', help='skip the view-sharded leg (config 5)')
     ap.add_argument('--no-train-step', action='store_true', help='skip the full train-step leg (config 3)')
     ap.add_argument('--view-sharded-views', type=int, default=40)
+    ap.add_argument('--view-sharded-graph', type=int, default=int(os.environ.get('SGC_VIEW_SHARDED_GRAPH', '0')),
+                    help='1: also capture the view-sharded step (NCCL inside) into a CUDA graph')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-kernel leg and the operator micro-bench')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the e2e and instrumented passes')
     args = ap.parse_args()
