@@ -163,11 +163,9 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     const float* __restrict__ samp, const float* __restrict__ grad_slots,
     int S, int H, int W, int D, int Q,
     float* __restrict__ grad_value, float* __restrict__ grad_G, float* __restrict__ grad_dist,
-    float* __restrict__ bias_partials, unsigned int* __restrict__ done_counter, float* __restrict__ grad_vbias,
-    float* __restrict__ grad_gbias) {
+    float* __restrict__ grad_vbias, float* __restrict__ grad_gbias) {
   constexpr int C = CPL * 32;
   __shared__ float s_part[8][C + 128];
-  __shared__ unsigned int s_ticket;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int n_pairs = __ldg(n_pairs_ptr);
@@ -298,42 +296,20 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
       }
     }
   }
-  // per-CTA reduction of the bias partials (same-address REDs from ~10^4 warps serialise in L2; instead each
-  // CTA stores one row of [C + 128] partials and bias_reduce_kernel sums the rows deterministically)
+  // per-CTA reduction of the bias partials in shared memory first (same-address REDs from ~10^4 warps would serialise in L2)
   const int wid = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < CPL; ++j) s_part[wid][lane_base<CPL>(lane) + (j >> 2) * 16 + (j & 3)] = gvb[j];
   s_part[wid][C + lane * 4 + 0] = ggb.x; s_part[wid][C + lane * 4 + 1] = ggb.y;
   s_part[wid][C + lane * 4 + 2] = ggb.z; s_part[wid][C + lane * 4 + 3] = ggb.w;
   __syncthreads();
+  // one reduction per CTA and channel straight into the two bias gradients (~1200 per address over the whole kernel,
+  // fire-and-forget): a separate reduce launch sat between this kernel and the projection's gradient kernels on the critical
+  // path of the backward and waited ~70 us for a free SM slot; a last-CTA reduce of the per-CTA rows was latency-bound
   for (int c = threadIdx.x; c < C + 128; c += blockDim.x) {
     float a = 0.f;
     for (int w = 0; w < warps_per_block; ++w) a += s_part[w][c];
-    bias_partials[(size_t)blockIdx.x * (C + 128) + c] = a;
-  }
-  // The CTA that finishes LAST sums the per-CTA rows in a fixed order (deterministic) -- in here rather than in a launch of
-  // its own: that launch sat between this kernel and the projection's gradient kernels on the critical path of the
-  // backward and waited ~70 us for a free SM slot behind the coarser levels' kernels.
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(done_counter, 1u);
-  __syncthreads();
-  if (s_ticket == gridDim.x - 1) {
-    __threadfence();
-    const int rows = gridDim.x;
-    for (int c = threadIdx.x; c < C + 128; c += blockDim.x) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int r = 0;
-      for (; r + 3 < rows; r += 4) {
-        a0 += __ldcg(bias_partials + (size_t)r * (C + 128) + c);
-        a1 += __ldcg(bias_partials + (size_t)(r + 1) * (C + 128) + c);
-        a2 += __ldcg(bias_partials + (size_t)(r + 2) * (C + 128) + c);
-        a3 += __ldcg(bias_partials + (size_t)(r + 3) * (C + 128) + c);
-      }
-      for (; r < rows; ++r) a0 += __ldcg(bias_partials + (size_t)r * (C + 128) + c);
-      const float t = (a0 + a1) + (a2 + a3);
-      if (c < C) grad_vbias[c] += t; else grad_gbias[c - C] += t;
-    }
+    if (a != 0.f) red_add1(c < C ? grad_vbias + c : grad_gbias + (c - C), a);
   }
 }
 
@@ -376,12 +352,9 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
-  // scratch: [grid][C + 128] partial rows, then one unsigned completion counter
-  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)grid * (C + 128));
-  cudaError_t me = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
-  if (me != cudaSuccess) return (int)me;
+  (void)scratch;   // kept in the signature (earlier versions reduced per-CTA rows through it)
 #define SGC_LIFT_BWD_ARGS value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp, grad_slots, S, H, W, D, Q, \
-                          grad_value, grad_G, grad_dist, scratch, counter, grad_vbias, grad_gbias
+                          grad_value, grad_G, grad_dist, grad_vbias, grad_gbias
   static const int minb = getenv("SGC_LIFT_MINB") ? atoi(getenv("SGC_LIFT_MINB")) : 2;
   if (C == 256) {
     if (minb == 2) sgc::lift_bwd_kernel<8, 2><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
