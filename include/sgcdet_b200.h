@@ -360,6 +360,26 @@ int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, int N, floa
 int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
 int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);
 
+/* Peer memory over NVLink (csrc/sgc_peer.cu) -- SURVEY.md section 8e: the collectives of view sharding (partial sums /
+ * counts, score maxima, partial-softmax sums, the backward's normaliser dot and query gradient) and the weight-gradient
+ * average of scene-batch data parallelism, as ONE kernel launch each that a CUDA graph can hold.
+ *
+ * sgc_peer_alloc: a symmetric allocation of `bytes` (zero-filled; synchronises the device) and its 64-byte CUDA IPC handle.
+ * The host exchanges the handles (torch.distributed) and maps the peers' allocations with sgc_peer_open.  The first
+ * sgc_peer_sig_bytes() of an allocation are used as the signal pad of one collective "channel"; collectives on the same
+ * channel must be issued in the same order on every rank, on one stream. */
+int sgc_peer_sig_bytes(void);
+int sgc_peer_alloc(long long bytes, void** ptr, void* handle64);
+int sgc_peer_open(const void* handle64, void** ptr);
+int sgc_peer_close(void* ptr);
+int sgc_peer_free(void* ptr);
+/* One-shot all-reduce: bufs / sigs are HOST arrays of `world` device pointers -- rank r's data buffer and signal pad as mapped
+ * into this process.  out[i] = scale * sum (op 0) or max (op 1, scale ignored) over the ranks of bufs[r][i], i < n, reduced
+ * in rank order on every rank (bit-identical results everywhere).  Every rank calls it with the same n; the cross-GPU
+ * barriers are flags in the signal pads (stateless: the launch can be replayed from a CUDA graph); world <= 8. */
+int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
+                       float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,12 @@ SIGNATURES = {
     'sgc_topk_select_grid': [P, I, I, P, P, P, P],
     'sgc_occ_loss_fwd': [P, P, I, P, P],
     'sgc_occ_loss_bwd': [P, P, P, I, P, P],
+    'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, P],
+    'sgc_peer_sig_bytes': [],
+    'sgc_peer_alloc': [LL, P, P],
+    'sgc_peer_open': [P, P],
+    'sgc_peer_close': [P],
+    'sgc_peer_free': [P],
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],
 }

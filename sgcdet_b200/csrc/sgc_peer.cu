@@ -1,0 +1,145 @@
+// sgc_peer_allreduce: one-shot all-reduce over NVLink PEER MEMORY for the view-sharded cross-view statistics
+// (partial sums / counts, score maxima, partial-softmax sums -- the log-sum-exp merge -- and in the
+// backward the softmax-normaliser dot and the query gradient) and for the weight gradients of scene-batch data parallelism.
+// Every rank exposes its partial in a SYMMETRIC buffer: one cudaMalloc per rank (sgc_peer_alloc) whose CUDA IPC handle the
+// host side exchanges through torch.distributed and maps into every peer's address space (sgc_peer_open); the first
+// kPeerSigBytes of the allocation are the signal pad, the rest is data.  This kernel
+//   1. meets the peers at a barrier built from flags in the symmetric signal pads (system-scope CAS, one flag per
+//      (CTA, peer): stateless, so the kernel can be replayed from a CUDA graph -- which an NCCL call in this stack cannot),
+//   2. streams its slice of EVERY rank's buffer through 16-byte loads (peer loads bypass L1) and reduces in registers,
+//   3. writes the result to a local tensor and meets the peers again, so that the symmetric buffer may be overwritten.
+// One launch, no host involvement, no staging copies on the peers' side: the transfer IS the reduction's operand fetch.
+#include "common.cuh"
+
+#include <cstring>
+
+namespace sgc {
+
+constexpr int kPeerThreads = 512;
+constexpr int kPeerMaxWorld = 8;
+constexpr int kPeerSigOffset = 0;      // uint32 slot offset inside the signal pad the caller passes (one pad per channel)
+constexpr int kPeerMaxBlocks = 128;
+constexpr int kPeerSigBytes = kPeerMaxBlocks * kPeerMaxWorld * 4;   // one channel of flags: (CTA, peer) -> uint32
+
+struct PeerPtrs {
+  const float* buf[kPeerMaxWorld];
+  uint32_t* sig[kPeerMaxWorld];
+};
+
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int world) {
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const int peer = threadIdx.x;
+    uint32_t* send = pp.sig[peer] + kPeerSigOffset + blockIdx.x * kPeerMaxWorld + rank;
+    uint32_t* recv = pp.sig[rank] + kPeerSigOffset + blockIdx.x * kPeerMaxWorld + peer;
+    __threadfence_system();
+    while (atomicCAS_system(send, 0u, 1u) != 0u) {}
+    while (atomicCAS_system(recv, 1u, 0u) != 1u) {}
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+template <bool MAXOP>
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __grid_constant__ PeerPtrs pp, int rank, int world,
+                                                                      long long n, float scale, float* __restrict__ out) {
+  peer_barrier(pp, rank, world);      // every rank's partial is complete and visible
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    // fetched starting with the next rank (spreads the load over the links), REDUCED in rank order on every rank: all ranks
+    // get bit-identical results, which the replicated voxel chain (and its deterministic top-k) relies on
+    float4 v[kPeerMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r) {
+      if (r < world) {
+        const int p = rank + r < world ? rank + r : rank + r - world;
+        v[r] = __ldcv(reinterpret_cast<const float4*>(pp.buf[p]) + i);
+      }
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kPeerMaxWorld; ++p) {
+      if (p < world) {
+        const int r = p >= rank ? p - rank : p - rank + world;     // slot that holds rank p's value
+        float4 b = v[0];
+#pragma unroll
+        for (int q = 1; q < kPeerMaxWorld; ++q) if (q == r) b = v[q];
+        if (p == 0) a = b;
+        else if (MAXOP) { a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w); }
+        else { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      }
+    }
+    if (!MAXOP) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float a = __ldcv(pp.buf[0] + i);
+      for (int p = 1; p < world; ++p) {
+        const float b = __ldcv(pp.buf[p] + i);
+        a = MAXOP ? fmaxf(a, b) : a + b;
+      }
+      out[i] = MAXOP ? a : a * scale;
+    }
+  }
+  peer_barrier(pp, rank, world);      // nobody still reads this rank's buffer when the caller overwrites it
+}
+
+}  // namespace sgc
+
+// bufs / sigs: HOST arrays of `world` device pointers (rank r's symmetric buffer / signal pad as mapped in THIS process).
+// The reduction runs in rank order on every rank: all ranks obtain bit-identical results.  n floats, 16-byte aligned buffers.
+// op 0: out = scale * sum over ranks (scale = 1 / world averages gradients); op 1: out = max over ranks (scale ignored).
+extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
+                                  float* out, void* stream) {
+  using namespace sgc;
+  if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || n < 0 || (op != 0 && op != 1) || !out) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  PeerPtrs pp;
+  for (int r = 0; r < kPeerMaxWorld; ++r) {
+    pp.buf[r] = r < world ? reinterpret_cast<const float*>(bufs[r]) : nullptr;
+    pp.sig[r] = r < world ? reinterpret_cast<uint32_t*>(sigs[r]) : nullptr;
+    if (r < world && (!pp.buf[r] || !pp.sig[r] || (reinterpret_cast<uintptr_t>(pp.buf[r]) & 15))) return (int)cudaErrorInvalidValue;
+  }
+  if (reinterpret_cast<uintptr_t>(out) & 15) return (int)cudaErrorInvalidValue;
+  long long blocks = ((n >> 2) + kPeerThreads - 1) / kPeerThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
+  // every rank must launch the SAME grid (the barrier pairs CTA b with CTA b of the peers): it depends on n only
+  if (op == 1) peer_allreduce_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+  else peer_allreduce_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Symmetric allocations.  sgc_peer_alloc: cudaMalloc + zero fill (the flags must start at 0) + the 64-byte CUDA IPC handle
+// the peers open.  The memory is NOT torch's: the owner frees it with sgc_peer_free after every peer has closed its mapping.
+extern "C" int sgc_peer_sig_bytes() { return sgc::kPeerSigBytes; }
+
+extern "C" int sgc_peer_alloc(long long bytes, void** ptr, void* handle64) {
+  if (bytes <= 0 || !ptr || !handle64) return (int)cudaErrorInvalidValue;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+  memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return 0;
+}
+
+extern "C" int sgc_peer_open(const void* handle64, void** ptr) {
+  if (!handle64 || !ptr) return (int)cudaErrorInvalidValue;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+extern "C" int sgc_peer_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : 0; }
+extern "C" int sgc_peer_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : 0; }
