@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -289,14 +290,30 @@ def run_ours(args):
         if ar_in_graph:
             allreduce_grads()      # captured with the step: no CPU launch gap between the backward and the collective
 
-    ar_in_graph = world > 1 and not args.no_grad_allreduce and not args.no_graph and args.allreduce_in_graph
+    # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks every step.
+    #   peer (default): ONE own kernel over NVLink peer memory (sgcdet_b200/peer.py, csrc/sgc_peer.cu) captured INTO the
+    #                   step's CUDA graph -- no CPU launch gap between the backward and the collective;
+    #   nccl:           cat -> ncclAllReduce(avg) -> copy, issued by the CPU after every graph replay (round 1).
+    ar_mode = 'none' if (world == 1 or args.no_grad_allreduce) else args.grad_allreduce
+    averager = None
+    if ar_mode == 'peer':
+        from sgcdet_b200 import peer
+        try:
+            averager = peer.GradAverager(params, device=dev)
+        except Exception as e:   # no peer access between the GPUs of this box: say so and use NCCL
+            print(f'[bench] peer memory unavailable ({type(e).__name__}: {e}); falling back to NCCL', file=sys.stderr)
+            ar_mode = 'nccl'
+        ok = torch.tensor([1 if ar_mode == 'peer' else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            ar_mode, averager = 'nccl', None
+    ar_in_graph = ar_mode == 'peer' and not args.no_graph
     avg_op = dist.ReduceOp.AVG if world > 1 else None
 
     def allreduce_grads():
-        # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks: one flattened
-        # NCCL all-reduce (ncclAvg) right after the backward -- captured INTO the step's CUDA graph (--allreduce-in-graph,
-        # the communicator is initialised by the eager warm-up steps first) or issued after the graph replay.
-        if world > 1 and not args.no_grad_allreduce:
+        if ar_mode == 'peer':
+            averager()
+        elif ar_mode == 'nccl':
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat, op=avg_op)
             torch._foreach_copy_([p.grad.view(-1) for p in params], list(flat.split([p.numel() for p in params])))
@@ -551,7 +568,8 @@ def run_ours(args):
                        'scenes_per_gpu': B,
                        'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
                        'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else
-                                                                  ' + NCCL weight-grad all-reduce' + (' (inside the CUDA graph)' if ar_in_graph else '')),
+                                                                  (' + weight-grad average: one peer-memory kernel over NVLink' + (' inside the CUDA graph' if ar_in_graph else '')
+                                                                   if ar_mode == 'peer' else ' + NCCL weight-grad all-reduce after the replay')),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
                        'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
                                'and the loss value evaluated on a side stream beside the backward',
@@ -616,15 +634,16 @@ def train_step_leg(args, rank, world, dev):
 
 
 def view_sharded_leg(args, rank, world, dev):
-    """BASELINE.json configs[4]: ``SGCDet_large_ARKit`` with the V views of ONE scene split over the N ranks
-    (``sgcdet_b200.parallel.forward_view_sharded``): projection / lift local to a view's owner, the cross-view statistics
-    (sum + count, score max, partial-softmax sums -- the log-sum-exp merge -- and in the backward the softmax-normaliser dot
-    and the query gradient) all-reduced with NCCL, the voxel chain replicated.  Eager (NCCL stays outside CUDA graphs in this
-    stack), eval mode (the replicated chain must be identical on every rank), device-timed, max over ranks.  Rank 0 also times
-    the unsharded eager step of the same scene on its GPU for comparison."""
+    """BASELINE.json configs[4]: ``SGCDet_large_ARKit`` with the V views of ONE scene split over the N ranks: projection / lift
+    local to a view's owner, the cross-view statistics (sum + count, score max, partial-softmax sums -- the log-sum-exp merge --
+    and in the backward the softmax-normaliser dot and the query gradient) exchanged as single kernel launches over NVLink peer
+    memory (``sgcdet_b200/peer.py``) inside the fused level, the voxel chain replicated; the parameter gradients that are
+    partial sums over views are reduced the same way.  The whole step (forward + backward + all exchanges) is ONE CUDA graph.
+    Eval mode (the replicated chain must be identical on every rank), device-timed, max over ranks.  Rank 0 also times the
+    unsharded step of the same scene (one CUDA graph as well) on its GPU and compares volume and gradients."""
     import torch.distributed as dist
-    from sgcdet_b200 import parallel, plugin, synthetic as syn
-    cfg = syn.CONFIGS['SGCDet_large_ARKit']
+    from sgcdet_b200 import functional as SF, parallel, plugin, synthetic as syn
+    cfg = syn.CONFIGS[args.view_sharded_config]
     V = args.view_sharded_views
     sc = syn.make_scene(cfg, V, shift_origin=True).to(dev)
     head = plugin.build_voxel_head(cfg)
@@ -632,82 +651,100 @@ def view_sharded_leg(args, rank, world, dev):
     head = head.to(dev).eval()
     views = parallel.shard_views(V, world, rank)
     f, m, d = parallel.shard_scene_inputs(sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, views)
-    from sgcdet_b200 import functional as SF
     m['sgc_projection'] = SF.compute_projection(m).to(dev)    # static device buffer: no H2D copy inside the step
     f = [t.requires_grad_(True) for t in f[:cfg.num_levels]]
     d = [t for t in d[:cfg.num_levels]]
     gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    xch = parallel.ViewShardExchange(head, device=dev)
+    params = list(head.parameters())
 
-    def sharded():
-        for p in list(head.parameters()) + f:
-            p.grad = None
-        vol, valid, occ = parallel.forward_view_sharded(head, [(f, m, d)])
-        loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
-        loss.backward()
-        parallel.allreduce_view_sharded_gradients(head)
-        return vol, valid
+    def make_step(feats, meta, dists, shard):
+        def step():
+            vol, valid, occ = head(feats, meta, dists, view_shard=shard)
+            loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
+            loss.backward()
+            if shard is not None:
+                shard.reduce_gradients(head)
+            return vol, valid
+        return step
 
-    def timed_eager(fn, warm, steps, sync_ranks):
+    def capture(step, inputs):
+        """Eager warm-up on a side stream, then the step as one CUDA graph; returns (replay, outputs, 'graph' | 'eager: why')."""
+        def zero():
+            for p in params + inputs:
+                p.grad = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                zero()
+                out = step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if args.no_graph:
+            return (lambda: (zero(), step())[1]), out, 'eager (--no-graph)'
+        try:
+            zero()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = step()
+            return (lambda: (g.replay(), out)[1]), out, 'one CUDA graph'
+        except Exception as e:   # say so and time the eager step instead
+            torch.cuda.synchronize()
+            return (lambda: (zero(), step())[1]), out, f'eager (capture failed: {type(e).__name__}: {e})'[:200]
+
+    def timed(fn, warm, steps, sync_ranks):
         for _ in range(warm):
-            out = fn()
+            fn()
         torch.cuda.synchronize()
         if sync_ranks and world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            out = fn()
+            fn()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
         if sync_ranks and world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
+        return float(ms.item())
 
-    ms, (vol, valid) = timed_eager(sharded, 3, 5, True)
-    ms_graph = None
-    if args.view_sharded_graph:
-        # the same step as ONE CUDA graph with the NCCL all-reduces captured inside (communicator warmed up above)
-        try:
-            for p in list(head.parameters()) + f:
-                p.grad = None
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(g, stream=side):
-                    vol_g, valid_g = sharded()
-            torch.cuda.current_stream().wait_stream(side)
-            ms_graph, _ = timed_eager(lambda: (g.replay(), (vol_g, valid_g))[1], 3, 10, True)
-            vol, valid = vol_g, valid_g
-        except Exception as e:
-            ms_graph = f'capture failed: {type(e).__name__}: {e}'[:200]
-    chk = torch.stack([vol.detach().double().sum(), valid.double().sum()])
+    replay, (vol, valid), mode = capture(make_step(f, m, d, xch), f)
+    ms = timed(replay, 3, 20, True)
+    xch.mem.check()
+    # every rank must hold the same volume / valid mask, and complete parameter gradients
+    gnames = [n_ for n_, p in head.named_parameters() if p.grad is not None]
+    gflat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).clone()
+    chk = torch.stack([vol.detach().double().sum(), valid.double().sum(), gflat.double().sum()])
     lo, hi = chk.clone(), chk.clone()
     if world > 1:
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    vol_s = vol.detach().clone()
     out = None
     if rank == 0:
         feats = [t.clone().requires_grad_(True) for t in sc.mlvl_feats[:cfg.num_levels]]
-
-        def unsharded():
-            for p in list(head.parameters()) + feats:
-                p.grad = None
-            v_, _, o_ = head(feats, sc.img_meta, sc.mlvl_dpt_dists[:cfg.num_levels])
-            ((v_ * gvol).sum() + head.occ_loss(o_, None, sc.geo_occ)['loss_occ']).backward()
-            return v_, None
-        ms1, (vol_r, _) = timed_eager(unsharded, 3, 5, False)
-        best = ms_graph if isinstance(ms_graph, float) else ms
-        out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(best, 3),
-                   ms_per_step_eager=round(ms, 3), ms_per_step_graph=round(ms_graph, 3) if isinstance(ms_graph, float) else ms_graph,
-                   value=round(1e3 / best, 2), unit=UNIT, unsharded_1gpu_eager_ms=round(ms1, 3),
-                   speedup_vs_unsharded_eager=round(ms1 / ms, 3), replicas_identical=bool(torch.allclose(lo, hi, rtol=1e-6)),
-                   volume_max_abs_diff_vs_unsharded=float((vol.detach() - vol_r.detach()).abs().max()),
-                   collective='NCCL all-reduce (sum, max) of the cross-view partial statistics' if world > 1 else 'none (1 rank)',
-                   mode='eager, eval, fwd+bwd, device-timed, max over ranks')
+        meta_full = dict(sc.img_meta)
+        meta_full['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)
+        replay1, (vol_r, _), mode1 = capture(make_step(feats, meta_full, sc.mlvl_dpt_dists[:cfg.num_levels], None), feats)
+        ms1 = timed(replay1, 3, 20, False)
+        gref = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+        gdiff = float((gflat - gref).norm() / gref.norm().clamp(min=1e-30))
+        out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(ms, 3),
+                   value=round(1e3 / ms, 2), unit='volumes/s', mode=mode + ', eval, fwd+bwd, device-timed, max over ranks',
+                   unsharded_1gpu_ms=round(ms1, 3), unsharded_mode=mode1, speedup_vs_unsharded=round(ms1 / ms, 3),
+                   replicas_identical=bool(torch.equal(lo, hi)),
+                   volume_max_abs_diff_vs_unsharded=float((vol_s - vol_r.detach()).abs().max()),
+                   param_grad_rel_diff_vs_unsharded=gdiff, param_grads_compared=len(gnames),
+                   collective='none (1 rank)' if world == 1 else
+                   'own one-launch all-reduce over NVLink peer memory (sum, max), 5 exchanges per level + 1 for the partial '
+                   'parameter gradients, inside the graph',
+                   exchange_bytes_per_rank_per_step=int(4 * sum(2 * q * (cfg.embed_dims + 8) + q * (cfg.embed_dims + 1) + 2 * q * 8
+                                                                for q in [math.prod(cfg.n_voxels_list[0])] + list(cfg.topk_list))))
     if world > 1:
         dist.barrier()
+    xch.close()
     return out
 
 
@@ -887,13 +924,12 @@ def main():
     ap.add_argument('--eval-mode', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-grad-allreduce', action='store_true')
-    ap.add_argument('--allreduce-in-graph', type=int, default=int(os.environ.get('SGC_ALLREDUCE_IN_GRAPH', '0')),
-                    help='1: capture the NCCL gradient all-reduce into the step graph')
+    ap.add_argument('--grad-allreduce', default=os.environ.get('SGC_GRAD_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
+                    help='N > 1: weight-gradient average as one peer-memory kernel inside the CUDA graph, or NCCL after the replay')
     ap.add_argument('--no-view-sharded', action='store_true', help='skip the view-sharded leg (config 5)')
     ap.add_argument('--no-train-step', action='store_true', help='skip the full train-step leg (config 3)')
     ap.add_argument('--view-sharded-views', type=int, default=40)
-    ap.add_argument('--view-sharded-graph', type=int, default=int(os.environ.get('SGC_VIEW_SHARDED_GRAPH', '0')),
-                    help='1: also capture the view-sharded step (NCCL inside) into a CUDA graph')
+    ap.add_argument('--view-sharded-config', default='SGCDet_large_ARKit')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-kernel leg and the operator micro-bench')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the e2e and instrumented passes')
     args = ap.parse_args()

@@ -267,6 +267,10 @@ int sgc_cvs_bwd_qt(const float* slots, const float* alpha, const float* galpha, 
 int sgc_cvs_bwd_slots(const float* qt, const float* alpha, const float* gscore, const int* pair_index, int V, int Q,
                       int C, const float* grad_t, const float* grad_mean, const int* count_glob, float* grad_slots,
                       void* stream);
+/* Finishing step after an exchange: y[r,c] = x[r,c] / max(s[r, c / (C/heads)], smin) (+ bias[c]); heads == 1 may also emit
+ * cnt[r] = (int)s[r] (the global view count).  x / y / bias 16-byte aligned, (C / heads) % 4 == 0. */
+int sgc_rows_headscale(const float* x, const float* s, int heads, float smin, const float* bias, int R, int C, float* y,
+                       int* cnt, void* stream);
 
 /* nn.LayerNorm backward over voxel rows [R,C] (the two norms of VoxFormerLayer, ENC:262-340), C in {128, 256}:
  * gx fully written; `partial` (sgc_layernorm_bwd_scratch_floats(R,C) floats) receives per-CTA sums that
@@ -369,6 +373,7 @@ int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, vo
  * sgc_peer_sig_bytes() of an allocation are used as the signal pad of one collective "channel"; collectives on the same
  * channel must be issued in the same order on every rank, on one stream. */
 int sgc_peer_sig_bytes(void);
+int sgc_peer_status_offset(void);   /* uint32 in the pad: 1 after a barrier gave up waiting (~4 s) for a peer */
 int sgc_peer_alloc(long long bytes, void** ptr, void* handle64);
 int sgc_peer_open(const void* handle64, void** ptr);
 int sgc_peer_close(void* ptr);

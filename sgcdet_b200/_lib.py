@@ -73,6 +73,7 @@ SIGNATURES = {
     'sgc_cvs_bwd_dot': [P, P, P, P, I, I, I, P, P, P, P, P],
     'sgc_cvs_bwd_qt': [P, P, P, P, P, I, I, I, P, P, P],
     'sgc_cvs_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P, P],
+    'sgc_rows_headscale': [P, P, I, F, P, I, I, P, P, P],
     'sgc_upsample2x_occ_fwd': [P, I, I, I, I, P, P, P, P, P],
     'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
     'sgc_upsample2x_occ_gradw': [P, I, I, I, I, P, P, P],
@@ -86,6 +87,7 @@ SIGNATURES = {
     'sgc_occ_loss_bwd': [P, P, P, I, P, P],
     'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, P],
     'sgc_peer_sig_bytes': [],
+    'sgc_peer_status_offset': [],
     'sgc_peer_alloc': [LL, P, P],
     'sgc_peer_open': [P, P],
     'sgc_peer_close': [P],

@@ -512,6 +512,30 @@ __global__ void __launch_bounds__(kCvWarps * 32) cvs_bwd_qt_kernel(const float* 
   for (int h = 0; h < 8; ++h) store_row_cv<CPL>(gqt + h * hq + off, gq[h]);
 }
 
+// Finishing step after an exchange of view sharding: y[r, c] = x[r, c] / max(s[r, c / (C / heads)], smin) (+ bias[c]) --
+// the mean over ALL views from the reduced sums and counts (heads = 1, smin = 1; cnt[r] = (int)s[r] is emitted for the row
+// masks of the layer), the softmax normalisation of the reduced per-head output partials (heads = 8, smin = 1e-30, bias =
+// the value in-projection's), and the matching scaling of the upstream gradient in the backward.
+__global__ void __launch_bounds__(256) rows_headscale_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                             int heads, float smin, const float* __restrict__ bias, int R,
+                                                             int C, float* __restrict__ y, int* __restrict__ cnt) {
+  const int c4 = C >> 2;
+  const long long n4 = (long long)R * c4;
+  const int dh = C / heads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), c = (int)(i - (long long)r * c4) * 4;
+    const float d = fmaxf(__ldg(s + (size_t)r * heads + c / dh), smin);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    reinterpret_cast<float4*>(y)[i] = v;
+    if (cnt && c == 0) cnt[r] = (int)__ldg(s + (size_t)r * heads);
+  }
+}
+
 }  // namespace sgc
 
 #define SGC_CV_LAUNCH(KERNEL, ...)                                                              \
@@ -610,4 +634,17 @@ extern "C" int sgc_cvs_bwd_slots(const float* qt, const float* alpha, const floa
                                  int Q, int C, const float* grad_t, const float* grad_mean, const int* count_glob,
                                  float* grad_slots, void* stream) {
   SGC_CV_LAUNCH2(attn_bwd_slots_kernel, qt, alpha, gscore, pair_index, V, Q, grad_t, grad_mean, grad_slots, count_glob);
+}
+
+extern "C" int sgc_rows_headscale(const float* x, const float* s, int heads, float smin, const float* bias, int R, int C,
+                                  float* y, int* cnt, void* stream) {
+  if (R <= 0 || C <= 0 || heads <= 0 || C % heads || (C / heads) % 4 || !x || !s || !y) return (int)cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15)
+    return (int)cudaErrorInvalidValue;
+  const long long n4 = (long long)R * (C >> 2);
+  long long grid = (n4 + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  sgc::rows_headscale_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, s, heads, smin, bias, R, C, y, cnt);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
 }

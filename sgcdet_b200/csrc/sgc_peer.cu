@@ -19,7 +19,9 @@ constexpr int kPeerThreads = 512;
 constexpr int kPeerMaxWorld = 8;
 constexpr int kPeerSigOffset = 0;      // uint32 slot offset inside the signal pad the caller passes (one pad per channel)
 constexpr int kPeerMaxBlocks = 128;
-constexpr int kPeerSigBytes = kPeerMaxBlocks * kPeerMaxWorld * 4;   // one channel of flags: (CTA, peer) -> uint32
+constexpr int kPeerStatusSlot = kPeerMaxBlocks * kPeerMaxWorld;     // uint32 after the flags: 1 = a barrier timed out
+constexpr int kPeerSigBytes = kPeerMaxBlocks * kPeerMaxWorld * 4 + 256;   // flags (CTA, peer) -> uint32, then the status word
+constexpr long long kPeerSpinCycles = 8000000000ll;                  // ~4 s at 1.9 GHz
 
 struct PeerPtrs {
   const float* buf[kPeerMaxWorld];
@@ -33,8 +35,17 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int w
     uint32_t* send = pp.sig[peer] + kPeerSigOffset + blockIdx.x * kPeerMaxWorld + rank;
     uint32_t* recv = pp.sig[rank] + kPeerSigOffset + blockIdx.x * kPeerMaxWorld + peer;
     __threadfence_system();
-    while (atomicCAS_system(send, 0u, 1u) != 0u) {}
-    while (atomicCAS_system(recv, 1u, 0u) != 1u) {}
+    // a peer that never arrives (died, different launch order) must not hang the GPU: give up after ~4 s and record it in
+    // the status word of the OWN pad (PeerMemory.check() reads it); the result of this launch is then garbage
+    const long long t0 = clock64();
+    bool dead = false;
+    while (atomicCAS_system(send, 0u, 1u) != 0u) {
+      if (clock64() - t0 > kPeerSpinCycles) { dead = true; break; }
+    }
+    while (!dead && atomicCAS_system(recv, 1u, 0u) != 1u) {
+      if (clock64() - t0 > kPeerSpinCycles) { dead = true; break; }
+    }
+    if (dead) atomicExch_system(pp.sig[rank] + kPeerStatusSlot, 1u);
     __threadfence_system();
   }
   __syncthreads();
@@ -117,6 +128,8 @@ extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, in
 // Symmetric allocations.  sgc_peer_alloc: cudaMalloc + zero fill (the flags must start at 0) + the 64-byte CUDA IPC handle
 // the peers open.  The memory is NOT torch's: the owner frees it with sgc_peer_free after every peer has closed its mapping.
 extern "C" int sgc_peer_sig_bytes() { return sgc::kPeerSigBytes; }
+// byte offset of the status word inside the signal pad (0 = fine, 1 = a barrier gave up waiting for a peer)
+extern "C" int sgc_peer_status_offset() { return sgc::kPeerStatusSlot * 4; }
 
 extern "C" int sgc_peer_alloc(long long bytes, void** ptr, void* handle64) {
   if (bytes <= 0 || !ptr || !handle64) return (int)cudaErrorInvalidValue;

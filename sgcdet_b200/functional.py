@@ -162,10 +162,11 @@ def rows_heads_in(x: torch.Tensor, wpack_heads: torch.Tensor, N: int, heads: int
     return y
 
 
-def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
+def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional[torch.Tensor] = None, n_cta: int = 0,
+                   out: Optional[torch.Tensor] = None):
     """y [R,H*dh]: y[:, h*dh:(h+1)*dh] = x[h] @ W[h*dh:(h+1)*dh]^T (+ bias) with ``wpack`` = the packed [H*dh,K] weight."""
     H, R, K = x.shape
-    y = torch.empty(R, H * dh, device=x.device, dtype=F32)
+    y = torch.empty(R, H * dh, device=x.device, dtype=F32) if out is None else out
     call('sgc_rows_gemm_tc', ptr(x), K, R * K, R, K, H, ptr(wpack), H * dh, 0, dh, ptr(bias), dh, dh, ptr(y), H * dh, dh,
          n_cta, stream())
     return y
@@ -181,11 +182,12 @@ def rows_heads_in_exp(x: torch.Tensor, wpack_exp: torch.Tensor, heads: int = NUM
     return y
 
 
-def rows_heads_out_exp(x: torch.Tensor, wpack_cat: torch.Tensor, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
+def rows_heads_out_exp(x: torch.Tensor, wpack_cat: torch.Tensor, bias: Optional[torch.Tensor] = None, n_cta: int = 0,
+                       out: Optional[torch.Tensor] = None):
     """y [R,C] = sum_h x[h] @ Wm_h^T with Wm_h the [C,C] weight masked to the output rows of head h (``wpack_cat`` = the packed
     [C, H*C] concatenation along K): the per-head output products of narrow heads as ONE K-concatenated GEMM."""
     H, R, C = x.shape
-    y = torch.empty(R, C, device=x.device, dtype=F32)
+    y = torch.empty(R, C, device=x.device, dtype=F32) if out is None else out
     call('sgc_rows_gemm_tc_ex', ptr(x), C, R * C, R, H * C, 1, ptr(wpack_cat), C, 0, 0, ptr(bias), 0, C, ptr(y), C, 0, n_cta, 2, H,
          stream())
     return y
@@ -970,6 +972,16 @@ def _ln_params(partial, R, N):
     return gg, gb
 
 
+def rows_headscale(x, s_, heads: int, smin: float, bias=None, want_count: bool = False):
+    """``sgc_rows_headscale``: y[r,c] = x[r,c] / max(s[r, head of c], smin) (+ bias[c]); with ``want_count`` (heads == 1)
+    also the int32 view counts (int)s[r].  The finishing step after an exchange of view sharding."""
+    R, C = x.shape
+    y = torch.empty(R, C, device=x.device, dtype=F32)
+    cnt = torch.empty(R, device=x.device, dtype=torch.int32) if want_count else None
+    call('sgc_rows_headscale', ptr(x), ptr(s_), heads, smin, ptr(bias), R, C, ptr(y), ptr(cnt), stream())
+    return (y, cnt) if want_count else y
+
+
 class EncoderLayerRows(torch.autograd.Function):
     """One VoxFormerLayer over the selected voxel rows (encoder.py:262-340 with operation_order cross_attn, norm, ffn,
     norm): masked mean over views -> output_proj -> 8-head attention pooling over views (DCA:815-837) -> LayerNorm ->
@@ -986,7 +998,13 @@ class EncoderLayerRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2,
-                lw, wstream, eps1, eps2, masks, drops):
+                lw, wstream, eps1, eps2, masks, drops, coll=None):
+        """``coll`` (view sharding, ``parallel.ViewShardExchange``): ``slots`` / ``pl`` hold only the views this rank owns;
+        every statistic over views becomes (local partial, written straight into peer memory) -> one all-reduce launch ->
+        (local finish).  Exchanged per level: sums + counts [Q,C+1], score maxima [Q,8], the per-head value products of the
+        partial softmax sums together with the normalisers [Q,C+8] (the per-head projection is applied to the PARTIAL sums:
+        8x fewer bytes on the links than the [8,Q,C] sums themselves), and in the backward the normaliser dot [Q,8] and the
+        query gradient after its per-head projection [Q,C]."""
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
         H = NUM_HEADS
@@ -1010,10 +1028,21 @@ class EncoderLayerRows(torch.autograd.Function):
                 return rows_linear(a, pk, w.shape[0], bias)
             return a @ w.t() if small else torch.mm(a_s, ws.t(), out_dtype=F32)
 
-        mean = torch.empty(Q, C, device=dev, dtype=F32)
-        mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
-        call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
-        fqo = htc and getattr(lw, 'fuse_qo', False)
+        if coll is not None and not (htc or hexp):
+            raise RuntimeError('sgcdet_b200: view sharding needs the tensor-core layer path (embed_dims 128 or 256, > SMALL_ROWS rows)')
+        cnt = pl.count
+        if coll is None:
+            mean = torch.empty(Q, C, device=dev, dtype=F32)
+            mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
+            call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
+        else:
+            # exchange 1: sums over the local views + local view counts -> mean over ALL views, global counts
+            call('sgc_crossview_sum_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(coll.view((Q, C))), stream())
+            coll.view((Q,), Q * C).copy_(pl.count)
+            red = coll.reduce(Q * C + Q, 'sum')
+            mean, cnt = rows_headscale(red[:Q * C].view(Q, C), red[Q * C:], 1, 1.0, want_count=True)
+            mean_s = None
+        fqo = htc and getattr(lw, 'fuse_qo', False) and coll is None
         if fqo:  # one GEMM on the chain; g (an input of the weight gradients only) is produced beside it
             qv, qv_hs = rows_linear(mean, lw.p_wqo, C, lw.bqo), None
             g = None
@@ -1048,9 +1077,28 @@ class EncoderLayerRows(torch.autograd.Function):
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
         t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
-        call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
-             stream())
-        if htc:     # o2[:, h] = t[h] @ Wv_h^T + bv_h, written straight into the [Q,C] layout
+        ssm = None
+        if coll is not None:
+            # exchange 2: score maxima; exchange 3: the partial softmax sums -- the log-sum-exp merge without a rescale pass.
+            # t = this rank's UNNORMALISED partial sum_v e_v s_v, alpha = e (both finished in the backward with ssm)
+            sc = torch.empty(pl.cap, H, device=dev, dtype=F32)
+            call('sgc_cvs_scores', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(sc), ptr(coll.view((Q, H))), stream())
+            m = coll.reduce(Q * H, 'max')
+            call('sgc_cvs_accum', ptr(sc), ptr(m), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(alpha),
+                 ptr(coll.view((Q, H), Q * C)), ptr(t), stream())
+            if htc:
+                rows_heads_out(t, lw.p_wv, dh, out=coll.view((Q, C)))
+            else:
+                rows_heads_out_exp(t, lw.p_wv_out, out=coll.view((Q, C)))
+            red = coll.reduce(Q * C + Q * H, 'sum')
+            ssm = red[Q * C:].view(Q, H)
+            o2, o2_s = rows_headscale(red[:Q * C].view(Q, C), ssm, H, 1e-30, bv), None
+        else:
+            call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
+                 stream())
+        if coll is not None:
+            pass
+        elif htc:   # o2[:, h] = t[h] @ Wv_h^T + bv_h, written straight into the [Q,C] layout
             o2, o2_s = rows_heads_out(t, lw.p_wv, dh, bv), None
         elif hexp:
             o2, o2_s = rows_heads_out_exp(t, lw.p_wv_out, bv), None
@@ -1062,7 +1110,7 @@ class EncoderLayerRows(torch.autograd.Function):
             o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
         # rows no view sees are zeroed (DCA:819-835) straight from the per-voxel view count
         x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
-                                  rowcount=pl.count, ln=(g1, be1, eps1), want_split=sp)
+                                  rowcount=cnt, ln=(g1, be1, eps1), want_split=sp)
         hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1, getattr(lw, 'p_w1', None)), Q, Fh, bias=b1, relu=True, mask=m1,
                                   mscale=s1, want_split=sp)
         y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2, getattr(lw, 'p_w2', None)), Q, C, bias=b2, mask=m2, mscale=s2,
@@ -1070,6 +1118,7 @@ class EncoderLayerRows(torch.autograd.Function):
         ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2,
                               w_out, in_w, wo, w1, w2)
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
+        ctx.coll, ctx.ssm, ctx.cnt = coll, ssm, cnt
         ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
         return y
 
@@ -1078,6 +1127,7 @@ class EncoderLayerRows(torch.autograd.Function):
         (slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2,
          w_out, in_w, wo, w1, w2) = ctx.saved_tensors
         pl, lw = ctx.pl, ctx.lw
+        coll, ssm, cnt = ctx.coll, ctx.ssm, ctx.cnt
         m0, m1, m2 = ctx.masks
         s0, s1, s2 = ctx.scales
         Q, V = pl.Q, pl.V
@@ -1109,6 +1159,8 @@ class EncoderLayerRows(torch.autograd.Function):
         # all seven weight-gradient products of the layer as ONE grouped launch at the end of this backward (also the per-head
         # key / value products of the 16-wide heads, which the per-layer launches leave to the library)
         grouped = wtc and WGRAD_GROUP and not getattr(lw, 'fuse_qo', False) and dh % 16 == 0
+        if coll is not None and not grouped:
+            raise RuntimeError('sgcdet_b200: view sharding needs the grouped weight-gradient launch (SGC_WGRAD_GROUP=1)')
         hwtc = wtc and htc and not grouped
         lgrads = linear_grads_tc if wtc else linear_grads
         if True:
@@ -1125,7 +1177,7 @@ class EncoderLayerRows(torch.autograd.Function):
                 g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
             gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
             gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
-                                               rowcount=pl.count, want_split=sp)
+                                               rowcount=cnt, want_split=sp)
             g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
             if not grouped:
                 g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
@@ -1163,9 +1215,31 @@ class EncoderLayerRows(torch.autograd.Function):
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
         gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
-        call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
-             ptr(gqt), ptr(gqt_s), stream())
-        if htc:     # gqv[:, h] = gqt[h] @ (scale Wk_h)^T, written straight into the [Q,C] layout
+        if coll is not None:
+            # exchange 4: the softmax-normaliser dot D[q,h] = sum over ALL views of alpha g_alpha; exchange 5: the query
+            # gradient, after its per-head projection (linear, so it applies to the partial sums).  `alpha` arrives as e.
+            a_n = torch.empty(pl.cap, H, device=dev, dtype=F32)
+            galpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
+            call('sgc_cvs_bwd_dot', ptr(slots), ptr(alpha), ptr(ssm), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(a_n), ptr(galpha),
+                 ptr(coll.view((Q, H))), stream())
+            dsum = coll.reduce(Q * H, 'sum')
+            call('sgc_cvs_bwd_qt', ptr(slots), ptr(a_n), ptr(galpha), ptr(dsum), ptr(pl.pair_index), V, Q, C, ptr(gscore), ptr(gqt),
+                 stream())
+            alpha = a_n
+            if htc:
+                rows_heads_out(gqt, lw.p_wk, dh, out=coll.view((Q, C)))
+            else:
+                rows_heads_out_exp(gqt, lw.p_wk_out, out=coll.view((Q, C)))
+            gqv, gqv_s = coll.reduce(Q * C, 'sum').view(Q, C), None
+            # the value-weight gradient pairs this rank's unnormalised partial t with go2 / ssm (per head): sum over ranks =
+            # go_h^T (sum_ranks t / ssm)
+            go2_n = rows_headscale(go2, ssm, H, 1e-30)
+        else:
+            call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
+                 ptr(gqt), ptr(gqt_s), stream())
+        if coll is not None:
+            pass
+        elif htc:   # gqv[:, h] = gqt[h] @ (scale Wk_h)^T, written straight into the [Q,C] layout
             gqv, gqv_s = rows_heads_out(gqt, lw.p_wk, dh), None
         elif hexp:
             gqv, gqv_s = rows_heads_out_exp(gqt, lw.p_wk_out), None
@@ -1204,8 +1278,12 @@ class EncoderLayerRows(torch.autograd.Function):
                 g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
             gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
         gslots = torch.empty_like(slots)
-        call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
-             ptr(gmean), ptr(gslots), stream())
+        if coll is not None:
+            call('sgc_cvs_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gmean),
+                 ptr(cnt), ptr(gslots), stream())
+        else:
+            call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
+                 ptr(gmean), ptr(gslots), stream())
         if grouped:
             def _group():
                 G = WgradGroup(Q, dev)
@@ -1215,8 +1293,12 @@ class EncoderLayerRows(torch.autograd.Function):
                 w1g = G.linear(gh, x1)
                 wog = G.linear(gout, o2)
                 # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
-                G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh,
-                      bias_out=gb_in[2 * C:], bias_from=2)
+                if coll is not None:   # partial over this rank's views (summed over the ranks after the backward)
+                    G.add(t, go2_n, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh)
+                    gb_in[2 * C:].copy_(colsum(go2))
+                else:
+                    G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh,
+                          bias_out=gb_in[2 * C:], bias_from=2)
                 # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
                 G.add(gqt, qv, C, dh, gw_in[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh, scale=scale)
                 G.linear(gqv, g, gw_in[:C], gb_in[:C])
@@ -1224,7 +1306,7 @@ class EncoderLayerRows(torch.autograd.Function):
                 G.launch()
                 return w2g + w1g + wog + woutg + (gw_in, gb_in)
             g_w2, g_b2, g_w1, g_b1, g_wo, g_bo, g_wout, g_bout, g_in_w, g_in_b = side.run(
-                _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean)
+                _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean, *((go2_n,) if coll is not None else ()))
             if side.detached and side_f.detached and side_f.side != side.side:
                 # the FFN parameters are aliased on the second weight stream: it only has to follow the grouped launch
                 side_f.side.wait_stream(side.side)
@@ -1237,7 +1319,7 @@ class EncoderLayerRows(torch.autograd.Function):
                                                torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
         side.join()
         return (gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -10,8 +10,12 @@
   GEMMs / LN / FFN / upsample / top-k are replicated, so every rank holds the same volume and the same
   (deterministic) selection.
 
-The same code drives a real process group (one shard per rank, NCCL) and an in-process simulation (several shards in
-one process, no group) -- the latter is how the single-GPU tests check the sharded math against the unsharded path.
+Two drivers of the same kernels:
+* ``ViewShardExchange`` + ``AdaptiveSparseHead.forward(..., view_shard=...)``: the product path.  The exchanges are single
+  kernel launches over NVLink peer memory inside the fused encoder layer (``functional.EncoderLayerRows``), on the own
+  tensor-core GEMMs, side streams and all; the whole step is one CUDA graph.
+* ``forward_view_sharded`` + ``Collective``: the reference formulation (eager, library GEMMs, NCCL / gloo or an in-process
+  simulation with several shards in one process) the single-GPU and CPU tests check the sharded math with.
 """
 from __future__ import annotations
 
@@ -224,6 +228,74 @@ def allreduce_view_sharded_gradients(head: torch.nn.Module, group=None) -> None:
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, group=group)
     torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
+
+
+class ViewShardExchange:
+    """The exchange steps of view sharding over NVLink peer memory (``sgcdet_b200.peer``): one symmetric buffer per rank,
+    every exchange ONE kernel launch, so the whole sharded step -- collectives included -- is captured into one CUDA graph.
+
+    Usage (one process per GPU, every rank holds the views ``shard_views(V, world, rank)`` of the SAME scene)::
+
+        xch = ViewShardExchange(head)                                   # once
+        vol, valid, occ = head(feats_local, meta_local, dists_local, view_shard=xch)
+        loss.backward()
+        xch.reduce_gradients(head)        # lift-side + per-head key / value weights hold partial sums over the views
+
+    The per-voxel chain is replicated: run it in eval mode or with identical RNG state on the ranks (FFN dropout)."""
+
+    def __init__(self, head, group=None, device=None, mem=None):
+        """``mem``: an existing ``peer.PeerMemory`` to use instead of allocating one (it has to hold ``required_bytes(head)``)."""
+        from . import peer
+        if mem is not None:
+            self.mem, self.device = mem, mem.device
+            return
+        self.mem = peer.PeerMemory(self.required_bytes(head), group, device)
+        self.device = self.mem.device
+
+    @staticmethod
+    def required_bytes(head) -> int:
+        C = head.embed_dims
+        rows = [head.base_heads[0].num_voxels] + [min(k, h.num_voxels) for k, h in zip(head.topk_list, head.base_heads[1:])]
+        rows += [h.num_voxels for h in head.base_heads[1 + len(head.topk_list):]]
+        n_grad = sum(p.numel() for p in head.parameters())
+        return 4 * max(max(rows) * (C + H) + 16, n_grad + 16)
+
+    def view(self, shape, offset_floats: int = 0) -> torch.Tensor:
+        return self.mem.view(shape, 4 * offset_floats)
+
+    def reduce(self, n: int, op: str) -> torch.Tensor:
+        out = torch.empty(n, device=self.device, dtype=F32)
+        return self.mem.all_reduce(n, out, op)
+
+    @staticmethod
+    def partial_gradients(head):
+        """The gradient tensors that hold PARTIAL sums over this rank's views after a view-sharded backward: the four
+        projection layers of the deformable attention (they act on the per-view feature maps) and the key / value rows of
+        ``attention_pooling.in_proj_weight`` (their products run over the per-view softmax partials)."""
+        out = []
+        for n_, p in head.named_parameters():
+            if p.grad is None:
+                continue
+            if any(k in n_ for k in LIFT_SIDE_PARAMS):
+                out.append(p.grad.view(-1))
+            elif n_.endswith('attention_pooling.in_proj_weight'):
+                C = p.shape[1]
+                out.append(p.grad[C:].reshape(-1))     # rows [C, 3C): key and value projections (a contiguous view)
+        return out
+
+    def reduce_gradients(self, head) -> None:
+        grads = self.partial_gradients(head)
+        if not grads or self.mem.world == 1:
+            return
+        sizes = [g.numel() for g in grads]
+        n = sum(sizes)
+        buf = self.view((n,))
+        torch._foreach_copy_(list(buf.split(sizes)), grads)
+        red = self.reduce(n, 'sum')
+        torch._foreach_copy_(grads, list(red.split(sizes)))
+
+    def close(self):
+        self.mem.close()
 
 
 def forward_view_sharded(head, shards, group=None, forced_selection=None, use_dist: Optional[bool] = None):

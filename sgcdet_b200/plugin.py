@@ -476,7 +476,7 @@ class DenseHead(nn.Module):
                     stream=cur, big=big_stream, params=params, wstream=wstream, masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
-                     proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None):
+                     proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None, coll=None):
         """feat [1,V,C,H0,W0] (uncropped), dpt_dist [1,V,D,H0,W0], hw = cropped (h,w), sel [Q] int32 or None.
         Returns y [Q,C] (rows of the dense volume at ``sel``)."""
         assert feat.shape[0] == 1  # bs == 1 (DenseHead.py:60)
@@ -509,8 +509,10 @@ class DenseHead(nn.Module):
                 widths = (C, ffn.layers[0][0].out_features, C)
                 if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
                     masks = _dropout_masks(pl.Q, widths, drops, feat.device)
-            x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops)
+            x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops, coll)
         else:
+            if coll is not None:
+                raise RuntimeError('sgcdet_b200: view sharding needs the fused encoder layer (SGC_FUSED_LAYER=1)')
             wa, wf = ws if ws is not None else (None, None)
             x = SF.CrossView.apply(slots, pl, *pp[:6], lw, wa)
             x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
@@ -566,8 +568,13 @@ class AdaptiveSparseHead(nn.Module):
         self.loss = nn.BCELoss()
 
     def forward(self, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection: Optional[List] = None,
-                return_intermediates: bool = False):
+                return_intermediates: bool = False, view_shard=None):
         """-> (volume [1,C,X,Y,Z], valid [1,1,X,Y,Z] int64, occ_preds [1, sum N]).
+
+        ``view_shard`` (``parallel.ViewShardExchange``): the inputs hold only the views THIS rank owns (config 5); the
+        cross-view statistics are exchanged over peer memory inside the level (``functional.EncoderLayerRows``), every rank
+        returns the same volume / valid / occ_preds, and ``view_shard.reduce_gradients(head)`` completes the parameter
+        gradients after the backward.
 
         ``forced_selection[i]`` (int32 ascending voxel ids) overrides the top-k of level i (parity tests).
         The returned volume is a channels_last_3d view of the internal [X,Y,Z,C] buffer.
@@ -581,11 +588,13 @@ class AdaptiveSparseHead(nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError('sgcdet_b200 has no CPU implementation: inputs must be CUDA tensors')
         with torch.cuda.device(dev):   # launches use the current device's current stream (_lib.stream)
-            return self._forward_streams(dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+            return self._forward_streams(dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates,
+                                         view_shard)
 
-    def _forward_streams(self, dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates):
+    def _forward_streams(self, dev, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates,
+                         view_shard=None):
         if os.environ.get('SGC_CHAIN_PRIORITY', '1') == '0':
-            return self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+            return self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates, view_shard)
         caller = torch.cuda.current_stream(dev)
         key = (torch.device(dev), caller.cuda_stream)
         chain = _CHAIN_STREAMS.get(key)
@@ -593,14 +602,14 @@ class AdaptiveSparseHead(nn.Module):
             chain = _CHAIN_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
         chain.wait_stream(caller)
         with torch.cuda.stream(chain):
-            out = self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates)
+            out = self._forward_impl(mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates, view_shard)
         caller.wait_stream(chain)
         for t in out[:3]:
             if isinstance(t, torch.Tensor):
                 t.record_stream(caller)
         return out
 
-    def _forward_impl(self, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates):
+    def _forward_impl(self, mlvl_feats, img_meta, mlvl_dpt_dists, forced_selection, return_intermediates, view_shard=None):
         bs = mlvl_feats[0].shape[0]
         assert bs == 1
         nl = len(self.base_heads)
@@ -615,11 +624,16 @@ class AdaptiveSparseHead(nn.Module):
         main = torch.cuda.current_stream(dev)
         streams = _side_streams(dev, nl, main) if os.environ.get('SGC_SIDE_PREPARE', '1') != '0' else [main] * nl
         lvl_streams = _level_chain_streams(dev, nl, main) if os.environ.get('SGC_LEVEL_STREAMS', '1') != '0' else None
+        if view_shard is not None:
+            # the exchanges of all levels share one signal pad and must run in the same order on every rank: all three
+            # per-voxel chains stay on ONE stream (also in the backward, where autograd replays them on it)
+            lvl_streams = None
 
         def level_rows(i, head, fi, hw, sel, pre):
             """forward_rows of level i on that level's own chain stream (see _level_chain_streams)."""
             if lvl_streams is None:
-                return head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre)
+                return head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre,
+                                         view_shard)
             s = lvl_streams[i]
             s.wait_stream(main)
             for t in (sel, proj, pre['vg'], pre['dist'], pre['vbias'], pre['gbias']) + tuple(pre.get('masks') or ()):
