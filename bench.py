@@ -212,6 +212,34 @@ def kernel_algorithmic_bytes(name: str, args, n_pairs_by_q: dict) -> float:
 # our arm
 # -------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads (and, by the kernel's local-allocation policy plus an explicit preferred-node policy,
+    its pinned staging buffers) to the NUMA node the GPU's PCIe root hangs off.  Round 1's e2e scaled 3.4x on 8 GPUs because
+    every rank's 270 MB of pinned inputs lived on node 0.  Returns the node or None (single-node host / not discoverable)."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        try:   # set_mempolicy(MPOL_PREFERRED, {node}): pinned allocations made from now on land on the GPU's node
+            import ctypes
+            mask = ctypes.c_ulong(1 << node)
+            ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+        except Exception:
+            pass
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from sgcdet_b200 import plugin, synthetic as syn
@@ -226,6 +254,7 @@ def run_ours(args):
         build.build()   # no-op when the in-tree library is up to date (it normally travels with the snapshot)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     cfg = syn.CONFIGS[args.config]
@@ -576,7 +605,7 @@ def run_ours(args):
                        'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
                        'cuda_graph': not args.no_graph, 'gemm': 'all GEMMs of the path are own tcgen05/TMEM/TMA kernels with the bf16 hi/lo split in shared memory and fp32 accumulation: feature-map projection (forward, data gradient, weight gradient) and the voxel-count layers (forward, data and weight gradients; 16-wide heads of the -L configs keep a library bf16 GEMM for the per-head products)', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                    'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'numa_node_rank0': numa_node,
                     'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),

@@ -364,6 +364,29 @@ int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, int N, floa
 int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
 int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);
 
+/* ---- the depth-distribution producer in front of the path (csrc/sgc_depth.cu) ----------------
+ * Plane-sweep cost volume of DepthNet_Fusion (mmdet3d_plugin/models/im2voxel/depth_utils/depth_est_fusion.py:85-126 homo_warping,
+ * :209-232 loop over the neighbour frames), fused: corr[v,d,y,x] = 1/(K sqrt(C)) sum_k sum_c f[v,c,y,x] *
+ * grid_sample(f[nbr[v,k]], H_{v,k,d}(x,y))[c].  feat_cl = channel-last [V, H*W, C] (C % 4 == 0, C <= 512, 16-byte aligned);
+ * nbr [V,K] int32 neighbour view ids; rt [V,K,12] = rows of (src_proj @ inverse(ref_proj))[:3,:3] then [:3,3]; depth [D]
+ * (D <= 32); corr [V,D,H,W].  The backward zero-fills grad_feat_cl ([V, H*W, C]) and accumulates both roles of a feature row. */
+int sgc_plane_sweep_fwd(const float* feat_cl, const int* nbr, const float* rt, const float* depth, int V, int K, int D, int H,
+                        int W, int C, float* corr, void* stream);
+int sgc_plane_sweep_bwd(const float* feat_cl, const int* nbr, const float* rt, const float* depth, const float* grad_corr, int V,
+                        int K, int D, int H, int W, int C, float* grad_feat_cl, void* stream);
+/* [B,C,S] <-> [B,S,C] tiled transposes (the FPN's NCHW maps <-> the channel-last gather layout). */
+int sgc_nchw_to_nhwc(const float* in, int B, int C, int S, float* out, void* stream);
+int sgc_nhwc_to_nchw(const float* in, int B, int C, int S, float* out, void* stream);
+/* softmax over the depth bins (depth_est_fusion.py:241) + the nearest x1/2, x1/4 pyramid of SGCDet.build_volume
+ * (detectors/SGCDet.py:83-85) + the cropped channel-last layout [V, h_l*w_l, D] the lift kernels read.  logits [V,D,H,W];
+ * prob [V,D,H,W] or NULL; cl_l NULL = level not wanted; (h_l, w_l) <= ceil((H, W) / 2^l).  Backward: grad_prob / gcl_l may be
+ * NULL. */
+int sgc_depth_pyramid_fwd(const float* logits, int V, int D, int H, int W, float* prob, float* cl0, int h0, int w0, float* cl1,
+                          int h1, int w1, float* cl2, int h2, int w2, void* stream);
+int sgc_depth_pyramid_bwd(const float* logits, int V, int D, int H, int W, const float* grad_prob, const float* gcl0, int h0,
+                          int w0, const float* gcl1, int h1, int w1, const float* gcl2, int h2, int w2, float* grad_logits,
+                          void* stream);
+
 /* Peer memory over NVLink (csrc/sgc_peer.cu) -- SURVEY.md section 8e: the collectives of view sharding (partial sums /
  * counts, score maxima, partial-softmax sums, the backward's normaliser dot and query gradient) and the weight-gradient
  * average of scene-batch data parallelism, as ONE kernel launch each that a CUDA graph can hold.

@@ -1429,3 +1429,78 @@ class ScatterAddRows(torch.autograd.Function):
         gy = torch.empty(sel.numel(), ctx.C, device=gvol.device, dtype=torch.float32)
         call('sgc_gather_rows', ptr(gvol), ptr(sel), ptr(gy), sel.numel(), ctx.C, stream())
         return gvol, gy, None
+
+
+# ----------------------------------------------------------------------------------------------
+# the depth-distribution producer in front of the path (csrc/sgc_depth.cu)
+# ----------------------------------------------------------------------------------------------
+
+@dataclass
+class DepthCL:
+    """A depth distribution already in the layout the lift kernels read: ``t`` [V, h*w, D] channel-last, cropped to (h, w).
+    ``DenseHead.prepare`` takes it in place of the reference's [1,V,D,H0,W0] tensor and skips its permute copy."""
+    t: torch.Tensor
+    h: int
+    w: int
+
+
+class PlaneSweep(torch.autograd.Function):
+    """corr [V,D,H,W] = plane-sweep correlation of the matching features ``feat`` [V,C,H,W] with their neighbour frames
+    (depth_est_fusion.py:85-126,209-232): ``nbr`` [V,K] int32, ``rt`` [V,K,12] (rows of src_proj @ inverse(ref_proj)),
+    ``depth`` [D].  One fused kernel each way on a channel-last copy of the map; the warped features never exist."""
+
+    @staticmethod
+    def forward(ctx, feat, nbr, rt, depth):
+        V, C, H, W = feat.shape
+        K, D = nbr.shape[1], depth.numel()
+        feat = feat.contiguous()
+        fcl = torch.empty(V, H * W, C, device=feat.device, dtype=F32)
+        call('sgc_nchw_to_nhwc', ptr(feat), V, C, H * W, ptr(fcl), stream())
+        corr = torch.empty(V, D, H, W, device=feat.device, dtype=F32)
+        call('sgc_plane_sweep_fwd', ptr(fcl), ptr(nbr), ptr(rt), ptr(depth), V, K, D, H, W, C, ptr(corr), stream())
+        ctx.save_for_backward(fcl, nbr, rt, depth)
+        ctx.dims = (V, C, H, W, K, D)
+        return corr
+
+    @staticmethod
+    def backward(ctx, gcorr):
+        fcl, nbr, rt, depth = ctx.saved_tensors
+        V, C, H, W, K, D = ctx.dims
+        gcl = torch.empty_like(fcl)
+        call('sgc_plane_sweep_bwd', ptr(fcl), ptr(nbr), ptr(rt), ptr(depth), ptr(gcorr.contiguous()), V, K, D, H, W, C, ptr(gcl),
+             stream())
+        gfeat = torch.empty(V, C, H, W, device=fcl.device, dtype=F32)
+        call('sgc_nhwc_to_nchw', ptr(gcl), V, C, H * W, ptr(gfeat), stream())
+        return gfeat, None, None, None
+
+
+class DepthPyramid(torch.autograd.Function):
+    """(prob [V,D,H,W], cl_0, cl_1, cl_2) from the depth logits [V,D,H,W]: softmax over D (depth_est_fusion.py:241), the
+    nearest x1/2 and x1/4 levels of SGCDet.build_volume (SGCDet.py:83-85) and, per level, the channel-last crop
+    [V, h*w, D] the lift kernels read -- one kernel each way.  ``crops`` = ((h, w) of the full, half and quarter level)."""
+
+    @staticmethod
+    def forward(ctx, logits, crops):
+        V, D, H, W = logits.shape
+        logits = logits.contiguous()
+        prob = torch.empty_like(logits)
+        cl = [torch.empty(V, h * w, D, device=logits.device, dtype=F32) for h, w in crops]
+        (h0, w0), (h1, w1), (h2, w2) = crops
+        call('sgc_depth_pyramid_fwd', ptr(logits), V, D, H, W, ptr(prob), ptr(cl[0]), h0, w0, ptr(cl[1]), h1, w1, ptr(cl[2]), h2, w2,
+             stream())
+        ctx.save_for_backward(logits)
+        ctx.crops = crops
+        ctx.set_materialize_grads(False)
+        return (prob, *cl)
+
+    @staticmethod
+    def backward(ctx, gprob, g0, g1, g2):
+        (logits,) = ctx.saved_tensors
+        V, D, H, W = logits.shape
+        (h0, w0), (h1, w1), (h2, w2) = ctx.crops
+        c = lambda t: None if t is None else t.contiguous()
+        gprob, g0, g1, g2 = c(gprob), c(g0), c(g1), c(g2)
+        gl = torch.empty_like(logits)
+        call('sgc_depth_pyramid_bwd', ptr(logits), V, D, H, W, ptr(gprob), ptr(g0), h0, w0, ptr(g1), h1, w1, ptr(g2), h2, w2, ptr(gl),
+             stream())
+        return gl, None

@@ -443,7 +443,12 @@ class DenseHead(nn.Module):
         # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
         # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
         # depth gradient's copies instead of queueing behind them on the same stream
-        dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
+        if isinstance(dpt_dist, SF.DepthCL):   # produced channel-last and cropped by sgcdet_b200.depth.depth_pyramid
+            if (dpt_dist.h, dpt_dist.w) != (h, w):
+                raise ValueError(f'sgcdet_b200: depth level cropped to {(dpt_dist.h, dpt_dist.w)}, the level needs {(h, w)}')
+            dist = dpt_dist.t
+        else:
+            dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw, big_stream)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain

@@ -14,7 +14,7 @@ RTOL, ATOL = 1e-3, 1e-4
 DEV = 'cuda'
 
 
-@pytest.mark.parametrize('world,n', [(1, 1000), (2, 4), (2, 100003), (4, 65536 + 7), (8, 3 * 1024 * 1024 + 1)])
+@pytest.mark.parametrize('world,n', [(1, 1000), (2, 4), (2, 100003), (4, 65536 + 7), (8, 40000 + 3), (2, 3 * 1024 * 1024 + 1)])
 def test_peer_allreduce_simulated_ranks(cuda_lib, world, n):
     mems = peer.PeerMemory.simulate(world, 4 * n)
     try:
