@@ -557,7 +557,7 @@ def run_ours(args):
                           how='eval mode, teacher-forced with the oracle selection, same scene and weights')
 
     # ---- the reference's own kernels on the same GPU (rank 0, N == 1, after the timed region) ---------------
-    ref_gpu, op_bench = None, None
+    ref_gpu, op_bench, depth_bench = None, None, None
     if rank == 0 and world == 1 and not args.no_reference_gpu:
         try:
             from oracle import gpu_ref
@@ -570,6 +570,10 @@ def run_ours(args):
             op_bench = operator_bench(dev)
         except Exception as e:
             op_bench = dict(unavailable=f'{type(e).__name__}: {e}'[:200])
+        try:
+            depth_bench = depth_producer_bench(dev)
+        except Exception as e:
+            depth_bench = dict(unavailable=f'{type(e).__name__}: {e}'[:200])
 
     # ---- config 5: view-sharded aggregation of ONE scene over the N ranks (every rank takes part) ---------
     vs = None
@@ -612,7 +616,7 @@ def run_ours(args):
             'clocks': clk, 'roofline': roof, 'path_roofline': path_roof, 'kernels': kernels, 'cpu_baseline': cpu,
             'loss': round(loss_val, 4), 'loss_check': loss_check,
             'loss_vs_oracle_rel': None if loss_check is None else loss_check['loss_vs_oracle_rel'],
-            'reference_gpu': ref_gpu, 'operator_bench': op_bench, 'view_sharded': vs, 'train_step': ts,
+            'reference_gpu': ref_gpu, 'operator_bench': op_bench, 'depth_producer_bench': depth_bench, 'view_sharded': vs, 'train_step': ts,
         }
         print(json.dumps(line))
     if world > 1:
@@ -687,14 +691,15 @@ def view_sharded_leg(args, rank, world, dev):
     xch = parallel.ViewShardExchange(head, device=dev)
     params = list(head.parameters())
 
-    def make_step(feats, meta, dists, shard):
+    def make_step(feats, meta, dists, shard, forced=None, want_sel=False):
         def step():
-            vol, valid, occ = head(feats, meta, dists, view_shard=shard)
+            out = head(feats, meta, dists, view_shard=shard, forced_selection=forced, return_intermediates=want_sel)
+            vol, valid, occ = out[:3]
             loss = (vol * gvol).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']
             loss.backward()
             if shard is not None:
                 shard.reduce_gradients(head)
-            return vol, valid
+            return (vol, valid, out[3]) if want_sel else (vol, valid)
         return step
 
     def capture(step, inputs):
@@ -739,36 +744,62 @@ def view_sharded_leg(args, rank, world, dev):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- parity first (untimed, eager): the unsharded step of the whole scene on rank 0 fixes the voxel selection; every
+    # rank then runs the sharded step teacher-forced with it (a free-running top-k may legitimately pick different voxels
+    # among near-ties, which makes volumes incomparable), and rank 0 compares volume and every parameter gradient
+    feats = [t.clone().requires_grad_(True) for t in sc.mlvl_feats[:cfg.num_levels]]
+    meta_full = dict(sc.img_meta)
+    meta_full['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)
+    dists_full = sc.mlvl_dpt_dists[:cfg.num_levels]
+    sels = [torch.empty(min(k, h.num_voxels), device=dev, dtype=torch.int32) for k, h in zip(head.topk_list, head.base_heads[1:])]
+    vol_r = gref = None
+    if rank == 0:
+        vol_r, _, its = make_step(feats, meta_full, dists_full, None, want_sel=True)()
+        gref = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).clone()
+        vol_r = vol_r.detach().clone()
+        for dst, it in zip(sels, its[1:]):
+            dst.copy_(it['sel'])
+    if world > 1:
+        for t in sels:
+            dist.broadcast(t, src=0)
+    for p in params + f:
+        p.grad = None
+    vol_f, valid_f = make_step(f, m, d, xch, forced=[None] + sels)()
+    torch.cuda.synchronize()
+    xch.mem.check()
+    gflat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).clone()
+    n_grads = sum(1 for p in params if p.grad is not None)
+    parity = None
+    if rank == 0:
+        parity = dict(volume_max_abs_diff_vs_unsharded=float((vol_f.detach() - vol_r).abs().max()),
+                      volume_rel_diff_vs_unsharded=float((vol_f.detach() - vol_r).norm() / vol_r.norm()),
+                      param_grad_rel_diff_vs_unsharded=float((gflat - gref).norm() / gref.norm().clamp(min=1e-30)),
+                      param_grads_compared=n_grads, how='eager, teacher-forced with the unsharded selection')
+
+    # ---- timed: free-running selection, the whole step one CUDA graph ------------------------------------------------------
     replay, (vol, valid), mode = capture(make_step(f, m, d, xch), f)
     ms = timed(replay, 3, 20, True)
     xch.mem.check()
-    # every rank must hold the same volume / valid mask, and complete parameter gradients
-    gnames = [n_ for n_, p in head.named_parameters() if p.grad is not None]
-    gflat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).clone()
-    chk = torch.stack([vol.detach().double().sum(), valid.double().sum(), gflat.double().sum()])
+    # replicated chain: volume / valid mask AND (after reduce_gradients) every parameter gradient bit-identical on all ranks
+    gflat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+    chk = torch.stack([vol.detach().double().sum(), vol.detach().double().abs().sum(), valid.double().sum(),
+                       gflat.double().sum(), gflat.double().abs().sum()])
     lo, hi = chk.clone(), chk.clone()
     if world > 1:
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    vol_s = vol.detach().clone()
     out = None
     if rank == 0:
-        feats = [t.clone().requires_grad_(True) for t in sc.mlvl_feats[:cfg.num_levels]]
-        meta_full = dict(sc.img_meta)
-        meta_full['sgc_projection'] = SF.compute_projection(sc.img_meta).to(dev)
-        replay1, (vol_r, _), mode1 = capture(make_step(feats, meta_full, sc.mlvl_dpt_dists[:cfg.num_levels], None), feats)
+        replay1, _, mode1 = capture(make_step(feats, meta_full, dists_full, None), feats)
         ms1 = timed(replay1, 3, 20, False)
-        gref = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-        gdiff = float((gflat - gref).norm() / gref.norm().clamp(min=1e-30))
         out = dict(config=cfg.name, views=V, n_gpus=world, views_per_rank=len(views), ms_per_step=round(ms, 3),
                    value=round(1e3 / ms, 2), unit='volumes/s', mode=mode + ', eval, fwd+bwd, device-timed, max over ranks',
                    unsharded_1gpu_ms=round(ms1, 3), unsharded_mode=mode1, speedup_vs_unsharded=round(ms1 / ms, 3),
-                   replicas_identical=bool(torch.equal(lo, hi)),
-                   volume_max_abs_diff_vs_unsharded=float((vol_s - vol_r.detach()).abs().max()),
-                   param_grad_rel_diff_vs_unsharded=gdiff, param_grads_compared=len(gnames),
+                   replicas_identical=dict(volume=bool(torch.equal(lo[:3], hi[:3])), gradients=bool(torch.equal(lo[3:], hi[3:]))),
+                   parity=parity,
                    collective='none (1 rank)' if world == 1 else
-                   'own one-launch all-reduce over NVLink peer memory (sum, max), 5 exchanges per level + 1 for the partial '
-                   'parameter gradients, inside the graph',
+                   'own one-launch all-reduce over NVLink peer memory (sum, max), 5 exchanges per level + 1 for the parameter '
+                   'gradients, inside the graph',
                    exchange_bytes_per_rank_per_step=int(4 * sum(2 * q * (cfg.embed_dims + 8) + q * (cfg.embed_dims + 1) + 2 * q * 8
                                                                 for q in [math.prod(cfg.n_voxels_list[0])] + list(cfg.topk_list))))
     if world > 1:
@@ -900,6 +931,78 @@ def operator_bench(dev, iters: int = 5):
                     'reference_gbs': gbs(r_b, 2 * maps + perq), 'ours_gbs': gbs(m_b, 2 * maps + perq),
                     'note': 'both sides include the zero-fill of their gradient buffers (caller-zeroed contract, F3D:319-339)'},
             'max_abs_diff': {'out': err[0], 'grad_value': err[1], 'grad_dist': err[2]}}
+
+
+def depth_producer_bench(dev, iters: int = 5):
+    """SURVEY.md 8f rank 1 at the SGCDet_ScanNet shape (V=40 frames, 128 matching channels on the 60x80 map, K=2 neighbours,
+    D=12 depth bins): the fused plane-sweep kernels + the softmax / pyramid kernel against the reference FORMULATION in eager
+    PyTorch on the same GPU (oracle/depth_ref.py: homography grids + F.grid_sample + the [V,C,D,H,W] product, which is what
+    depth_est_fusion.py:85-126,218-232 executes).  Algorithmic bytes = feature map read + correlation written (forward),
+    + gradient map written and correlation gradient read (backward)."""
+    from oracle import depth_ref
+    from sgcdet_b200 import depth as SD, functional as SF, synthetic as syn
+    cfg = syn.CONFIGS['SGCDet_ScanNet']
+    V, C, H, W, K = 40, 128, 60, 80, 2
+    g = torch.Generator().manual_seed(99)
+    meta = syn.make_img_meta(cfg, V, g)
+    base = meta['lidar2img']['extrinsic'][0]
+    ext = []
+    for i in range(V):           # a video-like trajectory: consecutive frames overlap
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3], T[2, 3] = 0.04 * i, -0.02 * i
+        ext.append((T @ base).astype(np.float32))
+    meta['lidar2img']['extrinsic'] = ext
+    depth = SD.depth_bin_centers(cfg.dbound)
+    D = int(depth.shape[0])
+    f = torch.randn(V, C, H, W, generator=g).to(dev)
+    gc = torch.randn(V, D, H, W, generator=g).to(dev)
+    intr = depth_ref.feature_intrinsic(torch.tensor(meta['lidar2img']['intrinsic']), meta['img_shape'], meta['ori_shape'], 4).to(dev)
+    w2c = torch.tensor(np.stack(ext)).to(dev)
+    dv = torch.tensor(depth).to(dev)
+
+    def t_ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    fo = f.clone().requires_grad_(True)
+    fr = f.clone().requires_grad_(True)
+    ours = SD.plane_sweep_correlation(fo, meta, 4, K, depth)
+    ref = depth_ref.plane_sweep_correlation(fr, w2c, intr, dv, K)
+    ours.backward(gc, retain_graph=True)
+    ref.backward(gc, retain_graph=True)
+    diff = dict(correlation=float((ours - ref).abs().max()), grad_feat=float((fo.grad - fr.grad).abs().max()),
+                inside_fraction=float((ref != 0).float().mean()))
+    with torch.no_grad():
+        ms_f = t_ms(lambda: SD.plane_sweep_correlation(f, meta, 4, K, depth))
+        ms_fr = t_ms(lambda: depth_ref.plane_sweep_correlation(f, w2c, intr, dv, K))
+
+    def bwd(x, y):
+        x.grad = None
+        y.backward(gc, retain_graph=True)
+    ms_b = t_ms(lambda: bwd(fo, ours))
+    ms_br = t_ms(lambda: bwd(fr, ref))
+    bf = 4.0 * (V * C * H * W + V * D * H * W)
+    logits = torch.randn(V, D, H, W, generator=g).to(dev)
+    crops = tuple(SD.pyramid_crops(meta))
+    with torch.no_grad():
+        ms_p = t_ms(lambda: SF.DepthPyramid.apply(logits, crops))
+        ms_pr = t_ms(lambda: depth_ref.depth_pyramid(logits, crops))
+    bp = 4.0 * V * D * (2 * H * W + sum(h * w for h, w in crops))
+    return dict(shape=f'V={V} C={C} HxW={H}x{W} K={K} D={D} (configs/SGCDet_ScanNet.py:3,91)',
+                plane_sweep_fwd=dict(reference_formulation_ms=round(ms_fr, 3), ours_fused_ms=round(ms_f, 3),
+                                     ours_gbs=round(bf / ms_f / 1e6, 1)),
+                plane_sweep_bwd=dict(reference_formulation_ms=round(ms_br, 3), ours_fused_ms=round(ms_b, 3),
+                                     ours_gbs=round(2 * bf / ms_b / 1e6, 1)),
+                softmax_pyramid_fwd=dict(reference_formulation_ms=round(ms_pr, 3), ours_fused_ms=round(ms_p, 3),
+                                         ours_gbs=round(bp / ms_p / 1e6, 1)),
+                max_abs_diff=diff)
 
 
 def run_reference(args):

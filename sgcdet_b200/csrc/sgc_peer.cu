@@ -11,6 +11,7 @@
 // One launch, no host involvement, no staging copies on the peers' side: the transfer IS the reduction's operand fetch.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace sgc {
@@ -97,6 +98,67 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __gr
   peer_barrier(pp, rank, world);      // nobody still reads this rank's buffer when the caller overwrites it
 }
 
+// Two-shot variant for more than two ranks and large payloads: every rank reduces ONE slice of the buffer (reading that
+// slice from all ranks, writing the result into its own symmetric buffer in place), the ranks meet again, and every rank
+// collects the world reduced slices: 2 (W-1)/W n words cross the links per rank instead of (W-1) n.  CTA b of every rank
+// works on the same element subset of every slice in both phases, so the per-CTA flags are all the synchronisation needed.
+struct PeerPtrsRW {
+  float* buf[kPeerMaxWorld];
+  uint32_t* sig[kPeerMaxWorld];
+};
+
+template <bool MAXOP>
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_2shot_kernel(const __grid_constant__ PeerPtrsRW pw, int rank,
+                                                                            int world, long long n, float scale,
+                                                                            float* __restrict__ out) {
+  PeerPtrs pp;
+#pragma unroll
+  for (int r = 0; r < kPeerMaxWorld; ++r) { pp.buf[r] = pw.buf[r]; pp.sig[r] = pw.sig[r]; }
+  peer_barrier(pp, rank, world);
+  const long long n4 = n >> 2;
+  const long long per = (n4 + world - 1) / world;          // float4 elements per slice
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // phase 1: my slice, reduced in rank order, written back into MY buffer
+  for (long long j = j0; j < per; j += stride) {
+    const long long i = (long long)rank * per + j;
+    if (i >= n4) break;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kPeerMaxWorld; ++p) {
+      if (p < world) {
+        const float4 b = __ldcv(reinterpret_cast<const float4*>(pw.buf[p]) + i);
+        if (p == 0) a = b;
+        else if (MAXOP) { a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w); }
+        else { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      }
+    }
+    if (!MAXOP) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+    __stcg(reinterpret_cast<float4*>(pw.buf[rank]) + i, a);
+  }
+  peer_barrier(pp, rank, world);      // every rank's slice is reduced (the elements this CTA is about to read)
+  // phase 2: collect the reduced slices (slice s from rank s), starting with the next rank
+  for (int r = 0; r < world; ++r) {
+    const int sidx = rank + r < world ? rank + r : rank + r - world;
+    for (long long j = j0; j < per; j += stride) {
+      const long long i = (long long)sidx * per + j;
+      if (i >= n4) break;
+      reinterpret_cast<float4*>(out)[i] = __ldcv(reinterpret_cast<const float4*>(pw.buf[sidx]) + i);
+    }
+  }
+  if (blockIdx.x == 0) {             // the (n mod 4) tail: nobody rewrote it, reduce it directly
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float a = __ldcv(pw.buf[0] + i);
+      for (int p = 1; p < world; ++p) {
+        const float b = __ldcv(pw.buf[p] + i);
+        a = MAXOP ? fmaxf(a, b) : a + b;
+      }
+      out[i] = MAXOP ? a : a * scale;
+    }
+  }
+  peer_barrier(pp, rank, world);      // nobody still reads this rank's buffer when the caller overwrites it
+}
+
 }  // namespace sgc
 
 // bufs / sigs: HOST arrays of `world` device pointers (rank r's symmetric buffer / signal pad as mapped in THIS process).
@@ -114,12 +176,24 @@ extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, in
     if (r < world && (!pp.buf[r] || !pp.sig[r] || (reinterpret_cast<uintptr_t>(pp.buf[r]) & 15))) return (int)cudaErrorInvalidValue;
   }
   if (reinterpret_cast<uintptr_t>(out) & 15) return (int)cudaErrorInvalidValue;
-  long long blocks = ((n >> 2) + kPeerThreads - 1) / kPeerThreads;
+  // more than two ranks and a payload worth a second meeting: two-shot (SGC_PEER_TWO_SHOT_MIN_BYTES, default 256 KB)
+  static const long long two_shot_min = getenv("SGC_PEER_TWO_SHOT_MIN_BYTES") ? atoll(getenv("SGC_PEER_TWO_SHOT_MIN_BYTES")) : (256ll << 10);
+  const bool two_shot = world > 2 && n * 4 >= two_shot_min;
+  const long long work4 = two_shot ? ((n >> 2) + world - 1) / world : (n >> 2);
+  long long blocks = (work4 + kPeerThreads - 1) / kPeerThreads;
   if (blocks < 1) blocks = 1;
   if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
-  // every rank must launch the SAME grid (the barrier pairs CTA b with CTA b of the peers): it depends on n only
-  if (op == 1) peer_allreduce_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
-  else peer_allreduce_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+  // every rank must launch the SAME grid (the barrier pairs CTA b with CTA b of the peers): it depends on n and world only
+  if (two_shot) {
+    PeerPtrsRW pw;
+    for (int r = 0; r < kPeerMaxWorld; ++r) { pw.buf[r] = const_cast<float*>(pp.buf[r]); pw.sig[r] = pp.sig[r]; }
+    if (op == 1) peer_allreduce_2shot_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
+    else peer_allreduce_2shot_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
+  } else if (op == 1) {
+    peer_allreduce_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+  } else {
+    peer_allreduce_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+  }
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

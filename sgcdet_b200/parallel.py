@@ -283,10 +283,34 @@ class ViewShardExchange:
                 out.append(p.grad[C:].reshape(-1))     # rows [C, 3C): key and value projections (a contiguous view)
         return out
 
-    def reduce_gradients(self, head) -> None:
-        grads = self.partial_gradients(head)
-        if not grads or self.mem.world == 1:
+    def reduce_gradients(self, head, sync_replicated: bool = True) -> None:
+        """Complete the parameter gradients after a view-sharded backward, ONE all-reduce launch: the partial ones are
+        summed over the ranks; with ``sync_replicated`` every other gradient is replaced by rank 0's copy (they are equal
+        up to the summation order of the few atomically accumulated ones -- bias and occupancy-head gradients -- and have to
+        stay BIT-identical, or the replicated weights and with them the top-k selection drift apart between the ranks)."""
+        if self.mem.world == 1:
             return
+        partial = {g.data_ptr() for g in self.partial_gradients(head)}
+        grads, zero = [], []
+        for n_, p in head.named_parameters():
+            if p.grad is None:
+                continue
+            if n_.endswith('attention_pooling.in_proj_weight'):
+                C = p.shape[1]
+                pieces = [(p.grad[:C].reshape(-1), False), (p.grad[C:].reshape(-1), True)]
+            else:
+                pieces = [(p.grad.view(-1), p.grad.data_ptr() in partial)]
+            for g, is_partial in pieces:
+                if is_partial:
+                    grads.append(g)
+                elif sync_replicated:
+                    grads.append(g)
+                    if self.mem.rank != 0:
+                        zero.append(g)
+        if not grads:
+            return
+        if zero:
+            torch._foreach_zero_(zero)         # sum over the ranks == rank 0's values, bit for bit
         sizes = [g.numel() for g in grads]
         n = sum(sizes)
         buf = self.view((n,))
