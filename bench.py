@@ -292,6 +292,8 @@ def run_ours(args):
 
     def step():
         main = torch.cuda.current_stream()
+        if averager is not None:
+            averager.begin_step()
         if B == 1:
             outs = [scene_fwd(scenes[0])]
         else:
@@ -316,12 +318,15 @@ def run_ours(args):
         torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
                                 [g for s in scenes for g in (s['gvol'], None)])
         main.wait_stream(loss_stream)
-        if ar_in_graph:
-            allreduce_grads()      # captured with the step: no CPU launch gap between the backward and the collective
+        if averager is not None:
+            # the bucketed peer all-reduces were issued from the backward as their gradients became final (captured with the
+            # step); this joins the communication stream
+            averager.finish_step()
 
     # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks every step.
-    #   peer (default): ONE own kernel over NVLink peer memory (sgcdet_b200/peer.py, csrc/sgc_peer.cu) captured INTO the
-    #                   step's CUDA graph -- no CPU launch gap between the backward and the collective;
+    #   peer (default): own all-reduce kernels over NVLink peer memory (sgcdet_b200/peer.py, csrc/sgc_peer.cu) captured INTO the
+    #                   step's CUDA graph, bucketed in the order the gradients become final and overlapped with the end of the
+    #                   backward (only a small tail bucket stays behind the last kernel);
     #   nccl:           cat -> ncclAllReduce(avg) -> copy, issued by the CPU after every graph replay (round 1).
     ar_mode = 'none' if (world == 1 or args.no_grad_allreduce) else args.grad_allreduce
     averager = None
@@ -335,14 +340,15 @@ def run_ours(args):
         ok = torch.tensor([1 if ar_mode == 'peer' else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
+            if averager is not None:
+                for h_ in averager._hooks:
+                    h_.remove()
             ar_mode, averager = 'nccl', None
     ar_in_graph = ar_mode == 'peer' and not args.no_graph
     avg_op = dist.ReduceOp.AVG if world > 1 else None
 
     def allreduce_grads():
-        if ar_mode == 'peer':
-            averager()
-        elif ar_mode == 'nccl':
+        if ar_mode == 'nccl':
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat, op=avg_op)
             torch._foreach_copy_([p.grad.view(-1) for p in params], list(flat.split([p.numel() for p in params])))
@@ -374,8 +380,7 @@ def run_ours(args):
 
         def run_step():
             graph.replay()
-            if not ar_in_graph:
-                allreduce_grads()
+            allreduce_grads()
     else:
         def run_step():
             zero_grads()
@@ -601,7 +606,7 @@ def run_ours(args):
                        'scenes_per_gpu': B,
                        'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
                        'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else
-                                                                  (' + weight-grad average: one peer-memory kernel over NVLink' + (' inside the CUDA graph' if ar_in_graph else '')
+                                                                  (' + weight-grad average: bucketed peer-memory all-reduce kernels over NVLink, overlapped with the backward' + (' inside the CUDA graph' if ar_in_graph else '')
                                                                    if ar_mode == 'peer' else ' + NCCL weight-grad all-reduce after the replay')),
                        'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
                        'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '

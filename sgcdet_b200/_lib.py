@@ -188,7 +188,7 @@ def ptr(t):
 
 def stream(device=None):
     """Raw handle of torch's current stream on ``device`` (default: the current device).  The module entry points
-    (``plugin.AdaptiveSparseHead.forward``, ``DenseHead.forward``, ``parallel.forward_view_sharded``, the dropin
+    (``plugin.AdaptiveSparseHead.forward``, ``DenseHead.forward``, the dropin
     ``_ext`` wrappers) make the tensors' device current around their launches, so the default is the tensors' device."""
     return torch.cuda.current_stream(device).cuda_stream
 

@@ -137,13 +137,25 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_2shot_kernel(cons
     __stcg(reinterpret_cast<float4*>(pw.buf[rank]) + i, a);
   }
   peer_barrier(pp, rank, world);      // every rank's slice is reduced (the elements this CTA is about to read)
-  // phase 2: collect the reduced slices (slice s from rank s), starting with the next rank
-  for (int r = 0; r < world; ++r) {
-    const int sidx = rank + r < world ? rank + r : rank + r - world;
-    for (long long j = j0; j < per; j += stride) {
-      const long long i = (long long)sidx * per + j;
-      if (i >= n4) break;
-      reinterpret_cast<float4*>(out)[i] = __ldcv(reinterpret_cast<const float4*>(pw.buf[sidx]) + i);
+  // phase 2: collect the reduced slices (slice s from rank s), starting with the next rank; the loads of all slices are
+  // issued before the first store (one link round trip per pass instead of one per slice)
+  for (long long j = j0; j < per; j += stride) {
+    float4 v[kPeerMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r) {
+      if (r < world) {
+        const int sidx = rank + r < world ? rank + r : rank + r - world;
+        const long long i = (long long)sidx * per + j;
+        if (i < n4) v[r] = __ldcv(reinterpret_cast<const float4*>(pw.buf[sidx]) + i);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r) {
+      if (r < world) {
+        const int sidx = rank + r < world ? rank + r : rank + r - world;
+        const long long i = (long long)sidx * per + j;
+        if (i < n4) reinterpret_cast<float4*>(out)[i] = v[r];
+      }
     }
   }
   if (blockIdx.x == 0) {             // the (n mod 4) tail: nobody rewrote it, reduce it directly

@@ -90,27 +90,13 @@ def project_compact(proj: torch.Tensor, ref3d: torch.Tensor, sel: Optional[torch
 BF16 = torch.bfloat16
 F32 = torch.float32
 import os as _os
-HEADS_WGRAD_FP32 = _os.environ.get('SGC_HEADS_WGRAD_FP32', '0') != '0'  # per-head K/V weight grads as plain fp32 bmm
-SMALL_ROWS = int(_os.environ.get('SGC_SMALL_ROWS', '0'))  # voxel-count GEMMs with at most this many rows stay plain fp32
-# voxel-count GEMMs of the encoder layer on the own tcgen05 kernel (csrc/sgc_rows_gemm_tc.cu) instead of the library's
-# bf16 GEMM on bf16x3 operand images
-ROWS_TC = _os.environ.get('SGC_ROWS_TC', '1') != '0'
-ROWS_WGRAD_TC = _os.environ.get('SGC_ROWS_WGRAD_TC', '1') != '0'  # ... and their weight gradients (sgc_rows_wgrad_tc)
-# all weight gradients of a layer as ONE grouped launch at the end of its backward (sgc_rows_wgrad_group_tc); 0 = one launch
-# per Linear layer as in round 1
-WGRAD_GROUP = _os.environ.get('SGC_WGRAD_GROUP', '1') != '0'
 # backward of the lift as a gather over pixel tiles (csrc/sgc_lift_tiles.cu) instead of the scatter kernel (REDs into a
 # zero-filled grad_vg).  Parity-green, but its first version is latency-bound per tile (830 us vs 195 + 58 us of fill at the
 # finest ScanNet level): off by default
 LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '0') != '0'
-# output_proj and the query in-projection are two back-to-back Linear layers: the chain evaluates their product
-# (mean -> qv in one GEMM, W_q W_out prepared per step) and the intermediate g, needed only by the weight gradients, is
-# produced off the chain on the weight-gradient stream; likewise gqv -> gmean in the backward
-FUSE_QO = _os.environ.get('SGC_FUSE_QO', '0') != '0'  # measured neutral (554 vs 550-572 volumes/s): off
 TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
 TOPK_GRID = _os.environ.get('SGC_TOPK_GRID', '1') != '0'   # one-launch grid top-k (round 2); 0 = the round-1 kernels
 _TOPK_SCRATCH = {}
-ROWS_NCTA = int(_os.environ.get('SGC_ROWS_NCTA', '0'))  # output columns per CTA of that kernel (0 = its own heuristic)
 
 
 def split_cols(x: torch.Tensor, pattern: int) -> torch.Tensor:
@@ -132,22 +118,10 @@ def split_rows(x: torch.Tensor, group: int, pattern: int) -> torch.Tensor:
     return out
 
 
-def mm_nt(a: torch.Tensor, w: torch.Tensor = None, ws: torch.Tensor = None) -> torch.Tensor:
-    """a [R,K] @ w[N,K]^T -> [R,N] fp32, tensor cores with bf16 hi/lo split (hi*hi + lo*hi + hi*lo).
-    ``ws`` = pre-split weight ``split_cols(w, 1)`` (computed once per step by ``LevelWeights``)."""
-    if a.shape[0] <= SMALL_ROWS and w is not None:
-        return a @ w.t()  # tiny problem: the plain fp32 GEMM is launch-bound either way, skip the two splits
-    if ws is None:
-        ws = split_cols(w, 1)
-    return torch.mm(split_cols(a, 0), ws.t(), out_dtype=F32)
-
-
 def rows_linear(x: torch.Tensor, wpack: torch.Tensor, N: int, bias: Optional[torch.Tensor] = None, n_cta: int = 0):
     """y [R,N] = x [R,K] @ W^T (+ bias) with ``wpack`` = the packed [N,K] weight (``sgc_rows_gemm_tc``)."""
     R, K = x.shape
     y = torch.empty(R, N, device=x.device, dtype=F32)
-    if n_cta == 0 and ROWS_NCTA and N % ROWS_NCTA == 0:
-        n_cta = ROWS_NCTA
     call('sgc_rows_gemm_tc', ptr(x), K, 0, R, K, 1, ptr(wpack), N, 0, 0, ptr(bias), 0, N, ptr(y), N, 0, n_cta, stream())
     return y
 
@@ -347,107 +321,53 @@ class _WeightJobs:
 
 
 class LevelWeights:
-    """Every bf16x3 split / tcgen05 slab image of one level's weights (both orientations), produced once per step by a
-    single launch -- normally on a side stream, off the critical path of the level.  Constants for the autograd
-    Functions below (weight gradients are formed from the fp32 activations, not from these)."""
+    """Every operand image of one level's weights, produced once per step by a single launch (``sgc_prepare_weights``) --
+    normally on a side stream, off the critical path of the level: the packed bf16 hi/lo slabs the tcgen05 kernels stream
+    (``p_x`` for y = a @ x^T, ``p_x_t`` for the data gradient g @ x) and, for the library fallback of the feature projection
+    only, the bf16x3 images of ``wcat``.  Constants for the autograd Functions below (weight gradients are formed from the
+    fp32 activations, not from these)."""
 
-    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS, images: bool = True, b_out=None,
-                 in_b=None):
-        """``images=False``: skip the bf16x3 images of the layer weights (operands of the library-GEMM path) wherever
-        the packed operands of the own voxel-count GEMM kernel replace them."""
+    def __init__(self, wcat, w_out, in_w, wo, w1, w2, num_heads: int = NUM_HEADS):
         with torch.no_grad():
             C = w_out.shape[0]
             dh = C // num_heads
+            if C % 128 or w1.shape[0] % 128 or dh % 8:
+                raise ValueError('sgcdet_b200: the voxel-count layers need embed_dims and feedforward_channels in multiples of '
+                                 f'128 and heads at least 8 wide (got {C}, {w1.shape[0]}, {dh})')
             scale = 1.0 / math.sqrt(dh)
             wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
             j = _WeightJobs(w_out.device)
-            self.wcat = j.split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T
+            self.wcat = j.split_cols(wcat, 1)          # [N,3C]   x @ Wcat^T   (library fallback of ProjectFeatures)
+            self.wcat_t = j.split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
             ok = wcat.shape[1] % 32 == 0 and wcat.shape[0] % 32 == 0
             self.wpack = j.pack(wcat) if ok else None
             self.wpack_t = j.pack(wcat.t()) if ok else None
-            self.wcat_t = j.split_cols(wcat.t(), 1)    # [C,3N]   g @ Wcat
-            self.rows_tc = ROWS_TC and C % 32 == 0 and w1.shape[0] % 32 == 0
-            self.heads_tc = self.rows_tc and dh % 32 == 0
-            self.fuse_qo = self.rows_tc and FUSE_QO and b_out is not None and in_b is not None
-            if self.fuse_qo:
-                wqo = torch.mm(wq, w_out)                        # qv = mean @ (W_q W_out)^T + (W_q b_out + b_q)
-                self.bqo = torch.addmv(in_b[:C], wq, b_out)
-                self.p_wqo, self.p_wqo_t = j.pack(wqo), j.pack(wqo.t())
-            if self.rows_tc:
-                # packed operands of sgc_rows_gemm_tc: p_x for y = a @ x^T, p_x_t for the data gradient g @ x
-                self.p_w_out, self.p_w_out_t = j.pack(w_out), j.pack(w_out.t())
-                self.p_wq, self.p_wq_t = j.pack(wq), j.pack(wq.t())
-                self.p_wo, self.p_wo_t = j.pack(wo), j.pack(wo.t())
-                self.p_w1, self.p_w1_t = j.pack(w1), j.pack(w1.t())
-                self.p_w2, self.p_w2_t = j.pack(w2), j.pack(w2.t())
-            # heads narrower than a 32-column k-slab (dh = 16 at C = 128): the per-head products run on the same kernel with
-            # zero-extended weights (rows_heads_in_exp / rows_heads_out_exp): 8x redundant MMA work on tiny matrices instead
-            # of bf16x3 operand images (315 MB each at Q = 51 200) + library GEMMs
-            self.heads_exp = self.rows_tc and not self.heads_tc and dh % 8 == 0 and _os.environ.get('SGC_HEADS_EXP', '1') != '0'
-            if self.heads_exp:
-                hm = _head_mask(w_out.device, C, num_heads)                                          # [H, C]
-                self.p_wk_in = j.pack(((wk.t() * scale).unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
-                self.p_wv_in = j.pack((wv.t().unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
-                self.p_wv_out = j.pack((wv.unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
-                self.p_wk_out = j.pack(((wk * scale).unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
+            self.p_w_out, self.p_w_out_t = j.pack(w_out), j.pack(w_out.t())
+            self.p_wq, self.p_wq_t = j.pack(wq), j.pack(wq.t())
+            self.p_wo, self.p_wo_t = j.pack(wo), j.pack(wo.t())
+            self.p_w1, self.p_w1_t = j.pack(w1), j.pack(w1.t())
+            self.p_w2, self.p_w2_t = j.pack(w2), j.pack(w2.t())
+            # per-head key / value products: heads as wide as a 32-column k-slab (C = 256) are addressed through strided
+            # tensor maps; narrower heads (dh = 16 at C = 128) run on the same kernel with zero-extended / K-concatenated
+            # weights: 8x redundant MMA work on tiny matrices instead of per-head operand images
+            self.heads_tc = dh % 32 == 0
             if self.heads_tc:
                 self.p_wk = j.pack(wk, scale)                          # gqv[:, h] = gqt[h] @ (scale Wk_h)^T
                 self.p_wv = j.pack(wv)                                 # o[:, h]   = t[h] @ Wv_h^T
                 self.p_wk_ht = j.pack_heads_t(wk, num_heads, scale)    # qt[h]     = qv_h @ (scale Wk_h)
                 self.p_wv_ht = j.pack_heads_t(wv, num_heads)           # gt[h]     = go_h @ Wv_h
-            for k in ('w_out', 'w_out_t', 'wq', 'wq_t', 'wo', 'wo_t', 'w1', 'w1_t', 'w2', 'w2_t', 'wk_rows', 'wk_cols',
-                      'wv_rows', 'wv_cols'):
-                setattr(self, k, None)
-            if images or not self.rows_tc:
-                self.w_out, self.w_out_t = j.split_cols(w_out, 1), j.split_cols(w_out.t(), 1)
-                self.wq, self.wq_t = j.split_cols(wq, 1), j.split_cols(wq.t(), 1)
-                self.wo, self.wo_t = j.split_cols(wo, 1), j.split_cols(wo.t(), 1)
-                self.w1, self.w1_t = j.split_cols(w1, 1), j.split_cols(w1.t(), 1)
-                self.w2, self.w2_t = j.split_cols(w2, 1), j.split_cols(w2.t(), 1)
-            if images or not (self.heads_tc or self.heads_exp):
-                self.wk_rows = j.split_rows(wk, dh, 1, scale)  # [8,3dh,C]  qv_h @ (scale Wk_h)
-                self.wk_cols = j.split_cols(wk, 1, scale)      # [C,3C]     gqt[h] @ (scale Wk_h)^T
-                self.wv_rows = j.split_rows(wv, dh, 1)     # [8,3dh,C]  go_h @ Wv_h
-                self.wv_cols = j.split_cols(wv, 1)         # [C,3C]     t[h] @ Wv_h^T
+            else:
+                hm = _head_mask(w_out.device, C, num_heads)                                          # [H, C]
+                self.p_wk_in = j.pack(((wk.t() * scale).unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
+                self.p_wv_in = j.pack((wv.t().unsqueeze(0) * hm.unsqueeze(1)).reshape(num_heads * C, C))
+                self.p_wv_out = j.pack((wv.unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
+                self.p_wk_out = j.pack(((wk * scale).unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
             j.launch()
 
     def record_stream(self, s):
         for t in self.__dict__.values():
             if isinstance(t, torch.Tensor):
                 t.record_stream(s)
-
-
-def mm_tn(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """g[Q,N]^T @ x[Q,K] -> [N,K] fp32 (reduction over the rows)."""
-    Q = g.shape[0]
-    if Q <= SMALL_ROWS:
-        return g.t() @ x
-    return torch.mm(split_rows(g, Q, 0)[0].t(), split_rows(x, Q, 1)[0], out_dtype=F32)
-
-
-def split_rows_colsum(g: torch.Tensor, pattern: int = 0):
-    """One pass over g [Q,N]: (rows-split [3Q,N] bf16, column sums [N])."""
-    g = g.contiguous()
-    R, C = g.shape
-    dev = g.device
-    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
-    ctr = _COUNTERS.get(key)
-    if ctr is None:
-        ctr = _COUNTERS[key] = torch.zeros(1, device=dev, dtype=torch.int32)
-    out = torch.empty(3 * R, C, device=dev, dtype=BF16)
-    sums = torch.empty(C, device=dev, dtype=F32)
-    scratch = torch.empty(_lib.load().sgc_colsum_scratch_floats(R, C), device=dev, dtype=F32)
-    call('sgc_split_rows_colsum', ptr(g), R, C, pattern, ptr(out), ptr(sums), ptr(scratch), ptr(ctr), stream())
-    return out, sums
-
-
-def linear_grads(g: torch.Tensor, x: torch.Tensor):
-    """(gW, gb) of y = x W^T + b given g = dL/dy: gW = g^T x [N,K], gb = colsum(g); one fused pass over g."""
-    Q = g.shape[0]
-    if _os.environ.get('SGC_FUSED_COLSUM', '1') == '0':
-        return mm_tn(g, x), colsum(g)
-    gs, gb = split_rows_colsum(g, 0)
-    return torch.mm(gs.t(), split_rows(x, Q, 1)[0], out_dtype=F32), gb
 
 
 _COUNTERS = {}
@@ -550,7 +470,7 @@ class ProjectFeatures(torch.autograd.Function):
         return acat
 
     @staticmethod
-    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None, big_stream=None):
+    def forward(ctx, feat: torch.Tensor, h: int, w: int, wcat: torch.Tensor, lw=None):
         # feat is [V,C,H0,W0] or the reference's [1,V,C,H0,W0]; taking the 5-D leaf directly keeps autograd from
         # materialising a zero-filled copy for the select() view on the way back
         ctx.feat_shape = tuple(feat.shape)
@@ -560,7 +480,6 @@ class ProjectFeatures(torch.autograd.Function):
         N = wcat.shape[0]
         ctx.dims = (V, C, H0, W0, h, w)
         ctx.lw = lw
-        ctx.big = big_stream   # optional dedicated stream for the two gradient kernels (see plugin._big_backward_streams)
         use_tc = (_os.environ.get('SGC_TC_PROJECT', '1') != '0' and w == W0 and feat.is_contiguous()
                   and (H0 * W0 * 4) % 16 == 0 and C % 32 == 0 and N % 32 == 0 and N <= 512)
         if use_tc:
@@ -591,31 +510,19 @@ class ProjectFeatures(torch.autograd.Function):
             gvg = gvg.contiguous()
             gfeat = gw = None
             lw = ctx.lw
-            cur = torch.cuda.current_stream(gvg.device)
-            big = ctx.big if ctx.big is not None and ctx.big != cur else None
-            if big is not None:
-                big.wait_stream(cur)
-                for t_ in (gvg, feat):
-                    t_.record_stream(big)
-            with torch.cuda.stream(big if big is not None else cur):
-                if ctx.needs_input_grad[0]:
-                    wpack_t = lw.wpack_t if lw is not None and getattr(lw, 'wpack_t', None) is not None \
-                        else pack_weight_tc(wcat.t().contiguous())
-                    gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
-                    if h != H0:
-                        gfeat[:, :, h:].zero_()
-                    call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
-                    gfeat = gfeat.view(ctx.feat_shape)
-                if ctx.needs_input_grad[3]:
-                    gw = torch.empty(N, C, device=gvg.device, dtype=F32)
-                    scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device=gvg.device, dtype=F32)
-                    call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
-            if big is not None:
-                cur.wait_stream(big)
-                for t_ in (gfeat, gw):
-                    if t_ is not None:
-                        t_.record_stream(cur)
-            return gfeat, None, None, gw, None, None
+            if ctx.needs_input_grad[0]:
+                wpack_t = lw.wpack_t if lw is not None and getattr(lw, 'wpack_t', None) is not None \
+                    else pack_weight_tc(wcat.t().contiguous())
+                gfeat = torch.empty(V, C, H0, W0, device=gvg.device, dtype=F32)
+                if h != H0:
+                    gfeat[:, :, h:].zero_()
+                call('sgc_project_tc_bwd_data', ptr(gvg), V, S, N, ptr(wpack_t), C, ptr(gfeat), H0 * W0, stream())
+                gfeat = gfeat.view(ctx.feat_shape)
+            if ctx.needs_input_grad[3]:
+                gw = torch.empty(N, C, device=gvg.device, dtype=F32)
+                scratch = torch.empty(_lib.load().sgc_project_tc_wgrad_scratch_floats(N, C), device=gvg.device, dtype=F32)
+                call('sgc_project_tc_wgrad', ptr(gvg), ptr(feat), H0 * W0, V, S, N, C, ptr(gw), ptr(scratch), stream())
+            return gfeat, None, None, gw, None
         if not ctx.have_acat:
             acat = ProjectFeatures._split_feat(acat, h, w) if ctx.needs_input_grad[3] else None
         gvg = gvg.contiguous()
@@ -645,7 +552,7 @@ class ProjectFeatures(torch.autograd.Function):
             gw = xs[:, :C] + xs[:, C:] + ys
         if gfeat is not None:
             gfeat = gfeat.view(ctx.feat_shape)
-        return gfeat, None, None, gw, None, None
+        return gfeat, None, None, gw, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -733,192 +640,6 @@ class Lift(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# cross-view fusion
-# ----------------------------------------------------------------------------------------------
-
-def _heads_cols(x: torch.Tensor, pattern: int, heads: int = NUM_HEADS) -> torch.Tensor:
-    """[Q, heads*dh] -> [heads, Q, 3dh] (strided view): per-head operand whose reduction axis is dh."""
-    Q, C = x.shape
-    dh = C // heads
-    return split_cols(x.reshape(Q * heads, dh), pattern).view(Q, heads, 3 * dh).transpose(0, 1)
-
-
-def _heads_rows_t(x: torch.Tensor, pattern: int, heads: int = NUM_HEADS) -> torch.Tensor:
-    """[Q, heads*dh] -> [heads, dh, 3Q] (strided view): per-head transposed operand, reduction over Q."""
-    Q, C = x.shape
-    dh = C // heads
-    return split_rows(x, Q, pattern)[0].view(3 * Q, heads, dh).permute(1, 2, 0)
-
-
-class CrossView(torch.autograd.Function):
-    """DCA:815-837: masked mean over views -> output_proj -> 8-head attention pooling over views.
-
-    The dense projections are voxel-count GEMMs (static shapes; library bf16 GEMMs on bf16x3-split operands,
-    fp32 accumulate) around the two cross-view kernels; the backward is written out by hand so that no
-    pair-capacity-sized tensor is ever touched outside the kernels.
-    """
-
-    @staticmethod
-    def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, lw=None, wstream=None):
-        ctx.wstream = wstream
-        Q, V = pl.Q, pl.V
-        C = slots.shape[1]
-        H = NUM_HEADS
-        if lw is None:
-            lw = LevelWeights(w_out, w_out, in_w, wo, w_out, w_out)
-        ctx.lw = lw
-        dh = C // H
-        scale = 1.0 / math.sqrt(dh)
-        dev = slots.device
-        mean = torch.empty(Q, C, device=dev, dtype=F32)
-        call('sgc_crossview_mean_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), stream())
-        bq, bv = in_b[:C], in_b[2 * C:]
-        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
-        small = Q <= SMALL_ROWS
-        g = mm_nt(mean, w_out, lw.w_out) + b_out
-        qv = mm_nt(g, wq, lw.wq) + bq
-        # qt[h] = qv_h @ (scale * Wk_h)   [8,Q,dh] x [8,dh,C]
-        if small:
-            qt = torch.bmm(qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C))
-        else:
-            qt = torch.bmm(_heads_cols(qv, 0), lw.wk_rows, out_dtype=F32)
-        t = torch.empty(H, Q, C, device=dev, dtype=F32)
-        alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
-        call('sgc_crossview_attn_fwd', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), stream())
-        # o[h] = t[h] @ Wv_h^T   [8,Q,C] x [8,C,dh]
-        if small:
-            o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
-        else:
-            o = torch.bmm(split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
-                          lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-        o2 = o.transpose(0, 1).reshape(Q, C) + bv
-        has = (pl.count > 0).to(F32).unsqueeze(1)
-        out = (mm_nt(o2, wo, lw.wo) + bo) * has
-        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, has, w_out, in_w, wo)
-        ctx.pl = pl
-        return out
-
-    @staticmethod
-    def backward(ctx, gout):
-        slots, mean, g, qv, qt, t, alpha, o2, has, w_out, in_w, wo = ctx.saved_tensors
-        pl = ctx.pl
-        Q, V = pl.Q, pl.V
-        C = slots.shape[1]
-        H = NUM_HEADS
-        dh = C // H
-        scale = 1.0 / math.sqrt(dh)
-        dev = slots.device
-        lw = ctx.lw
-        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
-        small = Q <= SMALL_ROWS
-        side = _Side(dev, ctx.wstream)
-        gout = gout * has
-        g_wo, g_bo = side.run(lambda: linear_grads(gout, o2), gout, o2)
-        go2 = mm_nt(gout, wo.t(), lw.wo_t)
-
-        # gt[h] = go_h @ Wv_h   [8,Q,dh] x [8,dh,C]
-        go_h = go2.view(Q, H, dh).transpose(0, 1)
-        if small:
-            gt = torch.bmm(go_h, wv.view(H, dh, C))
-        else:
-            gt = torch.bmm(_heads_cols(go2, 0), lw.wv_rows, out_dtype=F32)
-        # g_wv[h] = go_h^T @ t[h]   [8,dh,Q] x [8,Q,C]
-        if small:
-            g_wv = torch.bmm(go_h.transpose(1, 2), t).reshape(C, C)
-            g_bv = colsum(go2)
-        elif HEADS_WGRAD_FP32:
-            g_wv, g_bv = side.run(lambda: (torch.bmm(go_h.transpose(1, 2), t).reshape(C, C), colsum(go2)), go2, t)
-        else:
-            def _wv():
-                gs, gb = split_rows_colsum(go2, 0)  # [3Q,C] rows-split of go2 + the bias gradient of the value proj
-                a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
-                return torch.bmm(a, split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C), gb
-            g_wv, g_bv = side.run(_wv, go2, t)
-        gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
-        gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
-        call('sgc_crossview_attn_bwd_qt', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
-             ptr(gqt), stream())
-        # gqv[h] = gqt[h] @ (scale*Wk_h)^T   [8,Q,C] x [8,C,dh]
-        if small:
-            gqv_h = torch.bmm(gqt, wk.view(H, dh, C).transpose(1, 2))
-        else:
-            gqv_h = torch.bmm(split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
-                              lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-        gqv = gqv_h.transpose(0, 1).reshape(Q, C)
-        # g_wk[h] = scale * qv_h^T @ gqt[h]   [8,dh,Q] x [8,Q,C]
-        if small:
-            g_wk = torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
-        elif HEADS_WGRAD_FP32:
-            g_wk = side.run(lambda: torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale, qv, gqt)
-        else:
-            g_wk = side.run(lambda: torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1),
-                                              out_dtype=F32).reshape(C, C) * scale, qv, gqt)
-        g_wq, g_bq = side.run(lambda: linear_grads(gqv, g), gqv, g)
-        gg = mm_nt(gqv, wq.t(), lw.wq_t)
-        g_wout, g_bout = side.run(lambda: linear_grads(gg, mean), gg, mean)
-        gmean = mm_nt(gg, w_out.t(), lw.w_out_t)
-        gslots = torch.empty_like(slots)
-        call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
-             ptr(gmean), ptr(gslots), stream())
-        side.join()
-        g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
-                                           torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
-        side.join()
-        return gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None, None
-
-
-class Linear3(torch.autograd.Function):
-    """y = x W^T + b on the tensor cores with bf16x3-split operands (used for the FFN, encoder.py:335-338)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b, ws=None, ws_t=None, wstream=None):
-        ctx.save_for_backward(x, w)
-        ctx.ws_t, ctx.wstream = ws_t, wstream
-        return mm_nt(x, w, ws) + b
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        gy = gy.contiguous()
-        side = _Side(gy.device, ctx.wstream)
-        gw, gb = side.run(lambda: linear_grads(gy, x), gy, x)
-        gx = mm_nt(gy, w.t(), ctx.ws_t)
-        side.join()
-        return gx, gw, gb, None, None, None
-
-
-class LayerNormRows(torch.autograd.Function):
-    """nn.LayerNorm over voxel rows [R,C] (the norms of VoxFormerLayer, encoder.py:262-340): torch's forward kernel,
-    own backward (``sgc_layernorm_bwd``: one pass for gx, the gamma/beta reduction finishes on the weight stream)."""
-
-    @staticmethod
-    def forward(ctx, x, gamma, beta, eps: float, wstream=None):
-        x = x.contiguous()
-        y, mean, rstd = torch.native_layer_norm(x, (x.shape[1],), gamma, beta, eps)
-        ctx.save_for_backward(x, mean, rstd, gamma)
-        ctx.wstream = wstream
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, mean, rstd, gamma = ctx.saved_tensors
-        R, C = x.shape
-        gy = gy.contiguous()
-        gx = torch.empty_like(x)
-        partial = torch.empty(_lib.load().sgc_layernorm_bwd_scratch_floats(R, C), device=x.device, dtype=F32)
-        call('sgc_layernorm_bwd', ptr(x), ptr(gy), ptr(mean), ptr(rstd), ptr(gamma), R, C, ptr(gx), ptr(partial), stream())
-        side = _Side(x.device, ctx.wstream)
-
-        def _params():
-            gg, gb = torch.empty(C, device=x.device, dtype=F32), torch.empty(C, device=x.device, dtype=F32)
-            call('sgc_layernorm_bwd_params', ptr(partial), R, C, ptr(gg), ptr(gb), stream())
-            return gg, gb
-        gg, gb = side.run(_params, partial)
-        side.join()
-        return gx, gg, gb, None, None
-
-
-# ----------------------------------------------------------------------------------------------
 # fused encoder layer over voxel rows
 # ----------------------------------------------------------------------------------------------
 
@@ -985,100 +706,62 @@ def rows_headscale(x, s_, heads: int, smin: float, bias=None, want_count: bool =
 class EncoderLayerRows(torch.autograd.Function):
     """One VoxFormerLayer over the selected voxel rows (encoder.py:262-340 with operation_order cross_attn, norm, ffn,
     norm): masked mean over views -> output_proj -> 8-head attention pooling over views (DCA:815-837) -> LayerNorm ->
-    FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the dense GEMMs alternate with fused row kernels
-    (``sgc_rowop_fwd/bwd``) that carry bias, ReLU, dropout mask, row mask, residual, LayerNorm and the bf16x3 operand
-    image of the next GEMM.  The backward is written out by hand; weight / bias gradients are produced on ``wstream`` =
-    (stream of the attention-block parameters, stream of the FFN / norm parameters), see ``OnStream``.
+    FFN (+identity) -> LayerNorm, as ONE fixed sequence of launches: the own tcgen05 GEMMs (``sgc_rows_gemm_tc``, bias in the
+    epilogue) alternate with the cross-view kernels and fused row kernels (``sgc_rowop_fwd/bwd``) that carry ReLU, dropout
+    mask, row mask, residual and LayerNorm.  The backward is written out by hand; all seven weight-gradient products of the
+    layer are ONE grouped launch (``sgc_rows_wgrad_group_tc``) on ``wstream`` = (stream of the attention-block parameters,
+    stream of the FFN / norm parameters), see ``OnStream``.
 
-    GEMMs: tensor cores with bf16x3 operands and fp32 accumulation; levels with at most ``SMALL_ROWS`` voxels use plain
-    fp32 GEMMs instead (launch-bound either way, and the library's fp32 kernels need no thread-block cluster, so they
-    start at once next to the persistent projection kernels of the finer levels).
+    ``masks`` = (mask_attn, mask_ffn1, mask_ffn2) uint8 keep-masks or None (eval / p = 0), ``drops`` the matching p.
 
-    ``masks`` = (mask_attn, mask_ffn1, mask_ffn2) uint8 keep-masks or None (eval / p = 0), ``drops`` the matching p."""
+    ``coll`` (view sharding, ``parallel.ViewShardExchange``): ``slots`` / ``pl`` hold only the views this rank owns;
+    every statistic over views becomes (local partial, written straight into peer memory) -> one all-reduce launch ->
+    (local finish).  Exchanged per level: sums + counts [Q,C+1], score maxima [Q,8], the per-head value products of the
+    partial softmax sums together with the normalisers [Q,C+8] (the per-head projection is applied to the PARTIAL sums:
+    8x fewer bytes on the links than the [8,Q,C] sums themselves), and in the backward the normaliser dot [Q,8] and the
+    query gradient after its per-head projection [Q,C]."""
 
     @staticmethod
     def forward(ctx, slots, pl: PairList, w_out, b_out, in_w, in_b, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2,
                 lw, wstream, eps1, eps2, masks, drops, coll=None):
-        """``coll`` (view sharding, ``parallel.ViewShardExchange``): ``slots`` / ``pl`` hold only the views this rank owns;
-        every statistic over views becomes (local partial, written straight into peer memory) -> one all-reduce launch ->
-        (local finish).  Exchanged per level: sums + counts [Q,C+1], score maxima [Q,8], the per-head value products of the
-        partial softmax sums together with the normalisers [Q,C+8] (the per-head projection is applied to the PARTIAL sums:
-        8x fewer bytes on the links than the [8,Q,C] sums themselves), and in the backward the normaliser dot [Q,8] and the
-        query gradient after its per-head projection [Q,C]."""
         Q, V = pl.Q, pl.V
         C = slots.shape[1]
         H = NUM_HEADS
         dh = C // H
         Fh = w1.shape[0]
         dev = slots.device
-        small = Q <= SMALL_ROWS
-        tc = (not small) and getattr(lw, 'rows_tc', False)      # own tcgen05 GEMM for the plain Linear layers
-        htc = tc and getattr(lw, 'heads_tc', False)             # ... and for the per-head key / value projections
-        hexp = tc and getattr(lw, 'heads_exp', False)           # ... of heads narrower than a k-slab (zero-extended weights)
-        sp = not small and not tc                               # bf16x3 operand images for the library GEMMs
-        hsp = not small and not (htc or hexp)
-        scale = 1.0 / math.sqrt(dh)
+        wide = lw.heads_tc
         bq, bv = in_b[:C], in_b[2 * C:]
-        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
         m0, m1, m2 = masks if masks is not None else (None, None, None)
         s0, s1, s2 = (1.0 / (1.0 - p) if m is not None else 1.0 for m, p in zip((m0, m1, m2), drops))
 
-        def lin(a, a_s, w, ws, pk, bias=None):  # a @ w^T (+ bias, own kernel only)
-            if tc:
-                return rows_linear(a, pk, w.shape[0], bias)
-            return a @ w.t() if small else torch.mm(a_s, ws.t(), out_dtype=F32)
+        def heads_in(x, p_wide, p_narrow):      # y[h] = x[:, head h] @ W_h            -> [H,Q,C]
+            return rows_heads_in(x, p_wide, C, H) if wide else rows_heads_in_exp(x, p_narrow, H)
 
-        if coll is not None and not (htc or hexp):
-            raise RuntimeError('sgcdet_b200: view sharding needs the tensor-core layer path (embed_dims 128 or 256, > SMALL_ROWS rows)')
+        def heads_out(x, p_wide, p_narrow, bias=None, out=None):   # y[:, head h] = x[h] @ W_h^T (+ bias)  -> [Q,C]
+            return rows_heads_out(x, p_wide, dh, bias, out=out) if wide else rows_heads_out_exp(x, p_narrow, bias, out=out)
+
         cnt = pl.count
         if coll is None:
             mean = torch.empty(Q, C, device=dev, dtype=F32)
-            mean_s = torch.empty(Q, 3 * C, device=dev, dtype=BF16) if sp else None
-            call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), ptr(mean_s), stream())
+            call('sgc_crossview_mean_fwd_split', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(mean), None, stream())
         else:
             # exchange 1: sums over the local views + local view counts -> mean over ALL views, global counts
             call('sgc_crossview_sum_fwd', ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(coll.view((Q, C))), stream())
             coll.view((Q,), Q * C).copy_(pl.count)
             red = coll.reduce(Q * C + Q, 'sum')
             mean, cnt = rows_headscale(red[:Q * C].view(Q, C), red[Q * C:], 1, 1.0, want_count=True)
-            mean_s = None
-        fqo = htc and getattr(lw, 'fuse_qo', False) and coll is None
-        if fqo:  # one GEMM on the chain; g (an input of the weight gradients only) is produced beside it
-            qv, qv_hs = rows_linear(mean, lw.p_wqo, C, lw.bqo), None
-            g = None
-            if slots.requires_grad or w_out.requires_grad or in_w.requires_grad:
-                cur = torch.cuda.current_stream(dev)
-                gside = wstream[0] if wstream is not None and wstream[0] != cur else None
-                if gside is not None:
-                    gside.wait_stream(cur)
-                    mean.record_stream(gside)
-                with torch.cuda.stream(gside if gside is not None else cur):
-                    g = rows_linear(mean, lw.p_w_out, C, b_out)
-            else:
-                g = mean.new_empty(0)
-        elif tc:   # biases ride in the GEMM epilogue, no row kernel in between
-            g = lin(mean, None, w_out, None, lw.p_w_out, b_out)
-            if htc or hexp:
-                qv, qv_hs = lin(g, None, wq, None, lw.p_wq, bq), None
-            else:
-                qv, qv_hs, _ = rowop_fwd(lin(g, None, wq, None, lw.p_wq), Q, C, bias=bq, split_heads=H)
-        else:
-            g, g_s, _ = rowop_fwd(lin(mean, mean_s, w_out, lw.w_out, None), Q, C, bias=b_out, want_split=sp)
-            qv, qv_hs, _ = rowop_fwd(lin(g, g_s, wq, lw.wq, None), Q, C, bias=bq, split_heads=H, want_split=sp)
-        if small:   # qt[h] = scale * qv_h @ Wk_h
-            qt = torch.empty(H, Q, C, device=dev, dtype=F32)
-            torch.baddbmm(qt, qv.view(Q, H, dh).transpose(0, 1), wk.view(H, dh, C), beta=0, alpha=scale, out=qt)
-        elif htc:
-            qt = rows_heads_in(qv, lw.p_wk_ht, C, H)
-        elif hexp:
-            qt = rows_heads_in_exp(qv, lw.p_wk_in, H)
-        else:
-            qt = torch.bmm(qv_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wk_rows, out_dtype=F32)   # [H,Q,C]
+        g = rows_linear(mean, lw.p_w_out, C, b_out)
+        qv = rows_linear(g, lw.p_wq, C, bq)
+        qt = heads_in(qv, getattr(lw, 'p_wk_ht', None), getattr(lw, 'p_wk_in', None))          # scale Wk_h folded in
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
-        t_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         ssm = None
-        if coll is not None:
+        if coll is None:
+            call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), None,
+                 stream())
+            o2 = heads_out(t, getattr(lw, 'p_wv', None), getattr(lw, 'p_wv_out', None), bv)
+        else:
             # exchange 2: score maxima; exchange 3: the partial softmax sums -- the log-sum-exp merge without a rescale pass.
             # t = this rank's UNNORMALISED partial sum_v e_v s_v, alpha = e (both finished in the backward with ssm)
             sc = torch.empty(pl.cap, H, device=dev, dtype=F32)
@@ -1086,37 +769,17 @@ class EncoderLayerRows(torch.autograd.Function):
             m = coll.reduce(Q * H, 'max')
             call('sgc_cvs_accum', ptr(sc), ptr(m), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(alpha),
                  ptr(coll.view((Q, H), Q * C)), ptr(t), stream())
-            if htc:
-                rows_heads_out(t, lw.p_wv, dh, out=coll.view((Q, C)))
-            else:
-                rows_heads_out_exp(t, lw.p_wv_out, out=coll.view((Q, C)))
+            heads_out(t, getattr(lw, 'p_wv', None), getattr(lw, 'p_wv_out', None), out=coll.view((Q, C)))
             red = coll.reduce(Q * C + Q * H, 'sum')
             ssm = red[Q * C:].view(Q, H)
-            o2, o2_s = rows_headscale(red[:Q * C].view(Q, C), ssm, H, 1e-30, bv), None
-        else:
-            call('sgc_crossview_attn_fwd_split', ptr(qt), ptr(slots), ptr(pl.pair_index), V, Q, C, ptr(t), ptr(alpha), ptr(t_s),
-                 stream())
-        if coll is not None:
-            pass
-        elif htc:   # o2[:, h] = t[h] @ Wv_h^T + bv_h, written straight into the [Q,C] layout
-            o2, o2_s = rows_heads_out(t, lw.p_wv, dh, bv), None
-        elif hexp:
-            o2, o2_s = rows_heads_out_exp(t, lw.p_wv_out, bv), None
-        else:
-            if small:   # o[h] = t[h] @ Wv_h^T   [H,Q,dh]
-                o = torch.bmm(t, wv.view(H, dh, C).transpose(1, 2))
-            else:
-                o = torch.bmm(t_s.view(H, Q, 3 * C), lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-            o2, o2_s, _ = rowop_fwd(o, Q, C, bias=bv, in_heads=H, want_split=sp)
+            o2 = rows_headscale(red[:Q * C].view(Q, C), ssm, H, 1e-30, bv)
         # rows no view sees are zeroed (DCA:819-835) straight from the per-voxel view count
-        x1, x1_s, ln1 = rowop_fwd(lin(o2, o2_s, wo, lw.wo, getattr(lw, 'p_wo', None)), Q, C, bias=bo, mask=m0, mscale=s0,
-                                  rowcount=cnt, ln=(g1, be1, eps1), want_split=sp)
-        hdn, hdn_s, _ = rowop_fwd(lin(x1, x1_s, w1, lw.w1, getattr(lw, 'p_w1', None)), Q, Fh, bias=b1, relu=True, mask=m1,
-                                  mscale=s1, want_split=sp)
-        y, _, ln2 = rowop_fwd(lin(hdn, hdn_s, w2, lw.w2, getattr(lw, 'p_w2', None)), Q, C, bias=b2, mask=m2, mscale=s2,
-                              residual=x1, ln=(g2, be2, eps2), want_split=False)
-        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2,
-                              w_out, in_w, wo, w1, w2)
+        x1, _, ln1 = rowop_fwd(rows_linear(o2, lw.p_wo, C), Q, C, bias=bo, mask=m0, mscale=s0, rowcount=cnt,
+                               ln=(g1, be1, eps1), want_split=False)
+        hdn, _, _ = rowop_fwd(rows_linear(x1, lw.p_w1, Fh), Q, Fh, bias=b1, relu=True, mask=m1, mscale=s1, want_split=False)
+        y, _, ln2 = rowop_fwd(rows_linear(hdn, lw.p_w2, C), Q, C, bias=b2, mask=m2, mscale=s2, residual=x1,
+                              ln=(g2, be2, eps2), want_split=False)
+        ctx.save_for_backward(slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, *ln1, *ln2, g1, g2)
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
         ctx.coll, ctx.ssm, ctx.cnt = coll, ssm, cnt
         ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
@@ -1124,8 +787,7 @@ class EncoderLayerRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        (slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2,
-         w_out, in_w, wo, w1, w2) = ctx.saved_tensors
+        (slots, mean, g, qv, qt, t, alpha, o2, x1, hdn, pre1, mean1, rstd1, pre2, mean2, rstd2, g1, g2) = ctx.saved_tensors
         pl, lw = ctx.pl, ctx.lw
         coll, ssm, cnt = ctx.coll, ctx.ssm, ctx.cnt
         m0, m1, m2 = ctx.masks
@@ -1137,85 +799,39 @@ class EncoderLayerRows(torch.autograd.Function):
         Fh = hdn.shape[1]
         dev = slots.device
         scale = 1.0 / math.sqrt(dh)
-        small = Q <= SMALL_ROWS
-        tc = (not small) and getattr(lw, 'rows_tc', False)
-        htc = tc and getattr(lw, 'heads_tc', False)
-        hexp = tc and getattr(lw, 'heads_exp', False)
-        sp = not small and not tc
-        hsp = not small and not (htc or hexp)
-        fp32_heads = small or HEADS_WGRAD_FP32
-        wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
+        wide = lw.heads_tc
         ws_attn, ws_ffn = ctx.wstream if ctx.wstream is not None else (None, None)
         side = _Side(dev, ws_attn)     # attention-block parameters
         side_f = _Side(dev, ws_ffn)    # FFN + norms
         gy = gy.contiguous()
 
-        def lin_t(a, a_s, w, ws_t, pk_t):  # a @ w
-            if tc:
-                return rows_linear(a, pk_t, w.shape[1])
-            return a @ w if small else torch.mm(a_s, ws_t.t(), out_dtype=F32)
+        def heads_in(x, p_wide, p_narrow):
+            return rows_heads_in(x, p_wide, C, H) if wide else rows_heads_in_exp(x, p_narrow, H)
 
-        wtc = tc and ROWS_WGRAD_TC and C % 128 == 0 and Fh % 128 == 0   # own kernel for the weight gradients too
-        # all seven weight-gradient products of the layer as ONE grouped launch at the end of this backward (also the per-head
-        # key / value products of the 16-wide heads, which the per-layer launches leave to the library)
-        grouped = wtc and WGRAD_GROUP and not getattr(lw, 'fuse_qo', False) and dh % 16 == 0
-        if coll is not None and not grouped:
-            raise RuntimeError('sgcdet_b200: view sharding needs the grouped weight-gradient launch (SGC_WGRAD_GROUP=1)')
-        hwtc = wtc and htc and not grouped
-        lgrads = linear_grads_tc if wtc else linear_grads
-        if True:
-            # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
-            gf, gf_s, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
-                                               want_split=sp)
-            g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
-            if not grouped:
-                g_w2, g_b2 = side_f.run(lambda: lgrads(gf, hdn), gf, hdn)
-            ghdn = lin_t(gf, gf_s, w2, lw.w2_t, getattr(lw, 'p_w2_t', None))                            # [Q,F]
-            # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
-            gh, gh_s, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=sp)
-            if not grouped:
-                g_w1, g_b1 = side_f.run(lambda: lgrads(gh, x1), gh, x1)
-            gx1_raw = lin_t(gh, gh_s, w1, lw.w1_t, getattr(lw, 'p_w1_t', None))                         # [Q,C]
-            gout, gout_s, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
-                                               rowcount=cnt, want_split=sp)
-            g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
-            if not grouped:
-                g_wo, g_bo = side.run(lambda: lgrads(gout, o2), gout, o2)
-            go2 = lin_t(gout, gout_s, wo, lw.wo_t, getattr(lw, 'p_wo_t', None))                         # [Q,C]
-        if hwtc:
-            # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients
-            # (rows [0,C) query, [C,2C) key, [2C,3C) value; the key bias gradient is identically zero)
-            def _alloc_in():
-                gw_ = torch.empty(3 * C, C, device=dev, dtype=F32)
-                gb_ = torch.empty(3 * C, device=dev, dtype=F32)
-                gb_[C:2 * C].zero_()
-                return gw_, gb_
-            g_in_w, g_in_b = side.run(_alloc_in)
-        if small:   # gt[h] = go_h @ Wv_h
-            gt = torch.bmm(go2.view(Q, H, dh).transpose(0, 1), wv.view(H, dh, C))
-        elif htc:
-            gt = rows_heads_in(go2, lw.p_wv_ht, C, H)                                               # [H,Q,C]
-        elif hexp:
-            gt = rows_heads_in_exp(go2, lw.p_wv_in, H)
-        else:
-            _, go2_hs, _, _ = rowop_bwd(go2, Q, C, split_heads=H, want_gx=False)
-            gt = torch.bmm(go2_hs.view(Q, H, 3 * dh).transpose(0, 1), lw.wv_rows, out_dtype=F32)    # [H,Q,C]
+        def heads_out(x, p_wide, p_narrow, out=None):
+            return rows_heads_out(x, p_wide, dh, out=out) if wide else rows_heads_out_exp(x, p_narrow, out=out)
 
-        def _wv():
-            if hwtc:   # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
-                return (rows_wgrad(t, go2, C, dh, Q, g_in_w[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C,
-                                   batch_b=dh, bias_out=g_in_b[2 * C:], bias_from=2), g_in_b[2 * C:])
-            if fp32_heads:
-                return torch.bmm(go2.view(Q, H, dh).permute(1, 2, 0), t).reshape(C, C), colsum(go2)
-            gs, gb = split_rows_colsum(go2, 0)
-            a = gs.view(3 * Q, H, dh).permute(1, 2, 0)
-            return torch.bmm(a, split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C), gb
-        if not grouped:
-            g_wv, g_bv = side.run(_wv, go2, t)
+        # norm 2 + dropout of the second FFN layer; gpre2 also flows into the identity branch
+        gf, _, gpre2, part2 = rowop_bwd(gy, Q, C, ln=(pre2, mean2, rstd2, g2), mask=m2, mscale=s2, want_gpre=True,
+                                        want_split=False)
+        g_g2, g_be2 = side_f.run(lambda: _ln_params(part2, Q, C), part2)
+        ghdn = rows_linear(gf, lw.p_w2_t, Fh)                                                           # [Q,F]
+        # hdn = relu(.)*mask1*s1, so the ReLU gate and the dropout mask together are (hdn > 0)
+        gh, _, _, _ = rowop_bwd(ghdn, Q, Fh, gate=hdn, gscale=s1, want_split=False)
+        gx1_raw = rows_linear(gh, lw.p_w1_t, C)                                                         # [Q,C]
+        gout, _, _, part1 = rowop_bwd(gx1_raw, Q, C, g2=gpre2, ln=(pre1, mean1, rstd1, g1), mask=m0, mscale=s0,
+                                      rowcount=cnt, want_split=False)
+        g_g1, g_be1 = side_f.run(lambda: _ln_params(part1, Q, C), part1)
+        go2 = rows_linear(gout, lw.p_wo_t, C)                                                           # [Q,C]
+        gt = heads_in(go2, getattr(lw, 'p_wv_ht', None), getattr(lw, 'p_wv_in', None))                  # [H,Q,C]
         gscore = torch.empty(pl.cap, H, device=dev, dtype=F32)
         gqt = torch.empty(H, Q, C, device=dev, dtype=F32)
-        gqt_s = torch.empty(H * Q, 3 * C, device=dev, dtype=BF16) if hsp else None
-        if coll is not None:
+        go2_n = None
+        if coll is None:
+            call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
+                 ptr(gqt), None, stream())
+            gqv = heads_out(gqt, getattr(lw, 'p_wk', None), getattr(lw, 'p_wk_out', None))
+        else:
             # exchange 4: the softmax-normaliser dot D[q,h] = sum over ALL views of alpha g_alpha; exchange 5: the query
             # gradient, after its per-head projection (linear, so it applies to the partial sums).  `alpha` arrives as e.
             a_n = torch.empty(pl.cap, H, device=dev, dtype=F32)
@@ -1226,98 +842,52 @@ class EncoderLayerRows(torch.autograd.Function):
             call('sgc_cvs_bwd_qt', ptr(slots), ptr(a_n), ptr(galpha), ptr(dsum), ptr(pl.pair_index), V, Q, C, ptr(gscore), ptr(gqt),
                  stream())
             alpha = a_n
-            if htc:
-                rows_heads_out(gqt, lw.p_wk, dh, out=coll.view((Q, C)))
-            else:
-                rows_heads_out_exp(gqt, lw.p_wk_out, out=coll.view((Q, C)))
-            gqv, gqv_s = coll.reduce(Q * C, 'sum').view(Q, C), None
+            heads_out(gqt, getattr(lw, 'p_wk', None), getattr(lw, 'p_wk_out', None), out=coll.view((Q, C)))
+            gqv = coll.reduce(Q * C, 'sum').view(Q, C)
             # the value-weight gradient pairs this rank's unnormalised partial t with go2 / ssm (per head): sum over ranks =
             # go_h^T (sum_ranks t / ssm)
             go2_n = rows_headscale(go2, ssm, H, 1e-30)
-        else:
-            call('sgc_crossview_attn_bwd_qt_split', ptr(slots), ptr(alpha), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gscore),
-                 ptr(gqt), ptr(gqt_s), stream())
-        if coll is not None:
-            pass
-        elif htc:   # gqv[:, h] = gqt[h] @ (scale Wk_h)^T, written straight into the [Q,C] layout
-            gqv, gqv_s = rows_heads_out(gqt, lw.p_wk, dh), None
-        elif hexp:
-            gqv, gqv_s = rows_heads_out_exp(gqt, lw.p_wk_out), None
-        else:
-            if small:   # gqv[h] = scale * gqt[h] @ Wk_h^T   [H,Q,dh]
-                gqv_h = torch.empty(H, Q, dh, device=dev, dtype=F32)
-                torch.baddbmm(gqv_h, gqt, wk.view(H, dh, C).transpose(1, 2), beta=0, alpha=scale, out=gqv_h)
-            else:
-                gqv_h = torch.bmm(gqt_s.view(H, Q, 3 * C), lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-            gqv, gqv_s, _, _ = rowop_bwd(gqv_h, Q, C, in_heads=H, want_split=sp)
-
-        def _wk():
-            if hwtc:   # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
-                return rows_wgrad(gqt, qv, C, dh, Q, g_in_w[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C,
-                                  batch_b=dh, scale=scale)
-            if fp32_heads:
-                return torch.bmm(qv.view(Q, H, dh).permute(1, 2, 0), gqt).reshape(C, C) * scale
-            return torch.bmm(_heads_rows_t(qv, 0), split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
-        if grouped:
-            pass
-        elif hwtc:
-            g_wk = side.run(_wk, qv, gqt)
-            g_wq, g_bq = side.run(lambda: linear_grads_tc(gqv, g, g_in_w[:C], g_in_b[:C]), gqv, g)
-        else:
-            g_wk = side.run(_wk, qv, gqt)
-            g_wq, g_bq = side.run(lambda: lgrads(gqv, g), gqv, g)
-        if htc and getattr(lw, 'fuse_qo', False):
-            # chain: gmean = gqv @ (W_q W_out) in one GEMM; gg = gqv @ W_q (an input of output_proj's weight gradient only)
-            # is produced on the weight-gradient stream
-            gmean = rows_linear(gqv, lw.p_wqo_t, C)
-            g_wout, g_bout = side.run(lambda: lgrads(rows_linear(gqv, lw.p_wq_t, C), mean), gqv, mean)
-        else:
-            gg = lin_t(gqv, gqv_s, wq, lw.wq_t, getattr(lw, 'p_wq_t', None))
-            gg_s = split_cols(gg, 0) if sp else None
-            if not grouped:
-                g_wout, g_bout = side.run(lambda: lgrads(gg, mean), gg, mean)
-            gmean = lin_t(gg, gg_s, w_out, lw.w_out_t, getattr(lw, 'p_w_out_t', None))
+        gg = rows_linear(gqv, lw.p_wq_t, C)
+        gmean = rows_linear(gg, lw.p_w_out_t, C)
         gslots = torch.empty_like(slots)
-        if coll is not None:
-            call('sgc_cvs_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gmean),
-                 ptr(cnt), ptr(gslots), stream())
-        else:
+        if coll is None:
             call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
                  ptr(gmean), ptr(gslots), stream())
-        if grouped:
-            def _group():
-                G = WgradGroup(Q, dev)
-                gw_in = torch.empty(3 * C, C, device=dev, dtype=F32)
-                gb_in = torch.zeros(3 * C, device=dev, dtype=F32)    # the key bias gradient is identically zero
-                w2g = G.linear(gf, hdn)
-                w1g = G.linear(gh, x1)
-                wog = G.linear(gout, o2)
-                # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
-                if coll is not None:   # partial over this rank's views (summed over the ranks after the backward)
-                    G.add(t, go2_n, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh)
-                    gb_in[2 * C:].copy_(colsum(go2))
-                else:
-                    G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh,
-                          bias_out=gb_in[2 * C:], bias_from=2)
-                # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
-                G.add(gqt, qv, C, dh, gw_in[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh, scale=scale)
-                G.linear(gqv, g, gw_in[:C], gb_in[:C])
-                woutg = G.linear(gg, mean)
-                G.launch()
-                return w2g + w1g + wog + woutg + (gw_in, gb_in)
-            g_w2, g_b2, g_w1, g_b1, g_wo, g_bo, g_wout, g_bout, g_in_w, g_in_b = side.run(
-                _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean, *((go2_n,) if coll is not None else ()))
-            if side.detached and side_f.detached and side_f.side != side.side:
-                # the FFN parameters are aliased on the second weight stream: it only has to follow the grouped launch
-                side_f.side.wait_stream(side.side)
-                for t_ in (g_w2, g_b2, g_w1, g_b1):
-                    t_.record_stream(side_f.side)
+        else:
+            call('sgc_cvs_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gmean),
+                 ptr(cnt), ptr(gslots), stream())
+
+        def _group():
+            # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients (rows
+            # [0,C) query, [C,2C) key, [2C,3C) value; the key bias gradient is identically zero: it cancels in the softmax)
+            G = WgradGroup(Q, dev)
+            gw_in = torch.empty(3 * C, C, device=dev, dtype=F32)
+            gb_in = torch.zeros(3 * C, device=dev, dtype=F32)
+            w2g = G.linear(gf, hdn)
+            w1g = G.linear(gh, x1)
+            wog = G.linear(gout, o2)
+            # g_wv[h*dh + d, c] = sum_q t[h][q, c] go2[q, h*dh + d];  g_bv = column sums of go2
+            if coll is not None:   # partial over this rank's views (summed over the ranks after the backward)
+                G.add(t, go2_n, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh)
+                gb_in[2 * C:].copy_(colsum(go2))
+            else:
+                G.add(t, go2, C, dh, gw_in[2 * C:], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh,
+                      bias_out=gb_in[2 * C:], bias_from=2)
+            # g_wk[h*dh + d, c] = scale * sum_q gqt[h][q, c] qv[q, h*dh + d]
+            G.add(gqt, qv, C, dh, gw_in[C:2 * C], (dh * C, 1, C), B=H, lda=C, batch_a=Q * C, ldb=C, batch_b=dh, scale=scale)
+            G.linear(gqv, g, gw_in[:C], gb_in[:C])
+            woutg = G.linear(gg, mean)
+            G.launch()
+            return w2g + w1g + wog + woutg + (gw_in, gb_in)
+        g_w2, g_b2, g_w1, g_b1, g_wo, g_bo, g_wout, g_bout, g_in_w, g_in_b = side.run(
+            _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean, *((go2_n,) if coll is not None else ()))
+        if side.detached and side_f.detached and side_f.side != side.side:
+            # the FFN parameters are aliased on the second weight stream: it only has to follow the grouped launch
+            side_f.side.wait_stream(side.side)
+            for t_ in (g_w2, g_b2, g_w1, g_b1):
+                t_.record_stream(side_f.side)
         side.join()
         side_f.join()
-        if not hwtc and not grouped:
-            g_in_w, g_in_b = side.run(lambda: (torch.cat([g_wq, g_wk, g_wv], dim=0),
-                                               torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)))
-        side.join()
         return (gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2,
                 None, None, None, None, None, None, None)
 

@@ -10,12 +10,11 @@
   GEMMs / LN / FFN / upsample / top-k are replicated, so every rank holds the same volume and the same
   (deterministic) selection.
 
-Two drivers of the same kernels:
-* ``ViewShardExchange`` + ``AdaptiveSparseHead.forward(..., view_shard=...)``: the product path.  The exchanges are single
-  kernel launches over NVLink peer memory inside the fused encoder layer (``functional.EncoderLayerRows``), on the own
-  tensor-core GEMMs, side streams and all; the whole step is one CUDA graph.
-* ``forward_view_sharded`` + ``Collective``: the reference formulation (eager, library GEMMs, NCCL / gloo or an in-process
-  simulation with several shards in one process) the single-GPU and CPU tests check the sharded math with.
+``ViewShardExchange`` + ``AdaptiveSparseHead.forward(..., view_shard=...)`` is the product path: the exchanges are single
+kernel launches over NVLink peer memory inside the fused encoder layer (``functional.EncoderLayerRows``), on the own
+tensor-core GEMMs, side streams and all; the whole step is one CUDA graph.  ``Collective`` / ``merge_partial_softmax`` are the
+host-side reference formulation of the same exchange steps over a torch.distributed group (NCCL or gloo), which the CPU
+tests check the merge rules with (tests/test_parallel_cpu.py).
 """
 from __future__ import annotations
 
@@ -26,7 +25,6 @@ import torch
 import torch.distributed as dist
 
 from . import functional as SF
-from ._lib import call, ptr, stream
 
 F32 = torch.float32
 H = SF.NUM_HEADS
@@ -96,138 +94,8 @@ def shard_scene_inputs(mlvl_feats, img_meta, mlvl_dpt_dists, views: range):
     return [f[:, idx].contiguous() for f in mlvl_feats], meta, [d[:, idx].contiguous() for d in mlvl_dpt_dists]
 
 
-class CrossViewSharded(torch.autograd.Function):
-    """DCA:815-837 with the views split over shards; see the module docstring.  Inputs: per-shard pair lists and
-    per-shard slots; output: the fused rows [Q,C] (replicated)."""
-
-    @staticmethod
-    def forward(ctx, coll: Collective, pls: List[SF.PairList], w_out, b_out, in_w, in_b, wo, bo, lw, *slots_list):
-        Q = pls[0].Q
-        C = slots_list[0].shape[1]
-        dh = C // H
-        scale = 1.0 / math.sqrt(dh)
-        dev = slots_list[0].device
-        n = len(pls)
-        if lw is None:
-            lw = SF.LevelWeights(w_out, w_out, in_w, wo, w_out, w_out)
-        # exchange 1: sum over views + view count
-        sums = []
-        for pl, s in zip(pls, slots_list):
-            t_ = torch.empty(Q, C, device=dev, dtype=F32)
-            call('sgc_crossview_sum_fwd', ptr(s), ptr(pl.pair_index), pl.V, Q, C, ptr(t_), stream())
-            sums.append(t_)
-        ssum = coll.reduce(sums, 'sum')
-        count = coll.reduce([pl.count.to(F32) for pl in pls], 'sum')
-        mean = ssum / count.clamp(min=1.0).unsqueeze(1)
-        wq, wk, wv = in_w[:C], in_w[C:2 * C] * scale, in_w[2 * C:]
-        bq, bv = in_b[:C], in_b[2 * C:]
-        g = SF.mm_nt(mean, w_out, lw.w_out) + b_out
-        qv = SF.mm_nt(g, wq, lw.wq) + bq
-        qt = torch.bmm(SF._heads_cols(qv, 0), lw.wk_rows, out_dtype=F32)
-        # exchange 2a: max of the scores; 2b: partial softmax sums (the log-sum-exp merge)
-        scores, mloc = [], []
-        for pl, s in zip(pls, slots_list):
-            sc = torch.empty(pl.cap, H, device=dev, dtype=F32)
-            ml = torch.empty(Q, H, device=dev, dtype=F32)
-            call('sgc_cvs_scores', ptr(qt), ptr(s), ptr(pl.pair_index), pl.V, Q, C, ptr(sc), ptr(ml), stream())
-            scores.append(sc)
-            mloc.append(ml)
-        m = coll.reduce(mloc, 'max')
-        es, sl, ol = [], [], []
-        for pl, s, sc in zip(pls, slots_list, scores):
-            e = torch.empty(pl.cap, H, device=dev, dtype=F32)
-            s_ = torch.empty(Q, H, device=dev, dtype=F32)
-            o_ = torch.empty(H, Q, C, device=dev, dtype=F32)
-            call('sgc_cvs_accum', ptr(sc), ptr(m), ptr(s), ptr(pl.pair_index), pl.V, Q, C, ptr(e), ptr(s_), ptr(o_), stream())
-            es.append(e); sl.append(s_); ol.append(o_)
-        ssm = coll.reduce(sl, 'sum')                      # [Q,8]
-        osum = coll.reduce(ol, 'sum')                     # [8,Q,C]
-        t = (osum / ssm.t().clamp(min=1e-30).unsqueeze(-1)).contiguous()
-        o = torch.bmm(SF.split_cols(t.view(H * Q, C), 0).view(H, Q, 3 * C),
-                      lw.wv_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-        o2 = o.transpose(0, 1).reshape(Q, C) + bv
-        has = (count > 0).to(F32).unsqueeze(1)
-        out = (SF.mm_nt(o2, wo, lw.wo) + bo) * has
-        ctx.save_for_backward(mean, g, qv, qt, t, ssm, o2, has, count, w_out, in_w, wo, *slots_list, *es)
-        ctx.pls, ctx.coll, ctx.lw, ctx.n = pls, coll, lw, n
-        return out
-
-    @staticmethod
-    def backward(ctx, gout):
-        saved = ctx.saved_tensors
-        mean, g, qv, qt, t, ssm, o2, has, count, w_out, in_w, wo = saved[:12]
-        n = ctx.n
-        slots_list, es = saved[12:12 + n], saved[12 + n:12 + 2 * n]
-        pls, coll, lw = ctx.pls, ctx.coll, ctx.lw
-        Q = pls[0].Q
-        C = slots_list[0].shape[1]
-        dh = C // H
-        scale = 1.0 / math.sqrt(dh)
-        dev = gout.device
-        wq = in_w[:C]
-        gout = gout * has
-        g_wo = SF.mm_tn(gout, o2)
-        g_bo = SF.colsum(gout)
-        go2 = SF.mm_nt(gout, wo.t(), lw.wo_t)
-        g_bv = SF.colsum(go2)
-        gt = torch.bmm(SF._heads_cols(go2, 0), lw.wv_rows, out_dtype=F32)
-        g_wv = torch.bmm(SF._heads_rows_t(go2, 0), SF.split_rows(t.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C)
-        # exchange 3: the softmax-normaliser dot  D[q,h] = sum_v alpha g_alpha over ALL views
-        alphas, galphas, dloc = [], [], []
-        for pl, s, e in zip(pls, slots_list, es):
-            a = torch.empty(pl.cap, H, device=dev, dtype=F32)
-            ga = torch.empty(pl.cap, H, device=dev, dtype=F32)
-            d = torch.empty(Q, H, device=dev, dtype=F32)
-            call('sgc_cvs_bwd_dot', ptr(s), ptr(e), ptr(ssm), ptr(pl.pair_index), pl.V, Q, C, ptr(gt), ptr(a), ptr(ga), ptr(d),
-                 stream())
-            alphas.append(a); galphas.append(ga); dloc.append(d)
-        dsum = coll.reduce(dloc, 'sum')
-        # exchange 4: the query gradient
-        gscores, gqts = [], []
-        for pl, s, a, ga in zip(pls, slots_list, alphas, galphas):
-            gs = torch.empty(pl.cap, H, device=dev, dtype=F32)
-            gq = torch.empty(H, Q, C, device=dev, dtype=F32)
-            call('sgc_cvs_bwd_qt', ptr(s), ptr(a), ptr(ga), ptr(dsum), ptr(pl.pair_index), pl.V, Q, C, ptr(gs), ptr(gq), stream())
-            gscores.append(gs); gqts.append(gq)
-        gqt = coll.reduce(gqts, 'sum')
-        gqv_h = torch.bmm(SF.split_cols(gqt.view(H * Q, C), 0).view(H, Q, 3 * C),
-                          lw.wk_cols.view(H, dh, 3 * C).transpose(1, 2), out_dtype=F32)
-        gqv = gqv_h.transpose(0, 1).reshape(Q, C)
-        g_wk = torch.bmm(SF._heads_rows_t(qv, 0), SF.split_rows(gqt.view(H * Q, C), Q, 1), out_dtype=F32).reshape(C, C) * scale
-        g_wq = SF.mm_tn(gqv, g)
-        g_bq = SF.colsum(gqv)
-        gg = SF.mm_nt(gqv, wq.t(), lw.wq_t)
-        g_wout = SF.mm_tn(gg, mean)
-        g_bout = SF.colsum(gg)
-        gmean = SF.mm_nt(gg, w_out.t(), lw.w_out_t).contiguous()
-        cnt_i = count.to(torch.int32).contiguous()
-        gslots = []
-        for pl, s, a, gs in zip(pls, slots_list, alphas, gscores):
-            gsl = torch.empty_like(s)
-            call('sgc_cvs_bwd_slots', ptr(qt), ptr(a), ptr(gs), ptr(pl.pair_index), pl.V, Q, C, ptr(gt), ptr(gmean), ptr(cnt_i),
-                 ptr(gsl), stream())
-            gslots.append(gsl)
-        g_in_w = torch.cat([g_wq, g_wk, g_wv], dim=0)
-        g_in_b = torch.cat([g_bq, torch.zeros_like(g_bq), g_bv], dim=0)
-        return (None, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, None, *gslots)
-
-
 LIFT_SIDE_PARAMS = ('deformable_attention.value_proj', 'deformable_attention.sampling_offsets',
                     'deformable_attention.sampling_offsets_depth', 'deformable_attention.attention_weights')
-
-
-def allreduce_view_sharded_gradients(head: torch.nn.Module, group=None) -> None:
-    """After a view-sharded backward: the lift-side parameters (value_proj / offset / weight Linear layers) hold
-    PARTIAL gradients (sum over the local views) -> all-reduce SUM; every other parameter was computed from
-    replicated activations and already holds the full gradient on every rank."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return
-    grads = [p.grad for n_, p in head.named_parameters() if p.grad is not None and any(k in n_ for k in LIFT_SIDE_PARAMS)]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
-    torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
 
 
 class ViewShardExchange:
@@ -320,63 +188,3 @@ class ViewShardExchange:
 
     def close(self):
         self.mem.close()
-
-
-def forward_view_sharded(head, shards, group=None, forced_selection=None, use_dist: Optional[bool] = None):
-    """AdaptiveSparseHead.forward (AdaptiveSparseHead.py:43-93) with the views of the scene split over shards.
-
-    ``shards`` = list of ``(mlvl_feats, img_meta, mlvl_dpt_dists)`` owned by THIS process (one per rank with a real
-    process group; several for the in-process simulation).  Returns the same ``(volume, valid, occ_preds)`` on every
-    rank."""
-    from . import plugin as PL
-    coll = Collective(group, use_dist)
-    nl = len(head.base_heads)
-    meta0 = shards[0][1]
-    dev = shards[0][0][0].device
-    hws = [(meta0['img_shape'][0] // (4 * 2 ** (nl - 1 - i)), meta0['img_shape'][1] // (4 * 2 ** (nl - 1 - i))) for i in range(nl)]
-    projs = [PL.projection_on_device(sh[1], dev) for sh in shards]
-    vol = None
-    occ_list, masks = [], [None] * nl
-    for i in range(nl):
-        dh_ = head.base_heads[i]
-        fi = nl - 1 - i
-        layer = dh_.cross_transformer.encoder.layers[0]
-        attn = layer.attentions[0]
-        mha = attn.attention_pooling
-        dbound = dh_.cross_transformer.encoder.dbound
-        sel = None
-        if i > 0:
-            lin = head.occ_pred_heads[i - 1][0]
-            up, occ = SF.UpsampleOcc.apply(vol, lin.weight.view(-1), lin.bias)
-            occ_list.append(occ.view(1, -1))
-            if forced_selection is not None and forced_selection[i] is not None:
-                sel = forced_selection[i]
-                mask = torch.zeros(occ.numel(), device=dev, dtype=torch.uint8)
-                mask[sel.long()] = 1
-            else:
-                sel, mask = SF.topk_select(occ, min(head.topk_list[i - 1], occ.numel()))
-            masks[i] = mask
-        pls, slots_list, lw = [], [], None
-        for (feats, meta, dists), proj in zip(shards, projs):
-            # the sharded cross-view block runs its voxel-count GEMMs on the library path, which needs the bf16x3 images
-            pre = dh_.prepare(feats[fi], dists[fi], hws[i], images=True)
-            lw = pre['lw']
-            pl = SF.project_compact(proj, dh_.ref_3d, sel, meta, dbound)
-            slots, _ = SF.Lift.apply(pre['vg'], pre['dist'], pre['vbias'], pre['gbias'], pl, hws[i][0], hws[i][1])
-            pls.append(pl)
-            slots_list.append(slots)
-        x = CrossViewSharded.apply(coll, pls, attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight,
-                                   mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, lw, *slots_list)
-        x = attn.dropout(x)
-        x = layer.norms[0](x)
-        x = layer.ffns[0](x, lw=lw)
-        x = layer.norms[1](x)
-        if i == 0:
-            X, Y, Z = (int(v) for v in dh_.n_voxels)
-            vol = x.view(X, Y, Z, head.embed_dims)
-        else:
-            vol = SF.ScatterAddRows.apply(up, x, sel)
-    volume_out = vol.permute(3, 0, 1, 2).unsqueeze(0)
-    occ_preds = torch.cat(occ_list[::-1], dim=1)
-    valid = head.get_valid(masks[nl - 1]).unsqueeze(0).unsqueeze(0).detach()
-    return volume_out, valid, occ_preds

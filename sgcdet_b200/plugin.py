@@ -204,17 +204,10 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
         self.add_identity = add_identity
 
-    def forward(self, x, identity=None, lw=None, params=None, wstream=None):
-        if x.is_cuda and x.dim() == 2:
-            # same arithmetic as ``self.layers`` with the two Linear layers on the tensor cores (bf16x3 split)
-            l0, drop0 = self.layers[0][0], self.layers[0][2]
-            w = (lw.w1, lw.w1_t, lw.w2, lw.w2_t) if lw is not None else (None,) * 4
-            w1, b1, w2, b2 = params if params is not None else (l0.weight, l0.bias, self.layers[1].weight,
-                                                                self.layers[1].bias)
-            hdn = drop0(F.relu(SF.Linear3.apply(x, w1, b1, w[0], w[1], wstream)))
-            out = self.layers[2](SF.Linear3.apply(hdn, w2, b2, w[2], w[3], wstream))
-        else:
-            out = self.layers(x)
+    def forward(self, x, identity=None):
+        """Plain torch arithmetic (CPU inspection / state-dict round trips); on the path the layer runs inside
+        ``functional.EncoderLayerRows``."""
+        out = self.layers(x)
         if not self.add_identity:
             return out
         return (x if identity is None else identity) + out
@@ -320,42 +313,9 @@ def _level_chain_streams(device, n: int, main):
     backward run concurrently instead of back to back, each followed by its own large lift / projection gradient kernels."""
     key = (torch.device(device), main.cuda_stream)
     pool = _LEVEL_STREAMS.setdefault(key, [])
-    prio = _prio_list('SGC_CHAIN_PRIO', n, -1)
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=torch.device(device), priority=prio[len(pool)]))
+        pool.append(torch.cuda.Stream(device=torch.device(device), priority=-1))
     return pool[:n]
-
-
-def _prio_list(env: str, n: int, default):
-    """Per-level stream priorities from a comma list in the environment (coarsest level first; 'x' = ``default``)."""
-    vals = [v.strip() for v in os.environ.get(env, '').split(',') if v.strip()]
-    out = []
-    for i in range(n):
-        v = vals[i] if i < len(vals) else 'x'
-        out.append(default if v == 'x' else int(v))
-    return out
-
-
-_BIG_STREAMS = {}
-
-
-def _big_backward_streams(device, n: int, main):
-    """Optional dedicated streams (one per level, priorities from SGC_BIG_PRIO) for the large backward kernels of a level
-    (lift backward, the projection's data / weight gradients).  None for a level = they run on the level's prepare stream.
-    A dedicated high-priority stream for the finest level lets the kernels that end the step win the SMs over the coarser
-    levels' work, which has slack."""
-    prio = _prio_list('SGC_BIG_PRIO', n, None)
-    key = (torch.device(device), main.cuda_stream)
-    pool = _BIG_STREAMS.setdefault(key, {})
-    out = []
-    for i, p in enumerate(prio):
-        if p is None:
-            out.append(None)
-            continue
-        if (i, p) not in pool:
-            pool[(i, p)] = torch.cuda.Stream(device=torch.device(device), priority=p)
-        out.append(pool[(i, p)])
-    return out
 
 
 def _dropout_masks(rows: int, widths, drops, device):
@@ -415,14 +375,7 @@ class DenseHead(nn.Module):
     def num_voxels(self) -> int:
         return int(self.n_voxels.prod())
 
-    def _fused_layer(self) -> bool:
-        """Whether the VoxFormerLayer runs as ``functional.EncoderLayerRows`` (one autograd node, fused row kernels)."""
-        ffn = self.cross_transformer.encoder.layers[0].ffns[0]
-        return (os.environ.get('SGC_FUSED_LAYER', '1') != '0' and self.embed_dims in (128, 256) and ffn.add_identity
-                and ffn.layers[0][0].out_features in (128, 256, 512))
-
-    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None, big_stream=None,
-                images: Optional[bool] = None):
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
         map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
@@ -434,12 +387,8 @@ class DenseHead(nn.Module):
         mha = attn.attention_pooling
         ffn = layer.ffns[0]
         wcat, vbias, gbias = da.folded_weights()
-        # the fused layer runs its GEMMs on the own tcgen05 kernel from packed weights; only the unfused fallback
-        # still needs the bf16x3 images of the layer weights
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
-                             ffn.layers[0][0].weight, ffn.layers[1].weight,
-                             images=(not self._fused_layer()) if images is None else images,
-                             b_out=attn.output_proj.bias, in_b=mha.in_proj_bias)
+                             ffn.layers[0][0].weight, ffn.layers[1].weight)
         # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
         # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
         # depth gradient's copies instead of queueing behind them on the same stream
@@ -449,7 +398,7 @@ class DenseHead(nn.Module):
             dist = dpt_dist.t
         else:
             dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
-        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw, big_stream)
+        vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
         params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,
@@ -474,11 +423,8 @@ class DenseHead(nn.Module):
             # critical path -- and applied inside the fused row kernels
             masks = _dropout_masks(n_rows, (self.embed_dims, ffn.layers[0][0].out_features, self.embed_dims),
                                    (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p), feat.device)
-        cur = torch.cuda.current_stream(feat.device)
-        if big_stream is not None:
-            big_stream.wait_stream(cur)   # forked here so that its backward work can start without joining the chain
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
-                    stream=cur, big=big_stream, params=params, wstream=wstream, masks=masks)
+                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream, masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None, coll=None):
@@ -500,30 +446,18 @@ class DenseHead(nn.Module):
         if prepared is None:
             prepared = self.prepare(feat, dpt_dist, hw)
         lw = prepared['lw']
-        big = prepared.get('big')
         slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w,
-                                    big if big is not None else prepared.get('stream'),
-                                    prepared.get('stream') if big is not None else None)
+                                    prepared.get('stream'))
         pp, ws = prepared['params'], prepared['wstream']
         ffn = layer.ffns[0]
         C = self.embed_dims
-        if self._fused_layer():
-            drops = (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p)
-            masks = prepared.get('masks') if self.training else None
-            if self.training and any(p > 0 for p in drops):
-                widths = (C, ffn.layers[0][0].out_features, C)
-                if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
-                    masks = _dropout_masks(pl.Q, widths, drops, feat.device)
-            x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops, coll)
-        else:
-            if coll is not None:
-                raise RuntimeError('sgcdet_b200: view sharding needs the fused encoder layer (SGC_FUSED_LAYER=1)')
-            wa, wf = ws if ws is not None else (None, None)
-            x = SF.CrossView.apply(slots, pl, *pp[:6], lw, wa)
-            x = attn.dropout(x)  # + inp_residual, which is the all-zero query (DCA:837, DenseHead.py:63)
-            x = SF.LayerNormRows.apply(x, pp[10], pp[11], layer.norms[0].eps, wf)
-            x = layer.ffns[0](x, lw=lw, params=pp[6:10], wstream=wf)
-            x = SF.LayerNormRows.apply(x, pp[12], pp[13], layer.norms[1].eps, wf)
+        drops = (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p)
+        masks = prepared.get('masks') if self.training else None
+        if self.training and any(p > 0 for p in drops):
+            widths = (C, ffn.layers[0][0].out_features, C)
+            if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
+                masks = _dropout_masks(pl.Q, widths, drops, feat.device)
+        x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops, coll)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
         return x
@@ -650,7 +584,6 @@ class AdaptiveSparseHead(nn.Module):
             main.wait_stream(s)
             (r[0] if return_intermediates else r).record_stream(main)
             return r
-        big_streams = _big_backward_streams(dev, nl, main) if torch.is_grad_enabled() else [None] * nl
         prepared = []
         # The projections of the three levels are made to run back to back in level order (an event chain between the
         # prepare streams, forward only): left to itself the graph executor started the finest level's projection -- the
@@ -672,8 +605,7 @@ class AdaptiveSparseHead(nn.Module):
                     n_rows = min(self.topk_list[i - 1], self.base_heads[i].num_voxels)
                 else:
                     n_rows = self.base_heads[i].num_voxels
-                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i],
-                                                           n_rows, big_streams[i]))
+                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i], n_rows))
                 if chain_prepare and streams[i] != main:
                     prev_done = torch.cuda.Event()
                     prev_done.record(streams[i])

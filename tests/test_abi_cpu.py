@@ -174,13 +174,3 @@ def test_host_side_planning_helpers():
     assert lib.sgc_rows_gemm_tc(None, 256, 0, 10, 256, 1, None, 256, 0, 0, None, 0, 256, None, 256, 0, 0, None) == 1
     assert lib.sgc_rows_wgrad_tc(None, 256, 0, 256, None, 256, 0, 256, 10, 1, None, 0, 256, 1, 1.0, None, 0, None, None) == 1
     assert lib.sgc_topk_select_mc(None, 10, 11, None, None, None, None) == 1
-
-
-def test_stream_priority_lists(monkeypatch):
-    monkeypatch.delenv('SGC_CHAIN_PRIO', raising=False)
-    assert plugin._prio_list('SGC_CHAIN_PRIO', 3, -1) == [-1, -1, -1]
-    monkeypatch.setenv('SGC_CHAIN_PRIO', '-1, x,-3')
-    assert plugin._prio_list('SGC_CHAIN_PRIO', 3, -1) == [-1, -1, -3]
-    monkeypatch.setenv('SGC_BIG_PRIO', 'x,x,-2')
-    assert plugin._prio_list('SGC_BIG_PRIO', 3, None) == [None, None, -2]
-    assert plugin._prio_list('SGC_BIG_PRIO', 4, None) == [None, None, -2, None]

@@ -198,28 +198,26 @@ def test_full_size_forward_matches_reference_kernels(ref_ext, cuda_lib, monkeypa
     _close_but_for_outliers(vol, vol_r, f'{cfg_name} V={V} volume')
 
 
-def test_view_sharded_large_arkit_forward_matches_reference_kernels(ref_ext, cuda_lib, monkeypatch):
-    """BASELINE.json configs[4] at full size: ``SGCDet_large_ARKit`` with the views split into two in-process shards
-    (``parallel.forward_view_sharded``: partial sums / counts, score max and partial-softmax sums merged between the shards)
-    against the reference's own kernels under the restated glue on the WHOLE scene, at the north-star tolerance."""
-    from oracle import gpu_ref
-    from sgcdet_b200 import parallel
-    torch.backends.cuda.matmul.allow_tf32 = False
-    monkeypatch.setattr(gpu_ref, 'PINNED_PROJECTION', True)
-    cfg = syn.CONFIGS['SGCDet_large_ARKit']
-    V = 40
-    sc = syn.make_scene(cfg, V, shift_origin=True).to(DEV)
-    sd = syn.make_state_dict(cfg)
-    sdg = {k: v.to(DEV) for k, v in sd.items()}
-    with torch.no_grad():
-        vol_r, valid_r, occ_r, masks = gpu_ref.head_forward_gpu(sdg, sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, cfg,
-                                                                training=False, return_masks=True)
-    head = _build(cfg, sd)
-    shards = [parallel.shard_scene_inputs(sc.mlvl_feats, sc.img_meta, sc.mlvl_dpt_dists, parallel.shard_views(V, 2, r))
-              for r in range(2)]
-    with torch.no_grad():
-        vol, valid, occ = parallel.forward_view_sharded(head, shards, forced_selection=_selection(masks, cfg.num_levels),
-                                                        use_dist=False)
-    assert torch.equal(valid, valid_r)
-    torch.testing.assert_close(occ, occ_r, rtol=RTOL, atol=ATOL)
-    _close_but_for_outliers(vol, vol_r, 'view-sharded SGCDet_large_ARKit volume')
+def test_view_sharded_large_arkit_forward_matches_reference_kernels(ref_ext, cuda_lib, tmp_path):
+    """BASELINE.json configs[4] at full size: ``SGCDet_large_ARKit`` with the views split over TWO PROCESSES that share the
+    GPU (the product path: ``AdaptiveSparseHead.forward(view_shard=...)``, exchanges over CUDA-IPC peer memory) against the
+    reference's own kernels under the restated glue on the WHOLE scene, at the north-star tolerance
+    (tests/_peer_worker.py, mode ``refkernels``)."""
+    import subprocess
+    import sys
+    world = 2
+    store = tmp_path / 'rdzv'
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', '_peer_worker.py'), 'SGCDet_large_ARKit', '40', str(world),
+                               str(r), str(store), 'refkernels'], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              cwd=ROOT) for r in range(world)]
+    outs = []
+    for p_ in procs:
+        try:
+            out, _ = p_.communicate(timeout=400)
+        except subprocess.TimeoutExpired:
+            p_.kill()
+            out, _ = p_.communicate()
+            out += '\n[timeout]'
+        outs.append(out)
+    for r, (p_, out) in enumerate(zip(procs, outs)):
+        assert p_.returncode == 0 and 'PEER_WORKER_OK' in out, f'rank {r} failed:\n{out[-3000:]}'

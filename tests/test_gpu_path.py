@@ -197,13 +197,11 @@ def test_head_free_running_selection_overlap(cuda_lib):
     assert int(valid.sum()) == cfg.topk_list[-1]
 
 
-@pytest.mark.parametrize('cfg_name,legacy', [('tiny', False), ('tiny256', False), ('tiny256', True)])
-def test_head_backward_matches_oracle(cuda_lib, monkeypatch, cfg_name, legacy):
+@pytest.mark.parametrize('cfg_name', ['tiny', 'tiny256'])
+def test_head_backward_matches_oracle(cuda_lib, cfg_name):
     """Gradients of loss = sum(volume*G) + occ_loss w.r.t. every input map and every parameter.  'tiny256' has the 32-wide
-    heads of the C=256 configs (tensor-core per-head products and weight gradients); ``legacy`` runs the same through the
-    previous voxel-count GEMM path (own bf16x3 split kernels + library bf16 GEMM, SGC_ROWS_TC=0)."""
-    if legacy:
-        monkeypatch.setattr(SF, 'ROWS_TC', False)
+    heads of the C=256 configs (per-head products through strided tensor maps), 'tiny' the 16-wide heads of the "-L" configs
+    (zero-extended / K-concatenated per-head weights)."""
     cfg = syn.CONFIGS[cfg_name]
     V = 12
     sc = syn.make_scene(cfg, V, shift_origin=True)

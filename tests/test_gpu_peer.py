@@ -108,7 +108,7 @@ def _exclusive_compute_mode() -> bool:
         return False
 
 
-@pytest.mark.parametrize('cfg_name,V,world', [('tiny', 12, 2), ('tiny256', 13, 2)])
+@pytest.mark.parametrize('cfg_name,V,world', [('tiny', 12, 2), ('tiny256', 13, 2), ('tiny', 9, 3)])
 def test_view_sharded_product_path_two_processes(cuda_lib, cfg_name, V, world, tmp_path):
     """The real thing on one GPU: `world` PROCESSES (gloo group for the handle exchange, CUDA IPC mappings of each other's
     symmetric buffers) share cuda:0 by time slicing; every rank runs AdaptiveSparseHead.forward(view_shard=...) + backward +
@@ -134,3 +134,60 @@ def test_view_sharded_product_path_two_processes(cuda_lib, cfg_name, V, world, t
         outs.append(out)
     for r, (p_, out) in enumerate(zip(procs, outs)):
         assert p_.returncode == 0 and 'PEER_WORKER_OK' in out, f'rank {r} failed:\n{out[-3000:]}'
+
+
+def test_grad_averager_buckets_and_graph_capture(cuda_lib):
+    """GradAverager with a single rank (the average of one rank is the identity): the gradients are bucketed in the order
+    they become final, every bucket is reduced from its post-accumulate hook on the communication stream, and the whole step
+    -- hooks included -- is capturable into a CUDA graph.  Gradients must equal those of a step without the averager."""
+    cfg = syn.CONFIGS['tiny']
+    sc = syn.make_scene(cfg, 8, shift_origin=True).to(DEV)
+    head = plugin.build_voxel_head(cfg)
+    head.load_state_dict(syn.make_state_dict(cfg))
+    head = head.to(DEV).eval()
+    params = list(head.parameters())
+    feats = [f.clone().requires_grad_(True) for f in sc.mlvl_feats]
+
+    def fwd_bwd():
+        for p in params + feats:
+            p.grad = None
+        vol, valid, occ = head(feats, sc.img_meta, sc.mlvl_dpt_dists)
+        ((vol * sc.grad_volume).sum() + head.occ_loss(occ, None, sc.geo_occ)['loss_occ']).backward()
+
+    fwd_bwd()
+    torch.cuda.synchronize()
+    ref = [p.grad.clone() for p in params]
+    avg = peer.GradAverager(params, bucket_bytes=256 << 10, tail_bytes=64 << 10)
+    try:
+        def step():
+            avg.begin_step()
+            fwd_bwd()
+            avg.finish_step()
+
+        def check(what):
+            torch.cuda.synchronize()
+            avg.mem.check()
+            for k, (p, r) in enumerate(zip(params, ref)):
+                _close(f'{what}: param {k}', p.grad, r)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()                      # records the order in which the gradients become final
+            check('first step (one all-reduce)')
+            step()                      # bucketed from here on
+            check('bucketed step')
+        torch.cuda.current_stream().wait_stream(side)
+        assert avg.buckets is not None and len(avg.buckets) >= 3
+        assert sorted(i for g, _, _ in avg.buckets for i in g) == list(range(len(params)))
+        graph = torch.cuda.CUDAGraph()
+        for p in params + feats:
+            p.grad = None
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
+        check('graph replay')
+        graph.replay()
+        check('second replay')
+    finally:
+        avg.close()

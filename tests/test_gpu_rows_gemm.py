@@ -109,9 +109,7 @@ def test_level_weights_packs_match_single_kernel(cuda_lib):
     w_out, wo = torch.randn(C, C, generator=g).to(dev), torch.randn(C, C, generator=g).to(dev)
     in_w = torch.randn(3 * C, C, generator=g).to(dev)
     w1, w2 = torch.randn(F, C, generator=g).to(dev), torch.randn(C, F, generator=g).to(dev)
-    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
-    if not lw.rows_tc:
-        pytest.skip('SGC_ROWS_TC=0')
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2)
     dh = C // 8
     scale = 1.0 / math.sqrt(dh)
     wq, wk, wv = in_w[:C], in_w[C:2 * C], in_w[2 * C:]
@@ -239,8 +237,8 @@ def test_narrow_head_products_match_fp64(cuda_lib, R, C):
     in_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).cuda()
     w1, w2 = torch.randn(2 * C, C, generator=g).cuda(), torch.randn(C, 2 * C, generator=g).cuda()
     wcat = torch.randn(C + 128, C, generator=g).cuda()
-    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2, images=False)
-    if not getattr(lw, 'heads_exp', False):
+    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2)
+    if lw.heads_tc:
         pytest.skip('32-wide heads use the per-head tensor maps (heads_tc)')
     scale = 1.0 / math.sqrt(dh)
     wk, wv = in_w[C:2 * C].double(), in_w[2 * C:].double()
