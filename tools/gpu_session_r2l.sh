@@ -5,7 +5,7 @@ O=gpurun_out
 mkdir -p $O
 ts() { echo "[$(date +%H:%M:%S)] $*" | tee -a $O/r2l_times.log; }
 ts start
-timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > $O/r2l_suite.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 > $O/r2l_suite.log
 ts suite "$(tail -1 $O/r2l_suite.log)"
 timeout 300 python __graft_entry__.py smoke > $O/r2l_smoke.log 2>&1
 ts smoke "$(tail -1 $O/r2l_smoke.log)"
