@@ -319,8 +319,8 @@ def run_ours(args):
                                 [g for s in scenes for g in (s['gvol'], None)])
         main.wait_stream(loss_stream)
         if averager is not None:
-            # the bucketed peer all-reduces were issued from the backward as their gradients became final (captured with the
-            # step); this joins the communication stream
+            # the peer all-reduces of the parameter groups were issued from the backward as their gradients became final
+            # (captured with the step); this averages the remaining tail and joins the communication stream
             averager.finish_step()
 
     # scene-batch DP: the path's weight gradients (~8 MB) are averaged across ranks every step.
@@ -340,9 +340,6 @@ def run_ours(args):
         ok = torch.tensor([1 if ar_mode == 'peer' else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            if averager is not None:
-                for h_ in averager._hooks:
-                    h_.remove()
             ar_mode, averager = 'nccl', None
     ar_in_graph = ar_mode == 'peer' and not args.no_graph
     avg_op = dist.ReduceOp.AVG if world > 1 else None

@@ -374,18 +374,28 @@ _COUNTERS = {}
 _GRAD_STREAMS = {}
 
 
+GRAD_REDUCER = None   # set by peer.GradAverager: callable(params, grads) -> grads, applied to a parameter group's gradients
+
+
 class OnStream(torch.autograd.Function):
     """Identity on parameters, applied under ``with torch.cuda.stream(wstream)``: the aliases' backward node (and the
     AccumulateGrad behind it) belong to ``wstream``, so a backward that PRODUCES a weight gradient on ``wstream`` can
     hand it to autograd without making the calling stream wait for it (autograd orders consumers after the
-    producing stream, and joins every leaf stream when the backward pass ends)."""
+    producing stream, and joins every leaf stream when the backward pass ends).
+
+    Its backward is also the point where the gradients of a parameter group are final: with scene-batch data parallelism
+    (``peer.GradAverager`` installs ``GRAD_REDUCER``) they are averaged over the ranks right here, on a communication stream,
+    while the rest of the backward continues -- the averaged tensors are what autograd accumulates."""
 
     @staticmethod
     def forward(ctx, *ts):
+        ctx.params = ts if GRAD_REDUCER is not None else None
         return tuple(t.view_as(t) for t in ts)
 
     @staticmethod
     def backward(ctx, *gs):
+        if GRAD_REDUCER is not None and ctx.params is not None:
+            return GRAD_REDUCER(ctx.params, gs)
         return gs
 
 

@@ -145,122 +145,83 @@ class GradAverager:
     INSIDE the step's CUDA graph and overlap the end of the backward (replaces cat -> ncclAllReduce -> div -> copy issued by
     the CPU after every replay, which sat entirely behind the last kernel of the step).
 
-    The parameters are bucketed in the order their gradients become final (recorded during the first, eager step through
-    ``post_accumulate_grad`` hooks, like DDP's reverse-order buckets): every bucket is averaged on a communication stream as
-    soon as its last gradient is accumulated, while the large projection-gradient kernels of the finest level are still
-    running; only the small tail bucket (the gradients those kernels produce) remains behind the backward.
+    The path hands every parameter group to autograd through ``functional.OnStream`` on that group's weight-gradient stream;
+    its backward node runs exactly when the group's gradients are final.  While a GradAverager is active that node averages
+    them over the ranks -- on ONE communication stream, in autograd's (deterministic, rank-independent) execution order, each
+    group in its own slice of the symmetric buffer -- and returns the averaged tensors to autograd, so ``p.grad`` never holds
+    an unreduced value.  The large projection-gradient kernels of the finest level keep running meanwhile; only the gradients
+    those kernels produce (the four projection layers of every level, ~1.2 MB) are averaged after the backward, in
+    ``finish_step()``.
 
-    Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()`` (joins the communication stream;
-    in the first step it averages everything at once)."""
+    Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``."""
 
-    def __init__(self, params, group=None, device=None, bucket_bytes: int = 4 << 20, tail_bytes: int = 1 << 20):
+    def __init__(self, params, group=None, device=None):
         self.params = [p for p in params if p.requires_grad]
-        self.sizes = [p.numel() for p in self.params]
-        n = sum(self.sizes)
-        self.n = (n + 3) // 4 * 4 + 4 * len(self.params)        # every bucket starts 16-byte aligned
+        n = sum(p.numel() for p in self.params)
+        self.n = (n + 3) // 4 * 4
         self.mem = PeerMemory(4 * self.n, group, device)
         self.device = self.mem.device
         self.flat_in = self.mem.view((self.n,))
         self.flat_in.zero_()
-        self.flat_out = torch.empty(self.n, device=self.device, dtype=F32)
         self.scale = 1.0 / self.mem.world
-        self.bucket_bytes, self.tail_bytes = bucket_bytes, tail_bytes
         self.comm = torch.cuda.Stream(device=self.device, priority=-1)
-        self.order = []            # parameter indices in the order their gradients became final (first step)
-        self.buckets = None        # list of (param indices, offset, n) once the order is known
-        self._index = {id(p): i for i, p in enumerate(self.params)}
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
-        self._pending, self._events, self._main = None, None, None
+        self._ids = {id(p) for p in self.params}
+        self._done, self._active = set(), False
+        self.groups_last_step = 0
 
-    # ---- bucket plan ------------------------------------------------------------------------------------------------------
-    def _plan(self):
-        order = self.order + [i for i in range(len(self.params)) if i not in set(self.order)]
-        # tail bucket: the gradients that arrive last, up to tail_bytes; the rest in chunks of bucket_bytes
-        tail, acc = [], 0
-        for i in reversed(order):
-            if acc + 4 * self.sizes[i] > self.tail_bytes and tail:
-                break
-            tail.insert(0, i)
-            acc += 4 * self.sizes[i]
-        head = order[:len(order) - len(tail)]
-        groups, cur, acc = [], [], 0
-        for i in head:
-            cur.append(i)
-            acc += 4 * self.sizes[i]
-            if acc >= self.bucket_bytes:
-                groups.append(cur)
-                cur, acc = [], 0
-        if cur:
-            groups.append(cur)
-        groups.append(tail)
-        self.buckets, off = [], 0
-        for gidx in groups:
-            nb = sum(self.sizes[i] for i in gidx)
-            self.buckets.append((gidx, off, nb))
-            off += (nb + 3) // 4 * 4
-        self._bucket_of = {i: b for b, (gidx, _, _) in enumerate(self.buckets) for i in gidx}
+    def _reduce(self, grads):
+        """grads (final, on the current stream) -> averaged copies.  Every collective of this object runs on the communication
+        stream (or after it has been joined), one after the other, and ends with a barrier behind the peers' last read: the
+        symmetric buffer can be reused from offset 0 every time."""
+        sizes = [g.numel() for g in grads]
+        nb = sum(sizes)
+        torch._foreach_copy_(list(self.flat_in[:nb].split(sizes)), [g.reshape(-1) for g in grads])
+        out = torch.empty(nb, device=self.device, dtype=F32)
+        self.mem.all_reduce(nb, out, 'sum', self.scale)
+        return [o.view(g.shape) for o, g in zip(out.split(sizes), grads)]
 
-    def _reduce(self, idxs, off, nb):
-        grads = [self.params[i].grad.view(-1) for i in idxs]
-        sizes = [self.sizes[i] for i in idxs]
-        torch._foreach_copy_(list(self.flat_in[off:off + nb].split(sizes)), grads)
-        self.mem.all_reduce(nb, self.flat_out[off:off + nb], 'sum', self.scale, offset_bytes=4 * off)
-        torch._foreach_copy_(grads, list(self.flat_out[off:off + nb].split(sizes)))
-
-    # ---- per step -----------------------------------------------------------------------------------------------------------
-    def begin_step(self):
-        self._main = torch.cuda.current_stream(self.device)
-        if self.buckets is None:
-            self._pending = None
-            if self.order:           # second step: the first one recorded the order
-                self._plan()
-        if self.buckets is not None:
-            self._pending = [len(g) for g, _, _ in self.buckets]
-            self._events = [[] for _ in self.buckets]
-
-    def _on_grad(self, p):
-        i = self._index[id(p)]
-        if self.buckets is None:
-            if self._pending is None and i not in self.order:
-                self.order.append(i)
-            return
-        if self._pending is None:
-            return
-        b = self._bucket_of[i]
+    def _on_group(self, params, grads):
+        """``functional.GRAD_REDUCER``: called from OnStream.backward on the group's weight-gradient stream."""
+        if not self._active or any(g is None for g in grads) or any(id(p) not in self._ids for p in params):
+            return grads
+        cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))     # the stream this gradient was accumulated on
-        self._events[b].append(ev)
-        self._pending[b] -= 1
-        if self._pending[b] == 0:
-            for e in self._events[b]:
-                self.comm.wait_event(e)
-            idxs, off, nb = self.buckets[b]
-            with torch.cuda.stream(self.comm):
-                for j in idxs:
-                    self.params[j].grad.record_stream(self.comm)
-                self._reduce(idxs, off, nb)
+        ev.record(cur)
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            for g in grads:
+                g.record_stream(self.comm)
+            outs = self._reduce([g.contiguous() for g in grads])
+        cur.wait_stream(self.comm)
+        for o in outs:
+            o.record_stream(cur)
+        self._done.update(id(p) for p in params)
+        self.groups_last_step += 1
+        return tuple(outs)
+
+    def begin_step(self):
+        from . import functional as SF
+        SF.GRAD_REDUCER = self._on_group
+        self._done, self._active, self.groups_last_step = set(), True, 0
 
     def finish_step(self):
+        """After ``backward()``: average, in place, every gradient no OnStream node has seen (on the current stream, which
+        autograd has joined with all gradient streams), and make the current stream wait for the communication stream."""
+        self._active = False
         main = torch.cuda.current_stream(self.device)
-        if self.buckets is None or self._pending is None:
-            self._reduce(list(range(len(self.params))), 0, sum(self.sizes))      # first step: everything at once
-            return
-        for b, left in enumerate(self._pending):
-            if left:                 # a bucket with a parameter that received no gradient this step: reduce it here
-                idxs, off, nb = self.buckets[b]
-                idxs = [j for j in idxs if self.params[j].grad is not None]
-                if len(idxs) != len(self.buckets[b][0]):
-                    raise RuntimeError('sgcdet_b200.peer.GradAverager: a parameter received no gradient in this step')
-                main.wait_stream(self.comm)
-                self._reduce(idxs, off, nb)
         main.wait_stream(self.comm)
-        self._pending = None
+        rest = [p for p in self.params if id(p) not in self._done and p.grad is not None]
+        if rest:
+            grads = [p.grad for p in rest]
+            torch._foreach_copy_(grads, self._reduce(grads))
 
     def __call__(self):
-        """Everything at once on the current stream (no overlap): the round-1 placement, kept for comparison."""
-        self._reduce(list(range(len(self.params))), 0, sum(self.sizes))
+        """Everything at once on the current stream, after the backward (no overlap): the round-1 placement."""
+        self._done = set()
+        self.finish_step()
 
     def close(self):
-        for h in self._hooks:
-            h.remove()
+        from . import functional as SF
+        if SF.GRAD_REDUCER == self._on_group:
+            SF.GRAD_REDUCER = None
         self.mem.close()

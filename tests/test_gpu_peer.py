@@ -138,10 +138,10 @@ def test_view_sharded_product_path_two_processes(cuda_lib, cfg_name, V, world, t
         assert p_.returncode == 0 and 'PEER_WORKER_OK' in out, f'rank {r} failed:\n{out[-3000:]}'
 
 
-def test_grad_averager_buckets_and_graph_capture(cuda_lib):
-    """GradAverager with a single rank (the average of one rank is the identity): the gradients are bucketed in the order
-    they become final, every bucket is reduced from its post-accumulate hook on the communication stream, and the whole step
-    -- hooks included -- is capturable into a CUDA graph.  Gradients must equal those of a step without the averager."""
+def test_grad_averager_groups_and_graph_capture(cuda_lib):
+    """GradAverager with a single rank (the average of one rank is the identity): every parameter group is reduced from its
+    OnStream backward node on the communication stream, the projection layers' gradients in finish_step, and the whole step
+    is capturable into a CUDA graph.  Gradients must equal those of a step without the averager."""
     cfg = syn.CONFIGS['tiny']
     sc = syn.make_scene(cfg, 8, shift_origin=True).to(DEV)
     head = plugin.build_voxel_head(cfg)
@@ -159,7 +159,7 @@ def test_grad_averager_buckets_and_graph_capture(cuda_lib):
     fwd_bwd()
     torch.cuda.synchronize()
     ref = [p.grad.clone() for p in params]
-    avg = peer.GradAverager(params, bucket_bytes=256 << 10, tail_bytes=64 << 10)
+    avg = peer.GradAverager(params)
     try:
         def step():
             avg.begin_step()
@@ -175,13 +175,10 @@ def test_grad_averager_buckets_and_graph_capture(cuda_lib):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            step()                      # records the order in which the gradients become final
-            check('first step (one all-reduce)')
-            step()                      # bucketed from here on
-            check('bucketed step')
+            step()
+            check('eager step')
         torch.cuda.current_stream().wait_stream(side)
-        assert avg.buckets is not None and len(avg.buckets) >= 3
-        assert sorted(i for g, _, _ in avg.buckets for i in g) == list(range(len(params)))
+        assert avg.groups_last_step == 2 * cfg.num_levels + (cfg.num_levels - 1)   # attention + FFN blocks, occupancy heads
         graph = torch.cuda.CUDAGraph()
         for p in params + feats:
             p.grad = None
@@ -191,5 +188,8 @@ def test_grad_averager_buckets_and_graph_capture(cuda_lib):
         check('graph replay')
         graph.replay()
         check('second replay')
+        # without begin_step the path is untouched
+        fwd_bwd()
+        check('inactive averager')
     finally:
         avg.close()
