@@ -141,6 +141,9 @@ int sgc_project_tc_wgrad(const float* gvg, const float* feat, long long chan_str
  * wpack + b*pack_batch_elems (bf16 elements; 0 = one matrix shared by all batches).  Both operands are split into bf16
  * hi/lo in shared memory / at pack time and accumulate in fp32 (relative error ~1e-5).  n_cta = output columns per CTA
  * (32/64/128/256, 0 = sgc_rows_gemm_tc_auto_ncta).  No cluster launch: starts as soon as one SM is free. */
+/* Debug aid: CTA 0 of every following sgc_rows_gemm_tc launch stores clock64() at 13 points of its life into `stamps` (device,
+ * 16 x int64; NULL switches it off).  See tools/rows_gemm_timeline.py. */
+int sgc_rows_gemm_tc_set_debug(long long* stamps);
 int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B);
 int sgc_rows_gemm_tc(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
                      int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,

@@ -47,6 +47,7 @@ SIGNATURES = {
     'sgc_set_pdl': [I],
     'sgc_project_tc_wgrad': [P, P, LL, I, I, I, I, P, P, P],
     'sgc_rows_gemm_tc_auto_ncta': [I, I, I],
+    'sgc_rows_gemm_tc_set_debug': [P],
     'sgc_rows_gemm_tc': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, P],
     'sgc_rows_gemm_tc_ex': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, I, I, P],
     'sgc_rows_wgrad_tc_scratch_floats': [I, I, I, I],

@@ -53,7 +53,13 @@ struct RowsGemmParams {
   int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
   int a_bcast;                  // 1: every batch reads the SAME activation rows (batch coordinate 0)
   int kpb;                      // > 0: the reduction runs over the batches of A too, kpb k-slabs per batch (K-concatenation)
+  long long* dbg;               // optional [16] clock64 stamps of CTA 0 (sgc_rows_gemm_tc_set_debug): where a launch's time goes
 };
+
+#define RG_STAMP(i)                                                         \
+  do {                                                                      \
+    if (p.dbg && blockIdx.x == 0) p.dbg[i] = clock64();                     \
+  } while (0)
 
 __global__ void __launch_bounds__(RG_THREADS, 1)
 rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap omap,
@@ -71,11 +77,13 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   const int n_cta = p.n_cta, k_slabs = p.k_slabs, works = p.works;
 
   if (threadIdx.x == 0) {
+    RG_STAMP(0);
     for (int i = 0; i < RG_NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
     for (int i = 0; i < RG_NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
     for (int i = 0; i < RG_NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    RG_STAMP(1);
   }
   if (warp == 7) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
@@ -87,6 +95,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
+  if (threadIdx.x == 0) RG_STAMP(2);
   // barrier setup and the TMEM allocation above do not depend on the predecessor; everything below reads its output
   pdl_wait();
 
@@ -104,6 +113,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
           if (p.kpb) { bc = j / p.kpb; col = (j - bc * p.kpb) * BK; }
           if (p.a_swap) tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, bc, mt * BM, &sm->f_full[pf.stage]);
           else tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, mt * BM, bc, &sm->f_full[pf.stage]);
+          if (j == 0 && w == (int)blockIdx.x) RG_STAMP(3);
           pf.next();
         }
       }
@@ -115,6 +125,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     for (int w = blockIdx.x; w < works; w += gridDim.x) {
       for (int j = 0; j < k_slabs; ++j) {
         mbar_wait(&sm->f_full[pf.stage], pf.phase);
+        if (threadIdx.x == 0 && j == 0 && w == (int)blockIdx.x) RG_STAMP(4);
         float x[BK];
         const uint8_t* rowp = f_base + pf.stage * f_stage_bytes + m * 128;
 #pragma unroll
@@ -142,6 +153,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
         pf.next();
         fence_proxy_async();
         mbar_arrive(&sm->a_full[pa.stage]);
+        if (threadIdx.x == 0 && w == (int)blockIdx.x) { if (j == 0) RG_STAMP(5); if (j == k_slabs - 1) RG_STAMP(6); }
         pa.next();
       }
     }
@@ -200,9 +212,11 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
           tc_commit(&sm->b_empty[pb.stage]);
           pb.next();
           tc_commit(&sm->a_empty[pa.stage]);
+          if (w == (int)blockIdx.x && j == 0) RG_STAMP(7);
           pa.next();
         }
         tc_commit(&sm->tmem_full[buf]);
+        if (w == (int)blockIdx.x) RG_STAMP(8);
       }
     }
   } else if (warp >= 8) {
@@ -220,6 +234,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       const float* bias = p.bias ? p.bias + (size_t)b * p.bias_batch + np * n_cta : nullptr;
       mbar_wait(&sm->tmem_full[buf], ephase);
       tc_fence_after();
+      if (issuer && w == (int)blockIdx.x) RG_STAMP(9);
       for (int c0 = 0; c0 < n_cta; c0 += 32, ++chunk) {
         uint32_t r[32];
         asm volatile(
@@ -254,15 +269,18 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       }
       tc_fence_before();
       mbar_arrive(&sm->tmem_empty[buf]);
+      if (issuer && w == (int)blockIdx.x) RG_STAMP(10);
     }
     // the staging buffers only have to outlive the stores' READS; the writes are complete (and visible) at kernel end
     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (issuer) RG_STAMP(11);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 7) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
+    if (lane == 0) RG_STAMP(12);
   }
 }
 
@@ -309,6 +327,16 @@ extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
   return n_cta;
 }
 
+static long long* g_rows_gemm_dbg = nullptr;
+// Debug aid: `stamps` = device buffer of 16 int64 (or NULL to switch off): CTA 0 of every following sgc_rows_gemm_tc launch
+// records clock64() at 13 points of its life (0 entry, 1 barriers initialised, 2 TMEM allocated + CTA sync, 3 first TMA issued,
+// 4 first tile landed, 5 first / 6 last k-slab converted, 7 first slab's MMAs issued, 8 accumulator committed, 9 epilogue sees
+// it, 10 last store issued, 11 stores drained, 12 TMEM freed).  tools/rows_gemm_timeline.py prints the differences.
+extern "C" int sgc_rows_gemm_tc_set_debug(long long* stamps) {
+  g_rows_gemm_dbg = stamps;
+  return 0;
+}
+
 static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x, int R, int K, int B, const void* wpack,
                                int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias,
                                int bias_batch, int N, float* y, long long ldy, long long batch_y, int n_cta, int a_mode,
@@ -352,6 +380,7 @@ static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x,
   p.works = p.m_tiles * p.nsplit * B;
   p.k_slabs = K / BK;
   p.n_cta = n_cta;
+  p.dbg = g_rows_gemm_dbg;
   p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
   const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * n_cta * BK * 2 +
                       (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;

@@ -146,14 +146,17 @@ class GradAverager:
     the CPU after every replay, which sat entirely behind the last kernel of the step).
 
     The path hands every parameter group to autograd through ``functional.OnStream`` on that group's weight-gradient stream;
-    its backward node runs exactly when the group's gradients are final.  While a GradAverager is active that node averages
-    them over the ranks -- on ONE communication stream, in autograd's (deterministic, rank-independent) execution order, each
-    group in its own slice of the symmetric buffer -- and returns the averaged tensors to autograd, so ``p.grad`` never holds
-    an unreduced value.  The large projection-gradient kernels of the finest level keep running meanwhile; only the gradients
-    those kernels produce (the four projection layers of every level, ~1.2 MB) are averaged after the backward, in
-    ``finish_step()``.
+    its backward node runs exactly when the group's gradients are final.  While a GradAverager is active that node records an
+    event and returns PLACEHOLDER tensors to autograd (which adopts them as ``p.grad``: no kernel); when the last group of the
+    step has reported, ONE all-reduce over all of them is issued on a communication stream -- it waits for the recorded
+    events, gathers the gradients into the symmetric buffer, reduces, and scatters the averages into the placeholders --
+    while the large projection-gradient kernels of the finest level are still running.  Only the gradients those kernels
+    produce (the four projection layers of every level, ~1.2 MB) are averaged after the backward, in ``finish_step()``.
+    Eight separate collectives (one per group) were measured first: 995 vs 1 137 volumes/s on two GPUs -- they queue in
+    autograd's issue order, finest level first, and end up serialised behind the finest level's weight gradients.
 
-    Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``."""
+    Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``.  The number of groups per step is
+    learnt in the first step (which therefore reduces everything in ``finish_step``)."""
 
     def __init__(self, params, group=None, device=None):
         self.params = [p for p in params if p.requires_grad]
@@ -166,58 +169,87 @@ class GradAverager:
         self.scale = 1.0 / self.mem.world
         self.comm = torch.cuda.Stream(device=self.device, priority=-1)
         self._ids = {id(p) for p in self.params}
-        self._done, self._active = set(), False
-        self.groups_last_step = 0
+        self._active, self._expected = False, None
+        self._pending, self._done, self._adopted = [], set(), []
+        self.groups_last_step, self.copied_last_step = 0, 0
 
-    def _reduce(self, grads):
-        """grads (final, on the current stream) -> averaged copies.  Every collective of this object runs on the communication
-        stream (or after it has been joined), one after the other, and ends with a barrier behind the peers' last read: the
-        symmetric buffer can be reused from offset 0 every time."""
+    def _reduce_into(self, grads, outs):
+        """outs[i] = average over the ranks of grads[i] (final on the current stream).  Every collective of this object runs on
+        the communication stream (or after it has been joined), one after the other, and ends with a barrier behind the peers'
+        last read: the symmetric buffer is reused from offset 0 every time."""
         sizes = [g.numel() for g in grads]
         nb = sum(sizes)
         torch._foreach_copy_(list(self.flat_in[:nb].split(sizes)), [g.reshape(-1) for g in grads])
-        out = torch.empty(nb, device=self.device, dtype=F32)
-        self.mem.all_reduce(nb, out, 'sum', self.scale)
-        return [o.view(g.shape) for o, g in zip(out.split(sizes), grads)]
+        red = torch.empty(nb, device=self.device, dtype=F32)
+        self.mem.all_reduce(nb, red, 'sum', self.scale)
+        torch._foreach_copy_([o.view(-1) for o in outs], list(red.split(sizes)))
+
+    def _flush(self):
+        """All reported groups in one collective on the communication stream."""
+        if not self._pending:
+            return
+        grads, outs = [], []
+        for ev, gs, os_ in self._pending:
+            self.comm.wait_event(ev)
+            grads += gs
+            outs += os_
+        with torch.cuda.stream(self.comm):
+            for t in grads + outs:
+                t.record_stream(self.comm)
+            self._reduce_into(grads, outs)
+        self._pending = []
 
     def _on_group(self, params, grads):
         """``functional.GRAD_REDUCER``: called from OnStream.backward on the group's weight-gradient stream."""
         if not self._active or any(g is None for g in grads) or any(id(p) not in self._ids for p in params):
             return grads
         cur = torch.cuda.current_stream(self.device)
+        gs = [g.contiguous() for g in grads]
+        outs = [torch.empty_like(g) for g in gs]
         ev = torch.cuda.Event()
         ev.record(cur)
-        self.comm.wait_event(ev)
-        with torch.cuda.stream(self.comm):
-            for g in grads:
-                g.record_stream(self.comm)
-            outs = self._reduce([g.contiguous() for g in grads])
-        cur.wait_stream(self.comm)
-        for o in outs:
-            o.record_stream(cur)
+        # autograd adopts a returned tensor as p.grad only while nobody else holds it: keep storage ALIASES (.data: another
+        # tensor object on the same memory) for the collective to write through; finish_step verifies the adoption
+        aliases = [o.data for o in outs]
+        self._pending.append((ev, gs, aliases))
+        self._adopted += list(zip(params, aliases))
         self._done.update(id(p) for p in params)
         self.groups_last_step += 1
+        if self._expected is not None and self.groups_last_step == self._expected:
+            self._flush()
         return tuple(outs)
 
     def begin_step(self):
         from . import functional as SF
         SF.GRAD_REDUCER = self._on_group
-        self._done, self._active, self.groups_last_step = set(), True, 0
+        self._pending, self._done, self._active, self.groups_last_step, self._adopted = [], set(), True, 0, []
 
     def finish_step(self):
-        """After ``backward()``: average, in place, every gradient no OnStream node has seen (on the current stream, which
-        autograd has joined with all gradient streams), and make the current stream wait for the communication stream."""
+        """After ``backward()``: flush groups that were not flushed from the backward (first step), average in place every
+        gradient no OnStream node has seen (on the current stream, which autograd has joined with all gradient streams), and
+        make the current stream wait for the communication stream."""
         self._active = False
         main = torch.cuda.current_stream(self.device)
+        if self._pending:
+            self.comm.wait_stream(main)
+            self._flush()
+        if self._expected is None and self.groups_last_step:
+            self._expected = self.groups_last_step
         main.wait_stream(self.comm)
-        rest = [p for p in self.params if id(p) not in self._done and p.grad is not None]
+        # a gradient autograd copied instead of adopting (another holder, or an accumulation into an existing .grad) did not
+        # see the collective's result: hand it over explicitly
+        stale = [(p.grad, a) for p, a in self._adopted if p.grad is not None and p.grad.data_ptr() != a.data_ptr()]
+        if stale:
+            torch._foreach_copy_([g for g, _ in stale], [a for _, a in stale])
+        self.copied_last_step = len(stale)
+        self._adopted = []
+        rest = [p.grad for p in self.params if id(p) not in self._done and p.grad is not None]
         if rest:
-            grads = [p.grad for p in rest]
-            torch._foreach_copy_(grads, self._reduce(grads))
+            self._reduce_into(rest, rest)
 
     def __call__(self):
         """Everything at once on the current stream, after the backward (no overlap): the round-1 placement."""
-        self._done = set()
+        self._pending, self._done, self._adopted = [], set(), []
         self.finish_step()
 
     def close(self):

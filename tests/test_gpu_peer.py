@@ -142,8 +142,10 @@ def test_grad_averager_groups_and_graph_capture(cuda_lib):
     """GradAverager with a single rank (the average of one rank is the identity): every parameter group is reduced from its
     OnStream backward node on the communication stream, the projection layers' gradients in finish_step, and the whole step
     is capturable into a CUDA graph.  Gradients must equal those of a step without the averager."""
+    from sgcdet_b200 import functional as SF
     cfg = syn.CONFIGS['tiny']
     sc = syn.make_scene(cfg, 8, shift_origin=True).to(DEV)
+    sc.img_meta['sgc_projection'] = SF.compute_projection(sc.img_meta).to(DEV)   # static buffer: no H2D copy under capture
     head = plugin.build_voxel_head(cfg)
     head.load_state_dict(syn.make_state_dict(cfg))
     head = head.to(DEV).eval()
@@ -176,7 +178,10 @@ def test_grad_averager_groups_and_graph_capture(cuda_lib):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             step()
-            check('eager step')
+            check('first step (everything reduced after the backward)')
+            step()
+            check('second step (one collective issued from the backward)')
+            assert avg.copied_last_step == 0      # autograd adopted every placeholder the collective wrote into
         torch.cuda.current_stream().wait_stream(side)
         assert avg.groups_last_step == 2 * cfg.num_levels + (cfg.num_levels - 1)   # attention + FFN blocks, occupancy heads
         graph = torch.cuda.CUDAGraph()

@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 ts() { echo "[$(date +%H:%M:%S)] $*" | tee -a $O/r2m_times.log; }
 ts start
-timeout 600 python -m pytest tests/test_gpu_peer.py tests/test_gpu_rows_gemm.py -q 2>&1 | tail -60 > $O/r2m_tests.log
+timeout 600 python -m pytest tests/test_gpu_peer.py -q -k "averager" 2>&1 | tail -60 > $O/r2m_tests.log
 ts tests "$(tail -1 $O/r2m_tests.log)"
 T="timeout -k 5 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 for i in 1 2; do
@@ -18,3 +18,5 @@ ts n2-nccl "rc=$? $(python -c "import json;d=json.loads(open('$O/r2m_n2_nccl.jso
 $T --master-port 29544 bench.py --gpus 2 --steps 200 --no-cpu-baseline --no-view-sharded --no-train-step --skip-e2e --no-grad-allreduce > $O/r2m_n2_noar.json 2> $O/r2m_n2_noar.err
 ts n2-no-allreduce "rc=$? $(python -c "import json;d=json.loads(open('$O/r2m_n2_noar.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'])" 2>&1 | tail -1)"
 tail -8 $O/r2m_n2_peer1.err > $O/r2m_n2_peer1_tail.txt
+timeout 200 python tools/rows_gemm_timeline.py > $O/r2m_rows_gemm_timeline.txt 2>&1
+ts rows-gemm-timeline "$(head -3 $O/r2m_rows_gemm_timeline.txt | tr '\n' ' ')"
