@@ -407,9 +407,10 @@ int sgc_peer_free(void* ptr);
 /* One-shot all-reduce: bufs / sigs are HOST arrays of `world` device pointers -- rank r's data buffer and signal pad as mapped
  * into this process.  out[i] = scale * sum (op 0) or max (op 1, scale ignored) over the ranks of bufs[r][i], i < n, reduced
  * in rank order on every rank (bit-identical results everywhere).  Every rank calls it with the same n; the cross-GPU
- * barriers are flags in the signal pads (stateless: the launch can be replayed from a CUDA graph); world <= 8. */
+ * barriers are flags in the signal pads (stateless: the launch can be replayed from a CUDA graph); world <= 8.  max_blocks
+ * (0 = 128, the same on every rank) bounds the CTAs of a collective that runs beside other kernels. */
 int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
-                       float* out, void* stream);
+                       float* out, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -92,7 +92,7 @@ SIGNATURES = {
     'sgc_nhwc_to_nchw': [P, I, I, I, P, P],
     'sgc_depth_pyramid_fwd': [P, I, I, I, I, P, P, I, I, P, I, I, P, I, I, P],
     'sgc_depth_pyramid_bwd': [P, I, I, I, I, P, P, I, I, P, I, I, P, I, I, P, P],
-    'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, P],
+    'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, I, P],
     'sgc_peer_sig_bytes': [],
     'sgc_peer_status_offset': [],
     'sgc_peer_alloc': [LL, P, P],

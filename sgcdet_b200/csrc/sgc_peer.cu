@@ -52,38 +52,50 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int rank, int w
   __syncthreads();
 }
 
-template <bool MAXOP>
+// U float4 elements per thread and pass (all their loads -- U x world, (world - 1) of them over the links -- are in flight
+// together): a collective confined to a few CTAs beside the step's large kernels is bound by link latency x passes.
+// W = upper bound of `world` for this instantiation (U x W float4 registers hold one pass).
+template <bool MAXOP, int U, int W>
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __grid_constant__ PeerPtrs pp, int rank, int world,
                                                                       long long n, float scale, float* __restrict__ out) {
   peer_barrier(pp, rank, world);      // every rank's partial is complete and visible
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
     // fetched starting with the next rank (spreads the load over the links), REDUCED in rank order on every rank: all ranks
     // get bit-identical results, which the replicated voxel chain (and its deterministic top-k) relies on
-    float4 v[kPeerMaxWorld];
+    float4 v[U][W];
 #pragma unroll
-    for (int r = 0; r < kPeerMaxWorld; ++r) {
-      if (r < world) {
-        const int p = rank + r < world ? rank + r : rank + r - world;
-        v[r] = __ldcv(reinterpret_cast<const float4*>(pp.buf[p]) + i);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+#pragma unroll
+      for (int r = 0; r < W; ++r) {
+        if (r < world && i < n4) {
+          const int p = rank + r < world ? rank + r : rank + r - world;
+          v[u][r] = __ldcv(reinterpret_cast<const float4*>(pp.buf[p]) + i);
+        }
       }
     }
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < kPeerMaxWorld; ++p) {
-      if (p < world) {
-        const int r = p >= rank ? p - rank : p - rank + world;     // slot that holds rank p's value
-        float4 b = v[0];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) break;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 1; q < kPeerMaxWorld; ++q) if (q == r) b = v[q];
-        if (p == 0) a = b;
-        else if (MAXOP) { a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w); }
-        else { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      for (int p = 0; p < W; ++p) {
+        if (p < world) {
+          const int r = p >= rank ? p - rank : p - rank + world;     // slot that holds rank p's value
+          float4 b = v[u][0];
+#pragma unroll
+          for (int q = 1; q < W; ++q) if (q == r) b = v[u][q];
+          if (p == 0) a = b;
+          else if (MAXOP) { a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w); }
+          else { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        }
       }
+      if (!MAXOP) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+      reinterpret_cast<float4*>(out)[i] = a;
     }
-    if (!MAXOP) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
-    reinterpret_cast<float4*>(out)[i] = a;
   }
   if (blockIdx.x == 0) {
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_2shot_kernel(cons
 // The reduction runs in rank order on every rank: all ranks obtain bit-identical results.  n floats, 16-byte aligned buffers.
 // op 0: out = scale * sum over ranks (scale = 1 / world averages gradients); op 1: out = max over ranks (scale ignored).
 extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
-                                  float* out, void* stream) {
+                                  float* out, int max_blocks, void* stream) {
   using namespace sgc;
   if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || n < 0 || (op != 0 && op != 1) || !out) return (int)cudaErrorInvalidValue;
   if (n == 0) return 0;
@@ -194,17 +206,25 @@ extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, in
   const long long work4 = two_shot ? ((n >> 2) + world - 1) / world : (n >> 2);
   long long blocks = (work4 + kPeerThreads - 1) / kPeerThreads;
   if (blocks < 1) blocks = 1;
-  if (blocks > kPeerMaxBlocks) blocks = kPeerMaxBlocks;
+  // max_blocks (0 = 128): a collective that runs BESIDE the step's large kernels asks for a few CTAs only -- a spinning CTA of
+  // 512 threads keeps half an SM's registers from them
+  const long long cap = max_blocks > 0 && max_blocks < kPeerMaxBlocks ? max_blocks : kPeerMaxBlocks;
+  if (blocks > cap) blocks = cap;
   // every rank must launch the SAME grid (the barrier pairs CTA b with CTA b of the peers): it depends on n and world only
   if (two_shot) {
     PeerPtrsRW pw;
     for (int r = 0; r < kPeerMaxWorld; ++r) { pw.buf[r] = const_cast<float*>(pp.buf[r]); pw.sig[r] = pp.sig[r]; }
     if (op == 1) peer_allreduce_2shot_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
     else peer_allreduce_2shot_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
-  } else if (op == 1) {
-    peer_allreduce_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
   } else {
-    peer_allreduce_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pp, rank, world, n, scale, out);
+    // passes per thread decide: with few CTAs (or few ranks, i.e. few registers per element) fetch several elements at once
+    const long long passes = (work4 + blocks * kPeerThreads - 1) / (blocks * kPeerThreads);
+    const int U = passes >= 4 && world <= 2 ? 4 : (passes >= 2 && world <= 4 ? 2 : 1);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SGC_PEER_ONE_SHOT(MAXOP, UU) peer_allreduce_kernel<MAXOP, UU, 8 / UU><<<(int)blocks, kPeerThreads, 0, st>>>(pp, rank, world, n, scale, out)
+    if (op == 1) { if (U == 4) SGC_PEER_ONE_SHOT(true, 4); else if (U == 2) SGC_PEER_ONE_SHOT(true, 2); else SGC_PEER_ONE_SHOT(true, 1); }
+    else { if (U == 4) SGC_PEER_ONE_SHOT(false, 4); else if (U == 2) SGC_PEER_ONE_SHOT(false, 2); else SGC_PEER_ONE_SHOT(false, 1); }
+#undef SGC_PEER_ONE_SHOT
   }
   SGC_CUDA_CHECK_LAST();
   return 0;

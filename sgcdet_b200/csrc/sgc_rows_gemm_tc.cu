@@ -51,6 +51,7 @@ struct RowsGemmParams {
   int bias_batch;               // bias of batch b starts at bias + b * bias_batch
   int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols;
   int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
+  int rows;                     // R: voxel rows of one batch (TMA clips the stores; fully clipped 32-row slices are skipped)
   int a_bcast;                  // 1: every batch reads the SAME activation rows (batch coordinate 0)
   int kpb;                      // > 0: the reduction runs over the batches of A too, kpb k-slabs per batch (K-concatenation)
   long long* dbg;               // optional [16] clock64 stamps of CTA 0 (sgc_rows_gemm_tc_set_debug): where a launch's time goes
@@ -75,55 +76,86 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   uint8_t* e_base = b_base + RG_NB * b_stage_bytes;   // 1 KB aligned: every stage size is a multiple of 2 KB
   SmemRG* sm = reinterpret_cast<SmemRG*>(e_base + RG_NE * BM * 128);
   const int n_cta = p.n_cta, k_slabs = p.k_slabs, works = p.works;
+  // One work item per CTA (the latency-bound launches of the per-voxel chain): the four epilogue warps, idle until the
+  // accumulator is complete, convert every second k-slab.  Measured with the clock stamps below (tools/rows_gemm_timeline.py):
+  // 4 converter warps needed ~0.55 us per slab = 4.2 of the 8.4 us a CTA lived at K = 256.
+  const bool dual = works <= (int)gridDim.x;
 
-  if (threadIdx.x == 0) {
-    RG_STAMP(0);
+  // ---- producers keep their position in (work item, k-slab) order so that they can start BEFORE the CTA-wide sync ----
+  int a_w = blockIdx.x, a_j = 0;
+  Pipe a_pf(RG_NF);
+  auto produce_a = [&](int limit) {   // fp32 activation tiles [128 rows][32 k] by TMA
+    for (int cnt = 0; a_w < works && cnt < limit; ++cnt) {
+      const int t = a_w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
+      mbar_wait(&sm->f_empty[a_pf.stage], a_pf.phase ^ 1);
+      mbar_expect_tx(&sm->f_full[a_pf.stage], (uint32_t)f_stage_bytes);
+      int col = a_j * BK, bc = p.a_bcast ? 0 : b;
+      if (p.kpb) { bc = a_j / p.kpb; col = (a_j - bc * p.kpb) * BK; }
+      if (p.a_swap) tma_load_3d(f_base + a_pf.stage * f_stage_bytes, &amap, col, bc, mt * BM, &sm->f_full[a_pf.stage]);
+      else tma_load_3d(f_base + a_pf.stage * f_stage_bytes, &amap, col, mt * BM, bc, &sm->f_full[a_pf.stage]);
+      if (a_j == 0 && a_w == (int)blockIdx.x) RG_STAMP(3);
+      a_pf.next();
+      if (++a_j == k_slabs) { a_j = 0; a_w += gridDim.x; }
+    }
+  };
+  int b_w = blockIdx.x, b_q = 0;
+  Pipe b_pb(RG_NB);
+  auto produce_b = [&](int limit) {   // n_cta rows of every packed (slab, hi/lo) weight stage by bulk copy; q = 2*slab + (0 hi, 1 lo)
+    for (int cnt = 0; b_w < works && cnt < limit; ++cnt) {
+      const int np = b_w % p.nsplit, b = (b_w / p.nsplit) / p.m_tiles;
+      const uint8_t* src = p.wpack + (size_t)b * p.pack_batch_bytes +
+                           ((size_t)b * p.pack_batch_rows + (size_t)np * n_cta) * (BK * 2);
+      mbar_wait(&sm->b_empty[b_pb.stage], b_pb.phase ^ 1);
+      mbar_expect_tx(&sm->b_full[b_pb.stage], (uint32_t)b_stage_bytes);
+      bulk_g2s(b_base + b_pb.stage * b_stage_bytes, src + (size_t)b_q * p.pack_stage_bytes, (uint32_t)b_stage_bytes,
+               &sm->b_full[b_pb.stage]);
+      b_pb.next();
+      if (++b_q == 2 * k_slabs) { b_q = 0; b_w += gridDim.x; }
+    }
+  };
+
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the successor may be scheduled from here on
+  if (warp == 5 && lane == 0) {
+    // the TMA producer initialises its own barriers and has the first RG_NF tiles in flight while the rest of the CTA is
+    // still setting up (barriers, TMEM allocation, CTA sync)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
     for (int i = 0; i < RG_NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
-    for (int i = 0; i < RG_NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();              // the tiles are the predecessor's output
+    produce_a(RG_NF);
+  } else if (warp == 4 && lane == 0) {
     for (int i = 0; i < RG_NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();
+    produce_b(RG_NB);
+  } else if (threadIdx.x == 0) {
+    RG_STAMP(0);
+    for (int i = 0; i < RG_NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     RG_STAMP(1);
+  } else if (threadIdx.x == 8 * 32) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
   }
   if (warp == 7) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
                  "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the successor may be scheduled from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
   if (threadIdx.x == 0) RG_STAMP(2);
-  // barrier setup and the TMEM allocation above do not depend on the predecessor; everything below reads its output
+  // everything below reads the predecessor's output (or is ordered behind threads that do)
   pdl_wait();
 
-  if (warp == 5) {
-    // ===================== producer: TMA loads of the fp32 activation tiles [128 rows][32 k] =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
-      Pipe pf(RG_NF);
-      for (int w = blockIdx.x; w < works; w += gridDim.x) {
-        const int t = w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
-        for (int j = 0; j < k_slabs; ++j) {
-          mbar_wait(&sm->f_empty[pf.stage], pf.phase ^ 1);
-          mbar_expect_tx(&sm->f_full[pf.stage], (uint32_t)f_stage_bytes);
-          int col = j * BK, bc = p.a_bcast ? 0 : b;
-          if (p.kpb) { bc = j / p.kpb; col = (j - bc * p.kpb) * BK; }
-          if (p.a_swap) tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, bc, mt * BM, &sm->f_full[pf.stage]);
-          else tma_load_3d(f_base + pf.stage * f_stage_bytes, &amap, col, mt * BM, bc, &sm->f_full[pf.stage]);
-          if (j == 0 && w == (int)blockIdx.x) RG_STAMP(3);
-          pf.next();
-        }
-      }
-    }
-  } else if (warp < 4) {
-    // ===================== converters: swizzled fp32 [m][k] tile -> bf16 hi/lo core-matrix tiles =====================
-    const int m = threadIdx.x;  // row of the tile
-    Pipe pa(RG_NA), pf(RG_NF);
-    for (int w = blockIdx.x; w < works; w += gridDim.x) {
-      for (int j = 0; j < k_slabs; ++j) {
+  // ===================== converters: swizzled fp32 [m][k] tile -> bf16 hi/lo core-matrix tiles =====================
+  // group 0 = warps 0-3, group 1 = warps 8-11 (dual mode only): slab s of the CTA's running slab count goes to group s & 1
+  auto convert_item = [&](int g, int w, Pipe& pa, Pipe& pf, int& s) {
+    const int m = threadIdx.x & 127;  // row of the tile
+    for (int j = 0; j < k_slabs; ++j, ++s) {
+      if (!dual || (s & 1) == g) {
         mbar_wait(&sm->f_full[pf.stage], pf.phase);
         if (threadIdx.x == 0 && j == 0 && w == (int)blockIdx.x) RG_STAMP(4);
         float x[BK];
@@ -150,30 +182,23 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
         }
         // released only after every staged value has been consumed by the conversion (see project_tc_kernel)
         mbar_arrive(&sm->f_empty[pf.stage]);
-        pf.next();
         fence_proxy_async();
         mbar_arrive(&sm->a_full[pa.stage]);
-        if (threadIdx.x == 0 && w == (int)blockIdx.x) { if (j == 0) RG_STAMP(5); if (j == k_slabs - 1) RG_STAMP(6); }
-        pa.next();
+        if (threadIdx.x == 0 && w == (int)blockIdx.x) { if (j == 0) RG_STAMP(5); if (j >= k_slabs - 2) RG_STAMP(6); }
       }
+      pf.next();
+      pa.next();
     }
+  };
+
+  if (warp == 5) {
+    if (lane == 0) produce_a(0x7fffffff);
+  } else if (warp < 4) {
+    Pipe pa(RG_NA), pf(RG_NF);
+    int s = 0;
+    for (int w = blockIdx.x; w < works; w += gridDim.x) convert_item(0, w, pa, pf, s);
   } else if (warp == 4) {
-    // ===================== weight producer: bulk copies of n_cta rows of every packed (slab, hi/lo) stage =====================
-    if (lane == 0) {
-      Pipe pb(RG_NB);
-      for (int w = blockIdx.x; w < works; w += gridDim.x) {
-        const int np = w % p.nsplit, b = (w / p.nsplit) / p.m_tiles;
-        const uint8_t* src = p.wpack + (size_t)b * p.pack_batch_bytes +
-                             ((size_t)b * p.pack_batch_rows + (size_t)np * n_cta) * (BK * 2);
-        for (int q = 0; q < 2 * k_slabs; ++q) {  // q = 2*slab + (0: hi, 1: lo)
-          mbar_wait(&sm->b_empty[pb.stage], pb.phase ^ 1);
-          mbar_expect_tx(&sm->b_full[pb.stage], (uint32_t)b_stage_bytes);
-          bulk_g2s(b_base + pb.stage * b_stage_bytes, src + (size_t)q * p.pack_stage_bytes, (uint32_t)b_stage_bytes,
-                   &sm->b_full[pb.stage]);
-          pb.next();
-        }
-      }
-    }
+    if (lane == 0) produce_b(0x7fffffff);
   } else if (warp == 6) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -221,20 +246,26 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     }
   } else if (warp >= 8) {
     // ===================== epilogue: TMEM -> registers (+bias) -> swizzled smem -> TMA store =====================
+    // Every warp owns the 32 rows of its TMEM lane quarter end to end: its own slice of the staging tile, its own TMA stores
+    // (box = 32 columns x 32 rows) and bulk groups -- no CTA-wide barrier and no single issuing thread per 32-column chunk.
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;           // row of the tile == TMEM lane
-    const bool issuer = (threadIdx.x == 8 * 32);
+    const bool stamp = (threadIdx.x == 8 * 32);
     int chunk = 0;                               // running chunk counter -> staging buffer parity
     int it = 0;
+    Pipe pa(RG_NA), pf(RG_NF);
+    int s = 0;
     for (int w = blockIdx.x; w < works; w += gridDim.x, ++it) {
+      if (dual) convert_item(1, w, pa, pf, s);
       const int np = w % p.nsplit, t = w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
       const int buf = it & 1;
       const uint32_t ephase = (it >> 1) & 1;
       const uint32_t acc = tmem + buf * n_cta;
       const float* bias = p.bias ? p.bias + (size_t)b * p.bias_batch + np * n_cta : nullptr;
+      const bool rows_live = mt * BM + lane_base < p.rows;   // a slice entirely behind the last row stores nothing
       mbar_wait(&sm->tmem_full[buf], ephase);
       tc_fence_after();
-      if (issuer && w == (int)blockIdx.x) RG_STAMP(9);
+      if (stamp && w == (int)blockIdx.x) RG_STAMP(9);
       for (int c0 = 0; c0 < n_cta; c0 += 32, ++chunk) {
         uint32_t r[32];
         asm volatile(
@@ -252,28 +283,30 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bias + c0 + i));
         }
         uint8_t* ebuf = e_base + (chunk & 1) * (BM * 128);
-        // the TMA store that read this buffer two chunks ago must have finished reading it
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // the store that read this warp's slice of the buffer two chunks ago must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i)  // 16-byte chunk i of the 128-byte row, CU_TENSOR_MAP_SWIZZLE_128B pattern
           *reinterpret_cast<uint4*>(ebuf + row * 128 + ((i ^ (row & 7)) << 4)) =
               make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) {
-          if (p.o_swap) tma_store_3d(&omap, np * n_cta + c0, b, mt * BM, ebuf);
-          else tma_store_3d(&omap, np * n_cta + c0, mt * BM, b, ebuf);
+        __syncwarp();
+        if (lane == 0) {
+          if (rows_live) {
+            if (p.o_swap) tma_store_3d(&omap, np * n_cta + c0, b, mt * BM + lane_base, ebuf + lane_base * 128);
+            else tma_store_3d(&omap, np * n_cta + c0, mt * BM + lane_base, b, ebuf + lane_base * 128);
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       mbar_arrive(&sm->tmem_empty[buf]);
-      if (issuer && w == (int)blockIdx.x) RG_STAMP(10);
+      if (stamp && w == (int)blockIdx.x) RG_STAMP(10);
     }
     // the staging buffers only have to outlive the stores' READS; the writes are complete (and visible) at kernel end
-    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    if (issuer) RG_STAMP(11);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (stamp) RG_STAMP(11);
   }
   tc_fence_before();
   __syncthreads();
@@ -284,10 +317,11 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   }
 }
 
-// [cols, rows, batch] fp32 view with a [32, 128, 1] box (or [cols, batch, rows] with a [32, 1, 128] box when the batch
-// stride is the smaller one, e.g. the heads of a [R, H*dh] matrix): strides stay ascending for the descriptor.
+// [cols, rows, batch] fp32 view with a [32, box_rows, 1] box (or [cols, batch, rows] with a [32, 1, box_rows] box when the
+// batch stride is the smaller one, e.g. the heads of a [R, H*dh] matrix): strides stay ascending for the descriptor.
+// box_rows = 128 for the activation tiles, 32 for the per-warp stores of the epilogue.
 static inline bool make_rows_map(PFN_encodeTiled encode, CUtensorMap* map, const float* base, int cols, int rows, int batch,
-                                 long long ld, long long batch_stride, int* swapped) {
+                                 long long ld, long long batch_stride, int* swapped, int box_rows = BM) {
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || ld < cols) return false;
   if (batch > 1 && ((batch_stride * 4) % 16 || batch_stride <= 0)) return false;
   const bool swap = batch > 1 && batch_stride < ld;
@@ -301,11 +335,11 @@ static inline bool make_rows_map(PFN_encodeTiled encode, CUtensorMap* map, const
   if (swap) {
     gdim[1] = (cuuint64_t)batch; gdim[2] = (cuuint64_t)rows;
     gstr[0] = bs; gstr[1] = (cuuint64_t)ld * 4;
-    box[1] = 1; box[2] = (cuuint32_t)BM;
+    box[1] = 1; box[2] = (cuuint32_t)box_rows;
   } else {
     gdim[1] = (cuuint64_t)rows; gdim[2] = (cuuint64_t)batch;
     gstr[0] = (cuuint64_t)ld * 4; gstr[1] = bs;
-    box[1] = (cuuint32_t)BM; box[2] = 1;
+    box[1] = (cuuint32_t)box_rows; box[2] = 1;
   }
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -368,7 +402,7 @@ static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x,
   } else if (a_mode == 2) {
     if (!make_rows_map(encode, &amap, x, K / a_batches, R, a_batches, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
   } else if (!make_rows_map(encode, &amap, x, K, R, B, ldx, batch_x, &p.a_swap)) return (int)cudaErrorInvalidValue;
-  if (!make_rows_map(encode, &omap, y, N, R, B, ldy, batch_y, &p.o_swap)) return (int)cudaErrorInvalidValue;
+  if (!make_rows_map(encode, &omap, y, N, R, B, ldy, batch_y, &p.o_swap, 32)) return (int)cudaErrorInvalidValue;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack);
   p.bias = bias;
   p.pack_stage_bytes = (long long)pack_rows * BK * 2;
@@ -380,6 +414,7 @@ static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x,
   p.works = p.m_tiles * p.nsplit * B;
   p.k_slabs = K / BK;
   p.n_cta = n_cta;
+  p.rows = R;
   p.dbg = g_rows_gemm_dbg;
   p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
   const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * n_cta * BK * 2 +

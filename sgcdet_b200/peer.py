@@ -111,14 +111,16 @@ class PeerMemory:
             raise ValueError('sgcdet_b200.peer: view outside the symmetric allocation (or not 16-byte aligned)')
         return self._local[offset_bytes:offset_bytes + 4 * n].view(F32).view(*shape)
 
-    def all_reduce(self, n: int, out: torch.Tensor, op: str = 'sum', scale: float = 1.0, offset_bytes: int = 0) -> torch.Tensor:
-        """out[:n] = scale * sum | max over the ranks of the n floats at ``offset_bytes`` of every rank's data region."""
+    def all_reduce(self, n: int, out: torch.Tensor, op: str = 'sum', scale: float = 1.0, offset_bytes: int = 0,
+                   max_blocks: int = 0) -> torch.Tensor:
+        """out[:n] = scale * sum | max over the ranks of the n floats at ``offset_bytes`` of every rank's data region.
+        ``max_blocks`` (the same on every rank; 0 = up to 128) bounds the CTAs of a collective that overlaps other kernels."""
         if offset_bytes % 16 or offset_bytes + 4 * n > self.nbytes or out.numel() < n or out.dtype != F32:
             raise ValueError('sgcdet_b200.peer: bad all_reduce arguments')
         bufs = (ctypes.c_void_p * self.world)(*[b + self.sig_bytes + offset_bytes for b in self.bases])
         with torch.cuda.device(self.device):
             _lib.call('sgc_peer_allreduce', bufs, self._sigs, self.rank, self.world, int(n), 1 if op == 'max' else 0,
-                      float(scale), _lib.ptr(out), _lib.stream(self.device))
+                      float(scale), _lib.ptr(out), int(max_blocks), _lib.stream(self.device))
         return out
 
     def close(self):
@@ -158,7 +160,7 @@ class GradAverager:
     Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``.  The number of groups per step is
     learnt in the first step (which therefore reduces everything in ``finish_step``)."""
 
-    def __init__(self, params, group=None, device=None):
+    def __init__(self, params, group=None, device=None, overlap_blocks: int = 8):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         self.n = (n + 3) // 4 * 4
@@ -167,13 +169,14 @@ class GradAverager:
         self.flat_in = self.mem.view((self.n,))
         self.flat_in.zero_()
         self.scale = 1.0 / self.mem.world
-        self.comm = torch.cuda.Stream(device=self.device, priority=-1)
+        self.comm = torch.cuda.Stream(device=self.device)      # default priority: never ahead of the voxel chains
+        self.overlap_blocks = overlap_blocks
         self._ids = {id(p) for p in self.params}
         self._active, self._expected = False, None
         self._pending, self._done, self._adopted = [], set(), []
         self.groups_last_step, self.copied_last_step = 0, 0
 
-    def _reduce_into(self, grads, outs):
+    def _reduce_into(self, grads, outs, max_blocks: int = 0):
         """outs[i] = average over the ranks of grads[i] (final on the current stream).  Every collective of this object runs on
         the communication stream (or after it has been joined), one after the other, and ends with a barrier behind the peers'
         last read: the symmetric buffer is reused from offset 0 every time."""
@@ -181,11 +184,13 @@ class GradAverager:
         nb = sum(sizes)
         torch._foreach_copy_(list(self.flat_in[:nb].split(sizes)), [g.reshape(-1) for g in grads])
         red = torch.empty(nb, device=self.device, dtype=F32)
-        self.mem.all_reduce(nb, red, 'sum', self.scale)
+        self.mem.all_reduce(nb, red, 'sum', self.scale, max_blocks=max_blocks)
         torch._foreach_copy_([o.view(-1) for o in outs], list(red.split(sizes)))
 
-    def _flush(self):
-        """All reported groups in one collective on the communication stream."""
+    def _flush(self, overlapped: bool = True):
+        """All reported groups in one collective on the communication stream.  Issued from the backward it runs beside the
+        step's largest kernels and has ~0.3 ms to finish: a few CTAs only (a spinning 512-thread CTA takes half an SM's
+        registers away from ``lift_bwd`` or a persistent tcgen05 kernel, which measurably delayed the step with 128 CTAs)."""
         if not self._pending:
             return
         grads, outs = [], []
@@ -196,7 +201,7 @@ class GradAverager:
         with torch.cuda.stream(self.comm):
             for t in grads + outs:
                 t.record_stream(self.comm)
-            self._reduce_into(grads, outs)
+            self._reduce_into(grads, outs, self.overlap_blocks if overlapped else 0)
         self._pending = []
 
     def _on_group(self, params, grads):
@@ -232,7 +237,7 @@ class GradAverager:
         main = torch.cuda.current_stream(self.device)
         if self._pending:
             self.comm.wait_stream(main)
-            self._flush()
+            self._flush(overlapped=False)
         if self._expected is None and self.groups_last_step:
             self._expected = self.groups_last_step
         main.wait_stream(self.comm)
