@@ -32,7 +32,7 @@ namespace tc {
 
 constexpr int RG_NF = 4;        // fp32 staging stages filled by TMA (BM x BK floats = 16 KB each)
 constexpr int RG_NA = 2;        // converted A stages (hi 8 KB + lo 8 KB)
-constexpr int RG_NB = 4;        // weight stages (one of hi / lo per stage, n_cta * 64 bytes)
+constexpr int RG_NB = 8;        // weight stages at most (one of hi / lo per stage, n_cta * 64 bytes): 8 up to 128 columns per CTA, else 4
 constexpr int RG_NE = 2;        // epilogue staging buffers (BM rows x 32 floats)
 constexpr int RG_THREADS = 384;
 
@@ -40,6 +40,7 @@ struct SmemRG {
   uint64_t f_full[RG_NF], f_empty[RG_NF], a_full[RG_NA], a_empty[RG_NA], b_full[RG_NB], b_empty[RG_NB], tmem_full[2],
       tmem_empty[2];
   uint32_t tmem_base;
+  float bias[256];            // the work item's bias slice (read per 32-column chunk of the epilogue)
 };
 
 struct RowsGemmParams {
@@ -49,7 +50,7 @@ struct RowsGemmParams {
   long long pack_batch_bytes;   // bytes between the packed matrices of consecutive batches (0: one matrix for all)
   int pack_batch_rows;          // row offset of batch b inside a packed matrix: b * pack_batch_rows
   int bias_batch;               // bias of batch b starts at bias + b * bias_batch
-  int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols;
+  int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols, nb;   // nb = weight stages in use (<= RG_NB)
   int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
   int rows;                     // R: voxel rows of one batch (TMA clips the stores; fully clipped 32-row slices are skipped)
   int a_bcast;                  // 1: every batch reads the SAME activation rows (batch coordinate 0)
@@ -73,7 +74,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   uint8_t* f_base = smem_raw;
   uint8_t* a_base = f_base + RG_NF * f_stage_bytes;
   uint8_t* b_base = a_base + RG_NA * a_stage_bytes;
-  uint8_t* e_base = b_base + RG_NB * b_stage_bytes;   // 1 KB aligned: every stage size is a multiple of 2 KB
+  uint8_t* e_base = b_base + p.nb * b_stage_bytes;    // 1 KB aligned: every stage size is a multiple of 2 KB
   SmemRG* sm = reinterpret_cast<SmemRG*>(e_base + RG_NE * BM * 128);
   const int n_cta = p.n_cta, k_slabs = p.k_slabs, works = p.works;
   // One work item per CTA (the latency-bound launches of the per-voxel chain): the four epilogue warps, idle until the
@@ -99,7 +100,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     }
   };
   int b_w = blockIdx.x, b_q = 0;
-  Pipe b_pb(RG_NB);
+  Pipe b_pb(p.nb);
   auto produce_b = [&](int limit) {   // n_cta rows of every packed (slab, hi/lo) weight stage by bulk copy; q = 2*slab + (0 hi, 1 lo)
     for (int cnt = 0; b_w < works && cnt < limit; ++cnt) {
       const int np = b_w % p.nsplit, b = (b_w / p.nsplit) / p.m_tiles;
@@ -115,38 +116,34 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   };
 
   pdl_launch_dependents();   // programmatic dependent launch (common.cuh): the successor may be scheduled from here on
-  if (warp == 5 && lane == 0) {
-    // the TMA producer initialises its own barriers and has the first RG_NF tiles in flight while the rest of the CTA is
-    // still setting up (barriers, TMEM allocation, CTA sync)
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
-    for (int i = 0; i < RG_NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    pdl_wait();              // the tiles are the predecessor's output
-    produce_a(RG_NF);
-  } else if (warp == 4 && lane == 0) {
-    for (int i = 0; i < RG_NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    pdl_wait();
-    produce_b(RG_NB);
-  } else if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     RG_STAMP(0);
+    for (int i = 0; i < RG_NF; ++i) { mbar_init(&sm->f_full[i], 1); mbar_init(&sm->f_empty[i], 128); }
     for (int i = 0; i < RG_NA; ++i) { mbar_init(&sm->a_full[i], 128); mbar_init(&sm->a_empty[i], 1); }
+    for (int i = 0; i < RG_NB; ++i) { mbar_init(&sm->b_full[i], 1); mbar_init(&sm->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm->tmem_full[i], 1); mbar_init(&sm->tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     RG_STAMP(1);
+  } else if (threadIdx.x == 5 * 32) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");   // ~0.5 us to fetch: started at kernel entry
   } else if (threadIdx.x == 8 * 32) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
   }
-  if (warp == 7) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
-                 "r"(p.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  __syncthreads();           // barriers are live; producers and converters go ahead, they do not need the TMEM address
+  uint32_t tmem = 0;
+  if (warp >= 6) {
+    // TMEM allocation concerns the MMA issuer, the allocating warp and the epilogue warps only (192 threads)
+    if (warp == 7) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
+                   "r"(p.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 2, 192;" ::: "memory");
+    tc_fence_after();
+    tmem = sm->tmem_base;
+    if (threadIdx.x == 6 * 32) RG_STAMP(2);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm->tmem_base;
-  if (threadIdx.x == 0) RG_STAMP(2);
   // everything below reads the predecessor's output (or is ordered behind threads that do)
   pdl_wait();
 
@@ -203,7 +200,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cta >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      Pipe pa(RG_NA), pb(RG_NB);
+      Pipe pa(RG_NA), pb(p.nb);
       int it = 0;
       for (int w = blockIdx.x; w < works; w += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -256,12 +253,19 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     Pipe pa(RG_NA), pf(RG_NF);
     int s = 0;
     for (int w = blockIdx.x; w < works; w += gridDim.x, ++it) {
-      if (dual) convert_item(1, w, pa, pf, s);
       const int np = w % p.nsplit, t = w / p.nsplit, mt = t % p.m_tiles, b = t / p.m_tiles;
+      const float* bias = p.bias ? p.bias + (size_t)b * p.bias_batch + np * n_cta : nullptr;
+      if (bias) {
+        // the bias slice goes to shared memory while the accumulator is still being formed: read from global per chunk it
+        // cost a load round trip (~0.5 us) per 32 columns behind tcgen05.wait::ld
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the previous item's chunks have read their bias
+        for (int c = threadIdx.x - 8 * 32; c < n_cta; c += 128) sm->bias[c] = __ldg(bias + c);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (dual) convert_item(1, w, pa, pf, s);
       const int buf = it & 1;
       const uint32_t ephase = (it >> 1) & 1;
       const uint32_t acc = tmem + buf * n_cta;
-      const float* bias = p.bias ? p.bias + (size_t)b * p.bias_batch + np * n_cta : nullptr;
       const bool rows_live = mt * BM + lane_base < p.rows;   // a slice entirely behind the last row stores nothing
       mbar_wait(&sm->tmem_full[buf], ephase);
       tc_fence_after();
@@ -280,7 +284,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bias + c0 + i));
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + sm->bias[c0 + i]);
         }
         uint8_t* ebuf = e_base + (chunk & 1) * (BM * 128);
         // the store that read this warp's slice of the buffer two chunks ago must have finished reading it
@@ -416,12 +420,13 @@ static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x,
   p.n_cta = n_cta;
   p.rows = R;
   p.dbg = g_rows_gemm_dbg;
+  p.nb = n_cta <= 128 ? RG_NB : 4;
   p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
-  const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * n_cta * BK * 2 +
+  const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)p.nb * n_cta * BK * 2 +
                       (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
   // the opt-in limit is raised once to the widest configuration (n_cta = 256): launches captured into a CUDA graph with
   // different column splits must not depend on which of them set the attribute last
-  const size_t smem_max = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)RG_NB * 256 * BK * 2 +
+  const size_t smem_max = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)4 * 256 * BK * 2 +
                           (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
   cudaError_t e = cudaFuncSetAttribute(rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return (int)e;
