@@ -22,6 +22,7 @@
 // the work order so that their x tile is shared through L2.  Two TMEM accumulators: the MMAs of work item i+1 overlap
 // the epilogue of item i.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -30,8 +31,8 @@
 namespace sgc {
 namespace tc {
 
-constexpr int RG_NF = 4;        // fp32 staging stages filled by TMA (BM x BK floats = 16 KB each)
-constexpr int RG_NA = 2;        // converted A stages (hi 8 KB + lo 8 KB)
+constexpr int RG_NF = 3;        // fp32 staging stages filled by TMA (BM x BK floats = 16 KB each)
+constexpr int RG_NA = 4;        // converted A stages (hi 8 KB + lo 8 KB): the converters run up to 4 k-slabs ahead of the MMAs
 constexpr int RG_NB = 8;        // weight stages at most (one of hi / lo per stage, n_cta * 64 bytes): 8 up to 128 columns per CTA, else 4
 constexpr int RG_NE = 2;        // epilogue staging buffers (BM rows x 32 floats)
 constexpr int RG_THREADS = 384;
@@ -51,6 +52,7 @@ struct RowsGemmParams {
   int pack_batch_rows;          // row offset of batch b inside a packed matrix: b * pack_batch_rows
   int bias_batch;               // bias of batch b starts at bias + b * bias_batch
   int m_tiles, nsplit, works, k_slabs, n_cta, tmem_cols, nb;   // nb = weight stages in use (<= RG_NB)
+  int dual;                     // 0: the epilogue warps never convert (SGC_ROWS_DUAL=0, for A/B measurements)
   int a_swap, o_swap;           // tensor-map coordinate order: 0 = (col, row, batch), 1 = (col, batch, row)
   int rows;                     // R: voxel rows of one batch (TMA clips the stores; fully clipped 32-row slices are skipped)
   int a_bcast;                  // 1: every batch reads the SAME activation rows (batch coordinate 0)
@@ -80,7 +82,7 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   // One work item per CTA (the latency-bound launches of the per-voxel chain): the four epilogue warps, idle until the
   // accumulator is complete, convert every second k-slab.  Measured with the clock stamps below (tools/rows_gemm_timeline.py):
   // 4 converter warps needed ~0.55 us per slab = 4.2 of the 8.4 us a CTA lived at K = 256.
-  const bool dual = works <= (int)gridDim.x;
+  const bool dual = p.dual && works <= (int)gridDim.x;
 
   // ---- producers keep their position in (work item, k-slab) order so that they can start BEFORE the CTA-wide sync ----
   int a_w = blockIdx.x, a_j = 0;
@@ -420,7 +422,10 @@ static int rows_gemm_tc_launch(const float* x, long long ldx, long long batch_x,
   p.n_cta = n_cta;
   p.rows = R;
   p.dbg = g_rows_gemm_dbg;
-  p.nb = n_cta <= 128 ? RG_NB : 4;
+  static const int env_dual = getenv("SGC_ROWS_DUAL") ? atoi(getenv("SGC_ROWS_DUAL")) : 1;
+  static const int env_nb = getenv("SGC_ROWS_NB") ? atoi(getenv("SGC_ROWS_NB")) : RG_NB;
+  p.dual = env_dual;
+  p.nb = n_cta <= 128 ? (env_nb >= 2 && env_nb <= RG_NB ? env_nb : RG_NB) : 4;
   p.tmem_cols = 2 * n_cta < 32 ? 32 : 2 * n_cta;
   const size_t smem = (size_t)RG_NF * BK * BM * 4 + (size_t)RG_NA * 2 * BM * BK * 2 + (size_t)p.nb * n_cta * BK * 2 +
                       (size_t)RG_NE * BM * 128 + sizeof(SmemRG) + 64;
