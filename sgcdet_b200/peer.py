@@ -160,7 +160,7 @@ class GradAverager:
     Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``.  The number of groups per step is
     learnt in the first step (which therefore reduces everything in ``finish_step``)."""
 
-    def __init__(self, params, group=None, device=None, overlap_blocks: int = 8):
+    def __init__(self, params, group=None, device=None, overlap_blocks: int = 16):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         self.n = (n + 3) // 4 * 4
