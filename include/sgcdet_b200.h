@@ -367,6 +367,12 @@ int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, int N, floa
 int sgc_scatter_add_rows(float* vol, const int* sel, const float* y, int k, int C, void* stream);
 int sgc_gather_rows(const float* vol, const int* sel, float* y, int k, int C, void* stream);
 
+/* The head's per-level validity masks: nn.Upsample(size, mode='trilinear')(valid).round().bool() of
+ * dense_heads/imvoxel_head_v2.py:121-123,256-258 for levels of 1, 1/2 and 1/4 of the volume, bit-exact, one launch.  valid
+ * [X,Y,Z] int64; v0 / v1 / v2 uint8 0/1 outputs (NULL = not wanted); X, Y, Z multiples of 4 (of 2 without v2). */
+int sgc_valid_pyramid(const long long* valid, int X, int Y, int Z, unsigned char* v0, unsigned char* v1, unsigned char* v2,
+                      void* stream);
+
 /* ---- the depth-distribution producer in front of the path (csrc/sgc_depth.cu) ----------------
  * Plane-sweep cost volume of DepthNet_Fusion (mmdet3d_plugin/models/im2voxel/depth_utils/depth_est_fusion.py:85-126 homo_warping,
  * :209-232 loop over the neighbour frames), fused: corr[v,d,y,x] = 1/(K sqrt(C)) sum_k sum_c f[v,c,y,x] *
@@ -408,9 +414,13 @@ int sgc_peer_free(void* ptr);
  * into this process.  out[i] = scale * sum (op 0) or max (op 1, scale ignored) over the ranks of bufs[r][i], i < n, reduced
  * in rank order on every rank (bit-identical results everywhere).  Every rank calls it with the same n; the cross-GPU
  * barriers are flags in the signal pads (stateless: the launch can be replayed from a CUDA graph); world <= 8.  max_blocks
- * (0 = 128, the same on every rank) bounds the CTAs of a collective that runs beside other kernels. */
+ * (0 = 128, the same on every rank) and block_threads (0 = 512, or 128) bound the footprint of a collective that runs beside
+ * other kernels. */
 int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
-                       float* out, int max_blocks, void* stream);
+                       float* out, int max_blocks, int block_threads, void* stream);
+/* dst[k][0:n[k]] = src[k][0:n[k]] for `count` segments (HOST arrays of device pointers / lengths) as one launch of 128-thread
+ * CTAs per 64 segments: the gather of gradient tensors into the symmetric buffer and the scatter of the averages back. */
+int sgc_peer_copy_segments(const void* const* src, void* const* dst, const long long* n, int count, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

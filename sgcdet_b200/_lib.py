@@ -86,13 +86,15 @@ SIGNATURES = {
     'sgc_topk_select_grid': [P, I, I, P, P, P, P],
     'sgc_occ_loss_fwd': [P, P, I, P, P],
     'sgc_occ_loss_bwd': [P, P, P, I, P, P],
+    'sgc_valid_pyramid': [P, I, I, I, P, P, P, P],
     'sgc_plane_sweep_fwd': [P, P, P, P, I, I, I, I, I, I, P, P],
     'sgc_plane_sweep_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P],
     'sgc_nchw_to_nhwc': [P, I, I, I, P, P],
     'sgc_nhwc_to_nchw': [P, I, I, I, P, P],
     'sgc_depth_pyramid_fwd': [P, I, I, I, I, P, P, I, I, P, I, I, P, I, I, P],
     'sgc_depth_pyramid_bwd': [P, I, I, I, I, P, P, I, I, P, I, I, P, I, I, P, P],
-    'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, I, P],
+    'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, I, I, P],
+    'sgc_peer_copy_segments': [P, P, P, I, I, P],
     'sgc_peer_sig_bytes': [],
     'sgc_peer_status_offset': [],
     'sgc_peer_alloc': [LL, P, P],

@@ -183,16 +183,72 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_2shot_kernel(cons
   peer_barrier(pp, rank, world);      // nobody still reads this rank's buffer when the caller overwrites it
 }
 
+// Gather / scatter between a list of tensors and a flat buffer as ONE small-footprint launch (128-thread CTAs fit next to the
+// persistent tcgen05 kernels of the step's tail, which library copy kernels and 512-thread CTAs did not: the "overlapped"
+// gradient average then ran only after them).
+constexpr int kSegMax = 64;
+struct CopySegs {
+  const float* src[kSegMax];
+  float* dst[kSegMax];
+  long long n[kSegMax];
+  int count;
+};
+
+__global__ void __launch_bounds__(128) copy_segs_kernel(const __grid_constant__ CopySegs cs) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < cs.count; ++k) {
+    const float* __restrict__ src = cs.src[k];
+    float* __restrict__ dst = cs.dst[k];
+    const long long n = cs.n[k];
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const long long n4 = n >> 2;
+      for (long long i = t0; i < n4; i += stride) reinterpret_cast<float4*>(dst)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+      for (long long i = (n4 << 2) + t0; i < n; i += stride) dst[i] = src[i];
+    } else {
+      for (long long i = t0; i < n; i += stride) dst[i] = src[i];
+    }
+  }
+}
+
 }  // namespace sgc
 
 // bufs / sigs: HOST arrays of `world` device pointers (rank r's symmetric buffer / signal pad as mapped in THIS process).
 // The reduction runs in rank order on every rank: all ranks obtain bit-identical results.  n floats, 16-byte aligned buffers.
 // op 0: out = scale * sum over ranks (scale = 1 / world averages gradients); op 1: out = max over ranks (scale ignored).
+extern "C" int sgc_peer_copy_segments(const void* const* src, void* const* dst, const long long* n, int count, int max_blocks,
+                                      void* stream) {
+  using namespace sgc;
+  if (count < 0 || (count && (!src || !dst || !n))) return (int)cudaErrorInvalidValue;
+  for (int k0 = 0; k0 < count; k0 += kSegMax) {
+    CopySegs cs;
+    cs.count = count - k0 < kSegMax ? count - k0 : kSegMax;
+    long long total = 0;
+    for (int k = 0; k < cs.count; ++k) {
+      cs.src[k] = reinterpret_cast<const float*>(src[k0 + k]);
+      cs.dst[k] = reinterpret_cast<float*>(dst[k0 + k]);
+      cs.n[k] = n[k0 + k];
+      if (!cs.src[k] || !cs.dst[k] || cs.n[k] < 0) return (int)cudaErrorInvalidValue;
+      total += cs.n[k];
+    }
+    long long blocks = (total / 4 + 127) / 128;
+    const long long cap = max_blocks > 0 ? max_blocks : 148 * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    copy_segs_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(cs);
+    SGC_CUDA_CHECK_LAST();
+  }
+  return 0;
+}
+
+// block_threads: 0 = 512; 128 for a collective that has to fit next to the step's large kernels.
 extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int world, long long n, int op, float scale,
-                                  float* out, int max_blocks, void* stream) {
+                                  float* out, int max_blocks, int block_threads, void* stream) {
   using namespace sgc;
   if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || n < 0 || (op != 0 && op != 1) || !out) return (int)cudaErrorInvalidValue;
   if (n == 0) return 0;
+  const int threads = block_threads > 0 ? block_threads : kPeerThreads;
+  if (threads < 32 || threads > kPeerThreads || (threads & 31)) return (int)cudaErrorInvalidValue;
   PeerPtrs pp;
   for (int r = 0; r < kPeerMaxWorld; ++r) {
     pp.buf[r] = r < world ? reinterpret_cast<const float*>(bufs[r]) : nullptr;
@@ -204,7 +260,7 @@ extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, in
   static const long long two_shot_min = getenv("SGC_PEER_TWO_SHOT_MIN_BYTES") ? atoll(getenv("SGC_PEER_TWO_SHOT_MIN_BYTES")) : (256ll << 10);
   const bool two_shot = world > 2 && n * 4 >= two_shot_min;
   const long long work4 = two_shot ? ((n >> 2) + world - 1) / world : (n >> 2);
-  long long blocks = (work4 + kPeerThreads - 1) / kPeerThreads;
+  long long blocks = (work4 + threads - 1) / threads;
   if (blocks < 1) blocks = 1;
   // max_blocks (0 = 128): a collective that runs BESIDE the step's large kernels asks for a few CTAs only -- a spinning CTA of
   // 512 threads keeps half an SM's registers from them
@@ -214,14 +270,14 @@ extern "C" int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, in
   if (two_shot) {
     PeerPtrsRW pw;
     for (int r = 0; r < kPeerMaxWorld; ++r) { pw.buf[r] = const_cast<float*>(pp.buf[r]); pw.sig[r] = pp.sig[r]; }
-    if (op == 1) peer_allreduce_2shot_kernel<true><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
-    else peer_allreduce_2shot_kernel<false><<<(int)blocks, kPeerThreads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
+    if (op == 1) peer_allreduce_2shot_kernel<true><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
+    else peer_allreduce_2shot_kernel<false><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(pw, rank, world, n, scale, out);
   } else {
     // passes per thread decide: with few CTAs (or few ranks, i.e. few registers per element) fetch several elements at once
-    const long long passes = (work4 + blocks * kPeerThreads - 1) / (blocks * kPeerThreads);
+    const long long passes = (work4 + blocks * threads - 1) / (blocks * threads);
     const int U = passes >= 4 && world <= 2 ? 4 : (passes >= 2 && world <= 4 ? 2 : 1);
     cudaStream_t st = (cudaStream_t)stream;
-#define SGC_PEER_ONE_SHOT(MAXOP, UU) peer_allreduce_kernel<MAXOP, UU, 8 / UU><<<(int)blocks, kPeerThreads, 0, st>>>(pp, rank, world, n, scale, out)
+#define SGC_PEER_ONE_SHOT(MAXOP, UU) peer_allreduce_kernel<MAXOP, UU, 8 / UU><<<(int)blocks, threads, 0, st>>>(pp, rank, world, n, scale, out)
     if (op == 1) { if (U == 4) SGC_PEER_ONE_SHOT(true, 4); else if (U == 2) SGC_PEER_ONE_SHOT(true, 2); else SGC_PEER_ONE_SHOT(true, 1); }
     else { if (U == 4) SGC_PEER_ONE_SHOT(false, 4); else if (U == 2) SGC_PEER_ONE_SHOT(false, 2); else SGC_PEER_ONE_SHOT(false, 1); }
 #undef SGC_PEER_ONE_SHOT

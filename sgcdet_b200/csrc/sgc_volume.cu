@@ -937,3 +937,51 @@ extern "C" int sgc_occ_loss_bwd(const float* p, const float* t, const float* g, 
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------- valid-mask pyramid
+// The detection head derives per-level validity masks from the view transform's `valid` volume with
+//   nn.Upsample(size=level_shape, mode='trilinear')(valid).round().bool()      (dense_heads/imvoxel_head_v2.py:121-123,256-258)
+// for levels of 1, 1/2 and 1/4 of the volume's size.  With align_corners=False a x1/2 output voxel interpolates the two
+// source voxels 2d, 2d+1 with weights 1/2 per axis (the mean of a 2x2x2 block), a x1/4 voxel the two central voxels 4d+1,
+// 4d+2 of its 4x4x4 block; the mean of eight 0/1 values rounds (half to even: 0.5 -> 0) to 1 iff at least five are set.
+// One launch, bit-exact, no float volume in between.
+namespace sgc {
+__global__ void valid_pyramid_kernel(const long long* __restrict__ valid, int X, int Y, int Z, unsigned char* __restrict__ v0,
+                                     unsigned char* __restrict__ v1, unsigned char* __restrict__ v2) {
+  const int n0 = X * Y * Z, X1 = X >> 1, Y1 = Y >> 1, Z1 = Z >> 1, X2 = X >> 2, Y2 = Y >> 2, Z2 = Z >> 2;
+  const int n1 = v1 ? X1 * Y1 * Z1 : 0, n2 = v2 ? X2 * Y2 * Z2 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += gridDim.x * blockDim.x) {
+    if (i < n0) {
+      if (v0) v0[i] = valid[i] != 0;
+      continue;
+    }
+    const bool half = i < n0 + n1;
+    const int j = half ? i - n0 : i - n0 - n1;
+    const int Yl = half ? Y1 : Y2, Zl = half ? Z1 : Z2;
+    const int z = j % Zl, y = (j / Zl) % Yl, x = j / (Zl * Yl);
+    const int sx = half ? 2 * x : 4 * x + 1, sy = half ? 2 * y : 4 * y + 1, sz = half ? 2 * z : 4 * z + 1;
+    int cnt = 0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) cnt += valid[((size_t)(sx + a) * Y + (sy + b)) * Z + (sz + c)] != 0;
+    (half ? v1 : v2)[j] = cnt >= 5;
+  }
+}
+}  // namespace sgc
+
+// valid [X,Y,Z] int64 (AdaptiveSparseHead's return value); v0 [X,Y,Z], v1 [X/2,Y/2,Z/2], v2 [X/4,Y/4,Z/4] uint8 0/1 (any may be
+// NULL).  X, Y, Z multiples of 4 (2 when v2 is NULL).
+extern "C" int sgc_valid_pyramid(const long long* valid, int X, int Y, int Z, unsigned char* v0, unsigned char* v1,
+                                 unsigned char* v2, void* stream) {
+  if (!valid || X <= 0 || Y <= 0 || Z <= 0) return (int)cudaErrorInvalidValue;
+  const int m = v2 ? 3 : (v1 ? 1 : 0);
+  if ((X & m) || (Y & m) || (Z & m)) return (int)cudaErrorInvalidValue;
+  const int total = X * Y * Z + (v1 ? (X >> 1) * (Y >> 1) * (Z >> 1) : 0) + (v2 ? (X >> 2) * (Y >> 2) * (Z >> 2) : 0);
+  const int grid = (total + 255) / 256;
+  sgc::valid_pyramid_kernel<<<grid < 148 * 8 ? grid : 148 * 8, 256, 0, (cudaStream_t)stream>>>(valid, X, Y, Z, v0, v1, v2);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

@@ -112,15 +112,16 @@ class PeerMemory:
         return self._local[offset_bytes:offset_bytes + 4 * n].view(F32).view(*shape)
 
     def all_reduce(self, n: int, out: torch.Tensor, op: str = 'sum', scale: float = 1.0, offset_bytes: int = 0,
-                   max_blocks: int = 0) -> torch.Tensor:
+                   max_blocks: int = 0, block_threads: int = 0) -> torch.Tensor:
         """out[:n] = scale * sum | max over the ranks of the n floats at ``offset_bytes`` of every rank's data region.
-        ``max_blocks`` (the same on every rank; 0 = up to 128) bounds the CTAs of a collective that overlaps other kernels."""
+        ``max_blocks`` (0 = up to 128) and ``block_threads`` (0 = 512) -- the same on every rank -- bound the footprint of a
+        collective that overlaps other kernels."""
         if offset_bytes % 16 or offset_bytes + 4 * n > self.nbytes or out.numel() < n or out.dtype != F32:
             raise ValueError('sgcdet_b200.peer: bad all_reduce arguments')
         bufs = (ctypes.c_void_p * self.world)(*[b + self.sig_bytes + offset_bytes for b in self.bases])
         with torch.cuda.device(self.device):
             _lib.call('sgc_peer_allreduce', bufs, self._sigs, self.rank, self.world, int(n), 1 if op == 'max' else 0,
-                      float(scale), _lib.ptr(out), int(max_blocks), _lib.stream(self.device))
+                      float(scale), _lib.ptr(out), int(max_blocks), int(block_threads), _lib.stream(self.device))
         return out
 
     def close(self):
@@ -160,10 +161,10 @@ class GradAverager:
     Per step:  ``begin_step()`` before the forward, ``finish_step()`` after ``backward()``.  The number of groups per step is
     learnt in the first step (which therefore reduces everything in ``finish_step``)."""
 
-    def __init__(self, params, group=None, device=None, overlap_blocks: int = 16):
+    def __init__(self, params, group=None, device=None, overlap_blocks: int = 64):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
-        self.n = (n + 3) // 4 * 4
+        self.n = (n + 3) // 4 * 4 + 4 * len(self.params)
         self.mem = PeerMemory(4 * self.n, group, device)
         self.device = self.mem.device
         self.flat_in = self.mem.view((self.n,))
@@ -176,16 +177,34 @@ class GradAverager:
         self._pending, self._done, self._adopted = [], set(), []
         self.groups_last_step, self.copied_last_step = 0, 0
 
-    def _reduce_into(self, grads, outs, max_blocks: int = 0):
-        """outs[i] = average over the ranks of grads[i] (final on the current stream).  Every collective of this object runs on
-        the communication stream (or after it has been joined), one after the other, and ends with a barrier behind the peers'
-        last read: the symmetric buffer is reused from offset 0 every time."""
-        sizes = [g.numel() for g in grads]
+    def _copy_segments(self, srcs, dsts, max_blocks):
+        """dsts[k][:] = srcs[k][:] (contiguous fp32 tensors of equal sizes) as one small-footprint launch per 64 tensors."""
+        k = len(srcs)
+        a = (ctypes.c_void_p * k)(*[t.data_ptr() for t in srcs])
+        b = (ctypes.c_void_p * k)(*[t.data_ptr() for t in dsts])
+        n = (ctypes.c_longlong * k)(*[t.numel() for t in srcs])
+        with torch.cuda.device(self.device):
+            _lib.call('sgc_peer_copy_segments', a, b, n, k, int(max_blocks), _lib.stream(self.device))
+
+    def _reduce_into(self, grads, outs, overlapped: bool = False):
+        """outs[i] = average over the ranks of grads[i] (final on the current stream): gather into the symmetric buffer, one
+        all-reduce, scatter -- three own launches.  Every collective of this object runs on the communication stream (or after
+        it has been joined), one after the other, and ends with a barrier behind the peers' last read: the symmetric buffer is
+        reused from offset 0 every time.  ``overlapped``: 128-thread CTAs, at most ``overlap_blocks`` of them, so that the
+        launches find room beside the persistent tcgen05 kernels of the step's tail (whose CTAs leave < 20 K registers per SM)."""
+        sizes = [(g.numel() + 3) // 4 * 4 for g in grads]      # every tensor starts 16-byte aligned in the flat buffer
         nb = sum(sizes)
-        torch._foreach_copy_(list(self.flat_in[:nb].split(sizes)), [g.reshape(-1) for g in grads])
+        if nb > self.n:
+            raise RuntimeError('sgcdet_b200.peer.GradAverager: more gradient elements than the buffer holds')
+        offs = [0]
+        for z in sizes[:-1]:
+            offs.append(offs[-1] + z)
+        gs = [g if g.is_contiguous() else g.contiguous() for g in grads]
+        mb, bt = (self.overlap_blocks, 128) if overlapped else (0, 0)
+        self._copy_segments(gs, [self.flat_in[o:o + g.numel()] for o, g in zip(offs, gs)], mb)
         red = torch.empty(nb, device=self.device, dtype=F32)
-        self.mem.all_reduce(nb, red, 'sum', self.scale, max_blocks=max_blocks)
-        torch._foreach_copy_([o.view(-1) for o in outs], list(red.split(sizes)))
+        self.mem.all_reduce(nb, red, 'sum', self.scale, max_blocks=mb, block_threads=bt)
+        self._copy_segments([red[o:o + g.numel()] for o, g in zip(offs, gs)], outs, mb)
 
     def _flush(self, overlapped: bool = True):
         """All reported groups in one collective on the communication stream.  Issued from the backward it runs beside the
@@ -201,7 +220,7 @@ class GradAverager:
         with torch.cuda.stream(self.comm):
             for t in grads + outs:
                 t.record_stream(self.comm)
-            self._reduce_into(grads, outs, self.overlap_blocks if overlapped else 0)
+            self._reduce_into(grads, outs, overlapped)
         self._pending = []
 
     def _on_group(self, params, grads):

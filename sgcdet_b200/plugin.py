@@ -679,6 +679,35 @@ class AdaptiveSparseHead(nn.Module):
         return {'loss_occ': loss_occ}
 
 
+def valid_pyramid(valid: torch.Tensor, sizes) -> List[torch.Tensor]:
+    """The detection head's per-level validity masks from ``AdaptiveSparseHead``'s ``valid`` [1,1,X,Y,Z]:
+    ``[nn.Upsample(size=s, mode='trilinear')(valid.float()).round().bool() for s in sizes]`` of
+    dense_heads/imvoxel_head_v2.py:121-123,256-258, for level sizes of 1, 1/2 and 1/4 of the volume (what the three-scale neck
+    produces) -- one launch, bit-exact, no float volume in between (``sgc_valid_pyramid``)."""
+    if not valid.is_cuda:
+        raise RuntimeError('sgcdet_b200 has no CPU implementation: inputs must be CUDA tensors')
+    X, Y, Z = (int(v) for v in valid.shape[-3:])
+    outs = {}
+    for s in sizes:
+        s = tuple(int(v) for v in s)
+        for k in (1, 2, 4):
+            if s == (X // k, Y // k, Z // k) and X % k == 0 and Y % k == 0 and Z % k == 0:
+                outs[k] = torch.empty(1, 1, *s, device=valid.device, dtype=torch.uint8)
+                break
+        else:
+            raise ValueError(f'sgcdet_b200.valid_pyramid: level size {s} is not 1, 1/2 or 1/4 of the volume {(X, Y, Z)}')
+    from ._lib import call, ptr, stream
+    v = valid.contiguous().to(torch.int64)
+    with torch.cuda.device(valid.device):
+        call('sgc_valid_pyramid', ptr(v), X, Y, Z, ptr(outs.get(1)), ptr(outs.get(2)), ptr(outs.get(4)), stream())
+    res = []
+    for s in sizes:
+        s = tuple(int(v_) for v_ in s)
+        k = X // s[0] if s[0] else 1
+        res.append(outs[k].bool())
+    return res
+
+
 def build_voxel_head(cfg) -> AdaptiveSparseHead:
     """Build from a PathConfig (synthetic.py) or from the ``voxel_head`` dict of an ``SGCDet_*.py`` config."""
     if isinstance(cfg, dict):

@@ -340,3 +340,19 @@ def test_occ_loss_matches_torch_bce(cuda_lib, N):
     (ref * 3.0).backward()
     torch.testing.assert_close(loss.item(), ref.item(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(pg.grad.cpu().double(), p64.grad, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize('shape', [(40, 40, 16), (16, 16, 8), (8, 12, 4)])
+def test_valid_pyramid_matches_reference_expression(cuda_lib, shape):
+    """plugin.valid_pyramid == the head's own nn.Upsample(size, mode='trilinear')(valid).round().bool()
+    (dense_heads/imvoxel_head_v2.py:121-123), bit-exact, for random masks incl. blocks with exactly 4 of 8 voxels set
+    (mean 0.5 rounds to 0: half to even)."""
+    g = torch.Generator().manual_seed(sum(shape))
+    for p in (0.25, 0.5, 0.75):
+        valid = (torch.rand(1, 1, *shape, generator=g) < p).long()
+        sizes = [shape, tuple(v // 2 for v in shape), tuple(v // 4 for v in shape)]
+        ref = [torch.nn.Upsample(size=s, mode='trilinear')(valid.float()).round().bool() for s in sizes]
+        got = plugin.valid_pyramid(valid.to(DEV), sizes)
+        for a, b in zip(got, ref):
+            assert a.dtype == torch.bool and a.shape == b.shape
+            assert torch.equal(a.cpu(), b)

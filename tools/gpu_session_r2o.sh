@@ -5,9 +5,9 @@ O=gpurun_out
 mkdir -p $O
 ts() { echo "[$(date +%H:%M:%S)] $*" | tee -a $O/r2o_times.log; }
 ts start
-timeout 120 python tools/rows_gemm_timeline.py 6400 256 256 > $O/r2o_rows_gemm_timeline.txt 2>&1
-ts timeline "$(grep -c us $O/r2o_rows_gemm_timeline.txt)"
-timeout 200 python -m pytest tests/test_gpu_peer.py -q -k "averager or simulated" 2>&1 | tail -30 > $O/r2o_tests.log
+
+
+timeout 200 python -m pytest tests/test_gpu_peer.py tests/test_gpu_path.py -q -k "averager or simulated or valid_pyramid" 2>&1 | tail -30 > $O/r2o_tests.log
 ts tests "$(tail -1 $O/r2o_tests.log)"
 T="timeout -k 5 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 A="--gpus 2 --steps 300 --no-cpu-baseline --no-view-sharded --no-train-step --skip-e2e"
