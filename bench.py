@@ -599,17 +599,20 @@ def run_ours(args):
             'metric': METRIC, 'value': round(world * B * args.steps / (total_ms * 1e-3), 2), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(step_ms, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, {B} scene(s) per GPU per step',
-                       'scenes_per_gpu': B,
-                       'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]), 'topk': list(cfg.topk_list),
-                       'parallelism': f'scene-batch dp{world}' + ('' if world == 1 or args.no_grad_allreduce else
-                                                                  (' + weight-grad average: bucketed peer-memory all-reduce kernels over NVLink, overlapped with the backward' + (' inside the CUDA graph' if ar_in_graph else '')
-                                                                   if ar_mode == 'peer' else ' + NCCL weight-grad all-reduce after the replay')),
-                       'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)',
-                       'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
-                               'and the loss value evaluated on a side stream beside the backward',
-                       'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
-                       'cuda_graph': not args.no_graph, 'gemm': 'all GEMMs of the path are own tcgen05/TMEM/TMA kernels with the bf16 hi/lo split in shared memory and fp32 accumulation: feature-map projection (forward, data gradient, weight gradient) and the voxel-count layers (forward, data and weight gradients; 16-wide heads of the -L configs keep a library bf16 GEMM for the per-head products)', 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side streams; one CUDA graph'},
+            'config': workload_config(cfg, V, B, world),
+            'implementation': {
+                'grad_average': 'none' if ar_mode == 'none' else (
+                    'own peer-memory all-reduce kernels over NVLink, issued from the backward and overlapped with it'
+                    + (' inside the CUDA graph' if ar_in_graph else '') if ar_mode == 'peer' else 'NCCL all-reduce after the replay'),
+                'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
+                        'and the loss value evaluated on a side stream beside the backward',
+                'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
+                'cuda_graph': not args.no_graph,
+                'gemm': 'all GEMMs of the path are own tcgen05/TMEM/TMA kernels with the bf16 hi/lo split in shared memory and fp32 '
+                        'accumulation: feature-map projection (forward, data gradient, weight gradient) and the voxel-count layers '
+                        '(forward, data and weight gradients, 16- and 32-wide heads)',
+                'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side '
+                           'streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'numa_node_rank0': numa_node,
                     'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},
@@ -1007,6 +1010,14 @@ def depth_producer_bench(dev, iters: int = 5):
                 max_abs_diff=diff)
 
 
+def workload_config(cfg, V: int, B: int, world: int) -> dict:
+    """The line's ``config``: names the workload only, identical for the product arm and the reference arm."""
+    return {'workload': f'{cfg.name} view-transform fwd+bwd, V={V} views, {B} scene(s) per GPU per step',
+            'scenes_per_gpu': B, 'embed_dims': cfg.embed_dims, 'n_voxels': list(cfg.n_voxels_list[-1]),
+            'topk': list(cfg.topk_list), 'parallelism': f'scene-batch dp{world}',
+            'l2': 'inputs larger than L2 (>= 0.33 GB of maps per step, no flush)'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -1023,8 +1034,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
         'ms_per_step': round(1e3 / v, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': f'{cfg.name} view-transform fwd+bwd, V={args.views} views (CPU restatement of the reference path; '
-                               'the reference has no CPU implementation: DFA3D is CUDA only)'},
+        'config': workload_config(cfg, args.views, 1, world),
+        'implementation': {'what': 'CPU restatement of the reference path (oracle/path_ref.py, torch CPU fp32, all host threads); the '
+                                   'reference has no CPU implementation: DFA3D is CUDA only'},
         'cpu_baseline': cpu,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': f'steps/warmup clamped to {steps}/{warm} so the run ends within minutes; rank 0 only',

@@ -21,12 +21,24 @@ dists = [d.clone().requires_grad_(True) for d in sc.mlvl_dpt_dists[:3]]
 gvol = sc.grad_volume.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
 
 
+avg = None
+if os.environ.get('SGC_PROFILE_AVERAGER'):
+    # the gradient averager of scene-batch DP with a single rank (no process group): same launches, stream structure and SM
+    # footprint as on N ranks, without the link latency
+    from sgcdet_b200 import peer
+    avg = peer.GradAverager(list(head.parameters()))
+
+
 def step():
     for t in list(head.parameters()) + feats + dists:
         t.grad = None
+    if avg is not None:
+        avg.begin_step()
     vol, valid, occ = head(feats, sc.img_meta, dists)
     # as bench.py: the backward is seeded with G (the gradient of sum(volume*G)); the loss value is not on its path
     torch.autograd.backward([vol, head.occ_loss(occ, None, sc.geo_occ)['loss_occ']], [gvol, None])
+    if avg is not None:
+        avg.finish_step()
 
 
 for _ in range(3):
