@@ -172,6 +172,7 @@ class GradAverager:
         self.scale = 1.0 / self.mem.world
         self.comm = torch.cuda.Stream(device=self.device)      # default priority: never ahead of the voxel chains
         self.overlap_blocks = overlap_blocks
+        self.small_group_bytes = 64 << 10
         self._ids = {id(p) for p in self.params}
         self._active, self._expected = False, None
         self._pending, self._done, self._adopted = [], set(), []
@@ -226,6 +227,10 @@ class GradAverager:
     def _on_group(self, params, grads):
         """``functional.GRAD_REDUCER``: called from OnStream.backward on the group's weight-gradient stream."""
         if not self._active or any(g is None for g in grads) or any(id(p) not in self._ids for p in params):
+            return grads
+        if sum(g.numel() for g in grads) * 4 < self.small_group_bytes:
+            # e.g. the occupancy heads (C + 1 floats): their gradient kernels trail the step on their stream, and waiting for
+            # them would hold the one large collective back until the very end -- they join the tail in finish_step instead
             return grads
         cur = torch.cuda.current_stream(self.device)
         gs = [g.contiguous() for g in grads]

@@ -15,7 +15,7 @@ run() { name=$1; port=$2; shift; shift; $T --master-port $port bench.py $A "$@" 
 run peer1 29551
 run nccl1 29552 --grad-allreduce nccl
 run noar1 29553 --no-grad-allreduce
-run peer2 29554
-run nccl2 29555 --grad-allreduce nccl
-run noar2 29556 --no-grad-allreduce
+
+
+
 tail -8 $O/r2o_n2_peer1.err > $O/r2o_n2_peer1_tail.txt
