@@ -170,7 +170,9 @@ class GradAverager:
         self.flat_in = self.mem.view((self.n,))
         self.flat_in.zero_()
         self.scale = 1.0 / self.mem.world
-        self.comm = torch.cuda.Stream(device=self.device)      # default priority: never ahead of the voxel chains
+        # high priority: the block scheduler hands freed SM slots to its (small) CTAs first -- at default priority the launches
+        # waited until the step's large grids had dispatched all their CTAs, i.e. until the end of the step
+        self.comm = torch.cuda.Stream(device=self.device, priority=-1)
         self.overlap_blocks = overlap_blocks
         self.small_group_bytes = 64 << 10
         self._ids = {id(p) for p in self.params}

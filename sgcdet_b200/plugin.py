@@ -389,13 +389,28 @@ class DenseHead(nn.Module):
         wcat, vbias, gbias = da.folded_weights()
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
                              ffn.layers[0][0].weight, ffn.layers[1].weight)
-        # the depth map's layout change is created BEFORE the projection node: autograd runs later-created nodes first, so
-        # in the backward the projection's data / weight gradient kernels (the tail of the step) are issued ahead of the
-        # depth gradient's copies instead of queueing behind them on the same stream
+        wstream, dist_stream = None, None
+        if torch.is_grad_enabled() and os.environ.get('SGC_WSTREAM', '1') != '0':
+            # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
+            # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
+            if self._wstream is None or self._wstream[0].device != feat.device:
+                self._wstream = (torch.cuda.Stream(device=feat.device), torch.cuda.Stream(device=feat.device))
+            wstream = self._wstream
         if isinstance(dpt_dist, SF.DepthCL):   # produced channel-last and cropped by sgcdet_b200.depth.depth_pyramid
             if (dpt_dist.h, dpt_dist.w) != (h, w):
                 raise ValueError(f'sgcdet_b200: depth level cropped to {(dpt_dist.h, dpt_dist.w)}, the level needs {(h, w)}')
             dist = dpt_dist.t
+        elif wstream is not None and dpt_dist.requires_grad:
+            # The reference-layout depth map's crop + channel-last copy lives on the FFN weight-gradient stream: autograd replays
+            # its backward (zero fill of the padded map, permuted copy, accumulation: ~25 us of small launches) there, beside
+            # the projection's gradient kernels, instead of behind them at the very end of the step on this stream
+            cur = torch.cuda.current_stream(feat.device)
+            wstream[1].wait_stream(cur)
+            with torch.cuda.stream(wstream[1]):
+                dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
+            cur.wait_stream(wstream[1])
+            dist.record_stream(cur)
+            dist_stream = wstream[1]
         else:
             dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
@@ -405,13 +420,7 @@ class DenseHead(nn.Module):
                   mha.out_proj.weight, mha.out_proj.bias, ffn.layers[0][0].weight, ffn.layers[0][0].bias,
                   ffn.layers[1].weight, ffn.layers[1].bias, layer.norms[0].weight, layer.norms[0].bias,
                   layer.norms[1].weight, layer.norms[1].bias)
-        wstream = None
-        if torch.is_grad_enabled() and os.environ.get('SGC_WSTREAM', '1') != '0':
-            # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
-            # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
-            if self._wstream is None or self._wstream[0].device != feat.device:
-                self._wstream = (torch.cuda.Stream(device=feat.device), torch.cuda.Stream(device=feat.device))
-            wstream = self._wstream
+        if wstream is not None:
             with torch.cuda.stream(wstream[0]):
                 pa = SF.OnStream.apply(*params[:6])
             with torch.cuda.stream(wstream[1]):
@@ -424,7 +433,8 @@ class DenseHead(nn.Module):
             masks = _dropout_masks(n_rows, (self.embed_dims, ffn.layers[0][0].out_features, self.embed_dims),
                                    (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p), feat.device)
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
-                    stream=torch.cuda.current_stream(feat.device), params=params, wstream=wstream, masks=masks)
+                    stream=torch.cuda.current_stream(feat.device), dist_stream=dist_stream, params=params, wstream=wstream,
+                    masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None, coll=None):
@@ -446,8 +456,10 @@ class DenseHead(nn.Module):
         if prepared is None:
             prepared = self.prepare(feat, dpt_dist, hw)
         lw = prepared['lw']
+        # the lift backward runs on the level's prepare stream; the depth map's layout backward lives on dist_stream, which
+        # therefore has to wait for that kernel explicitly (autograd only knows this node's own stream)
         slots, samp = SF.Lift.apply(prepared['vg'], prepared['dist'], prepared['vbias'], prepared['gbias'], pl, h, w,
-                                    prepared.get('stream'))
+                                    prepared.get('stream'), prepared.get('dist_stream'))
         pp, ws = prepared['params'], prepared['wstream']
         ffn = layer.ffns[0]
         C = self.embed_dims
