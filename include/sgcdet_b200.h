@@ -50,6 +50,19 @@ int dfa3d_wms_bwd(const float* value, const int64_t* shapes2d, const int64_t* ls
                   const float* attn, const float* depth_score, const float* grad_out, int B, int S, int M, int Cm,
                   int L, int Q, int P, float* grad_value, float* grad_loc2d, float* grad_attn,
                   float* grad_depth_score, void* stream);
+/* fp64 instantiation of the four entry points above (the reference dispatches over float and double:
+ * csrc/cuda/ms_depth_score_sample_cuda.cu:95,153, csrc/cuda/wms_deform_attn_cuda.cu:267,344); plain scalar kernels
+ * (csrc/dfa3d_op_f64.cu), same argument meaning and accumulation rules. */
+int dfa3d_depth_score_fwd_f64(const double* dist, const int64_t* shapes3d, const int64_t* lsi, const double* loc, int B, int S,
+                              int M, int D, int L, int Q, int P, double* out, void* stream);
+int dfa3d_depth_score_bwd_f64(const double* dist, const int64_t* shapes3d, const int64_t* lsi, const double* loc,
+                              const double* grad_out, int B, int S, int M, int D, int L, int Q, int P, double* grad_dist,
+                              double* grad_loc, void* stream);
+int dfa3d_wms_fwd_f64(const double* value, const int64_t* shapes2d, const int64_t* lsi, const double* loc2d, const double* attn,
+                      const double* depth_score, int B, int S, int M, int Cm, int L, int Q, int P, double* out, void* stream);
+int dfa3d_wms_bwd_f64(const double* value, const int64_t* shapes2d, const int64_t* lsi, const double* loc2d, const double* attn,
+                      const double* depth_score, const double* grad_out, int B, int S, int M, int Cm, int L, int Q, int P,
+                      double* grad_value, double* grad_loc2d, double* grad_attn, double* grad_depth_score, void* stream);
 /* One-stage operator = MultiScale3DDeformableAttnFunction_fp32.forward/backward (F3D:277-351) without the
  * depth-score round trip.  depth_score_out may be NULL. */
 int dfa3d_fused_fwd(const float* value, const float* dist, const int64_t* shapes3d, const int64_t* lsi,

@@ -23,6 +23,10 @@ SIGNATURES = {
     'dfa3d_depth_score_bwd': [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
     'dfa3d_wms_fwd': [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P],
     'dfa3d_wms_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    'dfa3d_depth_score_fwd_f64': [P, P, P, P, I, I, I, I, I, I, I, P, P],
+    'dfa3d_depth_score_bwd_f64': [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
+    'dfa3d_wms_fwd_f64': [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P],
+    'dfa3d_wms_bwd_f64': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     'dfa3d_fused_fwd': [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P],
     'dfa3d_fused_bwd': [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P],
     'sgc_project_scratch_ints': [I, I],

@@ -5,7 +5,8 @@ argument order, keyword names and ownership rules, implemented over the sgcdet_b
   * ``batch % min(batch, im2col_step) == 0`` is checked like WMSL:250-253 (the value has no numerical effect);
   * forward functions allocate and return their output (WMSL:255-256, DSL:84-85);
   * backward functions accumulate into caller-allocated, caller-zeroed grads (F3D:319-322,338-339);
-  * fp32 only (the reference also dispatches fp64; the SGCDet path is fp32, fp16_enabled=False everywhere).
+  * float32 and float64 like the reference's AT_DISPATCH_FLOATING_TYPES (the SGCDet path itself is fp32; the fp64
+    instantiation is a plain scalar one, csrc/dfa3d_op_f64.cu); the one-stage additions at the end are fp32 only.
 """
 import torch
 
@@ -27,20 +28,29 @@ def _check(im2col_step, *tensors):
 def _f32(*ts):
     for t in ts:
         if t.dtype != torch.float32:
-            raise RuntimeError('sgcdet_b200 DFA3D kernels are fp32 only')
+            raise RuntimeError('sgcdet_b200: the one-stage DFA3D kernels are fp32 only')
+
+
+def _suffix(*ts):
+    """'' for float32, '_f64' for float64 operands (all of one dtype), like AT_DISPATCH_FLOATING_TYPES."""
+    dt = ts[0].dtype
+    if dt not in (torch.float32, torch.float64) or any(t.dtype != dt for t in ts):
+        raise RuntimeError(f'sgcdet_b200 DFA3D kernels are implemented for float32 and float64 operands of one dtype (got '
+                           f'{[str(t.dtype) for t in ts]})')
+    return '' if dt == torch.float32 else '_f64'
 
 
 def wms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
                             attention_weights, depth_scores, im2col_step):
     _check(im2col_step, value, value_spatial_shapes, value_level_start_index, sampling_locations,
            attention_weights, depth_scores)
-    _f32(value, sampling_locations, attention_weights, depth_scores)
+    sfx = _suffix(value, sampling_locations, attention_weights, depth_scores)
     B, S, M, Cm = value.shape
     L = value_spatial_shapes.size(0)
     Q, P = sampling_locations.size(1), sampling_locations.size(4)
     out = torch.empty(B, Q, M * Cm, device=value.device, dtype=value.dtype)
     with torch.cuda.device(value.device):
-        call('dfa3d_wms_fwd', ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
+        call('dfa3d_wms_fwd' + sfx, ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
              ptr(sampling_locations), ptr(attention_weights), ptr(depth_scores), B, S, M, Cm, L, Q, P, ptr(out),
              stream())
     return out
@@ -52,12 +62,13 @@ def wms_deform_attn_backward(value, value_spatial_shapes, value_level_start_inde
     _check(im2col_step, value, value_spatial_shapes, value_level_start_index, sampling_locations,
            attention_weights, depth_scores, grad_output, grad_value, grad_sampling_loc, grad_attn_weight,
            grad_depth_score)
-    _f32(value, grad_output)
+    sfx = _suffix(value, sampling_locations, attention_weights, depth_scores, grad_output, grad_value, grad_sampling_loc,
+                  grad_attn_weight, grad_depth_score)
     B, S, M, Cm = value.shape
     L = value_spatial_shapes.size(0)
     Q, P = sampling_locations.size(1), sampling_locations.size(4)
     with torch.cuda.device(value.device):
-        call('dfa3d_wms_bwd', ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
+        call('dfa3d_wms_bwd' + sfx, ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
              ptr(sampling_locations), ptr(attention_weights), ptr(depth_scores), ptr(grad_output), B, S, M, Cm, L, Q, P,
              ptr(grad_value), ptr(grad_sampling_loc), ptr(grad_attn_weight), ptr(grad_depth_score), stream())
 
@@ -65,13 +76,13 @@ def wms_deform_attn_backward(value, value_spatial_shapes, value_level_start_inde
 def ms_depth_score_sample_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
                                   im2col_step):
     _check(im2col_step, value, value_spatial_shapes, value_level_start_index, sampling_locations)
-    _f32(value, sampling_locations)
+    sfx = _suffix(value, sampling_locations)
     B, S, M, D = value.shape
     L = value_spatial_shapes.size(0)
     Q, P = sampling_locations.size(1), sampling_locations.size(4)
     out = torch.empty(B, Q, M, L, P, 4, device=value.device, dtype=value.dtype)
     with torch.cuda.device(value.device):
-        call('dfa3d_depth_score_fwd', ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
+        call('dfa3d_depth_score_fwd' + sfx, ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
              ptr(sampling_locations), B, S, M, D, L, Q, P, ptr(out), stream())
     return out
 
@@ -80,12 +91,12 @@ def ms_depth_score_sample_backward(value, value_spatial_shapes, value_level_star
                                    grad_output, grad_value, grad_sampling_loc, im2col_step):
     _check(im2col_step, value, value_spatial_shapes, value_level_start_index, sampling_locations, grad_output,
            grad_value, grad_sampling_loc)
-    _f32(value, grad_output)
+    sfx = _suffix(value, sampling_locations, grad_output, grad_value, grad_sampling_loc)
     B, S, M, D = value.shape
     L = value_spatial_shapes.size(0)
     Q, P = sampling_locations.size(1), sampling_locations.size(4)
     with torch.cuda.device(value.device):
-        call('dfa3d_depth_score_bwd', ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
+        call('dfa3d_depth_score_bwd' + sfx, ptr(value), ptr(value_spatial_shapes), ptr(value_level_start_index),
              ptr(sampling_locations), ptr(grad_output), B, S, M, D, L, Q, P, ptr(grad_value), ptr(grad_sampling_loc),
              stream())
 

@@ -375,6 +375,19 @@ _GRAD_STREAMS = {}
 
 
 GRAD_REDUCER = None   # set by peer.GradAverager: callable(params, grads) -> grads, applied to a parameter group's gradients
+GRAD_READY = {}       # data_ptr of a parameter gradient -> event recorded by its PRODUCER right behind the producing launch
+
+
+def mark_grads_ready(tensors, stream_) -> None:
+    """Called by a backward that produces parameter gradients on ``stream_`` while a gradient reducer is installed: the
+    reducer waits for this event instead of one recorded when the gradients reach ``OnStream.backward`` -- by then (it is
+    among the last nodes autograd executes) unrelated late work has been queued on the same stream (the occupancy head's
+    weight gradient, the depth map's layout backward), which held the collective back until the end of the step."""
+    ev = torch.cuda.Event()
+    ev.record(stream_)
+    for t in tensors:
+        if t is not None:
+            GRAD_READY[t.data_ptr()] = ev
 
 
 class OnStream(torch.autograd.Function):
@@ -898,6 +911,9 @@ class EncoderLayerRows(torch.autograd.Function):
                 t_.record_stream(side_f.side)
         side.join()
         side_f.join()
+        if GRAD_REDUCER is not None:
+            mark_grads_ready((g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo), side.side if side.detached else side.main)
+            mark_grads_ready((g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2), side_f.side if side_f.detached else side_f.main)
         return (gslots, None, g_wout, g_bout, g_in_w, g_in_b, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_g1, g_be1, g_g2, g_be2,
                 None, None, None, None, None, None, None)
 

@@ -216,8 +216,9 @@ class GradAverager:
         if not self._pending:
             return
         grads, outs = [], []
-        for ev, gs, os_ in self._pending:
-            self.comm.wait_event(ev)
+        for evs, gs, os_ in self._pending:
+            for ev in evs:
+                self.comm.wait_event(ev)
             grads += gs
             outs += os_
         with torch.cuda.stream(self.comm):
@@ -234,11 +235,18 @@ class GradAverager:
             # e.g. the occupancy heads (C + 1 floats): their gradient kernels trail the step on their stream, and waiting for
             # them would hold the one large collective back until the very end -- they join the tail in finish_step instead
             return grads
+        from . import functional as SF
         cur = torch.cuda.current_stream(self.device)
         gs = [g.contiguous() for g in grads]
         outs = [torch.empty_like(g) for g in gs]
-        ev = torch.cuda.Event()
-        ev.record(cur)
+        # readiness: the event the producing backward recorded right behind its launch (functional.mark_grads_ready); only
+        # when a gradient carries none, an event on this node's stream (which may have unrelated late work queued)
+        evs = [SF.GRAD_READY.pop(g.data_ptr(), None) for g in grads]
+        if any(e is None for e in evs):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            evs = [e for e in evs if e is not None] + [ev]
+        ev = list({id(e): e for e in evs}.values())
         # autograd adopts a returned tensor as p.grad only while nobody else holds it: keep storage ALIASES (.data: another
         # tensor object on the same memory) for the collective to write through; finish_step verifies the adoption
         aliases = [o.data for o in outs]
@@ -254,6 +262,7 @@ class GradAverager:
         from . import functional as SF
         SF.GRAD_REDUCER = self._on_group
         self._pending, self._done, self._active, self.groups_last_step, self._adopted = [], set(), True, 0, []
+        SF.GRAD_READY.clear()
 
     def finish_step(self):
         """After ``backward()``: flush groups that were not flushed from the backward (first step), average in place every

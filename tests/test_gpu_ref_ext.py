@@ -133,3 +133,27 @@ def test_product_matches_reference_kernels_end_to_end(ref_ext, cuda_lib, V):
     assert torch.equal(valid, valid_r)
     torch.testing.assert_close(occ, occ_r, rtol=RTOL, atol=ATOL)
     torch.testing.assert_close(vol, vol_r, rtol=RTOL, atol=ATOL)
+
+
+def test_two_stage_exports_fp64_match_reference(ref_ext, cuda_lib):
+    """The reference dispatches the four `_ext` functions over float AND double (wms_deform_attn_cuda.cu:267,344,
+    ms_depth_score_sample_cuda.cu:95,153): the drop-in's fp64 instantiation (csrc/dfa3d_op_f64.cu) against the reference's own
+    kernels on double inputs, and against the fp32 path."""
+    sgcdet_b200.install_dropin()
+    from dfa3D import ext_loader
+    ext = ext_loader.load_ext('_ext', ['wms_deform_attn_backward', 'wms_deform_attn_forward',
+                                       'ms_depth_score_sample_forward', 'ms_depth_score_sample_backward'])
+    for name in ('sgcdet_stage2', 'unittest_family'):
+        c = make_case(*CASES[name], seed=33)
+        cd = {k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in c.items()}
+        ref = reference_fwd_bwd(ref_ext, cd['value'], cd['dist'], cd['s3'], cd['lsi'], cd['loc'], cd['attn'], cd['gout'])
+        got = reference_fwd_bwd(ext, cd['value'], cd['dist'], cd['s3'], cd['lsi'], cd['loc'], cd['attn'], cd['gout'])
+        for k in ref:
+            assert got[k].dtype == torch.float64
+            torch.testing.assert_close(got[k], ref[k], rtol=1e-9, atol=1e-10, msg=lambda m: f'{name}/{k}: {m}')
+        cf = {k: v.cuda() for k, v in c.items()}
+        g32 = reference_fwd_bwd(ext, cf['value'], cf['dist'], cf['s3'], cf['lsi'], cf['loc'], cf['attn'], cf['gout'])
+        torch.testing.assert_close(g32['out'].double(), got['out'], rtol=RTOL, atol=ATOL)
+    # mixed dtypes are refused like a failed dispatch
+    with pytest.raises(RuntimeError):
+        ext.ms_depth_score_sample_forward(cd['dist'], cd['s3'], cd['lsi'], cd['loc'].float(), im2col_step=64)
