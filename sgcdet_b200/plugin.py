@@ -394,7 +394,13 @@ class DenseHead(nn.Module):
             # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
             # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
             if self._wstream is None or self._wstream[0].device != feat.device:
-                self._wstream = (torch.cuda.Stream(device=feat.device), torch.cuda.Stream(device=feat.device))
+                # high priority (SGC_WSTREAM_PRIO, default -1): besides the grouped weight-gradient launch these streams carry small
+                # trailing work (occupancy weight gradient, the depth map's layout backward, gradient accumulation); at default
+                # priority the block scheduler left it waiting until the projection-gradient grids had dispatched every CTA,
+                # i.e. it ran AFTER them and ended the step ~40 us late
+                prio = int(os.environ.get('SGC_WSTREAM_PRIO', '-1'))
+                self._wstream = (torch.cuda.Stream(device=feat.device, priority=prio),
+                                 torch.cuda.Stream(device=feat.device, priority=prio))
             wstream = self._wstream
         if isinstance(dpt_dist, SF.DepthCL):   # produced channel-last and cropped by sgcdet_b200.depth.depth_pyramid
             if (dpt_dist.h, dpt_dist.w) != (h, w):
