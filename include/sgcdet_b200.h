@@ -434,6 +434,10 @@ int sgc_peer_allreduce(const void* const* bufs, void* const* sigs, int rank, int
 /* dst[k][0:n[k]] = src[k][0:n[k]] for `count` segments (HOST arrays of device pointers / lengths) as one launch of 128-thread
  * CTAs per 64 segments: the gather of gradient tensors into the symmetric buffer and the scatter of the averages back. */
 int sgc_peer_copy_segments(const void* const* src, void* const* dst, const long long* n, int count, int max_blocks, void* stream);
+/* tensors[k][0:n[k]] <- scale * sum over the ranks, in place, for count <= 64 tensors as ONE launch (gather into the symmetric
+ * buffers, meet, reduce in rank order, scatter): the tail of the gradient average. */
+int sgc_peer_allreduce_tensors(const void* const* bufs, void* const* sigs, int rank, int world, void* const* tensors,
+                               const long long* n, int count, float scale, void* stream);
 
 #ifdef __cplusplus
 }

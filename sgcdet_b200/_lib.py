@@ -99,6 +99,7 @@ SIGNATURES = {
     'sgc_depth_pyramid_bwd': [P, I, I, I, I, P, P, I, I, P, I, I, P, I, I, P, P],
     'sgc_peer_allreduce': [P, P, I, I, LL, I, F, P, I, I, P],
     'sgc_peer_copy_segments': [P, P, P, I, I, P],
+    'sgc_peer_allreduce_tensors': [P, P, I, I, P, P, I, F, P],
     'sgc_peer_sig_bytes': [],
     'sgc_peer_status_offset': [],
     'sgc_peer_alloc': [LL, P, P],

@@ -124,6 +124,20 @@ class PeerMemory:
                       float(scale), _lib.ptr(out), int(max_blocks), int(block_threads), _lib.stream(self.device))
         return out
 
+    def all_reduce_tensors(self, tensors, scale: float = 1.0) -> None:
+        """tensors[k] <- scale * sum over the ranks, in place (contiguous fp32, at most 64 per launch, every rank the same
+        sizes in the same order): gather, barrier, reduce, scatter in ONE launch (``sgc_peer_allreduce_tensors``)."""
+        bufs = (ctypes.c_void_p * self.world)(*[b + self.sig_bytes for b in self.bases])
+        with torch.cuda.device(self.device):
+            for i in range(0, len(tensors), 64):
+                ts = tensors[i:i + 64]
+                if sum((t.numel() + 3) // 4 * 16 for t in ts) > self.nbytes or any(t.dtype != F32 or not t.is_contiguous() for t in ts):
+                    raise ValueError('sgcdet_b200.peer: bad all_reduce_tensors arguments')
+                a = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+                n = (ctypes.c_longlong * len(ts))(*[t.numel() for t in ts])
+                _lib.call('sgc_peer_allreduce_tensors', bufs, self._sigs, self.rank, self.world, a, n, len(ts), float(scale),
+                          _lib.stream(self.device))
+
     def close(self):
         """Unmap the peers' allocations and free the own one (collective: every rank calls it)."""
         if self._closed:
@@ -284,7 +298,9 @@ class GradAverager:
         self.copied_last_step = len(stale)
         self._adopted = []
         rest = [p.grad for p in self.params if id(p) not in self._done and p.grad is not None]
-        if rest:
+        if rest and all(g.is_contiguous() for g in rest):
+            self.mem.all_reduce_tensors(rest, self.scale)      # one launch: this is the part behind the step's last kernel
+        elif rest:
             self._reduce_into(rest, rest)
 
     def __call__(self):

@@ -198,3 +198,35 @@ def test_grad_averager_groups_and_graph_capture(cuda_lib):
         check('inactive averager')
     finally:
         avg.close()
+
+
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_peer_allreduce_tensor_list_in_place(cuda_lib, world):
+    """sgc_peer_allreduce_tensors: a list of tensors of odd sizes (one of them a misaligned view) averaged in place by one
+    launch per rank (gather, barrier, rank-ordered reduce, scatter)."""
+    sizes = [5, 1024, 3, 98304 + 1, 256 * 384, 17]
+    mems = peer.PeerMemory.simulate(world, 4 * (sum(sizes) + 4 * len(sizes)))
+    try:
+        g = torch.Generator().manual_seed(11)
+        base = [[torch.randn(n + 1, generator=g).to(DEV) for n in sizes] for _ in range(world)]
+        tens = [[b[1:] if i == 3 else b[:-1] for i, b in enumerate(bs)] for bs in base]     # tensor 3: 4-byte aligned only
+        ref = []
+        for i in range(len(sizes)):
+            a = tens[0][i].clone()
+            for r in range(1, world):
+                a = a + tens[r][i]
+            ref.append(a * 0.25)
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                mems[r].all_reduce_tensors([t for t in tens[r]], 0.25)
+        torch.cuda.synchronize()
+        for m in mems:
+            m.check()
+        for r in range(world):
+            for t, a in zip(tens[r], ref):
+                assert torch.equal(t, a)
+    finally:
+        for m in mems:
+            m.close()
