@@ -699,8 +699,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kch, int elems, float* __restrict__ gw) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= elems) return;
+  // the last kernel of the step: 8 partials in flight per thread (the additions stay in k order: deterministic); one load per
+  // iteration made it a chain of ~49 dependent L2 round trips (23 us for 98 K outputs)
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < kch; ++k) {
+  int k = 0;
+  for (; k + 8 <= kch; k += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(partial + (size_t)(k + u) * elems + i));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; k < kch; ++k) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * elems + i));
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
