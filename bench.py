@@ -522,9 +522,9 @@ def run_ours(args):
         avg0 = d0['ms'] / d0['n']
         ach = d0['bytes'] / (avg0 * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the same shape from the committed
-        # `ncu --set full` capture (profiles/r1_ncu_traffic.json, written by tools/summarize_ncu.py); None if absent
+        # `ncu --set full` capture (profiles/r2_ncu_traffic.json, written by tools/summarize_ncu.py); None if absent
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')
         if os.path.exists(tpath) and args.config == 'SGCDet_ScanNet' and V == 40:
             traffic = json.load(open(tpath)).get(k0)
         roof = dict(bound='hbm', kernel=k0, achieved=round(ach, 1), peak=peaks['hbm_gbs'], unit='GB/s',
