@@ -74,8 +74,8 @@ __device__ __forceinline__ float4 lift_params(const float* __restrict__ G, int l
   return r;
 }
 
-template <int CPL>
-__global__ void __launch_bounds__(256) lift_fwd_kernel(
+template <int CPL, int MINB>
+__global__ void __launch_bounds__(256, MINB) lift_fwd_kernel(
     const float* __restrict__ value, int ldv, const float* __restrict__ G, int ldg,
     const float* __restrict__ dist, const float* __restrict__ vbias, const float* __restrict__ gbias,
     const int* __restrict__ pair_vq, const int* __restrict__ n_pairs_ptr, const float* __restrict__ ref_cam,
@@ -85,13 +85,27 @@ __global__ void __launch_bounds__(256) lift_fwd_kernel(
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int n_pairs = __ldg(n_pairs_ptr);
-  for (int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < n_pairs;
-       pair += gridDim.x * warps_per_block) {
-    const int flat = __ldg(pair_vq + pair);
+  // the pair id and its reference point are fetched one iteration ahead: two dependent global round trips less in front of
+  // every pair's (dependent) G -> depth -> value gathers
+  const int stride = gridDim.x * warps_per_block;
+  int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  int flat_n = 0;
+  float rx_n = 0.f, ry_n = 0.f, rz_n = 0.f;
+  if (pair < n_pairs) {
+    flat_n = __ldg(pair_vq + pair);
+    rx_n = __ldg(ref_cam + (size_t)flat_n * 3); ry_n = __ldg(ref_cam + (size_t)flat_n * 3 + 1);
+    rz_n = __ldg(ref_cam + (size_t)flat_n * 3 + 2);
+  }
+  for (; pair < n_pairs; pair += stride) {
+    const int flat = flat_n;
+    const float rx = rx_n, ry = ry_n, rz = rz_n;
+    if (pair + stride < n_pairs) {
+      flat_n = __ldg(pair_vq + pair + stride);
+      rx_n = __ldg(ref_cam + (size_t)flat_n * 3); ry_n = __ldg(ref_cam + (size_t)flat_n * 3 + 1);
+      rz_n = __ldg(ref_cam + (size_t)flat_n * 3 + 2);
+    }
     const int v = flat / Q;
     const size_t vS = (size_t)v * S;
-    const float rx = __ldg(ref_cam + (size_t)flat * 3), ry = __ldg(ref_cam + (size_t)flat * 3 + 1),
-                rz = __ldg(ref_cam + (size_t)flat * 3 + 2);
     const float4 sp = lift_params(G, ldg, dist, gbias, vS, rx, ry, rz, H, W, D, lane);
     reinterpret_cast<float4*>(samp)[(size_t)pair * 32 + lane] = sp;
 
@@ -117,21 +131,34 @@ __global__ void __launch_bounds__(256) lift_fwd_kernel(
     for (int p = 0; p < 4; ++p) {
       const int src = (lane & ~3) | p;
       const float a = __shfl_sync(SGC_FULL_MASK, sp.w, src);
+      int pk[4];
+      float wk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pk[k] = __shfl_sync(SGC_FULL_MASK, px[k], src);
+        wk[k] = __shfl_sync(SGC_FULL_MASK, cw[k], src);
+      }
+      // the four corner rows of the point are fetched together (4 x CPL/4 independent 16-byte gathers in flight per lane:
+      // the kernel is bound by the latency of these L2 gathers, not by their bandwidth)
+      float x[4][CPL];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (wk[k] != 0.f) {
+          load_row<CPL>(x[k], vbase + (vS + pk[k]) * ldv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) x[k][j] = 0.f;
+        }
+      }
       float val[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) val[j] = 0.f;
       float ws = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int pk = __shfl_sync(SGC_FULL_MASK, px[k], src);
-        const float wk = __shfl_sync(SGC_FULL_MASK, cw[k], src);
-        if (wk != 0.f) {
-          float x[CPL];
-          load_row<CPL>(x, vbase + (vS + pk) * ldv);
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) val[j] += wk * x[j];
-          ws += wk;
-        }
+        for (int j = 0; j < CPL; ++j) val[j] += wk[k] * x[k][j];
+        ws += wk[k];
       }
 #pragma unroll
       for (int j = 0; j < CPL; ++j) acc[j] += val[j] * a;
@@ -332,12 +359,17 @@ extern "C" int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
-  if (C == 256)
-    sgc::launch_chain(sgc::lift_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
-                      ref_cam, S, H, W, D, Q, samp, slots);
-  else
-    sgc::launch_chain(sgc::lift_fwd_kernel<4>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
-                      ref_cam, S, H, W, D, Q, samp, slots);
+  // 3 CTAs of 8 warps per SM (85 registers): room for the 4 corner rows of a point in flight per lane
+  static const int minb = getenv("SGC_LIFT_FWD_MINB") ? atoi(getenv("SGC_LIFT_FWD_MINB")) : 3;
+#define SGC_LIFT_FWD_ARGS value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs, ref_cam, S, H, W, D, Q, samp, slots
+  if (C == 256) {
+    if (minb == 4) sgc::launch_chain(sgc::lift_fwd_kernel<8, 4>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
+    else if (minb == 2) sgc::launch_chain(sgc::lift_fwd_kernel<8, 2>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
+    else sgc::launch_chain(sgc::lift_fwd_kernel<8, 3>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
+  } else {
+    if (minb == 3) sgc::launch_chain(sgc::lift_fwd_kernel<4, 3>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
+    else sgc::launch_chain(sgc::lift_fwd_kernel<4, 4>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
+  }
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

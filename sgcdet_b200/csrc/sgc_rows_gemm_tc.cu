@@ -362,6 +362,14 @@ extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
   if (R <= 0 || N <= 0 || N % 32 || B <= 0) return 0;
   const int m_tiles = (R + BM - 1) / BM;
   int n_cta = 256;
+  // A/B (SGC_ROWS_SMALL_WORKS=n, 0 = off): problems of at most 4 row tiles (the coarsest level) settle for n work items -- in
+  // the forward their chain runs beside the persistent projection kernel of the finest level, which leaves 16 SMs free
+  static const int small_works = getenv("SGC_ROWS_SMALL_WORKS") ? atoi(getenv("SGC_ROWS_SMALL_WORKS")) : 0;
+  if (small_works > 0 && m_tiles <= 4) {
+    while (n_cta > 32 && (N % n_cta || (long long)m_tiles * B * (N / n_cta) < small_works)) n_cta >>= 1;
+    while (N % n_cta) n_cta >>= 1;
+    return n_cta;
+  }
   while (n_cta > 32 && (N % n_cta || (long long)m_tiles * B * (N / n_cta) * 2 <= 148)) n_cta >>= 1;
   while (N % n_cta) n_cta >>= 1;
   return n_cta;

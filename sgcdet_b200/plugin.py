@@ -294,12 +294,27 @@ _STREAMS = {}
 _CHAIN_STREAMS = {}
 
 
+def _prepare_priorities(n: int):
+    """Stream priority of every level's prepare stream (coarsest level first).  The finest level's stream stays at default
+    priority, the coarser ones are raised: in the backward all three lift kernels become ready within a few microseconds, and
+    at equal priority the block scheduler dispatches every CTA of the finest level's (RED-issue-bound, ~0.2 ms) kernel before
+    the first CTA of the coarser levels' -- their lift / projection-gradient kernels then ran AFTER it and ended the step;
+    raised, they take the SM slots it frees and run beside it (tensor pipe and DRAM are idle under the scatter kernel).
+    ``SGC_PREP_PRIO="a,b,c"`` overrides (A/B)."""
+    env = os.environ.get('SGC_PREP_PRIO')
+    if env:
+        pr = [int(v) for v in env.split(',')]
+        return (pr + [pr[-1]] * n)[:n]
+    return [-1] * (n - 1) + [0]
+
+
 def _side_streams(device, n: int, main=None):
     """n side streams private to (device, calling stream): concurrent scenes on different streams never share them."""
-    key = (torch.device(device), main.cuda_stream if main is not None else 0)
+    prios = _prepare_priorities(n)
+    key = (torch.device(device), main.cuda_stream if main is not None else 0, tuple(prios))
     pool = _STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=torch.device(device)))
+        pool.append(torch.cuda.Stream(device=torch.device(device), priority=prios[len(pool)]))
     return pool[:n]
 
 
