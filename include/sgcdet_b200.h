@@ -346,6 +346,19 @@ int sgc_rowop_fwd(const sgc_rowop_fwd_args* args, void* stream);
 
 int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream);
 
+/* The keep-masks of all dropouts of a step (every level, every layer) in ONE launch: out[j][i] = 1 with probability keep_j,
+ * else 0 -- nn.Dropout's mask (FFN / attention dropouts of the VoxFormerLayer, encoder.py:262-340; the reference draws them
+ * with ATen's bernoulli_, two launches per layer); applied by sgc_rowop_fwd / _bwd (mask, mscale = 1/keep).
+ * Philox4x32-10 keyed by `seed`, counter = (position, job, step).  state = two int64 on the device, zero-initialised once,
+ * private to the call site: state[0] is the step number, advanced by the kernel itself, so a CUDA-graph replay draws
+ * fresh masks.  out pointers 16-byte aligned, njobs <= 12. */
+typedef struct sgc_mask_job {
+  unsigned char* out;
+  long long n;
+  float keep;
+} sgc_mask_job;
+int sgc_dropout_masks(const sgc_mask_job* jobs, int njobs, long long seed, long long* state, void* stream);
+
 /* Sparse volume construction on channel-last volumes [X,Y,Z,C].
  * upsample: F.interpolate(x2, trilinear, align_corners=False) (ASH:64-69) fused with the occupancy head
  * Linear(C,1)+Sigmoid (ASH:37-39,71).  bwd: grad_in written; grad_w [C], grad_b [1] accumulated. */
@@ -353,7 +366,10 @@ int sgc_upsample2x_occ_fwd(const float* vol_in, int X, int Y, int Z, int C, cons
                            float* vol_out, float* occ, void* stream);
 int sgc_upsample2x_occ_bwd(const float* vol_in, int X, int Y, int Z, int C, const float* w_occ, const float* occ,
                            const float* grad_up, const float* grad_occ, float* gpre_scratch, float* grad_in,
-                           float* grad_w, float* grad_b, void* stream);
+                           float* grad_w, float* grad_b, float* scratch, void* stream);
+/* floats of `scratch` above: the gradient is then evaluated axis by axis (three streaming passes over whole rows);
+ * scratch = NULL selects the one-launch form (one warp per input voxel gathering its <= 64 output rows). */
+long long sgc_upsample2x_occ_bwd_scratch_floats(int X, int Y, int Z, int C);
 /* The weight-gradient part of the call above on its own (grad_w accumulated); pass grad_w = NULL above to skip it
  * there and issue it on another stream. */
 int sgc_upsample2x_occ_gradw(const float* vol_in, int X, int Y, int Z, int C, const float* gpre, float* grad_w,

@@ -36,6 +36,7 @@ SIGNATURES = {
     'sgc_prepare_weights': [P, I, P],
     'sgc_rowop_fwd': [P, P],
     'sgc_rowop_bwd': [P, P],
+    'sgc_dropout_masks': [P, I, LL, P, P],
     'sgc_crossview_mean_fwd_split': [P, P, I, I, I, P, P, P],
     'sgc_crossview_attn_fwd_split': [P, P, P, I, I, I, P, P, P, P],
     'sgc_crossview_attn_bwd_qt_split': [P, P, P, I, I, I, P, P, P, P, P],
@@ -80,7 +81,8 @@ SIGNATURES = {
     'sgc_cvs_bwd_slots': [P, P, P, P, I, I, I, P, P, P, P, P],
     'sgc_rows_headscale': [P, P, I, F, P, I, I, P, P, P],
     'sgc_upsample2x_occ_fwd': [P, I, I, I, I, P, P, P, P, P],
-    'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P],
+    'sgc_upsample2x_occ_bwd': [P, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
+    'sgc_upsample2x_occ_bwd_scratch_floats': [I, I, I, I],
     'sgc_upsample2x_occ_gradw': [P, I, I, I, I, P, P, P],
     'sgc_topk_select': [P, I, I, P, P, P],
     'sgc_topk_scratch_ints': [I],
@@ -109,6 +111,11 @@ SIGNATURES = {
     'sgc_scatter_add_rows': [P, P, P, I, I, P],
     'sgc_gather_rows': [P, P, P, I, I, P],
 }
+
+
+class MaskJob(ctypes.Structure):
+    """``sgc_mask_job`` of include/sgcdet_b200.h."""
+    _fields_ = [('out', c_void_p), ('n', c_longlong), ('keep', c_float)]
 
 
 class WeightJob(ctypes.Structure):
@@ -174,7 +181,8 @@ def load() -> ctypes.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = c_longlong if name in ('sgc_rows_wgrad_group_scratch_floats', 'sgc_lift_bwd_tiles_workspace_bytes') else c_int
+            fn.restype = c_longlong if name in ('sgc_rows_wgrad_group_scratch_floats', 'sgc_lift_bwd_tiles_workspace_bytes',
+                                                 'sgc_upsample2x_occ_bwd_scratch_floats') else c_int
         lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
         lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
         lib.sgc_set_pdl(int(os.environ.get('SGC_PDL', '0')))

@@ -182,7 +182,7 @@ __device__ __forceinline__ void scatter_dist(float* gd_px, const Tap& t, int D, 
   if (t.d0 + 1 <= D - 1) red_add1(gd_px + t.d0 + 1, t.ld * gds);
 }
 
-template <int CPL, int MINB>
+template <int CPL, int MINB, bool PF>
 __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     const float* __restrict__ value, int ldv, const float* __restrict__ G, int ldg,
     const float* __restrict__ dist, const float* __restrict__ vbias,
@@ -203,12 +203,31 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
   float vb[CPL];
   load_row<CPL>(vb, vbias + lane_base<CPL>(lane));
 
-  for (int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < n_pairs;
-       pair += gridDim.x * warps_per_block) {
-    const int flat = __ldg(pair_vq + pair);
+  // pair id and the lane's saved sampling point are fetched one iteration ahead (two dependent round trips less per pair)
+  const int stride = gridDim.x * warps_per_block;
+  int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  int flat_n = 0;
+  float4 sp_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (PF && pair < n_pairs) {
+    flat_n = __ldg(pair_vq + pair);
+    sp_n = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
+  }
+  for (; pair < n_pairs; pair += stride) {
+    int flat;
+    float4 sp;
+    if (PF) {
+      flat = flat_n;
+      sp = sp_n;
+      if (pair + stride < n_pairs) {
+        flat_n = __ldg(pair_vq + pair + stride);
+        sp_n = ldg4(samp + ((size_t)(pair + stride) * 32 + lane) * 4);
+      }
+    } else {
+      flat = __ldg(pair_vq + pair);
+      sp = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
+    }
     const int v = flat / Q;
     const size_t vS = (size_t)v * S;
-    const float4 sp = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
     const Tap t = make_tap(sp.x, sp.y, sp.z, H, W, D);
     float ds[4], dlo[4], dhi[4], cw[4];
     int px[4];
@@ -359,8 +378,9 @@ extern "C" int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg
   if ((ldv & 3) || (ldg & 3)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = lift_grid(cap_pairs);
-  // 3 CTAs of 8 warps per SM (85 registers): room for the 4 corner rows of a point in flight per lane
-  static const int minb = getenv("SGC_LIFT_FWD_MINB") ? atoi(getenv("SGC_LIFT_FWD_MINB")) : 3;
+  // 4 CTAs of 8 warps per SM (64 registers) measured better inside the step than 3 (80 registers) or 2: 591.5 / 588.2 / ~585
+  // volumes/s (session U), although the kernel alone is fastest with 3
+  static const int minb = getenv("SGC_LIFT_FWD_MINB") ? atoi(getenv("SGC_LIFT_FWD_MINB")) : 4;
 #define SGC_LIFT_FWD_ARGS value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs, ref_cam, S, H, W, D, Q, samp, slots
   if (C == 256) {
     if (minb == 4) sgc::launch_chain(sgc::lift_fwd_kernel<8, 4>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
@@ -388,12 +408,14 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
 #define SGC_LIFT_BWD_ARGS value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp, grad_slots, S, H, W, D, Q, \
                           grad_value, grad_G, grad_dist, grad_vbias, grad_gbias
   static const int minb = getenv("SGC_LIFT_MINB") ? atoi(getenv("SGC_LIFT_MINB")) : 2;
+  static const int pf = getenv("SGC_LIFT_BWD_PF") ? atoi(getenv("SGC_LIFT_BWD_PF")) : 1;
   if (C == 256) {
-    if (minb == 2) sgc::lift_bwd_kernel<8, 2><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-    else if (minb == 4) sgc::lift_bwd_kernel<8, 4><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-    else sgc::lift_bwd_kernel<8, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    if (minb == 3) sgc::lift_bwd_kernel<8, 3, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    else if (pf) sgc::lift_bwd_kernel<8, 2, true><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    else sgc::lift_bwd_kernel<8, 2, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   } else {
-    sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    if (pf) sgc::lift_bwd_kernel<4, 3, true><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+    else sgc::lift_bwd_kernel<4, 3, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   }
   SGC_CUDA_CHECK_LAST();
   return 0;

@@ -369,3 +369,95 @@ extern "C" int sgc_rowop_bwd(const sgc_rowop_bwd_args* args, void* stream) {
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sgc_dropout_masks: the keep-masks of every dropout of a step (all levels, all layers) in ONE launch.
+// nn.Dropout semantics (custom_base_transformer_layer.py / FFN of encoder.py:262-340: x * mask / (1 - p), mask ~
+// Bernoulli(1 - p)); the masks are applied inside sgc_rowop_fwd / _bwd.  Philox4x32-10 (Salmon et al., SC'11) keyed by
+// `seed`, counter = (16-byte chunk index, job, step): the step number lives in device memory and is advanced by the last
+// CTA of the launch, so a CUDA-graph replay draws fresh masks without any host-side RNG bookkeeping.
+// state = {step, ticket} (two int64, zero-initialised by the caller, private to one launch site).
+namespace sgc {
+
+constexpr int kMaxMaskJobs = 12;
+struct MaskJobs {
+  unsigned char* out[kMaxMaskJobs];
+  long long chunks_end[kMaxMaskJobs];   // running sum of 16-byte chunks
+  long long n[kMaxMaskJobs];
+  unsigned int thr[kMaxMaskJobs];       // keep iff r <= thr  (thr = keep * 2^32 - 1)
+  int njobs;
+};
+
+__device__ __forceinline__ void philox4x32_10(unsigned int (&c)[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_masks_kernel(const __grid_constant__ MaskJobs jobs, unsigned long long seed,
+                                                            unsigned long long* __restrict__ state) {
+  __shared__ unsigned long long s_step;
+  if (threadIdx.x == 0) s_step = *reinterpret_cast<volatile unsigned long long*>(state);
+  __syncthreads();
+  const unsigned long long step = s_step;
+  const long long total = jobs.chunks_end[jobs.njobs - 1];
+  for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < total; ch += (long long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (ch >= jobs.chunks_end[j]) ++j;
+    const long long local = ch - (j ? jobs.chunks_end[j - 1] : 0);
+    const unsigned int thr = jobs.thr[j];
+    unsigned int bytes[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unsigned int c[4] = {(unsigned int)(local * 4 + q), (unsigned int)((unsigned long long)(local * 4 + q) >> 32) ^ ((unsigned int)j << 24),
+                           (unsigned int)step, (unsigned int)(step >> 32)};
+      philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+      bytes[q] = (c[0] <= thr ? 1u : 0u) | (c[1] <= thr ? 0x100u : 0u) | (c[2] <= thr ? 0x10000u : 0u) | (c[3] <= thr ? 0x1000000u : 0u);
+    }
+    unsigned char* dst = jobs.out[j] + local * 16;
+    if (local * 16 + 16 <= jobs.n[j]) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+    } else {
+      for (int b = 0; local * 16 + b < jobs.n[j]; ++b) dst[b] = (unsigned char)((bytes[b >> 2] >> (8 * (b & 3))) & 1u);
+    }
+  }
+  // every CTA has read the step before it takes its ticket; the last one advances the step for the next launch / replay
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(state + 1, 1ULL);
+    if (t == (unsigned long long)gridDim.x - 1) {
+      state[1] = 0;
+      state[0] = step + 1;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace sgc
+
+extern "C" int sgc_dropout_masks(const sgc_mask_job* in, int njobs, long long seed, long long* state, void* stream) {
+  if (!in || njobs <= 0 || njobs > sgc::kMaxMaskJobs || !state) return (int)cudaErrorInvalidValue;
+  sgc::MaskJobs jobs;
+  long long chunks = 0;
+  for (int j = 0; j < njobs; ++j) {
+    if (!in[j].out || in[j].n <= 0 || (reinterpret_cast<uintptr_t>(in[j].out) & 15) || !(in[j].keep > 0.f) || in[j].keep > 1.f)
+      return (int)cudaErrorInvalidValue;
+    jobs.out[j] = in[j].out;
+    jobs.n[j] = in[j].n;
+    chunks += (in[j].n + 15) / 16;
+    jobs.chunks_end[j] = chunks;
+    const double t = (double)in[j].keep * 4294967296.0 - 1.0;
+    jobs.thr[j] = t >= 4294967295.0 ? 0xFFFFFFFFu : (unsigned int)t;
+  }
+  jobs.njobs = njobs;
+  long long blocks = (chunks + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  sgc::dropout_masks_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(jobs, (unsigned long long)seed,
+                                                                           reinterpret_cast<unsigned long long*>(state));
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}

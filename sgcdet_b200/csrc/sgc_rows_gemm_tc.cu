@@ -365,7 +365,8 @@ extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
   // A/B (SGC_ROWS_SMALL_WORKS=n, 0 = off): problems of at most 4 row tiles (the coarsest level) settle for n work items -- in
   // the forward their chain runs beside the persistent projection kernel of the finest level, which leaves 16 SMs free
   static const int small_works = getenv("SGC_ROWS_SMALL_WORKS") ? atoi(getenv("SGC_ROWS_SMALL_WORKS")) : 0;
-  if (small_works > 0 && m_tiles <= 4) {
+  static const int small_tiles = getenv("SGC_ROWS_SMALL_TILES") ? atoi(getenv("SGC_ROWS_SMALL_TILES")) : 4;
+  if (small_works > 0 && m_tiles <= small_tiles) {
     while (n_cta > 32 && (N % n_cta || (long long)m_tiles * B * (N / n_cta) < small_works)) n_cta >>= 1;
     while (N % n_cta) n_cta >>= 1;
     return n_cta;

@@ -95,6 +95,7 @@ import os as _os
 # finest ScanNet level): off by default
 LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '0') != '0'
 TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
+UP_BWD_SEPARABLE = _os.environ.get('SGC_UP_BWD_SEP', '1') != '0'   # A/B: 0 = the one-launch gather form
 TOPK_GRID = _os.environ.get('SGC_TOPK_GRID', '1') != '0'   # one-launch grid top-k (round 2); 0 = the round-1 kernels
 _TOPK_SCRATCH = {}
 
@@ -710,6 +711,39 @@ def rowop_bwd(g, R, N, *, g2=None, ln=None, mask=None, mscale=1.0, gate=None, gs
     return gx, gs, gpre, partial
 
 
+class DropoutMasks:
+    """Keep-masks of all dropouts of a step in one launch (``sgc_dropout_masks``: Philox4x32-10, the step counter lives on the
+    device and advances with every launch, so CUDA-graph replays draw fresh masks).  One instance per call site."""
+
+    def __init__(self, device, seed: Optional[int] = None):
+        self.device = torch.device(device)
+        self.state = torch.zeros(2, device=self.device, dtype=torch.int64)
+        # torch's seed at creation plus a per-instance salt: two call sites never share a stream of masks
+        DropoutMasks._instances += 1
+        s = (torch.initial_seed() if seed is None else int(seed)) + 0x9E3779B97F4A7C15 * DropoutMasks._instances
+        self.seed = ((s + 2 ** 63) % 2 ** 64) - 2 ** 63   # as a signed 64-bit integer for the C ABI
+
+    _instances = 0
+
+    def draw(self, specs):
+        """specs: [(rows, width, p)] -> list of uint8 [rows, width] keep-masks (None where p == 0)."""
+        todo = [(i, r, w, p) for i, (r, w, p) in enumerate(specs) if p > 0 and r * w > 0]
+        out = [None] * len(specs)
+        if not todo:
+            return out
+        sizes = [(r * w + 15) // 16 * 16 for _, r, w, _ in todo]
+        buf = torch.empty(sum(sizes), device=self.device, dtype=torch.uint8)
+        jobs = (_lib.MaskJob * len(todo))()
+        off = 0
+        for k, ((i, r, w, p), sz) in enumerate(zip(todo, sizes)):
+            m = buf[off:off + r * w].view(r, w)
+            jobs[k].out, jobs[k].n, jobs[k].keep = ptr(m), r * w, 1.0 - p
+            out[i] = m
+            off += sz
+        call('sgc_dropout_masks', ctypes.addressof(jobs), len(todo), self.seed, ptr(self.state), stream())
+        return out
+
+
 def _ln_params(partial, R, N):
     gg, gb = torch.empty(N, device=partial.device, dtype=F32), torch.empty(N, device=partial.device, dtype=F32)
     call('sgc_layernorm_bwd_params', ptr(partial), R, N, ptr(gg), ptr(gb), stream())
@@ -948,9 +982,12 @@ class UpsampleOcc(torch.autograd.Function):
         gpre = torch.empty_like(occ) if gocc is not None else None
         side = _Side(dev, ctx.wstream)
         detached = side.detached and gocc is not None
+        scratch = None
+        if UP_BWD_SEPARABLE:
+            scratch = torch.empty(_lib.load().sgc_upsample2x_occ_bwd_scratch_floats(X, Y, Z, C), device=dev, dtype=torch.float32)
         call('sgc_upsample2x_occ_bwd', ptr(vol), X, Y, Z, C, ptr(w_occ), ptr(occ), ptr(gup),
              ptr(gocc.contiguous()) if gocc is not None else None, ptr(gpre), ptr(gin),
-             None if detached else ptr(gw), ptr(gb), stream())
+             None if detached else ptr(gw), ptr(gb), ptr(scratch), stream())
         if detached:   # the weight gradient (a full pass over the upsampled volume) leaves the voxel chain
             def _gw():
                 g = torch.zeros(C, device=dev, dtype=torch.float32)

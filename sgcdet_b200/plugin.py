@@ -295,17 +295,15 @@ _CHAIN_STREAMS = {}
 
 
 def _prepare_priorities(n: int):
-    """Stream priority of every level's prepare stream (coarsest level first).  The finest level's stream stays at default
-    priority, the coarser ones are raised: in the backward all three lift kernels become ready within a few microseconds, and
-    at equal priority the block scheduler dispatches every CTA of the finest level's (RED-issue-bound, ~0.2 ms) kernel before
-    the first CTA of the coarser levels' -- their lift / projection-gradient kernels then ran AFTER it and ended the step;
-    raised, they take the SM slots it frees and run beside it (tensor pipe and DRAM are idle under the scatter kernel).
-    ``SGC_PREP_PRIO="a,b,c"`` overrides (A/B)."""
+    """Stream priority of every level's prepare stream (coarsest level first): all default.  ``SGC_PREP_PRIO="a,b,c"`` (A/B):
+    raising the coarser levels' streams makes their lift / projection-gradient kernels run beside the finest level's lift
+    backward instead of after it, as intended -- but that kernel then keeps one CTA per SM instead of two while a persistent
+    tcgen05 CTA is resident and takes 450 instead of 293 us: 570 vs 591.5 volumes/s (session U, three runs each)."""
     env = os.environ.get('SGC_PREP_PRIO')
     if env:
         pr = [int(v) for v in env.split(',')]
         return (pr + [pr[-1]] * n)[:n]
-    return [-1] * (n - 1) + [0]
+    return [0] * n
 
 
 def _side_streams(device, n: int, main=None):
@@ -333,10 +331,29 @@ def _level_chain_streams(device, n: int, main):
     return pool[:n]
 
 
-def _dropout_masks(rows: int, widths, drops, device):
-    """uint8 keep-masks [rows, width] for every dropout with p > 0 (None otherwise)."""
-    return tuple(torch.empty(rows, w, device=device, dtype=torch.uint8).bernoulli_(1.0 - p) if p > 0 else None
-                 for w, p in zip(widths, drops))
+_MASK_RNG = {}
+
+
+def _mask_rng(owner, device) -> 'SF.DropoutMasks':
+    """The dropout-mask generator of a module on a device (its step counter lives on that device)."""
+    key = (id(owner), torch.device(device))
+    rng = _MASK_RNG.get(key)
+    if rng is None:
+        rng = _MASK_RNG[key] = SF.DropoutMasks(device)
+    return rng
+
+
+def _dropout_specs(head, rows: int):
+    """(rows, width, p) of the three dropouts of a DenseHead's encoder layer: attention residual, FFN hidden, FFN output."""
+    layer = head.cross_transformer.encoder.layers[0]
+    attn, ffn = layer.attentions[0], layer.ffns[0]
+    return [(rows, head.embed_dims, attn.dropout.p), (rows, ffn.layers[0][0].out_features, ffn.layers[0][2].p),
+            (rows, head.embed_dims, ffn.layers[2].p)]
+
+
+def _dropout_masks(head, rows: int, device):
+    """uint8 keep-masks [rows, width] for every dropout with p > 0 (None otherwise), one launch."""
+    return tuple(_mask_rng(head, device).draw(_dropout_specs(head, rows)))
 
 
 def projection_on_device(img_meta: dict, device) -> torch.Tensor:
@@ -390,7 +407,7 @@ class DenseHead(nn.Module):
     def num_voxels(self) -> int:
         return int(self.n_voxels.prod())
 
-    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None):
+    def prepare(self, feat: torch.Tensor, dpt_dist: torch.Tensor, hw, n_rows: Optional[int] = None, masks=None):
         """Everything of a level that does not depend on the voxel selection: the bf16x3 splits of the weights,
         the dense projection of the feature maps (value + folded offset/weight channels) and the channel-last depth
         map.  AdaptiveSparseHead issues this for all levels up front on side streams so that the large, bandwidth-bound
@@ -447,12 +464,10 @@ class DenseHead(nn.Module):
             with torch.cuda.stream(wstream[1]):
                 pf = SF.OnStream.apply(*params[6:])
             params = tuple(pa) + tuple(pf)
-        masks = None
-        if self.training and n_rows:
+        if masks is None and self.training and n_rows:
             # keep-masks of the layer's dropouts (nn.Dropout semantics: x * mask / (1-p)), drawn here -- off the
-            # critical path -- and applied inside the fused row kernels
-            masks = _dropout_masks(n_rows, (self.embed_dims, ffn.layers[0][0].out_features, self.embed_dims),
-                                   (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p), feat.device)
+            # critical path -- and applied inside the fused row kernels (AdaptiveSparseHead draws all levels' at once)
+            masks = _dropout_masks(self, n_rows, feat.device)
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
                     stream=torch.cuda.current_stream(feat.device), dist_stream=dist_stream, params=params, wstream=wstream,
                     masks=masks)
@@ -487,9 +502,8 @@ class DenseHead(nn.Module):
         drops = (attn.dropout.p, ffn.layers[0][2].p, ffn.layers[2].p)
         masks = prepared.get('masks') if self.training else None
         if self.training and any(p > 0 for p in drops):
-            widths = (C, ffn.layers[0][0].out_features, C)
             if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
-                masks = _dropout_masks(pl.Q, widths, drops, feat.device)
+                masks = _dropout_masks(self, pl.Q, feat.device)
         x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops, coll)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
@@ -603,6 +617,8 @@ class AdaptiveSparseHead(nn.Module):
 
         def level_rows(i, head, fi, hw, sel, pre):
             """forward_rows of level i on that level's own chain stream (see _level_chain_streams)."""
+            if mask_ev is not None:
+                (main if lvl_streams is None else lvl_streams[i]).wait_event(mask_ev)
             if lvl_streams is None:
                 return head.forward_rows(mlvl_feats[fi], mlvl_dpt_dists[fi], img_meta, hw, sel, proj, return_intermediates, pre,
                                          view_shard)
@@ -618,6 +634,7 @@ class AdaptiveSparseHead(nn.Module):
             (r[0] if return_intermediates else r).record_stream(main)
             return r
         prepared = []
+        mask_ev = None
         # The projections of the three levels are made to run back to back in level order (an event chain between the
         # prepare streams, forward only): left to itself the graph executor started the finest level's projection -- the
         # one big kernel the coarse levels' latency-bound chains are supposed to hide -- only ~250 us into the step, and
@@ -625,20 +642,38 @@ class AdaptiveSparseHead(nn.Module):
         # replays it on the level's own stream) is not serialised behind the other levels.
         chain_prepare = os.environ.get('SGC_CHAIN_PREPARE', '1') != '0'
         prev_done = None
+        n_rows = []
+        for i in range(nl):
+            if i == 0:
+                n_rows.append(self.base_heads[i].num_voxels)
+            elif forced_selection is not None and forced_selection[i] is not None:
+                n_rows.append(int(forced_selection[i].numel()))
+            elif (i - 1) < len(self.topk_list):
+                n_rows.append(min(self.topk_list[i - 1], self.base_heads[i].num_voxels))
+            else:
+                n_rows.append(self.base_heads[i].num_voxels)
+        # the keep-masks of every dropout of the step (3 levels x up to 3 dropouts) are ONE launch at the head of the finest
+        # level's prepare stream, which has nothing else to do until the coarser projections are through (the reference
+        # draws them with 2 bernoulli_ launches per layer in the middle of each level's chain)
+        lvl_masks = [None] * nl
+        if self.training:
+            specs = [sp for i in range(nl) for sp in _dropout_specs(self.base_heads[i], n_rows[i])]
+            if any(sp[2] > 0 for sp in specs):
+                ms = streams[nl - 1]
+                ms.wait_stream(main)
+                with torch.cuda.stream(ms):
+                    drawn = _mask_rng(self, dev).draw(specs)
+                    if ms != main:
+                        mask_ev = torch.cuda.Event()
+                        mask_ev.record(ms)
+                lvl_masks = [tuple(drawn[3 * i:3 * i + 3]) for i in range(nl)]
         for i in range(nl):
             streams[i].wait_stream(main)
             if chain_prepare and prev_done is not None and streams[i] != main:
                 streams[i].wait_event(prev_done)
             with torch.cuda.stream(streams[i]):
-                if i == 0:
-                    n_rows = self.base_heads[i].num_voxels
-                elif forced_selection is not None and forced_selection[i] is not None:
-                    n_rows = int(forced_selection[i].numel())
-                elif (i - 1) < len(self.topk_list):
-                    n_rows = min(self.topk_list[i - 1], self.base_heads[i].num_voxels)
-                else:
-                    n_rows = self.base_heads[i].num_voxels
-                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i], n_rows))
+                prepared.append(self.base_heads[i].prepare(mlvl_feats[nl - 1 - i], mlvl_dpt_dists[nl - 1 - i], hws[i], n_rows[i],
+                                                           lvl_masks[i]))
                 if chain_prepare and streams[i] != main:
                     prev_done = torch.cuda.Event()
                     prev_done.record(streams[i])

@@ -96,8 +96,12 @@ def _check_topk(occ, k):
 
 # ------------------------------------------------------------------------------ volume kernels
 
-@pytest.mark.parametrize('dims,C', [((10, 10, 4), 256), ((20, 20, 8), 128), ((3, 5, 2), 128), ((1, 1, 1), 256)])
-def test_upsample_occ_forward_backward(cuda_lib, dims, C):
+@pytest.mark.parametrize('dims,C,separable', [((10, 10, 4), 256, True), ((20, 20, 8), 128, True), ((3, 5, 2), 128, True),
+                                               ((1, 1, 1), 256, True), ((2, 1, 3), 256, True), ((40, 40, 16), 128, True),
+                                               ((10, 10, 4), 256, False), ((3, 5, 2), 128, False)])
+def test_upsample_occ_forward_backward(cuda_lib, monkeypatch, dims, C, separable):
+    """``separable``: the backward evaluated axis by axis (three streaming passes, the product path) or as one gather launch."""
+    monkeypatch.setattr(SF, 'UP_BWD_SEPARABLE', separable)
     g = torch.Generator().manual_seed(1)
     X, Y, Z = dims
     vol = torch.randn(X, Y, Z, C, generator=g)

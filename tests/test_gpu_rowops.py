@@ -147,3 +147,40 @@ def test_fold_weights_matches_cat_and_unfolds_gradients(cuda_lib):
                 continue
             assert p.grad is not None and p.grad.is_contiguous(), k
             assert torch.equal(p.grad.cpu(), q.grad), k
+
+
+def test_dropout_masks_match_the_philox_oracle_and_advance_per_launch(cuda_lib):
+    """sgc_dropout_masks: bit-exact against oracle/philox_ref.py for every job of a launch, ragged tails included; the step
+    counter on the device advances with every launch (so a CUDA-graph replay draws fresh masks)."""
+    import numpy as np
+    from oracle.philox_ref import keep_mask
+    rng = SF.DropoutMasks('cuda', seed=1234)
+    specs = [(37, 16, 0.0), (400, 256, 0.1), (401, 33, 0.25), (6400, 512, 0.1)]
+    for step in range(3):
+        masks = rng.draw(specs)
+        torch.cuda.synchronize()
+        assert masks[0] is None
+        job = 0
+        for (r, w, p), m in zip(specs[1:], masks[1:]):
+            assert m.shape == (r, w) and m.dtype == torch.uint8
+            ref = keep_mask(r * w, 1.0 - p, rng.seed, job, step).reshape(r, w)
+            assert np.array_equal(m.cpu().numpy(), ref), (step, job)
+            job += 1
+        assert abs(masks[3].float().mean().item() - 0.9) < 1e-3
+    assert int(rng.state[0]) == 3 and int(rng.state[1]) == 0
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        rng.draw(specs[1:2])           # warm-up outside the capture
+        with torch.cuda.graph(g, stream=side):
+            m = rng.draw(specs[1:2])[0]
+    torch.cuda.current_stream().wait_stream(side)
+    step0 = int(rng.state[0])
+    seen = []
+    for k in range(2):
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(m.cpu().numpy(), keep_mask(400 * 256, 0.9, rng.seed, 0, step0 + k).reshape(400, 256))
+        seen.append(m.clone())
+    assert not torch.equal(seen[0], seen[1])
