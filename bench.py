@@ -95,7 +95,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 
 # kernels launched per C-ABI entry point (csrc/*.cu)
-LAUNCHES = dict(sgc_project_compact=3, sgc_lift_fwd=1, sgc_lift_bwd=1, sgc_crossview_mean_fwd=1,
+LAUNCHES = dict(sgc_project_compact=2, sgc_lift_fwd=1, sgc_lift_bwd=1, sgc_crossview_mean_fwd=1,
                 sgc_crossview_attn_fwd=1, sgc_crossview_attn_bwd_qt=1, sgc_crossview_attn_bwd_slots=1,
                 sgc_upsample2x_occ_fwd=1, sgc_upsample2x_occ_bwd=4, sgc_dropout_masks=1, sgc_topk_select=1, sgc_scatter_add_rows=1,
                 sgc_gather_rows=1, sgc_split_bf16x3=1, sgc_colsum=1, sgc_pack_weight_tc=1, sgc_project_tc_bwd_data=1, sgc_project_tc_wgrad=2, sgc_split_rows_colsum=1, sgc_project_tc_fwd=1, sgc_rows_gemm_tc=1,

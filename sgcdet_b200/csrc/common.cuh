@@ -73,6 +73,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SGC_FULL_MASK, v, o);
   return v;
 }
+__device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(SGC_FULL_MASK, v); }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(SGC_FULL_MASK, v, o));

@@ -2,7 +2,7 @@
 //
 // Replaces VoxFormerEncoder_DFA3D.point_sampling (transformer_utils/encoder.py:179-223) and the V
 // host-synchronising nonzero()/rebatch loops of DeformCrossAttention_DFA3D.forward
-// (deformable_cross_attention.py:758-773) with three device passes and no host sync.
+// (deformable_cross_attention.py:758-773) with two device passes and no host sync.
 //
 // Arithmetic contract (bit-exact against oracle/path_ref.py:point_sampling): every operation is a
 // separately rounded fp32 operation, no FMA:
@@ -69,61 +69,25 @@ __global__ void __launch_bounds__(kTile) project_kernel(const float* __restrict_
   if (threadIdx.x == 0) tile_counts[v * gridDim.x + tile] = c;
 }
 
-// pass 2: exclusive scan of the (view-major) tile counts by one CTA
-__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ tile_counts, int n_tiles_per_view, int V,
-                                                   int* __restrict__ tile_offsets, int* __restrict__ view_offsets) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry;
-  pdl_sync();
-  const int n = n_tiles_per_view * V;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int x = (i < n) ? tile_counts[i] : 0;
-    int inc = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(SGC_FULL_MASK, inc, o);
-      if (lane >= o) inc += y;
-    }
-    if (lane == 31) warp_tot[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      int t = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(SGC_FULL_MASK, t, o);
-        if (lane >= o) t += y;
-      }
-      warp_tot[lane] = t;  // inclusive over warps
-    }
-    __syncthreads();
-    const int before = carry + (wid ? warp_tot[wid - 1] : 0) + inc - x;
-    if (i < n) {
-      tile_offsets[i] = before;
-      if (i % n_tiles_per_view == 0) view_offsets[i / n_tiles_per_view] = before;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = before + x;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) view_offsets[V] = carry;
-}
-
-// pass 3: rank inside the tile, emit pair ids
-__global__ void __launch_bounds__(kTile) emit_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ tile_offsets,
+// pass 2: every CTA sums the counts of the (view-major) tiles in front of its own -- at most a few thousand integers, one
+// block reduction, instead of a scan launch of its own between the two passes (the three launches sat on the critical
+// path of every level's chain) --, ranks its voxels inside the tile and emits the pair ids
+__global__ void __launch_bounds__(kTile) emit_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ tile_counts,
                                                     int Q, int* __restrict__ pair_index, int* __restrict__ pair_vq,
-                                                    int* __restrict__ count) {
+                                                    int* __restrict__ count, int* __restrict__ view_offsets) {
   __shared__ int warp_tot[32];
+  __shared__ int warp_pre[32];
   pdl_sync();
   const int v = blockIdx.y, tile = blockIdx.x;
   const int q = tile * kTile + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int me = v * gridDim.x + tile, n_tiles = gridDim.x * gridDim.y;
+  int before = 0;
+  for (int i = threadIdx.x; i < me; i += kTile) before += __ldg(tile_counts + i);
+  before = warp_sum_int(before);
   const bool vis = (q < Q) && mask[(size_t)v * Q + q];
   const unsigned b = __ballot_sync(SGC_FULL_MASK, vis);
-  if (lane == 0) warp_tot[wid] = __popc(b);
+  if (lane == 0) { warp_tot[wid] = __popc(b); warp_pre[wid] = before; }
   __syncthreads();
   if (wid == 0) {
     int t = warp_tot[lane];
@@ -133,12 +97,19 @@ __global__ void __launch_bounds__(kTile) emit_kernel(const uint8_t* __restrict__
       if (lane >= o) t += y;
     }
     warp_tot[lane] = t;
+    const int pre = warp_sum_int(warp_pre[lane]);
+    if (lane == 0) warp_pre[0] = pre;
   }
   __syncthreads();
+  const int tile_offset = warp_pre[0];
+  if (threadIdx.x == 0) {
+    if (tile == 0) view_offsets[v] = tile_offset;
+    if (me == n_tiles - 1) view_offsets[gridDim.y] = tile_offset + warp_tot[31];
+  }
   if (q < Q) {
     int id = -1;
     if (vis) {
-      id = tile_offsets[v * gridDim.x + tile] + (wid ? warp_tot[wid - 1] : 0) + __popc(b & ((1u << lane) - 1));
+      id = tile_offset + (wid ? warp_tot[wid - 1] : 0) + __popc(b & ((1u << lane) - 1));
       pair_vq[id] = v * Q + q;
       atomicAdd(count + q, 1);
     }
@@ -150,7 +121,7 @@ __global__ void __launch_bounds__(kTile) emit_kernel(const uint8_t* __restrict__
 
 extern "C" int sgc_project_scratch_ints(int V, int Q) {
   const int tiles = (Q + sgc::kTile - 1) / sgc::kTile;
-  return 2 * V * tiles;
+  return V * tiles;
 }
 
 extern "C" int sgc_project_compact(const float* proj, const float* ref3d, const int* sel, int V, int Q, float ox,
@@ -161,15 +132,12 @@ extern "C" int sgc_project_compact(const float* proj, const float* ref3d, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = (Q + sgc::kTile - 1) / sgc::kTile;
   int* tile_counts = scratch;
-  int* tile_offsets = scratch + V * tiles;
   dim3 grid(tiles, V);
   sgc::launch_chain(sgc::project_kernel, grid, dim3(sgc::kTile), 0, st, proj, ref3d, sel, Q, ox, oy, oz, eps, one_minus_eps, img_w,
                     img_h, dbound0, dscale, ref_cam, mask, tile_counts, count);
   SGC_CUDA_CHECK_LAST();
-  sgc::launch_chain(sgc::scan_kernel, dim3(1), dim3(1024), 0, st, (const int*)tile_counts, tiles, V, tile_offsets, view_offsets);
-  SGC_CUDA_CHECK_LAST();
-  sgc::launch_chain(sgc::emit_kernel, grid, dim3(sgc::kTile), 0, st, (const uint8_t*)mask, (const int*)tile_offsets, Q, pair_index,
-                    pair_vq, count);
+  sgc::launch_chain(sgc::emit_kernel, grid, dim3(sgc::kTile), 0, st, (const uint8_t*)mask, (const int*)tile_counts, Q, pair_index,
+                    pair_vq, count, view_offsets);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

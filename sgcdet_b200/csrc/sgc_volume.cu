@@ -822,11 +822,22 @@ __global__ void __launch_bounds__(1024) occ_loss_fwd_kernel(const float* __restr
                                                             float* __restrict__ loss) {
   __shared__ float s_part[32];
   pdl_sync();
+  // eight elements per thread and trip: the loads of a trip are issued together (the kernel sits between the forward and the
+  // backward on the step's critical path and is pure latency: 28 dependent trips took 10.7 us), summed in the fixed order
   float a = 0.f;
-  for (int i = threadIdx.x; i < N; i += 1024) {
-    const float pi = __ldg(p + i), ti = __ldg(t + i);
-    const float l1 = fmaxf(logf(pi), -100.f), l0 = fmaxf(log1pf(-pi), -100.f);
-    a -= ti * l1 + (1.f - ti) * l0;
+  for (int base = threadIdx.x; base < N; base += 8 * 1024) {
+    float pv[8], tv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 1024;
+      pv[u] = i < N ? __ldg(p + i) : 1.f;   // p = t = 1 contributes exactly 0
+      tv[u] = i < N ? __ldg(t + i) : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float l1 = fmaxf(logf(pv[u]), -100.f), l0 = fmaxf(log1pf(-pv[u]), -100.f);
+      a -= tv[u] * l1 + (1.f - tv[u]) * l0;
+    }
   }
   a = warp_sum(a);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = a;

@@ -158,7 +158,9 @@ def test_host_side_planning_helpers():
     # the widest column part of {256,128,64,32} dividing N that still yields enough work items to spread over the SMs
     assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 256, 1) == 128      # 50 row tiles x 2 parts
     assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 512, 1) == 256      # 50 x 2
-    assert lib.sgc_rows_gemm_tc_auto_ncta(400, 256, 1) == 32        # 4 row tiles: split as far as possible
+    assert lib.sgc_rows_gemm_tc_auto_ncta(400, 256, 1) == 64        # 4 row tiles (coarsest level): 16 work items
+    assert lib.sgc_rows_gemm_tc_auto_ncta(400, 512, 1) == 128
+    assert lib.sgc_rows_gemm_tc_auto_ncta(800, 256, 1) == 32        # 7 row tiles: split as far as possible
     assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 256, 8) == 256      # 8 heads: 400 work items already
     assert lib.sgc_rows_gemm_tc_auto_ncta(6400, 32, 8) == 32        # per-head output of 32 columns
     assert lib.sgc_rows_gemm_tc_auto_ncta(100, 96, 1) == 32         # 96 = 3 x 32
