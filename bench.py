@@ -282,13 +282,15 @@ def run_ours(args):
     loss_buf = torch.zeros(1, device=dev)
 
     loss_stream = torch.cuda.Stream(device=dev)
+    LOSS_ON_SIDE = os.environ.get('SGC_LOSS_ON_SIDE', '1') != '0'
 
     def scene_fwd(s):
         """Forward of one scene.  loss = sum(volume * G) + occ_loss.  The gradient of the first term
         w.r.t. the volume is G itself, so the backward is seeded with G directly and the VALUE of the first term (needed
         only for the loss read-back) is evaluated beside the backward instead of in front of it."""
         vol, valid, occ = head(s['feats'], s['sc'].img_meta, s['dists'])
-        return vol, head.occ_loss(occ, None, s['sc'].geo_occ)['loss_occ']
+        # the occupancy loss (value and gradient) on the loss stream: it is not on the path from the volume to its gradient
+        return vol, head.occ_loss(occ, None, s['sc'].geo_occ, stream=loss_stream if LOSS_ON_SIDE else None)['loss_occ']
 
     def step():
         main = torch.cuda.current_stream()

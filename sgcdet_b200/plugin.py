@@ -703,6 +703,11 @@ class AdaptiveSparseHead(nn.Module):
                         w_occ, b_occ = SF.OnStream.apply(w_occ, b_occ)
                 up, occ = SF.UpsampleOcc.apply(vol, w_occ, b_occ, ws)
                 occ_list.append(occ.view(1, -1))
+                if i == nl - 1:
+                    # all occupancy predictions exist: concatenated here rather than after the finest level's chain, so that in
+                    # the backward (autograd runs later-created nodes first) the volume's gradient enters that chain before the
+                    # occupancy loss's gradient is split up again on the same stream
+                    occ_preds = torch.cat(occ_list[::-1], dim=1)
                 if (i - 1) < len(self.topk_list):
                     if forced_selection is not None and forced_selection[i] is not None:
                         sel = forced_selection[i]
@@ -727,7 +732,6 @@ class AdaptiveSparseHead(nn.Module):
             occ_preds = None
             valid = torch.ones([bs, 1, *vol.shape[:3]], device=vol.device)
         else:
-            occ_preds = torch.cat(occ_list[::-1], dim=1)
             valid = self.get_valid(masks[nl - 1]).unsqueeze(0).unsqueeze(0).detach()
         if return_intermediates:
             return volume_out, valid, occ_preds, inters
@@ -737,12 +741,21 @@ class AdaptiveSparseHead(nn.Module):
         n = self.n_voxels_list[-1]
         return indices_0.view(n[0], n[1], n[2]).bool().long()
 
-    def occ_loss(self, occ_pred, sem_occ_gt, geo_occ_gt):
+    def occ_loss(self, occ_pred, sem_occ_gt, geo_occ_gt, stream=None):
+        """AdaptiveSparseHead.py:95-103.  ``stream`` (optional, not in the reference): evaluate the loss on that CUDA stream,
+        forked from the current one -- the result then belongs to ``stream`` (the caller joins it, as with any side stream).
+        The value of the loss is not on the backward's critical path; autograd replays the loss's backward on ``stream`` too,
+        so neither direction sits between the forward and the backward of the volume."""
         bs, N = occ_pred.shape
-        gt = geo_occ_gt[:, 0:N].float()
         if occ_pred.is_cuda and occ_pred.dtype == torch.float32:
             with torch.cuda.device(occ_pred.device):
-                return {'loss_occ': SF.OccLoss.apply(occ_pred, gt)}
+                if stream is None:
+                    return {'loss_occ': SF.OccLoss.apply(occ_pred, geo_occ_gt[:, 0:N].float())}
+                stream.wait_stream(torch.cuda.current_stream(occ_pred.device))
+                occ_pred.record_stream(stream)
+                with torch.cuda.stream(stream):
+                    return {'loss_occ': SF.OccLoss.apply(occ_pred, geo_occ_gt[:, 0:N].float())}
+        gt = geo_occ_gt[:, 0:N].float()
         loss_occ = self.loss(occ_pred, gt).mean() * 0.5
         return {'loss_occ': loss_occ}
 
