@@ -308,17 +308,28 @@ def run_ours(args):
                     outs.append(scene_fwd(s))
             for s in scenes:
                 main.wait_stream(s['stream'])
-        # loss value on its own stream, concurrently with the backward
-        loss_stream.wait_stream(main)
-        with torch.cuda.stream(loss_stream):
-            with torch.no_grad():
-                val = outs[0][1].detach().new_zeros(())
-                for (vol, l_occ), s in zip(outs, scenes):
-                    vol.record_stream(loss_stream)
-                    val = val + (vol * s['gvol']).sum() + l_occ
-                loss_buf.copy_(val.view(1))
-        torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
-                                [g for s in scenes for g in (s['gvol'], None)])
+        def loss_value():
+            # loss value on its own stream, concurrently with the backward
+            with torch.cuda.stream(loss_stream):
+                with torch.no_grad():
+                    val = outs[0][1].detach().new_zeros(())
+                    for (vol, l_occ), s in zip(outs, scenes):
+                        vol.record_stream(loss_stream)
+                        val = val + (vol * s['gvol']).sum() + l_occ
+                    loss_buf.copy_(val.view(1))
+
+        if LOSS_ON_SIDE:
+            # the loss stream has joined the end of the forward inside occ_loss(stream=...); the backward is issued first, so that
+            # the occupancy loss's gradient kernels (replayed by autograd on the loss stream) are not queued behind the
+            # evaluation of the loss VALUE, which nothing in the step waits for
+            torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
+                                    [g for s in scenes for g in (s['gvol'], None)])
+            loss_value()
+        else:
+            loss_stream.wait_stream(main)
+            loss_value()
+            torch.autograd.backward([t for vol, l_occ in outs for t in (vol, l_occ)],
+                                    [g for s in scenes for g in (s['gvol'], None)])
         main.wait_stream(loss_stream)
         if averager is not None:
             # the peer all-reduces of the parameter groups were issued from the backward as their gradients became final

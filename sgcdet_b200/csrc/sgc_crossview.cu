@@ -54,6 +54,25 @@ __device__ __forceinline__ void store_split_cv(__nv_bfloat16* __restrict__ split
   }
 }
 
+// Rows ids[i .. i+U) of `slots` (this lane's CPL channels), all U gathers issued before any is consumed; rows past n read as 0
+// (their loads are aimed at row n-1, so every load is unconditional and the compiler can hoist all of them).
+template <int CPL, int U>
+__device__ __forceinline__ void load_rows_cv(float (&x)[U][CPL], const float* __restrict__ slots, const int* ids, int i, int n,
+                                             int lane) {
+  constexpr int C = CPL * 32;
+  int id[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) id[u] = ids[i + u < n ? i + u : n - 1];
+#pragma unroll
+  for (int u = 0; u < U; ++u) load_row_cv<CPL>(x[u], slots + (size_t)id[u] * C + lane * CPL);
+#pragma unroll
+  for (int u = 1; u < U; ++u)
+    if (i + u >= n) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) x[u][j] = 0.f;
+    }
+}
+
 // Collect the pair ids of the views that see voxel q into ids[] (warp-shared), return how many.
 __device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, int V, int Q, int q, int lane,
                                             int* ids) {
@@ -69,7 +88,10 @@ __device__ __forceinline__ int gather_views(const int* __restrict__ pair_index, 
   return n;
 }
 
-template <int CPL, bool DIVIDE = true>
+// U = rows fetched together per trip.  The levels with few voxels run a handful of warps per SM, so a warp's time IS the
+// kernel's time and it is the chain of dependent row gathers (one per visible view) that sets it: U = 4 there, 1 where
+// thousands of warps hide each other's latency (and registers are better spent on occupancy).
+template <int CPL, bool DIVIDE = true, int U = 1>
 __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __restrict__ slots,
                                                                  const int* __restrict__ pair_index, int V, int Q,
                                                                  float* __restrict__ mean,
@@ -85,11 +107,13 @@ __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __
   float acc[CPL];
 #pragma unroll
   for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
-  for (int i = 0; i < n; ++i) {
-    float x[CPL];
-    load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+  for (int i = 0; i < n; i += U) {
+    float x[U][CPL];
+    load_rows_cv<CPL, U>(x, slots, ids, i, n, lane);
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] += x[j];
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[j] += x[u][j];
   }
   if (DIVIDE && n > 0) {
     const float fn = (float)n;
@@ -100,7 +124,7 @@ __global__ void __launch_bounds__(kCvWarps * 32) mean_fwd_kernel(const float* __
   if (split) store_split_cv<CPL>(split, (size_t)q, lane, acc);
 }
 
-template <int CPL>
+template <int CPL, int U = 1>
 __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __restrict__ qt,
                                                                  const float* __restrict__ slots,
                                                                  const int* __restrict__ pair_index, int V, int Q,
@@ -133,16 +157,19 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
     float qv[8][CPL];
 #pragma unroll
     for (int h = 0; h < 8; ++h) load_row_cv<CPL>(qv[h], qt + h * hq + off);
-    for (int i = 0; i < n; ++i) {
-      float x[CPL];
-      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+    for (int i = 0; i < n; i += U) {
+      float x[U][CPL];
+      load_rows_cv<CPL, U>(x, slots, ids, i, n, lane);
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        float p = 0.f;
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) p += qv[h][j] * x[j];
-        p = warp_sum(p);
-        if (lane == h) sc[i][h] = p;
+        for (int h = 0; h < 8; ++h) {
+          float p = 0.f;
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) p += qv[h][j] * x[u][j];
+          p = warp_sum(p);
+          if (lane == h && i + u < n) sc[i + u][h] = p;
+        }
       }
     }
   }
@@ -175,14 +202,19 @@ __global__ void __launch_bounds__(kCvWarps * 32) attn_fwd_kernel(const float* __
     for (int h = 0; h < 8; ++h)
 #pragma unroll
       for (int j = 0; j < CPL; ++j) t[h][j] = 0.f;
-    for (int i = 0; i < n; ++i) {
-      float x[CPL];
-      load_row_cv<CPL>(x, slots + (size_t)ids[i] * C + lane * CPL);
+    for (int i = 0; i < n; i += U) {
+      float x[U][CPL];
+      load_rows_cv<CPL, U>(x, slots, ids, i, n, lane);
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float a = sc[i][h];
+      for (int u = 0; u < U; ++u) {
+        if (i + u < n) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) t[h][j] += a * x[j];
+          for (int h = 0; h < 8; ++h) {
+            const float a = sc[i + u][h];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) t[h][j] += a * x[u][j];
+          }
+        }
       }
     }
 #pragma unroll
@@ -549,14 +581,47 @@ __global__ void __launch_bounds__(256) rows_headscale_kernel(const float* __rest
     return 0;                                                                                   \
   } while (0)
 
+// levels of at most kCvSmallQ voxels fetch four rows per trip (see mean_fwd_kernel)
+static const int kCvSmallQ = getenv("SGC_CV_SMALL_Q") ? atoi(getenv("SGC_CV_SMALL_Q")) : 2048;
+
+static int cv_mean_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* mean, __nv_bfloat16* split,
+                       void* stream) {
+  if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
+  if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;
+  const dim3 grid((Q + sgc::kCvWarps - 1) / sgc::kCvWarps), block(sgc::kCvWarps * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool small = Q <= kCvSmallQ;
+  if (C == 256 && small) sgc::launch_chain(sgc::mean_fwd_kernel<8, true, 4>, grid, block, 0, st, slots, pair_index, V, Q, mean, split);
+  else if (C == 256) sgc::launch_chain(sgc::mean_fwd_kernel<8, true, 1>, grid, block, 0, st, slots, pair_index, V, Q, mean, split);
+  else if (small) sgc::launch_chain(sgc::mean_fwd_kernel<4, true, 4>, grid, block, 0, st, slots, pair_index, V, Q, mean, split);
+  else sgc::launch_chain(sgc::mean_fwd_kernel<4, true, 1>, grid, block, 0, st, slots, pair_index, V, Q, mean, split);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
+static int cv_attn_fwd(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C, float* t_out,
+                       float* alpha, __nv_bfloat16* split, void* stream) {
+  if (C != 256 && C != 128) return (int)cudaErrorInvalidValue;
+  if (V > sgc::kMaxViews) return (int)cudaErrorInvalidValue;
+  const dim3 grid((Q + sgc::kCvWarps - 1) / sgc::kCvWarps), block(sgc::kCvWarps * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool small = Q <= kCvSmallQ;
+  if (C == 256 && small) sgc::launch_chain(sgc::attn_fwd_kernel<8, 4>, grid, block, 0, st, qt, slots, pair_index, V, Q, t_out, alpha, split);
+  else if (C == 256) sgc::launch_chain(sgc::attn_fwd_kernel<8, 1>, grid, block, 0, st, qt, slots, pair_index, V, Q, t_out, alpha, split);
+  else if (small) sgc::launch_chain(sgc::attn_fwd_kernel<4, 4>, grid, block, 0, st, qt, slots, pair_index, V, Q, t_out, alpha, split);
+  else sgc::launch_chain(sgc::attn_fwd_kernel<4, 1>, grid, block, 0, st, qt, slots, pair_index, V, Q, t_out, alpha, split);
+  SGC_CUDA_CHECK_LAST();
+  return 0;
+}
+
 extern "C" int sgc_crossview_mean_fwd(const float* slots, const int* pair_index, int V, int Q, int C, float* mean,
                                       void* stream) {
-  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean, nullptr);
+  return cv_mean_fwd(slots, pair_index, V, Q, C, mean, nullptr, stream);
 }
 
 extern "C" int sgc_crossview_attn_fwd(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
                                       float* t_out, float* alpha, void* stream) {
-  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha, nullptr);
+  return cv_attn_fwd(qt, slots, pair_index, V, Q, C, t_out, alpha, nullptr, stream);
 }
 
 extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
@@ -568,11 +633,11 @@ extern "C" int sgc_crossview_attn_bwd_qt(const float* slots, const float* alpha,
 // for the tensor-core GEMM that follows: mean [Q,3C], t [8*Q,3C], grad_qt [8*Q,3C].
 extern "C" int sgc_crossview_mean_fwd_split(const float* slots, const int* pair_index, int V, int Q, int C, float* mean,
                                             void* split, void* stream) {
-  SGC_CV_LAUNCH(mean_fwd_kernel, slots, pair_index, V, Q, mean, (__nv_bfloat16*)split);
+  return cv_mean_fwd(slots, pair_index, V, Q, C, mean, (__nv_bfloat16*)split, stream);
 }
 extern "C" int sgc_crossview_attn_fwd_split(const float* qt, const float* slots, const int* pair_index, int V, int Q, int C,
                                             float* t_out, float* alpha, void* split, void* stream) {
-  SGC_CV_LAUNCH(attn_fwd_kernel, qt, slots, pair_index, V, Q, t_out, alpha, (__nv_bfloat16*)split);
+  return cv_attn_fwd(qt, slots, pair_index, V, Q, C, t_out, alpha, (__nv_bfloat16*)split, stream);
 }
 extern "C" int sgc_crossview_attn_bwd_qt_split(const float* slots, const float* alpha, const int* pair_index, int V, int Q,
                                                int C, const float* grad_t, float* gscore, float* grad_qt, void* split,
