@@ -294,79 +294,49 @@ extern "C" int sgc_unfold_wcat_grad(const float* gwcat, const float* ggbias, int
 // critical path), so nothing differentiates through these products.
 namespace sgc {
 
-// Both kernels are pure latency (33 MFLOP): every thread issues ALL its global loads before the first use.
-// stage 1: one block per row j of A1; warp w owns the reduction slice e in [w*C/8, (w+1)*C/8), lane owns columns lane + 32k
-// (coalesced 128-byte reads of W_out rows); the eight slices meet in shared memory.
-template <int C>
+// one block per row j of A1, thread = column c; the last warp-sized tail computes a1b[j]
 __global__ void __launch_bounds__(256) fuse_q_stage1_kernel(const float* __restrict__ w_out, const float* __restrict__ b_out,
-                                                            const float* __restrict__ w_q, const float* __restrict__ b_q,
+                                                            const float* __restrict__ w_q, const float* __restrict__ b_q, int C,
                                                             float* __restrict__ a1, float* __restrict__ a1b) {
-  constexpr int ES = C / 8, CL = C / 32;   // reduction slice per warp, columns per lane
-  __shared__ float s_part[8][C + 1];
-  const int j = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // this lane's W_q value: e = w*ES + lane % ES -- ES is 32 (C = 256) or 16 (C = 128)
-  const int e_lane = w * ES + (lane % ES);
-  const float wq_l = __ldg(w_q + (size_t)j * C + e_lane);
-  const float bo_l = __ldg(b_out + e_lane);
-  float x[ES][CL];
-#pragma unroll
-  for (int e = 0; e < ES; ++e)
-#pragma unroll
-    for (int k = 0; k < CL; ++k) x[e][k] = __ldg(w_out + (size_t)(w * ES + e) * C + lane + 32 * k);
-  float acc[CL];
-#pragma unroll
-  for (int k = 0; k < CL; ++k) acc[k] = 0.f;
-#pragma unroll
-  for (int e = 0; e < ES; ++e) {
-    const float q = __shfl_sync(SGC_FULL_MASK, wq_l, e);
-#pragma unroll
-    for (int k = 0; k < CL; ++k) acc[k] = fmaf(q, x[e][k], acc[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < CL; ++k) s_part[w][lane + 32 * k] = acc[k];
-  float bpart = lane < ES ? wq_l * bo_l : 0.f;
-  bpart = warp_sum(bpart);
-  if (lane == 0) s_part[w][C] = bpart;
+  __shared__ float s_wq[256];
+  __shared__ float s_red[8];
+  const int j = blockIdx.x, c = threadIdx.x;
+  if (c < C) s_wq[c] = __ldg(w_q + (size_t)j * C + c);
   __syncthreads();
-  for (int c = threadIdx.x; c <= C; c += 256) {
+  if (c < C) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < C; ++e) acc = fmaf(s_wq[e], __ldg(w_out + (size_t)e * C + c), acc);
+    a1[(size_t)j * C + c] = acc;
+  }
+  float part = c < C ? s_wq[c] * __ldg(b_out + c) : 0.f;
+  part = warp_sum(part);
+  if ((c & 31) == 0) s_red[c >> 5] = part;
+  __syncthreads();
+  if (c == 0) {
     float t = 0.f;
-#pragma unroll
-    for (int ww = 0; ww < 8; ++ww) t += s_part[ww][c];
-    if (c < C) a1[(size_t)j * C + c] = t;
-    else a1b[j] = t + __ldg(b_q + j);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    a1b[j] = t + __ldg(b_q + j);
   }
 }
 
-// stage 2: one block per (head h, 32 output rows c'); A1_h [dh, C] and the W_k tile [dh, 32] staged in shared memory, thread =
-// column c with 32 accumulators:  Wf[h*C + c', c] = scale * sum_d W_k[h*dh + d, c'] A1[h*dh + d, c]
-template <int C, int DH>
-__global__ void __launch_bounds__(C) fuse_q_stage2_kernel(const float* __restrict__ w_k, const float* __restrict__ a1,
-                                                          const float* __restrict__ a1b, float scale, float* __restrict__ wf,
-                                                          float* __restrict__ bf) {
-  __shared__ float s_a1[DH][C];
-  __shared__ float s_wk[DH][32];
-  __shared__ float s_b[DH];
-  const int tiles = C / 32, h = blockIdx.x / tiles, cp0 = (blockIdx.x % tiles) * 32, c = threadIdx.x;
-#pragma unroll
-  for (int d = 0; d < DH; ++d) s_a1[d][c] = __ldg(a1 + (size_t)(h * DH + d) * C + c);
-  for (int i = c; i < DH * 32; i += C) s_wk[i >> 5][i & 31] = __ldg(w_k + (size_t)(h * DH + (i >> 5)) * C + cp0 + (i & 31)) * scale;
-  if (c < DH) s_b[c] = __ldg(a1b + h * DH + c);
+// one block per (head h, output row c'), thread = column c:  Wf[h*C + c', c] = scale * sum_d W_k[h*dh + d, c'] A1[h*dh + d, c]
+__global__ void __launch_bounds__(256) fuse_q_stage2_kernel(const float* __restrict__ w_k, const float* __restrict__ a1,
+                                                            const float* __restrict__ a1b, int C, int dh, float scale,
+                                                            float* __restrict__ wf, float* __restrict__ bf) {
+  __shared__ float s_wk[64];
+  const int row = blockIdx.x, h = row / C, cp = row - h * C, c = threadIdx.x;
+  if (c < dh) s_wk[c] = __ldg(w_k + (size_t)(h * dh + c) * C + cp) * scale;
   __syncthreads();
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-#pragma unroll 4
-  for (int d = 0; d < DH; ++d) {
-    const float a = s_a1[d][c];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = fmaf(s_wk[d][i], a, acc[i]);
+  if (c < C) {
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(s_wk[d], __ldg(a1 + (size_t)(h * dh + d) * C + c), acc);
+    wf[(size_t)row * C + c] = acc;
   }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) wf[(size_t)(h * C + cp0 + i) * C + c] = acc[i];
-  if (c < 32) {
+  if (c == 0) {
     float t = 0.f;
-    for (int d = 0; d < DH; ++d) t = fmaf(s_wk[d][c], s_b[d], t);
-    bf[h * C + cp0 + c] = t;
+    for (int d = 0; d < dh; ++d) t = fmaf(s_wk[d], __ldg(a1b + h * dh + d), t);
+    bf[row] = t;
   }
 }
 
@@ -375,18 +345,12 @@ __global__ void __launch_bounds__(C) fuse_q_stage2_kernel(const float* __restric
 extern "C" int sgc_fuse_query_weights(const float* w_out, const float* b_out, const float* w_q, const float* b_q,
                                       const float* w_k, int C, int heads, float scale, float* a1, float* a1b, float* wf,
                                       float* bf, void* stream) {
-  if ((C != 256 && C != 128) || heads != 8) return (int)cudaErrorInvalidValue;
+  if (C <= 0 || C > 256 || C % 32 || heads <= 0 || C % heads || C / heads > 64) return (int)cudaErrorInvalidValue;
   if (!w_out || !b_out || !w_q || !b_q || !w_k || !a1 || !a1b || !wf || !bf) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 256) {
-    sgc::fuse_q_stage1_kernel<256><<<C, 256, 0, st>>>(w_out, b_out, w_q, b_q, a1, a1b);
-    SGC_CUDA_CHECK_LAST();
-    sgc::fuse_q_stage2_kernel<256, 32><<<heads * (C / 32), C, 0, st>>>(w_k, a1, a1b, scale, wf, bf);
-  } else {
-    sgc::fuse_q_stage1_kernel<128><<<C, 256, 0, st>>>(w_out, b_out, w_q, b_q, a1, a1b);
-    SGC_CUDA_CHECK_LAST();
-    sgc::fuse_q_stage2_kernel<128, 16><<<heads * (C / 32), C, 0, st>>>(w_k, a1, a1b, scale, wf, bf);
-  }
+  sgc::fuse_q_stage1_kernel<<<C, 256, 0, st>>>(w_out, b_out, w_q, b_q, C, a1, a1b);
+  SGC_CUDA_CHECK_LAST();
+  sgc::fuse_q_stage2_kernel<<<heads * C, 256, 0, st>>>(w_k, a1, a1b, C, C / heads, scale, wf, bf);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -422,7 +422,7 @@ class DenseHead(nn.Module):
         wcat, vbias, gbias = da.folded_weights()
         lw = SF.LevelWeights(wcat, attn.output_proj.weight, mha.in_proj_weight, mha.out_proj.weight,
                              ffn.layers[0][0].weight, ffn.layers[1].weight)
-        wstream, dist_stream, fuse_ev = None, None, None
+        wstream, dist_stream = None, None
         if torch.is_grad_enabled() and os.environ.get('SGC_WSTREAM', '1') != '0':
             # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
             # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
@@ -435,19 +435,6 @@ class DenseHead(nn.Module):
                 self._wstream = (torch.cuda.Stream(device=feat.device, priority=prio),
                                  torch.cuda.Stream(device=feat.device, priority=prio))
             wstream = self._wstream
-        if FUSE_QUERY:
-            # the fused query weights depend on the parameters only: on the attention block's weight-gradient stream (idle in the
-            # forward), so that neither the level's projection nor the start of its chain waits for them; the chain joins
-            # through fuse_ev right before the layer
-            cur = torch.cuda.current_stream(feat.device)
-            fs = wstream[0] if wstream is not None else cur
-            if fs != cur:
-                fs.wait_stream(cur)
-            with torch.cuda.stream(fs):
-                lw.fuse_query(attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias)
-                if fs != cur:
-                    fuse_ev = torch.cuda.Event()
-                    fuse_ev.record(fs)
         if isinstance(dpt_dist, SF.DepthCL):   # produced channel-last and cropped by sgcdet_b200.depth.depth_pyramid
             if (dpt_dist.h, dpt_dist.w) != (h, w):
                 raise ValueError(f'sgcdet_b200: depth level cropped to {(dpt_dist.h, dpt_dist.w)}, the level needs {(h, w)}')
@@ -466,6 +453,8 @@ class DenseHead(nn.Module):
         else:
             dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
+        if FUSE_QUERY:
+            lw.fuse_query(attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
         params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,
@@ -484,7 +473,7 @@ class DenseHead(nn.Module):
             masks = _dropout_masks(self, n_rows, feat.device)
         return dict(lw=lw, vg=vg, dist=dist, vbias=vbias.contiguous().view(-1), gbias=gbias,
                     stream=torch.cuda.current_stream(feat.device), dist_stream=dist_stream, params=params, wstream=wstream,
-                    masks=masks, fuse_ev=fuse_ev)
+                    masks=masks)
 
     def forward_rows(self, feat: torch.Tensor, dpt_dist: torch.Tensor, img_meta: dict, hw, sel: Optional[torch.Tensor],
                      proj: Optional[torch.Tensor] = None, return_intermediates: bool = False, prepared=None, coll=None):
@@ -518,8 +507,6 @@ class DenseHead(nn.Module):
         if self.training and any(p > 0 for p in drops):
             if masks is None or any(m is not None and m.shape[0] != pl.Q for m in masks):
                 masks = _dropout_masks(self, pl.Q, feat.device)
-        if prepared.get('fuse_ev') is not None:
-            torch.cuda.current_stream(feat.device).wait_event(prepared['fuse_ev'])
         x = SF.EncoderLayerRows.apply(slots, pl, *pp, lw, ws, layer.norms[0].eps, layer.norms[1].eps, masks, drops, coll)
         if return_intermediates:
             return x, dict(pairs=pl, slots=slots, samp=samp)
