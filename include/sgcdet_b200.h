@@ -169,13 +169,6 @@ int sgc_rows_gemm_tc_ex(const float* x, long long ldx, long long batch_x, int R,
                         int pack_rows, long long pack_batch_elems, int pack_batch_rows, const float* bias, int bias_batch,
                         int N, float* y, long long ldy, long long batch_y, int n_cta, int a_mode, int a_batches, void* stream);
 
-/* output_proj -> query in-projection -> per-head key product of the attention pooling (DCA:826-833,
- * nn.MultiheadAttention) as ONE linear map per head, recomputed from the current weights every step:
- * a1 [C,C] = W_q W_out, a1b [C] = W_q b_out + b_q, wf [heads*C, C] rows h*C + c' = scale W_k,h^T a1_h, bf [heads*C] alike.
- * w_q / w_k: the first / second C rows of in_proj_weight; b_q: the first C entries of in_proj_bias. */
-int sgc_fuse_query_weights(const float* w_out, const float* b_out, const float* w_q, const float* b_q, const float* w_k,
-                           int C, int heads, float scale, float* a1, float* a1b, float* wf, float* bf, void* stream);
-
 /* Folded projection weights of MSDeformableAttention3D_DFA3D (DCA:417-436): Wcat [C + 4MP, C] = value_proj.weight rows
  * followed by the offset / depth-offset / attention-weight rows permuted to [head*P + point][off_x, off_y, off_d, logit];
  * gbias [4MP] the same permutation of the three small biases.  unfold: the gradients of Wcat / gbias scattered back into

@@ -57,7 +57,6 @@ SIGNATURES = {
     'sgc_rows_gemm_tc_ex': [P, LL, LL, I, I, I, P, I, LL, I, P, I, I, P, LL, LL, I, I, I, P],
     'sgc_rows_wgrad_tc_scratch_floats': [I, I, I, I],
     'sgc_rows_wgrad_tc': [P, LL, LL, I, P, LL, LL, I, I, I, P, LL, LL, LL, F, P, I, P, P],
-    'sgc_fuse_query_weights': [P, P, P, P, P, I, I, F, P, P, P, P, P],
     'sgc_fold_wcat': [P, P, P, P, P, P, P, I, I, P, P, P],
     'sgc_unfold_wcat_grad': [P, P, I, I, P, P, P, P, P, P, P, P],
     'sgc_rows_wgrad_group_scratch_floats': [P, I, I],

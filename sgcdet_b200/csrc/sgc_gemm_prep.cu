@@ -282,75 +282,3 @@ extern "C" int sgc_unfold_wcat_grad(const float* gwcat, const float* ggbias, int
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
-
-// ---------------------------------------------------------------------------------------------------------------------
-// sgc_fuse_query_weights: the three linear maps between the masked mean over views and the per-head key products of the
-// attention pooling (DCA:826-833: output_proj -> MultiheadAttention's query in-projection -> q . k_v) have no non-linearity
-// between them, so the per-voxel chain evaluates them as ONE product per head:
-//     qt_h = scale * (W_q,h (W_out m + b_out) + b_q,h) W_k,h  =  m Wf_h^T + bf_h ,
-//     A1 = W_q W_out [C,C],  a1b = W_q b_out + b_q [C],  Wf_h = scale W_k,h^T A1_h [C,C],  bf_h = scale W_k,h^T a1b_h [C].
-// Two launches of plain fp32 FMA loops per step and level (33 MFLOP; exact fp32, the bf16 hi/lo split happens when the result
-// is packed for the tensor cores).  The weight GRADIENTS are still formed from the unfused activations (recomputed off the
-// critical path), so nothing differentiates through these products.
-namespace sgc {
-
-// one block per row j of A1, thread = column c; the last warp-sized tail computes a1b[j]
-__global__ void __launch_bounds__(256) fuse_q_stage1_kernel(const float* __restrict__ w_out, const float* __restrict__ b_out,
-                                                            const float* __restrict__ w_q, const float* __restrict__ b_q, int C,
-                                                            float* __restrict__ a1, float* __restrict__ a1b) {
-  __shared__ float s_wq[256];
-  __shared__ float s_red[8];
-  const int j = blockIdx.x, c = threadIdx.x;
-  if (c < C) s_wq[c] = __ldg(w_q + (size_t)j * C + c);
-  __syncthreads();
-  if (c < C) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < C; ++e) acc = fmaf(s_wq[e], __ldg(w_out + (size_t)e * C + c), acc);
-    a1[(size_t)j * C + c] = acc;
-  }
-  float part = c < C ? s_wq[c] * __ldg(b_out + c) : 0.f;
-  part = warp_sum(part);
-  if ((c & 31) == 0) s_red[c >> 5] = part;
-  __syncthreads();
-  if (c == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    a1b[j] = t + __ldg(b_q + j);
-  }
-}
-
-// one block per (head h, output row c'), thread = column c:  Wf[h*C + c', c] = scale * sum_d W_k[h*dh + d, c'] A1[h*dh + d, c]
-__global__ void __launch_bounds__(256) fuse_q_stage2_kernel(const float* __restrict__ w_k, const float* __restrict__ a1,
-                                                            const float* __restrict__ a1b, int C, int dh, float scale,
-                                                            float* __restrict__ wf, float* __restrict__ bf) {
-  __shared__ float s_wk[64];
-  const int row = blockIdx.x, h = row / C, cp = row - h * C, c = threadIdx.x;
-  if (c < dh) s_wk[c] = __ldg(w_k + (size_t)(h * dh + c) * C + cp) * scale;
-  __syncthreads();
-  if (c < C) {
-    float acc = 0.f;
-    for (int d = 0; d < dh; ++d) acc = fmaf(s_wk[d], __ldg(a1 + (size_t)(h * dh + d) * C + c), acc);
-    wf[(size_t)row * C + c] = acc;
-  }
-  if (c == 0) {
-    float t = 0.f;
-    for (int d = 0; d < dh; ++d) t = fmaf(s_wk[d], __ldg(a1b + h * dh + d), t);
-    bf[row] = t;
-  }
-}
-
-}  // namespace sgc
-
-extern "C" int sgc_fuse_query_weights(const float* w_out, const float* b_out, const float* w_q, const float* b_q,
-                                      const float* w_k, int C, int heads, float scale, float* a1, float* a1b, float* wf,
-                                      float* bf, void* stream) {
-  if (C <= 0 || C > 256 || C % 32 || heads <= 0 || C % heads || C / heads > 64) return (int)cudaErrorInvalidValue;
-  if (!w_out || !b_out || !w_q || !b_q || !w_k || !a1 || !a1b || !wf || !bf) return (int)cudaErrorInvalidValue;
-  cudaStream_t st = (cudaStream_t)stream;
-  sgc::fuse_q_stage1_kernel<<<C, 256, 0, st>>>(w_out, b_out, w_q, b_q, C, a1, a1b);
-  SGC_CUDA_CHECK_LAST();
-  sgc::fuse_q_stage2_kernel<<<heads * C, 256, 0, st>>>(w_k, a1, a1b, C, C / heads, scale, wf, bf);
-  SGC_CUDA_CHECK_LAST();
-  return 0;
-}

@@ -147,14 +147,13 @@ def rows_heads_out(x: torch.Tensor, wpack: torch.Tensor, dh: int, bias: Optional
     return y
 
 
-def rows_heads_in_exp(x: torch.Tensor, wpack_exp: torch.Tensor, heads: int = NUM_HEADS, n_cta: int = 0,
-                      bias: Optional[torch.Tensor] = None):
+def rows_heads_in_exp(x: torch.Tensor, wpack_exp: torch.Tensor, heads: int = NUM_HEADS, n_cta: int = 0):
     """y [H,R,C]: y[h] = x[:, head h] @ W_h for heads NARROWER than a k-slab (16 wide): every head reads the whole row and its
     weights are zero-extended over all C columns (``wpack_exp`` = the packed [H*C, C] matrix, C rows per head)."""
     R, C = x.shape
     y = torch.empty(heads, R, C, device=x.device, dtype=F32)
-    call('sgc_rows_gemm_tc_ex', ptr(x), C, 0, R, C, heads, ptr(wpack_exp), heads * C, 0, C, ptr(bias), C, C, ptr(y), C, R * C,
-         n_cta, 1, 0, stream())
+    call('sgc_rows_gemm_tc_ex', ptr(x), C, 0, R, C, heads, ptr(wpack_exp), heads * C, 0, C, None, 0, C, ptr(y), C, R * C, n_cta,
+         1, 0, stream())
     return y
 
 
@@ -365,27 +364,6 @@ class LevelWeights:
                 self.p_wv_out = j.pack((wv.unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
                 self.p_wk_out = j.pack(((wk * scale).unsqueeze(1) * hm.t().unsqueeze(2)).reshape(C, num_heads * C))
             j.launch()
-
-    def fuse_query(self, w_out, b_out, in_w, in_b, num_heads: int = NUM_HEADS):
-        """The query side of the attention pooling as one product per head (``sgc_fuse_query_weights``): ``p_wf`` / ``bf`` for
-        qt[h] = mean @ Wf_h^T + bf_h (forward) and ``p_a1_t`` for gmean = gqv @ (W_q W_out) (backward).  Issued after the level's
-        feature projection on the same side stream: ready long before the per-voxel chain needs it."""
-        with torch.no_grad():
-            C = w_out.shape[0]
-            dev = w_out.device
-            a1 = torch.empty(C, C, device=dev, dtype=F32)
-            a1b = torch.empty(C, device=dev, dtype=F32)
-            wf = torch.empty(num_heads * C, C, device=dev, dtype=F32)
-            self.bf = torch.empty(num_heads * C, device=dev, dtype=F32)
-            in_w, in_b = in_w.contiguous(), in_b.contiguous()
-            base = ptr(in_w)
-            call('sgc_fuse_query_weights', ptr(w_out.contiguous()), ptr(b_out.contiguous()), base, ptr(in_b), base + 4 * C * C, C,
-                 num_heads, 1.0 / math.sqrt(C // num_heads), ptr(a1), ptr(a1b), ptr(wf), ptr(self.bf), stream())
-            j = _WeightJobs(dev)
-            self.p_wf = j.pack(wf)
-            self.p_a1_t = j.pack(a1.t())
-            j.launch()
-            self.fused_query = True
 
     def record_stream(self, s):
         for t in self.__dict__.values():
@@ -830,16 +808,9 @@ class EncoderLayerRows(torch.autograd.Function):
             coll.view((Q,), Q * C).copy_(pl.count)
             red = coll.reduce(Q * C + Q, 'sum')
             mean, cnt = rows_headscale(red[:Q * C].view(Q, C), red[Q * C:], 1, 1.0, want_count=True)
-        fused = coll is None and getattr(lw, 'fused_query', False)
-        if fused:
-            # output_proj -> query in-projection -> per-head key product as ONE GEMM (LevelWeights.fuse_query): two launches
-            # less on the chain; g and qv are recomputed beside the backward for the weight gradients only
-            qt = rows_heads_in_exp(mean, lw.p_wf, H, bias=lw.bf)
-            g = qv = mean   # placeholders for save_for_backward
-        else:
-            g = rows_linear(mean, lw.p_w_out, C, b_out)
-            qv = rows_linear(g, lw.p_wq, C, bq)
-            qt = heads_in(qv, getattr(lw, 'p_wk_ht', None), getattr(lw, 'p_wk_in', None))      # scale Wk_h folded in
+        g = rows_linear(mean, lw.p_w_out, C, b_out)
+        qv = rows_linear(g, lw.p_wq, C, bq)
+        qt = heads_in(qv, getattr(lw, 'p_wk_ht', None), getattr(lw, 'p_wk_in', None))          # scale Wk_h folded in
         t = torch.empty(H, Q, C, device=dev, dtype=F32)
         alpha = torch.empty(pl.cap, H, device=dev, dtype=F32)
         ssm = None
@@ -869,7 +840,6 @@ class EncoderLayerRows(torch.autograd.Function):
         ctx.pl, ctx.lw, ctx.wstream = pl, lw, wstream
         ctx.coll, ctx.ssm, ctx.cnt = coll, ssm, cnt
         ctx.masks, ctx.scales = (m0, m1, m2), (s0, s1, s2)
-        ctx.fused, ctx.q_biases = fused, ((b_out.detach(), bq.detach()) if fused else None)
         return y
 
     @staticmethod
@@ -934,12 +904,8 @@ class EncoderLayerRows(torch.autograd.Function):
             # the value-weight gradient pairs this rank's unnormalised partial t with go2 / ssm (per head): sum over ranks =
             # go_h^T (sum_ranks t / ssm)
             go2_n = rows_headscale(go2, ssm, H, 1e-30)
-        if ctx.fused:
-            gmean = rows_linear(gqv, lw.p_a1_t, C)      # (W_q W_out)^T applied at once; gg is formed in _group for W_out's gradient
-            gg = None
-        else:
-            gg = rows_linear(gqv, lw.p_wq_t, C)
-            gmean = rows_linear(gg, lw.p_w_out_t, C)
+        gg = rows_linear(gqv, lw.p_wq_t, C)
+        gmean = rows_linear(gg, lw.p_w_out_t, C)
         gslots = torch.empty_like(slots)
         if coll is None:
             call('sgc_crossview_attn_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt),
@@ -948,15 +914,7 @@ class EncoderLayerRows(torch.autograd.Function):
             call('sgc_cvs_bwd_slots', ptr(qt), ptr(alpha), ptr(gscore), ptr(pl.pair_index), V, Q, C, ptr(gt), ptr(gmean),
                  ptr(cnt), ptr(gslots), stream())
 
-        fused = ctx.fused
-
         def _group():
-            nonlocal g, qv, gg
-            if fused:
-                # the unfused activations the weight gradients pair with, recomputed here on the weight-gradient stream
-                g = rows_linear(mean, lw.p_w_out, C, ctx.q_biases[0])
-                qv = rows_linear(g, lw.p_wq, C, ctx.q_biases[1])
-                gg = rows_linear(gqv, lw.p_wq_t, C)
             # the three in-projection gradients are written straight into in_proj_weight's / in_proj_bias's gradients (rows
             # [0,C) query, [C,2C) key, [2C,3C) value; the key bias gradient is identically zero: it cancels in the softmax)
             G = WgradGroup(Q, dev)
@@ -979,7 +937,7 @@ class EncoderLayerRows(torch.autograd.Function):
             G.launch()
             return w2g + w1g + wog + woutg + (gw_in, gb_in)
         g_w2, g_b2, g_w1, g_b1, g_wo, g_bo, g_wout, g_bout, g_in_w, g_in_b = side.run(
-            _group, *(t_ for t_ in (gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean, go2_n) if t_ is not None))
+            _group, gf, hdn, gh, x1, gout, o2, t, go2, gqt, qv, gqv, g, gg, mean, *((go2_n,) if coll is not None else ()))
         if side.detached and side_f.detached and side_f.side != side.side:
             # the FFN parameters are aliased on the second weight stream: it only has to follow the grouped launch
             side_f.side.wait_stream(side.side)

@@ -292,7 +292,6 @@ class PerceptionTransformer_DFA3D(nn.Module):
 
 _STREAMS = {}
 _CHAIN_STREAMS = {}
-FUSE_QUERY = os.environ.get('SGC_FUSE_QUERY', '1') != '0'   # A/B: 0 = output_proj, query projection, key product as three GEMMs
 
 
 def _prepare_priorities(n: int):
@@ -453,8 +452,6 @@ class DenseHead(nn.Module):
         else:
             dist = dpt_dist[0, :, :, :h, :w].permute(0, 2, 3, 1).reshape(feat.shape[1], h * w, -1).contiguous()
         vg = SF.ProjectFeatures.apply(feat, h, w, wcat, lw)
-        if FUSE_QUERY:
-            lw.fuse_query(attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias)
         # the remaining parameters of the layer, aliased on this head's weight-gradient stream (functional.OnStream):
         # their gradients are produced on that stream by the backward and never joined into the per-voxel chain
         params = (attn.output_proj.weight, attn.output_proj.bias, mha.in_proj_weight, mha.in_proj_bias,

@@ -253,33 +253,3 @@ def test_narrow_head_products_match_fp64(cuda_lib, R, C):
     check(gt, torch.einsum('rhd,hdc->hrc', qv.double().view(R, H, dh), wv.view(H, dh, C)))
     check(o2, torch.einsum('hrk,hdk->rhd', t.double(), wv.view(H, dh, C)).reshape(R, C) + bv.double())
     check(gqv, torch.einsum('hrk,hdk->rhd', t.double(), wk.view(H, dh, C)).reshape(R, C) * scale)
-
-
-@pytest.mark.parametrize('R,C', [(400, 256), (6400, 256), (800, 128), (77, 256)])
-def test_fused_query_chain_matches_fp64(cuda_lib, R, C):
-    """``LevelWeights.fuse_query`` (sgc_fuse_query_weights + the a_mode 1 GEMM): output_proj -> query in-projection -> per-head
-    key product as one product per head, against the three separate maps in fp64 (DCA:826-833 + nn.MultiheadAttention's
-    in-projection); and the fused data gradient gmean = gqv @ (W_q W_out)."""
-    H = 8
-    dh = C // H
-    g = torch.Generator().manual_seed(R * 3 + C)
-    w_out, wo = (torch.randn(C, C, generator=g) / C ** 0.5).cuda(), torch.randn(C, C, generator=g).cuda()
-    b_out = torch.randn(C, generator=g).cuda()
-    in_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).cuda()
-    in_b = torch.randn(3 * C, generator=g).cuda()
-    w1, w2 = torch.randn(2 * C, C, generator=g).cuda(), torch.randn(C, 2 * C, generator=g).cuda()
-    wcat = torch.randn(C + 128, C, generator=g).cuda()
-    lw = SF.LevelWeights(wcat, w_out, in_w, wo, w1, w2)
-    lw.fuse_query(w_out, b_out, in_w, in_b)
-    mean = torch.randn(R, C, generator=g).cuda()
-    gqv = torch.randn(R, C, generator=g).cuda()
-    qt = SF.rows_heads_in_exp(mean, lw.p_wf, H, bias=lw.bf)
-    gmean = SF.rows_linear(gqv, lw.p_a1_t, C)
-    torch.cuda.synchronize()
-    d = lambda t: t.double().cpu()
-    scale = 1.0 / math.sqrt(dh)
-    wq, wk, bq = d(in_w[:C]), d(in_w[C:2 * C]), d(in_b[:C])
-    qv = (d(mean) @ d(w_out).t() + d(b_out)) @ wq.t() + bq
-    qt_ref = torch.einsum('rhd,hdc->hrc', qv.view(R, H, dh), wk.view(H, dh, C)) * scale
-    check(qt.cpu(), qt_ref)
-    check(gmean.cpu(), d(gqv) @ wq @ d(w_out))
