@@ -426,11 +426,12 @@ class DenseHead(nn.Module):
             # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
             # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
             if self._wstream is None or self._wstream[0].device != feat.device:
-                # high priority (SGC_WSTREAM_PRIO, default -1): besides the grouped weight-gradient launch these streams carry small
-                # trailing work (occupancy weight gradient, the depth map's layout backward, gradient accumulation); at default
-                # priority the block scheduler left it waiting until the projection-gradient grids had dispatched every CTA,
-                # i.e. it ran AFTER them and ended the step ~40 us late
-                prio = int(os.environ.get('SGC_WSTREAM_PRIO', '-1'))
+                # default priority (SGC_WSTREAM_PRIO: A/B).  High priority had been adopted when the small trailing work of these
+                # streams (occupancy weight gradient, the depth map's layout backward) ended the step ~40 us late; with that
+                # work rearranged since, default priority measures better: 615.9 vs 613.1 volumes/s on one GPU (three runs
+                # each, session Y), 1 223 vs 1 208 on two (session AC) -- the grouped weight-gradient launch no longer takes
+                # the SMs from the finest level's lift backward, which is the longer pole
+                prio = int(os.environ.get('SGC_WSTREAM_PRIO', '0'))
                 self._wstream = (torch.cuda.Stream(device=feat.device, priority=prio),
                                  torch.cuda.Stream(device=feat.device, priority=prio))
             wstream = self._wstream

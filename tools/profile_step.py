@@ -29,14 +29,19 @@ if os.environ.get('SGC_PROFILE_AVERAGER'):
     avg = peer.GradAverager(list(head.parameters()))
 
 
+loss_stream = torch.cuda.Stream()
+
+
 def step():
     for t in list(head.parameters()) + feats + dists:
         t.grad = None
     if avg is not None:
         avg.begin_step()
     vol, valid, occ = head(feats, sc.img_meta, dists)
-    # as bench.py: the backward is seeded with G (the gradient of sum(volume*G)); the loss value is not on its path
-    torch.autograd.backward([vol, head.occ_loss(occ, None, sc.geo_occ)['loss_occ']], [gvol, None])
+    # as bench.py: the backward is seeded with G (the gradient of sum(volume*G)); the occupancy loss (value and gradient) lives
+    # on the loss stream, off the path from the volume to its gradient
+    torch.autograd.backward([vol, head.occ_loss(occ, None, sc.geo_occ, stream=loss_stream)['loss_occ']], [gvol, None])
+    torch.cuda.current_stream().wait_stream(loss_stream)
     if avg is not None:
         avg.finish_step()
 
