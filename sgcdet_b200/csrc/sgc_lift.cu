@@ -74,8 +74,8 @@ __device__ __forceinline__ float4 lift_params(const float* __restrict__ G, int l
   return r;
 }
 
-template <int CPL, int MINB>
-__global__ void __launch_bounds__(256, MINB) lift_fwd_kernel(
+template <int CPL>
+__global__ void __launch_bounds__(256, 4) lift_fwd_kernel(
     const float* __restrict__ value, int ldv, const float* __restrict__ G, int ldg,
     const float* __restrict__ dist, const float* __restrict__ vbias, const float* __restrict__ gbias,
     const int* __restrict__ pair_vq, const int* __restrict__ n_pairs_ptr, const float* __restrict__ ref_cam,
@@ -182,7 +182,7 @@ __device__ __forceinline__ void scatter_dist(float* gd_px, const Tap& t, int D, 
   if (t.d0 + 1 <= D - 1) red_add1(gd_px + t.d0 + 1, t.ld * gds);
 }
 
-template <int CPL, int MINB, bool PF>
+template <int CPL, int MINB>
 __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
     const float* __restrict__ value, int ldv, const float* __restrict__ G, int ldg,
     const float* __restrict__ dist, const float* __restrict__ vbias,
@@ -203,29 +203,12 @@ __global__ void __launch_bounds__(256, MINB) lift_bwd_kernel(
   float vb[CPL];
   load_row<CPL>(vb, vbias + lane_base<CPL>(lane));
 
-  // pair id and the lane's saved sampling point are fetched one iteration ahead (two dependent round trips less per pair)
-  const int stride = gridDim.x * warps_per_block;
-  int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  int flat_n = 0;
-  float4 sp_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (PF && pair < n_pairs) {
-    flat_n = __ldg(pair_vq + pair);
-    sp_n = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
-  }
-  for (; pair < n_pairs; pair += stride) {
-    int flat;
-    float4 sp;
-    if (PF) {
-      flat = flat_n;
-      sp = sp_n;
-      if (pair + stride < n_pairs) {
-        flat_n = __ldg(pair_vq + pair + stride);
-        sp_n = ldg4(samp + ((size_t)(pair + stride) * 32 + lane) * 4);
-      }
-    } else {
-      flat = __ldg(pair_vq + pair);
-      sp = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
-    }
+  // (fetching the next pair's id and sampling point one iteration ahead, as lift_fwd does, measured slightly slower here:
+  // 597.7 vs 600.6 volumes/s -- the kernel sits at its register limit)
+  for (int pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < n_pairs;
+       pair += gridDim.x * warps_per_block) {
+    const int flat = __ldg(pair_vq + pair);
+    const float4 sp = ldg4(samp + ((size_t)pair * 32 + lane) * 4);
     const int v = flat / Q;
     const size_t vS = (size_t)v * S;
     const Tap t = make_tap(sp.x, sp.y, sp.z, H, W, D);
@@ -380,16 +363,12 @@ extern "C" int sgc_lift_fwd(const float* value, int ldv, const float* G, int ldg
   const int grid = lift_grid(cap_pairs);
   // 4 CTAs of 8 warps per SM (64 registers) measured better inside the step than 3 (80 registers) or 2: 591.5 / 588.2 / ~585
   // volumes/s (session U), although the kernel alone is fastest with 3
-  static const int minb = getenv("SGC_LIFT_FWD_MINB") ? atoi(getenv("SGC_LIFT_FWD_MINB")) : 4;
-#define SGC_LIFT_FWD_ARGS value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs, ref_cam, S, H, W, D, Q, samp, slots
-  if (C == 256) {
-    if (minb == 4) sgc::launch_chain(sgc::lift_fwd_kernel<8, 4>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
-    else if (minb == 2) sgc::launch_chain(sgc::lift_fwd_kernel<8, 2>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
-    else sgc::launch_chain(sgc::lift_fwd_kernel<8, 3>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
-  } else {
-    if (minb == 3) sgc::launch_chain(sgc::lift_fwd_kernel<4, 3>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
-    else sgc::launch_chain(sgc::lift_fwd_kernel<4, 4>, dim3(grid), dim3(256), 0, st, SGC_LIFT_FWD_ARGS);
-  }
+  if (C == 256)
+    sgc::launch_chain(sgc::lift_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
+                      ref_cam, S, H, W, D, Q, samp, slots);
+  else
+    sgc::launch_chain(sgc::lift_fwd_kernel<4>, dim3(grid), dim3(256), 0, st, value, ldv, G, ldg, dist, vbias, gbias, pair_vq, n_pairs,
+                      ref_cam, S, H, W, D, Q, samp, slots);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }
@@ -407,17 +386,10 @@ extern "C" int sgc_lift_bwd(const float* value, int ldv, const float* G, int ldg
   (void)scratch;   // kept in the signature (earlier versions reduced per-CTA rows through it)
 #define SGC_LIFT_BWD_ARGS value, ldv, G, ldg, dist, vbias, pair_vq, n_pairs, ref_cam, samp, grad_slots, S, H, W, D, Q, \
                           grad_value, grad_G, grad_dist, grad_vbias, grad_gbias
-  static const int minb = getenv("SGC_LIFT_MINB") ? atoi(getenv("SGC_LIFT_MINB")) : 2;
-  // next-pair prefetch (as in lift_fwd): measured slightly slower here (597.7 vs 600.6 volumes/s, session V) -> off
-  static const int pf = getenv("SGC_LIFT_BWD_PF") ? atoi(getenv("SGC_LIFT_BWD_PF")) : 0;
-  if (C == 256) {
-    if (minb == 3) sgc::lift_bwd_kernel<8, 3, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-    else if (pf) sgc::lift_bwd_kernel<8, 2, true><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-    else sgc::lift_bwd_kernel<8, 2, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-  } else {
-    if (pf) sgc::lift_bwd_kernel<4, 3, true><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-    else sgc::lift_bwd_kernel<4, 3, false><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
-  }
+  // 2 CTAs of 8 warps per SM at C = 256 (128 registers, no spills; 3 CTAs with 80 registers + spills measured the same or
+  // slower: 589 vs 592 volumes/s), 3 at C = 128
+  if (C == 256) sgc::lift_bwd_kernel<8, 2><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
+  else sgc::lift_bwd_kernel<4, 3><<<grid, 256, 0, st>>>(SGC_LIFT_BWD_ARGS);
   SGC_CUDA_CHECK_LAST();
   return 0;
 }

@@ -364,11 +364,10 @@ extern "C" int sgc_rows_gemm_tc_auto_ncta(int R, int N, int B) {
   int n_cta = 256;
   // Problems of at most 4 row tiles (the coarsest level) settle for 16 work items: in the forward their chain runs beside the
   // persistent projection kernel of the finest level, which leaves 16 SMs free, and a CTA's lifetime hardly depends on its
-  // column count (the conversion of the shared A tile dominates).  Measured (session V, SGC_ROWS_SMALL_WORKS = 0 / 4 / 8 / 16):
+  // column count (the conversion of the shared A tile dominates).  Measured (session V; split as far as possible / 4 / 8 / 16 work items):
   // 597.7 / 605.1 / 609.9 / 613.5 volumes/s; extending it to 8 row tiles (the middle level) gave 611.9.
-  static const int small_works = getenv("SGC_ROWS_SMALL_WORKS") ? atoi(getenv("SGC_ROWS_SMALL_WORKS")) : 16;
-  static const int small_tiles = getenv("SGC_ROWS_SMALL_TILES") ? atoi(getenv("SGC_ROWS_SMALL_TILES")) : 4;
-  if (small_works > 0 && m_tiles <= small_tiles) {
+  constexpr int small_works = 16, small_tiles = 4;
+  if (m_tiles <= small_tiles) {
     while (n_cta > 32 && (N % n_cta || (long long)m_tiles * B * (N / n_cta) < small_works)) n_cta >>= 1;
     while (N % n_cta) n_cta >>= 1;
     return n_cta;

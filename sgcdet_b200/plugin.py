@@ -294,25 +294,16 @@ _STREAMS = {}
 _CHAIN_STREAMS = {}
 
 
-def _prepare_priorities(n: int):
-    """Stream priority of every level's prepare stream (coarsest level first): all default.  ``SGC_PREP_PRIO="a,b,c"`` (A/B):
-    raising the coarser levels' streams makes their lift / projection-gradient kernels run beside the finest level's lift
-    backward instead of after it, as intended -- but that kernel then keeps one CTA per SM instead of two while a persistent
-    tcgen05 CTA is resident and takes 450 instead of 293 us: 570 vs 591.5 volumes/s (session U, three runs each)."""
-    env = os.environ.get('SGC_PREP_PRIO')
-    if env:
-        pr = [int(v) for v in env.split(',')]
-        return (pr + [pr[-1]] * n)[:n]
-    return [0] * n
-
-
 def _side_streams(device, n: int, main=None):
-    """n side streams private to (device, calling stream): concurrent scenes on different streams never share them."""
-    prios = _prepare_priorities(n)
-    key = (torch.device(device), main.cuda_stream if main is not None else 0, tuple(prios))
+    """n side streams private to (device, calling stream): concurrent scenes on different streams never share them.
+    All at default priority.  Raising the coarse levels' prepare streams was measured (session U): their lift / projection
+    gradient kernels then run beside the finest level's lift backward instead of after it, as intended -- but that kernel keeps
+    one CTA per SM instead of two while a persistent tcgen05 CTA is resident and takes 450 instead of 293 us: 570 vs 591.5
+    volumes/s, three runs each."""
+    key = (torch.device(device), main.cuda_stream if main is not None else 0)
     pool = _STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=torch.device(device), priority=prios[len(pool)]))
+        pool.append(torch.cuda.Stream(device=torch.device(device)))
     return pool[:n]
 
 
