@@ -240,6 +240,31 @@ def bind_to_gpu_numa_node(local: int):
         return None
 
 
+def gpu_numa_node(local: int):
+    """NUMA node the GPU's PCIe root hangs off, or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def prefer_numa_node(node) -> bool:
+    """set_mempolicy(MPOL_PREFERRED, {node}) for this thread (node None: back to MPOL_DEFAULT).  Memory only -- the CPU
+    affinity stays as it is, so the CPU baseline of a single-rank run keeps all host cores."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        if node is None:
+            return libc.syscall(238, 0, None, ctypes.c_ulong(0)) == 0
+        mask = ctypes.c_ulong(1 << node)
+        return libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64)) == 0
+    except Exception:
+        return False
+
+
 def run_ours(args):
     import torch.distributed as dist
     from sgcdet_b200 import plugin, synthetic as syn
@@ -428,7 +453,16 @@ def run_ours(args):
     loss_val = float(loss_buf.item())
 
     # ---- end to end: host buffers -> H2D -> step -> D2H of the loss, every step -------------------------
+    # single rank: the pinned staging buffers are placed on the GPU's NUMA node (memory policy only; multi-rank runs bound the
+    # whole process in bind_to_gpu_numa_node): a remote node costs ~6 % of the PCIe rate on these boxes
+    e2e_node = numa_node
+    if world == 1 and not args.skip_e2e:
+        e2e_node = gpu_numa_node(local)
+        if e2e_node is not None and not prefer_numa_node(e2e_node):
+            e2e_node = None
     host_in = [t.detach().cpu().pin_memory() for t in all_inputs]
+    if world == 1 and e2e_node is not None:
+        prefer_numa_node(None)
     dev_in = all_inputs
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     loss_host = torch.zeros(1).pin_memory()
@@ -617,9 +651,10 @@ def run_ours(args):
                 'grad_average': 'none' if ar_mode == 'none' else (
                     'own peer-memory all-reduce kernels over NVLink, issued from the backward and overlapped with it'
                     + (' inside the CUDA graph' if ar_in_graph else '') if ar_mode == 'peer' else 'NCCL all-reduce after the replay'),
-                'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term) '
-                        'and the loss value evaluated on a side stream beside the backward',
-                'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active)',
+                'loss': 'sum(volume*G) + occ_loss every step; backward seeded with G (the gradient of the first term); the loss value '
+                        'and the occupancy loss (forward and, through autograd, backward) run on a side stream beside the backward',
+                'mode': 'eval' if args.eval_mode else 'train (FFN dropout 0.1 active; keep-masks of all levels drawn by one own Philox '
+                                                     'launch per step, fresh on every graph replay)',
                 'cuda_graph': not args.no_graph,
                 'gemm': 'all GEMMs of the path are own tcgen05/TMEM/TMA kernels with the bf16 hi/lo split in shared memory and fp32 '
                         'accumulation: feature-map projection (forward, data gradient, weight gradient) and the voxel-count layers '
@@ -627,7 +662,7 @@ def run_ours(args):
                 'streams': 'per-voxel chain on a high-priority stream; projections, lift backward and weight gradients on side '
                            'streams; one CUDA graph'},
             'e2e': {'value': None if args.skip_e2e else round(world * B * e2e_steps / (e2e_ms * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'numa_node_rank0': numa_node,
+                    'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'numa_node_rank0': e2e_node,
                     'pipeline': 'double-buffered: H2D of step k+1 (copy stream) overlaps compute of step k'},
             'gpu_launches': int(launches_per_step * args.steps),
             'gpu_launches_per_step': int(launches_per_step),
