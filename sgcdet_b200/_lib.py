@@ -183,10 +183,13 @@ def load() -> ctypes.CDLL:
             fn.argtypes = argtypes
             fn.restype = c_longlong if name in ('sgc_rows_wgrad_group_scratch_floats', 'sgc_lift_bwd_tiles_workspace_bytes',
                                                  'sgc_upsample2x_occ_bwd_scratch_floats') else c_int
-        lib.sgc_project_tc_set_max_ctas(int(os.environ.get('SGC_TC_MAX_CTAS', '0')))
-        lib.sgc_project_tc_set_max_ctas_fwd(int(os.environ.get('SGC_TC_MAX_CTAS_FWD', '132')))
-        lib.sgc_set_pdl(int(os.environ.get('SGC_PDL', '0')))
-        lib.sgc_project_tc_set_tiles_per_cta(int(os.environ.get('SGC_TC_TILES_PER_CTA', '0')))
+        # measured settings (profiles/README.md): the forward projection leaves 16 SMs to the coarser levels' voxel chains (caps
+        # of 100..148 measured: 132 best), no cap for the gradient kernels, no programmatic dependent launch (neutral under
+        # graph replay), persistent CTAs walk all their tiles
+        lib.sgc_project_tc_set_max_ctas(0)
+        lib.sgc_project_tc_set_max_ctas_fwd(132)
+        lib.sgc_set_pdl(0)
+        lib.sgc_project_tc_set_tiles_per_cta(0)
         _lib = lib
     return _lib
 

@@ -94,8 +94,8 @@ import os as _os
 # zero-filled grad_vg).  Parity-green, but its first version is latency-bound per tile (830 us vs 195 + 58 us of fill at the
 # finest ScanNet level): off by default
 LIFT_TILES = _os.environ.get('SGC_LIFT_TILES', '0') != '0'
-TOPK_MC_MIN = int(_os.environ.get('SGC_TOPK_MC_MIN', '32768'))  # levels with more voxels use the many-CTA top-k
-UP_BWD_SEPARABLE = _os.environ.get('SGC_UP_BWD_SEP', '1') != '0'   # A/B: 0 = the one-launch gather form
+TOPK_MC_MIN = 32768  # levels with more voxels use the many-CTA top-k
+UP_BWD_SEPARABLE = True   # False = the one-launch gather form of the upsample backward (kept for its tests)
 TOPK_GRID = _os.environ.get('SGC_TOPK_GRID', '1') != '0'   # one-launch grid top-k (round 2); 0 = the round-1 kernels
 _TOPK_SCRATCH = {}
 

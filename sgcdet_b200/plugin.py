@@ -417,14 +417,12 @@ class DenseHead(nn.Module):
             # two weight-gradient streams per head (attention block / FFN + norms): the per-voxel chain emits
             # weight-gradient jobs faster than one stream retires them, and the backlog would be the tail of the step
             if self._wstream is None or self._wstream[0].device != feat.device:
-                # default priority (SGC_WSTREAM_PRIO: A/B).  High priority had been adopted when the small trailing work of these
+                # default priority.  High priority had been adopted when the small trailing work of these
                 # streams (occupancy weight gradient, the depth map's layout backward) ended the step ~40 us late; with that
                 # work rearranged since, default priority measures better: 615.9 vs 613.1 volumes/s on one GPU (three runs
                 # each, session Y), 1 223 vs 1 208 on two (session AC) -- the grouped weight-gradient launch no longer takes
                 # the SMs from the finest level's lift backward, which is the longer pole
-                prio = int(os.environ.get('SGC_WSTREAM_PRIO', '0'))
-                self._wstream = (torch.cuda.Stream(device=feat.device, priority=prio),
-                                 torch.cuda.Stream(device=feat.device, priority=prio))
+                self._wstream = (torch.cuda.Stream(device=feat.device), torch.cuda.Stream(device=feat.device))
             wstream = self._wstream
         if isinstance(dpt_dist, SF.DepthCL):   # produced channel-last and cropped by sgcdet_b200.depth.depth_pyramid
             if (dpt_dist.h, dpt_dist.w) != (h, w):
